@@ -1,0 +1,240 @@
+/*
+ * twotower.h -- C-ABI of libtwotower.so: the B200 (sm_100a) two-tower training + retrieval
+ * hot path.
+ *
+ * Boundary.  The reference repository declares this path but ships no code and no FFI for it
+ * (/root/reference/src/models/__init__.py:1, src/training/__init__.py:1,
+ * src/serving/__init__.py:1, src/evaluation/__init__.py:1), so each entry point below cites
+ * the upstream TensorFlow-Recommenders / Keras / FAISS routine that the reference's declared
+ * dependencies (/root/reference/pyproject.toml:22,24,39) would dispatch for that step, plus the
+ * in-repo line that parameterises it.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - extern "C", plain pointers + sizes.  Every pointer is a DEVICE pointer unless named
+ *     host_*.  The caller owns every buffer, including workspaces (sizes from
+ *     tt_*_workspace_bytes).  The library allocates nothing persistent.
+ *   - Every call enqueues on `stream` (a cudaStream_t passed as void*) and returns without
+ *     synchronising; it is CUDA-graph capturable.
+ *   - Return value: 0 = TT_OK, negative = error; the message is in tt_last_error()
+ *     (thread-local).  Nothing throws or exits across the ABI.  There is no CPU fallback.
+ *   - Matrices are row-major.  bf16 values are passed as uint16_t bit patterns.
+ */
+#ifndef TWOTOWER_H_
+#define TWOTOWER_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TT_VERSION 100 /* 0.1.0 */
+
+enum tt_status {
+  TT_OK = 0,
+  TT_ERR_INVALID_ARG = -1,
+  TT_ERR_CUDA = -2,
+  TT_ERR_UNSUPPORTED = -3,
+  TT_ERR_WORKSPACE = -4
+};
+
+enum tt_dtype { TT_F32 = 0, TT_BF16 = 1 };
+enum tt_pool { TT_POOL_SUM = 0, TT_POOL_MEAN = 1 };
+
+int tt_version(void);
+const char* tt_last_error(void);
+/* 0 when the current CUDA device is compute capability 10.x, TT_ERR_UNSUPPORTED otherwise. */
+int tt_device_check(void);
+
+/* ---------------------------------------------------------------------------------------
+ * K1  tower input: Embedding gather and multi-hot sum/mean pooling.
+ * Replaces tf.keras.layers.Embedding -> tf.nn.embedding_lookup and
+ * safe_embedding_lookup_sparse(combiner); ids are the int64 codes of
+ * /root/reference/src/data/preprocessor.py:481-482,485-489.
+ * ------------------------------------------------------------------------------------- */
+typedef struct tt_feature {
+  const float* table;     /* [vocab, d] fp32 */
+  const int64_t* values;  /* ids: [B] when offsets == NULL, else CSR values [nnz] */
+  const int64_t* offsets; /* NULL (one id per row) or CSR offsets [B+1] */
+  int64_t vocab;
+  int32_t mode;           /* tt_pool, used when offsets != NULL */
+  int32_t reserved;
+} tt_feature;
+
+#define TT_MAX_FEATURES 8
+
+/* out[b,:] = sum_f pool_f(table_f[bag_f(b)]).  Either output may be NULL (not both).
+ * `host_feats` is a HOST array of num_feats descriptors (copied into kernel parameters).
+ * d % 4 == 0, rows 16-byte aligned.  Ids outside [0, vocab) raise a device-side flag that
+ * the next tt_check_id_fault() returns (TF raises on CPU; a GPU kernel cannot). */
+int tt_tower_input_fwd(const tt_feature* host_feats, int32_t num_feats, float* out_f32,
+                       uint16_t* out_bf16, int64_t B, int64_t d, int32_t* id_fault_flag,
+                       void* stream);
+int tt_embedding_gather_f32(const float* table, const int64_t* ids, float* out, int64_t B,
+                            int64_t d, int64_t vocab, void* stream);
+int tt_embedding_gather_bf16(const float* table, const int64_t* ids, uint16_t* out, int64_t B,
+                             int64_t d, int64_t vocab, void* stream);
+int tt_embedding_bag_fwd(const float* table, const int64_t* values, const int64_t* offsets,
+                         int32_t mode, void* out, int32_t out_dtype, int64_t num_bags, int64_t d,
+                         int64_t vocab, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K5  sparse gradient -> dedup -> row-wise optimizer.
+ * Replaces Keras optimizer._deduplicate_sparse_grad (tf.unique + unsorted_segment_sum) and
+ * the sparse Adagrad/Adam update_step; learning_rate from
+ * /root/reference/configs/data_config.yaml:63.
+ * The gradient is given un-expanded: grad[num_rows, d] is d(loss)/d(tower input) and entry j
+ * of `values` belongs to row bag(j) (offsets == NULL: bag(j) = j); mean pooling scales by
+ * 1/len(bag).  first_flag (nullable, [nnz] bytes) is set to 1 where entry j is the first
+ * occurrence of its id: values[first_flag] in order is exactly tf.unique(values).
+ * The workspace must have been initialised once with tt_sparse_workspace_init; every
+ * successful update leaves it clean.
+ * ------------------------------------------------------------------------------------- */
+int64_t tt_sparse_workspace_bytes(int64_t nnz, int64_t d);
+int tt_sparse_workspace_init(void* workspace, int64_t workspace_bytes, int64_t nnz, int64_t d,
+                             void* stream);
+int tt_sparse_adagrad_update(float* table, float* accum, int64_t vocab, int64_t d,
+                             const int64_t* values, const int64_t* offsets, int32_t mode,
+                             int64_t num_rows, int64_t nnz, const float* grad, float lr, float eps,
+                             void* workspace, int64_t workspace_bytes, uint8_t* first_flag,
+                             void* stream);
+/* LazyAdam (touched rows only; NOT Keras Adam).  alpha =
+ * lr*sqrt(1-b2^t)/(1-b1^t) is computed by the caller. */
+int tt_sparse_lazy_adam_update(float* table, float* m, float* v, int64_t vocab, int64_t d,
+                               const int64_t* values, const int64_t* offsets, int32_t mode,
+                               int64_t num_rows, int64_t nnz, const float* grad, float alpha,
+                               float beta1, float beta2, float eps, void* workspace,
+                               int64_t workspace_bytes, uint8_t* first_flag, void* stream);
+
+/* Dense Keras Adagrad / Adam on a [rows, cols] variable.  grad_parts holds `num_parts`
+ * stacked partial gradients [num_parts, rows, cols] (split-K partials of the wgrad GEMM) that
+ * are summed in index order (deterministic).  l2 adds 2*l2*w (kernel_regularizer=l2,
+ * /root/reference/configs/data_config.yaml:59).  Optional bf16 shadow copies of the updated
+ * variable: shadow [rows, cols] and shadow_t [cols, rows]. */
+int tt_dense_adagrad_update(float* w, float* accum, const float* grad_parts, int32_t num_parts,
+                            int64_t rows, int64_t cols, float lr, float eps, float l2,
+                            uint16_t* shadow, uint16_t* shadow_t, void* stream);
+int tt_dense_adam_update(float* w, float* m, float* v, const float* grad_parts, int32_t num_parts,
+                         int64_t rows, int64_t cols, float alpha, float beta1, float beta2,
+                         float eps, float l2, uint16_t* shadow, uint16_t* shadow_t, void* stream);
+
+/* out[0] (+)= scale * sum(x^2) in a fixed order: the kernel_regularizer=l2 term of
+ * tfrs.models.Model.train_step's regularization_loss (sum(model.losses)). */
+int tt_sum_squares(const float* x, int64_t n, float scale, float* out, int32_t accumulate,
+                   void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K2  tower MLP: tf.keras.layers.Dense forward / backward (layer sizes
+ * /root/reference/configs/data_config.yaml:56-57).  kernel is the Keras layout [in, out].
+ *
+ * precision TT_F32 : x, kernel, y fp32 (CUDA-core FFMA path, 1e-5 parity).
+ * precision TT_BF16: x bf16 [M,in], kernel_t bf16 [out,in] (the shadow_t copy), fp32
+ *                    accumulation on tcgen05; y bf16 [M,out]; y_t (nullable) bf16 [out,M]
+ *                    transposed copy (the wgrad operand); y_f32 (nullable) fp32 copy.
+ * ------------------------------------------------------------------------------------- */
+int tt_dense_fwd(int32_t precision, const void* x, const void* kernel, const float* bias,
+                 void* y, void* y_t, float* y_f32, int64_t M, int64_t in_dim, int64_t out_dim,
+                 int32_t relu, void* stream);
+/* dx = (dy @ kernel^T) [* (x > 0) when relu_mask_x != 0: x is the relu OUTPUT of the previous
+ * layer, so the mask applies the previous layer's activation gradient];
+ * dkernel_parts[p] partial x^T @ dy over the p-th M-slice; dbias = colsum(dy).
+ * TT_F32 : everything fp32, num_parts must be 1.
+ * TT_BF16: dy bf16 [M,out] + dy_t bf16 [out,M]; x bf16 [M,in] + x_t bf16 [in,M]; kernel bf16
+ *          [in,out] (the shadow copy); dx bf16 [M,in] (+ dx_t [in,M] nullable);
+ *          dkernel_parts fp32 [num_parts, in, out]; dbias fp32 [out].
+ * dx may be NULL (first layer: only the embedding gradient dx_f32 is wanted) and dx_f32
+ * (nullable) receives an fp32 copy of dx. */
+int tt_dense_bwd(int32_t precision, const void* dy, const void* dy_t, const void* x,
+                 const void* x_t, const void* kernel, void* dx, void* dx_t, float* dx_f32,
+                 float* dkernel_parts, int32_t num_parts, float* dbias, int64_t M,
+                 int64_t in_dim, int64_t out_dim, int32_t relu_mask_x, void* stream);
+int32_t tt_dense_bwd_num_parts(int32_t precision, int64_t M, int64_t in_dim, int64_t out_dim);
+
+/* bf16 [rows, cols] -> bf16 [cols, rows] */
+int tt_transpose_bf16(const uint16_t* in, uint16_t* out, int64_t rows, int64_t cols, void* stream);
+int tt_cast_f32_to_bf16(const float* in, uint16_t* out, uint16_t* out_t, int64_t rows,
+                        int64_t cols, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K3/K4  tfrs.tasks.Retrieval: in-batch softmax cross-entropy, logits never written to HBM.
+ * Replaces matmul(q, c, transpose_b) [/ temperature] [- log clip(p)] [accidental-hit mask]
+ * + CategoricalCrossentropy(from_logits=True, reduction=SUM) with labels = eye(nq, nc)
+ * (in_batch + temperature per /root/reference/configs/data_config.yaml:68-70).
+ *
+ * q [nq, d], c [nc, d] (fp32 for TT_F32, bf16 for TT_BF16).  Row i's positive is column
+ * label_offset + i (label_offset = rank * nq under all-gathered candidates).
+ * Optional: sample_weight [nq] fp32; cand_log_q [nc] fp32 = log(clip(p, 1e-6, 1)) subtracted
+ * from every row; accidental-hit removal when cand_ids != NULL (int64 [nc]): column j of row
+ * i gets MIN_FLOAT added when cand_ids[j] == cand_ids[label(i)] and j != label(i).
+ * Outputs: row_lse [nq], row_pos [nq] (the transformed positive logit), loss[1] =
+ * sum_i w_i (lse_i - pos_i) reduced in a fixed order.
+ * ------------------------------------------------------------------------------------- */
+int64_t tt_retrieval_workspace_bytes(int32_t precision, int64_t nq, int64_t nc, int64_t d);
+int tt_retrieval_loss_fwd(int32_t precision, const void* q, const void* c, int64_t nq, int64_t nc,
+                          int64_t d, float inv_temperature, int64_t label_offset,
+                          const float* sample_weight, const float* cand_log_q,
+                          const int64_t* cand_ids, float* row_lse, float* row_pos, float* loss,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+/* dq [nq, d] fp32, dc [nc, d] fp32 (this rank's partial when candidates are all-gathered).
+ * TT_BF16 additionally takes q_t [d, nq] and c_t [d, nc] bf16 transposed copies and can emit
+ * bf16 copies dq_bf16 [nq,d], dq_bf16_t [d,nq], dc_bf16, dc_bf16_t (each nullable) for the
+ * MLP backward that follows. grad_scale multiplies the upstream gradient (1.0 for SUM). */
+int tt_retrieval_loss_bwd(int32_t precision, const void* q, const void* c, const void* q_t,
+                          const void* c_t, int64_t nq, int64_t nc, int64_t d,
+                          float inv_temperature, int64_t label_offset,
+                          const float* sample_weight, const float* cand_log_q,
+                          const int64_t* cand_ids, const float* row_lse, float grad_scale,
+                          float* dq, float* dc, uint16_t* dq_bf16, uint16_t* dq_bf16_t,
+                          uint16_t* dc_bf16, uint16_t* dc_bf16_t, void* workspace,
+                          int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K6  brute-force scoring + top-k.
+ * Replaces tfrs.layers.factorized_top_k.BruteForce.call (matmul + tf.math.top_k) and
+ * faiss.IndexFlatIP.search (ks from
+ * /root/reference/configs/data_config.yaml:71).  Result rows are sorted by score descending,
+ * ties by LOWER candidate index first (the tf.math.top_k rule).
+ * out_ids[q, j] = identifiers ? identifiers[idx] : cand_index_base + idx.
+ * The candidate range may be split over `num_splits` CTAs columns (workspace holds the
+ * partial lists) and merged with the same ordering rule.
+ * ------------------------------------------------------------------------------------- */
+int32_t tt_topk_num_splits(int32_t precision, int64_t nq, int64_t nc, int64_t d, int32_t k);
+int64_t tt_topk_workspace_bytes(int32_t precision, int64_t nq, int64_t nc, int64_t d, int32_t k);
+int tt_topk_bruteforce(int32_t precision, const void* queries, const void* candidates, int64_t nq,
+                       int64_t nc, int64_t d, int32_t k, int64_t cand_index_base,
+                       const int64_t* identifiers, float* out_scores, int64_t* out_ids,
+                       void* workspace, int64_t workspace_bytes, void* stream);
+/* Merge `num_lists` sorted top-k lists per query: scores/ids are [num_lists, nq, k_in]
+ * (list-major, as written by per-shard searches after an all-gather); ordering rule
+ * (score desc, id asc).  Writes [nq, k_out]. */
+int tt_topk_merge(const float* scores, const int64_t* ids, int32_t num_lists, int64_t nq,
+                  int32_t k_in, int32_t k_out, float* out_scores, int64_t* out_ids, void* stream);
+/* FactorizedTopK hit counting.  Score mode (true_ids == NULL): hit@k iff
+ * fewer than k of topk_scores[i,:] are strictly greater than positive[i].  Id mode: hit@k iff
+ * true_ids[i] appears in topk_ids[i,:k].  hits_out[j] += sum_i w_i * hit_{ks[j]}(i);
+ * weight_out[0] += sum_i w_i.  host_ks: HOST array of num_ks ints (<= 8). */
+int tt_topk_hits(const float* positive, const float* topk_scores, const int64_t* topk_ids,
+                 const int64_t* true_ids, const float* sample_weight, int64_t nq, int32_t k,
+                 const int32_t* host_ks, int32_t num_ks, float* hits_out, float* weight_out,
+                 void* stream);
+/* positive[i] = <q[i,:], c[i,:]> in fp32 (inputs of `precision`). */
+int tt_rowwise_dot(int32_t precision, const void* q, const void* c, float* out, int64_t n,
+                   int64_t d, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Row-sharded tables across ranks: stable partition of ids by owner.
+ * owner(id) = id % world (cyclic).  Outputs: perm [n] (position of entry j in the
+ * owner-major send buffer), send_ids [n] = local row (id / world) in owner-major order,
+ * counts [world].  Stable: entries of one owner keep their batch order, so per-owner
+ * buckets are bit-reproducible.
+ * ------------------------------------------------------------------------------------- */
+int tt_partition_ids(const int64_t* ids, int64_t n, int32_t world, int64_t* send_ids,
+                     int64_t* perm, int64_t* counts, void* stream);
+/* out[perm[j], :] = in[j, :]  (inverse = 0)   or   out[j, :] = in[perm[j], :]  (inverse = 1) */
+int tt_permute_rows_f32(const float* in, const int64_t* perm, float* out, int64_t n, int64_t d,
+                        int32_t inverse, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TWOTOWER_H_ */

@@ -1,0 +1,86 @@
+"""Build libtwotower.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the tree)."""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+CSRC = PKG_DIR / "csrc"
+LIB_PATH = PKG_DIR / "libtwotower.so"
+OBJ_DIR = PKG_DIR / "build"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found; libtwotower.so cannot be built")
+
+
+def _digest(path: Path, headers) -> str:
+    h = hashlib.sha256()
+    h.update(" ".join(NVCC_FLAGS).encode())
+    for p in [path, *headers]:
+        h.update(p.read_bytes())
+    return h.hexdigest()
+
+
+def sources():
+    return sorted(CSRC.glob("*.cu"))
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile every csrc/*.cu (one nvcc per file, in parallel) and link libtwotower.so."""
+    nvcc = _nvcc()
+    OBJ_DIR.mkdir(exist_ok=True)
+    headers = sorted(CSRC.glob("*.cuh")) + [PKG_DIR.parent / "include" / "twotower.h"]
+    jobs = []
+    for src in sources():
+        obj = OBJ_DIR / (src.stem + ".o")
+        stamp = OBJ_DIR / (src.stem + ".sha")
+        dg = _digest(src, headers)
+        if force or not obj.exists() or not stamp.exists() or stamp.read_text() != dg:
+            jobs.append((src, obj, stamp, dg))
+
+    def compile_one(job):
+        src, obj, stamp, dg = job
+        cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src.name}:\n{r.stdout}\n{r.stderr}")
+        if verbose:
+            sys.stderr.write(r.stderr)
+        stamp.write_text(dg)
+        return src.name
+
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+            list(ex.map(compile_one, jobs))
+    objs = [str(OBJ_DIR / (s.stem + ".o")) for s in sources()]
+    # drop objects whose source was deleted
+    for o in OBJ_DIR.glob("*.o"):
+        if str(o) not in objs:
+            o.unlink()
+    if jobs or not LIB_PATH.exists():
+        cmd = [nvcc, "-shared", "-o", str(LIB_PATH), *objs]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    p = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(p)

@@ -1,0 +1,160 @@
+"""Minimal tape, tensor and variable types behind the TFRS-shaped Python surface.
+
+A ``Tensor`` is a handle to device buffers produced by libtwotower kernels (torch tensors are
+only the memory owners).  ``GradientTape`` records one backward closure per layer/task call,
+mirroring what tfrs.models.Model.train_step does with tf.GradientTape.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, List, Optional
+
+import numpy as np
+import torch
+
+
+class _Config:
+    precision = "bf16"          # "fp32" (CUDA-core, 1e-5 parity) | "bf16" (tcgen05, 2e-2 parity)
+    seed = 0
+
+
+config = _Config()
+
+
+def set_precision(precision: str) -> None:
+    if precision not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    config.precision = precision
+
+
+def set_seed(seed: int) -> None:
+    config.seed = int(seed)
+
+
+def device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("two_tower_b200 needs a CUDA device (sm_100a); there is no CPU path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class Tensor:
+    """Activations of one layer: any of an fp32 copy, a bf16 copy and a transposed bf16 copy.
+    ``grad_formats`` tells the consumer which gradient representations the producer needs."""
+
+    def __init__(self, f32=None, bf16=None, bf16_t=None, grad_formats=("f32",), producer=None):
+        self.f32: Optional[torch.Tensor] = f32
+        self.bf16: Optional[torch.Tensor] = bf16
+        self.bf16_t: Optional[torch.Tensor] = bf16_t
+        self.grad_formats = tuple(grad_formats)
+        self.producer = producer
+        self.grad = None          # dict(f32=..., bf16=..., bf16_t=...) set by the consumer's backward
+        self.relu_output = False  # True when this is the output of a relu Dense
+        self.producer_needs_grad = True   # False for constants fed in by the user
+
+    @property
+    def shape(self):
+        t = self.f32 if self.f32 is not None else self.bf16
+        return tuple(t.shape)
+
+    def torch(self) -> torch.Tensor:
+        """fp32 view of the activations (device)."""
+        return self.f32 if self.f32 is not None else self.bf16.float()
+
+    def numpy(self) -> np.ndarray:
+        return self.torch().detach().cpu().numpy()
+
+
+class Scalar:
+    """A device scalar (loss) with a tape node."""
+
+    def __init__(self, value: torch.Tensor):
+        self.value = value        # [1] fp32 device tensor
+
+    def item(self) -> float:
+        return float(self.value.item())
+
+    def numpy(self):
+        return self.value.detach().cpu().numpy()[0]
+
+
+@dataclass
+class IndexedSlices:
+    """Sparse gradient of an embedding table: un-expanded rows + CSR membership
+    (tf.IndexedSlices with duplicates)."""
+    values: torch.Tensor              # ids [nnz] int64
+    offsets: Optional[torch.Tensor]   # CSR offsets [rows+1] or None (one id per row)
+    mode: str                         # "sum" | "mean"
+    rows: torch.Tensor                # [num_rows, d] fp32 upstream gradient
+
+
+@dataclass
+class DenseGrad:
+    parts: torch.Tensor               # [P, rows, cols] fp32 partial sums
+    num_parts: int
+
+
+class Variable:
+    def __init__(self, name: str, value: torch.Tensor, kind: str, l2: float = 0.0):
+        self.name = name
+        self.value = value            # fp32 master copy
+        self.kind = kind              # "table" | "kernel" | "bias"
+        self.l2 = float(l2)
+        self.want_shadows = False     # keep bf16 copies of the value in step with it
+        self.shadow = None            # bf16 [rows, cols]   (kernel only, bf16 precision)
+        self.shadow_t = None          # bf16 [cols, rows]
+        self.grad = None
+        self.slots = {}               # optimizer state
+
+    @property
+    def shape(self):
+        return tuple(self.value.shape)
+
+    def numpy(self):
+        return self.value.detach().cpu().numpy()
+
+    def assign(self, array) -> None:
+        from . import ops
+        a = torch.as_tensor(np.asarray(array), dtype=torch.float32)
+        if tuple(a.shape) != self.shape:
+            raise ValueError(f"assign: shape {tuple(a.shape)} != {self.shape}")
+        self.value.copy_(a.to(self.value.device))
+        self.refresh_shadows()
+
+    def refresh_shadows(self) -> None:
+        from . import ops
+        if self.want_shadows:
+            self.shadow, self.shadow_t = ops.cast_f32_to_bf16(self.value, want=True, want_t=True)
+
+
+class GradientTape:
+    _stack: List["GradientTape"] = []
+
+    def __init__(self):
+        self.nodes: List[Callable[[], None]] = []
+
+    def __enter__(self):
+        GradientTape._stack.append(self)
+        return self
+
+    def __exit__(self, *exc):
+        GradientTape._stack.pop()
+        return False
+
+    @staticmethod
+    def current() -> Optional["GradientTape"]:
+        return GradientTape._stack[-1] if GradientTape._stack else None
+
+    @staticmethod
+    def record(fn: Callable[[], None]) -> None:
+        t = GradientTape.current()
+        if t is not None:
+            t.nodes.append(fn)
+
+    def gradient(self, target, variables):
+        """Run the recorded backward closures in reverse order; returns [v.grad for v in variables]."""
+        for v in variables:
+            v.grad = None
+        for fn in reversed(self.nodes):
+            fn()
+        self.nodes.clear()
+        return [v.grad for v in variables]

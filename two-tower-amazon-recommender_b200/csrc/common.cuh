@@ -1,0 +1,68 @@
+// Shared helpers for libtwotower.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/twotower.h"
+
+namespace tt {
+
+// thread-local error text behind tt_last_error()
+char* error_buffer();
+int set_error(int code, const char* fmt, ...);
+
+#define TT_REQUIRE(cond, ...)                                        \
+  do {                                                               \
+    if (!(cond)) return ::tt::set_error(TT_ERR_INVALID_ARG, __VA_ARGS__); \
+  } while (0)
+
+#define TT_CUDA_OK(expr)                                                                   \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return ::tt::set_error(TT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                  \
+                             cudaGetErrorString(_e), __FILE__, __LINE__);                  \
+  } while (0)
+
+#define TT_LAUNCH_OK(name)                                                                 \
+  do {                                                                                     \
+    cudaError_t _e = cudaGetLastError();                                                   \
+    if (_e != cudaSuccess)                                                                 \
+      return ::tt::set_error(TT_ERR_CUDA, "launch of %s failed: %s", name,                 \
+                             cudaGetErrorString(_e));                                      \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+int num_sms();
+
+__device__ __forceinline__ float bf16_bits_to_float(uint16_t b) {
+  return __uint_as_float(static_cast<uint32_t>(b) << 16);
+}
+__device__ __forceinline__ uint16_t float_to_bf16_bits(float f) {
+  return __bfloat16_as_ushort(__float2bfloat16_rn(f));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// tfrs/layers/loss.py: MIN_FLOAT = np.finfo(np.float32).min / 100.0
+#define TT_MIN_FLOAT (-3.4028234663852886e36f)
+
+}  // namespace tt

@@ -1,0 +1,324 @@
+// K5 -- sparse embedding gradient: dedup + scatter-add fused with the row-wise optimizer;
+// dense Adagrad/Adam for the Dense kernels.
+//
+// Restates Keras optimizer._deduplicate_sparse_grad (tf.unique, first-occurrence order, +
+// unsorted_segment_sum) followed by the sparse update_step of Adagrad (exactly row-wise) or
+// LazyAdam.
+//
+// Three launches, no sort:
+//   (1) insert    thread per entry j: open-addressing insert of values[j] into a 2x
+//                 over-provisioned hash table (atomicCAS), remember its slot, atomicMin the
+//                 slot's first-occurrence position.
+//   (2) accumulate warp per entry: add grad[bag(j)] (/L for mean pooling) into the fp32
+//                 accumulation row of the id's FIRST occurrence with 128-bit vector atomics
+//                 (L2-resident: nnz*d*4 bytes).
+//   (3) apply     warp per entry; only first occurrences act: read accumulated row + table
+//                 row + slot row(s), write table + slot(s), and clear the accumulation row
+//                 and the hash slot so the workspace is clean for the next step.
+// HBM-bound.  Algorithmic bytes (Adagrad, U unique of nnz): nnz*d*4 (grad) +
+// U*d*4*(2 reads + 2 writes) + nnz*8.
+// Duplicate rows are summed with atomics: the SET of updated rows is exact, the fp32 sum
+// order over duplicates is not fixed (same as TF's GPU unsorted_segment_sum).
+#include "common.cuh"
+#include <limits.h>
+
+namespace tt {
+
+static constexpr unsigned long long kEmpty = 0xFFFFFFFFFFFFFFFFull;
+
+struct SparseWs {
+  unsigned long long* keys;  // [cap]
+  int* first;                // [cap]
+  int* hpos;                 // [nnz]
+  int* bag_of;               // [nnz]
+  float* accum;              // [nnz, d]
+  int64_t cap;
+};
+
+static int64_t hash_capacity(int64_t nnz) {
+  int64_t cap = 1024;
+  while (cap < 2 * nnz) cap <<= 1;
+  return cap;
+}
+
+static int64_t ws_layout(int64_t nnz, int64_t d, void* base, SparseWs* ws) {
+  const int64_t cap = hash_capacity(nnz);
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) { int64_t o = off; off += round_up(bytes, 256); return o; };
+  int64_t o_keys = take(cap * 8), o_first = take(cap * 4), o_hpos = take(nnz * 4),
+          o_bag = take(nnz * 4), o_acc = take(nnz * d * 4);
+  if (ws) {
+    char* b = (char*)base;
+    ws->keys = (unsigned long long*)(b + o_keys);
+    ws->first = (int*)(b + o_first);
+    ws->hpos = (int*)(b + o_hpos);
+    ws->bag_of = (int*)(b + o_bag);
+    ws->accum = (float*)(b + o_acc);
+    ws->cap = cap;
+  }
+  return off;
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+  return x;
+}
+
+__global__ void sparse_ws_init_kernel(SparseWs ws, int64_t nnz, int64_t d) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = i; k < ws.cap; k += stride) { ws.keys[k] = kEmpty; ws.first[k] = INT_MAX; }
+  for (int64_t k = i; k < nnz * d; k += stride) ws.accum[k] = 0.f;
+}
+
+__global__ void __launch_bounds__(256)
+sparse_insert_kernel(SparseWs ws, const int64_t* __restrict__ values, const int64_t* __restrict__ offsets,
+                     int64_t num_rows, int64_t nnz, int64_t vocab) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nnz) return;
+  const int64_t id = values[j];
+  if (id < 0 || id >= vocab) { ws.hpos[j] = -1; return; }   // out-of-range ids are dropped
+  const uint64_t mask = (uint64_t)ws.cap - 1;
+  uint64_t h = mix64((uint64_t)id) & mask;
+  while (true) {
+    unsigned long long prev = atomicCAS(&ws.keys[h], kEmpty, (unsigned long long)id);
+    if (prev == kEmpty || prev == (unsigned long long)id) break;
+    h = (h + 1) & mask;
+  }
+  ws.hpos[j] = (int)h;
+  atomicMin(&ws.first[h], (int)j);
+  if (offsets) {   // bag(j): last b with offsets[b] <= j
+    int64_t lo = 0, hi = num_rows;
+    while (hi - lo > 1) {
+      int64_t mid = (lo + hi) >> 1;
+      if (offsets[mid] <= j) lo = mid; else hi = mid;
+    }
+    ws.bag_of[j] = (int)lo;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sparse_accumulate_kernel(SparseWs ws, const int64_t* __restrict__ offsets, int mode, int64_t nnz,
+                         int64_t d, const float* __restrict__ grad) {
+  const int lane = threadIdx.x & 31;
+  const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= nnz) return;
+  const int h = ws.hpos[j];
+  if (h < 0) return;
+  const int leader = ws.first[h];
+  int64_t row = j;
+  float L = 1.f;
+  if (offsets) {
+    row = ws.bag_of[j];
+    if (mode == TT_POOL_MEAN) L = (float)(offsets[row + 1] - offsets[row]);
+  }
+  const float4* g = reinterpret_cast<const float4*>(grad + row * d);
+  float4* a = reinterpret_cast<float4*>(ws.accum + (int64_t)leader * d);
+  for (int c = lane; c < (int)(d >> 2); c += 32) {
+    float4 v = __ldg(g + c);
+    if (L != 1.f) { v.x = __fdiv_rn(v.x, L); v.y = __fdiv_rn(v.y, L); v.z = __fdiv_rn(v.z, L); v.w = __fdiv_rn(v.w, L); }
+    atomicAdd(a + c, v);     // sm_90+: 128-bit vector reduction at L2
+  }
+}
+
+struct AdagradRule {
+  float* acc; float lr, eps;
+  __device__ __forceinline__ void apply(float* w_row, int64_t row_off, int c, float4 g) const {
+    float4* wp = reinterpret_cast<float4*>(w_row) + c;
+    float4* ap = reinterpret_cast<float4*>(acc + row_off) + c;
+    float4 w = *wp, a = *ap;
+#define TT_ADAGRAD_1(X)                                                        \
+    a.X = __fadd_rn(a.X, __fmul_rn(g.X, g.X));                                 \
+    w.X = __fsub_rn(w.X, __fdiv_rn(__fmul_rn(lr, g.X), __fsqrt_rn(__fadd_rn(a.X, eps))));
+    TT_ADAGRAD_1(x) TT_ADAGRAD_1(y) TT_ADAGRAD_1(z) TT_ADAGRAD_1(w)
+#undef TT_ADAGRAD_1
+    *wp = w; *ap = a;
+  }
+};
+
+struct LazyAdamRule {
+  float* m; float* v; float alpha, b1, b2, eps;
+  __device__ __forceinline__ void apply(float* w_row, int64_t row_off, int c, float4 g) const {
+    float4* wp = reinterpret_cast<float4*>(w_row) + c;
+    float4* mp = reinterpret_cast<float4*>(m + row_off) + c;
+    float4* vp = reinterpret_cast<float4*>(v + row_off) + c;
+    float4 w = *wp, mm = *mp, vv = *vp;
+#define TT_ADAM_1(X)                                                                         \
+    mm.X = __fadd_rn(mm.X, __fmul_rn(__fsub_rn(g.X, mm.X), 1.f - b1));                       \
+    vv.X = __fadd_rn(vv.X, __fmul_rn(__fsub_rn(__fmul_rn(g.X, g.X), vv.X), 1.f - b2));       \
+    w.X = __fsub_rn(w.X, __fdiv_rn(__fmul_rn(mm.X, alpha), __fadd_rn(__fsqrt_rn(vv.X), eps)));
+    TT_ADAM_1(x) TT_ADAM_1(y) TT_ADAM_1(z) TT_ADAM_1(w)
+#undef TT_ADAM_1
+    *wp = w; *mp = mm; *vp = vv;
+  }
+};
+
+template <class Rule>
+__global__ void __launch_bounds__(256)
+sparse_apply_kernel(SparseWs ws, Rule rule, float* __restrict__ table, int64_t nnz, int64_t d,
+                    uint8_t* __restrict__ first_flag) {
+  const int lane = threadIdx.x & 31;
+  const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= nnz) return;
+  const int h = ws.hpos[j];
+  const bool is_first = (h >= 0) && (ws.first[h] == (int)j);
+  if (first_flag && lane == 0) first_flag[j] = is_first ? 1 : 0;
+  if (!is_first) return;
+  const int64_t id = (int64_t)ws.keys[h];
+  float4* a = reinterpret_cast<float4*>(ws.accum + j * d);
+  for (int c = lane; c < (int)(d >> 2); c += 32) {
+    float4 g = a[c];
+    a[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    rule.apply(table + id * d, id * d, c, g);
+  }
+  __syncwarp();
+  if (lane == 0) { ws.keys[h] = kEmpty; ws.first[h] = INT_MAX; }
+}
+
+template <class Rule>
+static int run_sparse(const char* name, Rule rule, float* table, int64_t vocab, int64_t d,
+                      const int64_t* values, const int64_t* offsets, int mode, int64_t num_rows,
+                      int64_t nnz, const float* grad, void* workspace, int64_t workspace_bytes,
+                      uint8_t* first_flag, cudaStream_t stream) {
+  TT_REQUIRE(table && values && grad && workspace, "%s: null buffer", name);
+  TT_REQUIRE(d > 0 && d % 4 == 0, "%s: d must be a multiple of 4, got %lld", name, (long long)d);
+  TT_REQUIRE(aligned16(table) && aligned16(grad) && aligned16(workspace), "%s: buffers must be 16-byte aligned", name);
+  TT_REQUIRE(nnz >= 0 && nnz < INT_MAX && num_rows >= 0, "%s: bad sizes", name);
+  TT_REQUIRE(offsets != nullptr || nnz == num_rows, "%s: without offsets nnz must equal num_rows", name);
+  TT_REQUIRE(mode == TT_POOL_SUM || mode == TT_POOL_MEAN, "%s: bad pooling mode", name);
+  if (workspace_bytes < ws_layout(nnz, d, nullptr, nullptr))
+    return set_error(TT_ERR_WORKSPACE, "%s: workspace too small (%lld < %lld)", name,
+                     (long long)workspace_bytes, (long long)ws_layout(nnz, d, nullptr, nullptr));
+  if (nnz == 0) return TT_OK;
+  SparseWs ws;
+  ws_layout(nnz, d, workspace, &ws);
+  sparse_insert_kernel<<<(unsigned)ceil_div(nnz, 256), 256, 0, stream>>>(ws, values, offsets, num_rows, nnz, vocab);
+  TT_LAUNCH_OK("sparse_insert_kernel");
+  sparse_accumulate_kernel<<<(unsigned)ceil_div(nnz, 8), 256, 0, stream>>>(ws, offsets, mode, nnz, d, grad);
+  TT_LAUNCH_OK("sparse_accumulate_kernel");
+  sparse_apply_kernel<Rule><<<(unsigned)ceil_div(nnz, 8), 256, 0, stream>>>(ws, rule, table, nnz, d, first_flag);
+  TT_LAUNCH_OK("sparse_apply_kernel");
+  return TT_OK;
+}
+
+// ---- dense optimizers (Dense kernels and biases) --------------------------------------
+template <bool ADAM>
+__global__ void __launch_bounds__(256)
+dense_opt_kernel(float* __restrict__ w, float* __restrict__ s0, float* __restrict__ s1,
+                 const float* __restrict__ parts, int num_parts, int64_t rows, int64_t cols,
+                 float lr_or_alpha, float b1, float b2, float eps, float l2,
+                 uint16_t* __restrict__ shadow, uint16_t* __restrict__ shadow_t) {
+  const int64_t n = rows * cols;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float g = 0.f;
+  for (int p = 0; p < num_parts; ++p) g = __fadd_rn(g, parts[(int64_t)p * n + i]);
+  float wv = w[i];
+  if (l2 != 0.f) g = __fadd_rn(g, __fmul_rn(2.f * l2, wv));
+  if (ADAM) {
+    float m = s0[i], v = s1[i];
+    m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), 1.f - b1));
+    v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(g, g), v), 1.f - b2));
+    wv = __fsub_rn(wv, __fdiv_rn(__fmul_rn(m, lr_or_alpha), __fadd_rn(__fsqrt_rn(v), eps)));
+    s0[i] = m; s1[i] = v;
+  } else {
+    float a = __fadd_rn(s0[i], __fmul_rn(g, g));
+    wv = __fsub_rn(wv, __fdiv_rn(__fmul_rn(lr_or_alpha, g), __fsqrt_rn(__fadd_rn(a, eps))));
+    s0[i] = a;
+  }
+  w[i] = wv;
+  if (shadow) shadow[i] = float_to_bf16_bits(wv);
+  if (shadow_t) { int64_t r = i / cols, c = i % cols; shadow_t[c * rows + r] = float_to_bf16_bits(wv); }
+}
+
+__global__ void __launch_bounds__(1024)
+sum_squares_kernel(const float* __restrict__ x, int64_t n, float scale, float* __restrict__ out, int accumulate) {
+  __shared__ float part[1024];
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) s = fmaf(x[i], x[i], s);
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (accumulate ? out[0] : 0.f) + scale * part[0];
+}
+
+}  // namespace tt
+
+using namespace tt;
+
+extern "C" int tt_sum_squares(const float* x, int64_t n, float scale, float* out, int32_t accumulate, void* stream) {
+  TT_REQUIRE(x && out && n >= 0, "tt_sum_squares: bad arguments");
+  sum_squares_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, n, scale, out, accumulate);
+  TT_LAUNCH_OK("sum_squares_kernel");
+  return TT_OK;
+}
+
+extern "C" int64_t tt_sparse_workspace_bytes(int64_t nnz, int64_t d) {
+  if (nnz < 0 || d <= 0) return 0;
+  return ws_layout(nnz, d, nullptr, nullptr);
+}
+
+extern "C" int tt_sparse_workspace_init(void* workspace, int64_t workspace_bytes, int64_t nnz,
+                                        int64_t d, void* stream) {
+  TT_REQUIRE(workspace && aligned16(workspace), "tt_sparse_workspace_init: workspace null or unaligned");
+  TT_REQUIRE(nnz >= 0 && d > 0, "tt_sparse_workspace_init: bad sizes");
+  if (workspace_bytes < ws_layout(nnz, d, nullptr, nullptr))
+    return set_error(TT_ERR_WORKSPACE, "tt_sparse_workspace_init: workspace too small");
+  SparseWs ws;
+  ws_layout(nnz, d, workspace, &ws);
+  sparse_ws_init_kernel<<<num_sms() * 4, 256, 0, (cudaStream_t)stream>>>(ws, nnz, d);
+  TT_LAUNCH_OK("sparse_ws_init_kernel");
+  return TT_OK;
+}
+
+extern "C" int tt_sparse_adagrad_update(float* table, float* accum, int64_t vocab, int64_t d,
+                                        const int64_t* values, const int64_t* offsets, int32_t mode,
+                                        int64_t num_rows, int64_t nnz, const float* grad, float lr,
+                                        float eps, void* workspace, int64_t workspace_bytes,
+                                        uint8_t* first_flag, void* stream) {
+  TT_REQUIRE(accum && aligned16(accum), "tt_sparse_adagrad_update: accumulator null or unaligned");
+  AdagradRule rule{accum, lr, eps};
+  return run_sparse("tt_sparse_adagrad_update", rule, table, vocab, d, values, offsets, mode, num_rows,
+                    nnz, grad, workspace, workspace_bytes, first_flag, (cudaStream_t)stream);
+}
+
+extern "C" int tt_sparse_lazy_adam_update(float* table, float* m, float* v, int64_t vocab, int64_t d,
+                                          const int64_t* values, const int64_t* offsets, int32_t mode,
+                                          int64_t num_rows, int64_t nnz, const float* grad, float alpha,
+                                          float beta1, float beta2, float eps, void* workspace,
+                                          int64_t workspace_bytes, uint8_t* first_flag, void* stream) {
+  TT_REQUIRE(m && v && aligned16(m) && aligned16(v), "tt_sparse_lazy_adam_update: slots null or unaligned");
+  LazyAdamRule rule{m, v, alpha, beta1, beta2, eps};
+  return run_sparse("tt_sparse_lazy_adam_update", rule, table, vocab, d, values, offsets, mode, num_rows,
+                    nnz, grad, workspace, workspace_bytes, first_flag, (cudaStream_t)stream);
+}
+
+static int dense_opt(bool adam, float* w, float* s0, float* s1, const float* parts, int num_parts,
+                     int64_t rows, int64_t cols, float lr, float b1, float b2, float eps, float l2,
+                     uint16_t* shadow, uint16_t* shadow_t, cudaStream_t stream) {
+  TT_REQUIRE(w && s0 && parts && (!adam || s1), "dense optimizer: null buffer");
+  TT_REQUIRE(rows > 0 && cols > 0 && num_parts >= 1, "dense optimizer: bad sizes");
+  const int64_t n = rows * cols;
+  unsigned blocks = (unsigned)ceil_div(n, 256);
+  if (adam) dense_opt_kernel<true><<<blocks, 256, 0, stream>>>(w, s0, s1, parts, num_parts, rows, cols, lr, b1, b2, eps, l2, shadow, shadow_t);
+  else dense_opt_kernel<false><<<blocks, 256, 0, stream>>>(w, s0, s1, parts, num_parts, rows, cols, lr, b1, b2, eps, l2, shadow, shadow_t);
+  TT_LAUNCH_OK("dense_opt_kernel");
+  return TT_OK;
+}
+
+extern "C" int tt_dense_adagrad_update(float* w, float* accum, const float* grad_parts, int32_t num_parts,
+                                       int64_t rows, int64_t cols, float lr, float eps, float l2,
+                                       uint16_t* shadow, uint16_t* shadow_t, void* stream) {
+  return dense_opt(false, w, accum, nullptr, grad_parts, num_parts, rows, cols, lr, 0.f, 0.f, eps, l2,
+                   shadow, shadow_t, (cudaStream_t)stream);
+}
+
+extern "C" int tt_dense_adam_update(float* w, float* m, float* v, const float* grad_parts, int32_t num_parts,
+                                    int64_t rows, int64_t cols, float alpha, float beta1, float beta2,
+                                    float eps, float l2, uint16_t* shadow, uint16_t* shadow_t, void* stream) {
+  return dense_opt(true, w, m, v, grad_parts, num_parts, rows, cols, alpha, beta1, beta2, eps, l2,
+                   shadow, shadow_t, (cudaStream_t)stream);
+}

@@ -1,0 +1,288 @@
+// K6 (fp32 precision) -- brute-force scoring fused with a running top-k; list merge; hit@k.
+// Restates tfrs.layers.factorized_top_k.BruteForce.call (matmul + tf.math.top_k: sorted
+// descending, ties -> lower index first), faiss.IndexFlatIP.search and
+// tfrs.metrics.FactorizedTopK.  The [nq, nc] score matrix is never
+// written: each CTA keeps 64 queries stationary, streams a candidate range in 64-row tiles,
+// filters scores against the row's current k-th best and folds survivors into a sorted
+// shared-memory list (topk_select.cuh).  bf16/tcgen05 scoring is topk_tc.cu.
+#include "simt_tile.cuh"
+#include "topk_select.cuh"
+#include <limits.h>
+
+namespace tt {
+
+int tc_topk(const void* queries, const void* candidates, int64_t nq, int64_t nc, int64_t d, int k,
+            int64_t cand_index_base, const int64_t* identifiers, float* out_scores, int64_t* out_ids, void* ws,
+            int64_t ws_bytes, cudaStream_t st);
+int tc_topk_num_splits(int64_t nq, int64_t nc, int64_t d, int k);
+
+// Partial (or final) result writer shared with the tensor-core kernel: row r of the state ->
+// out arrays, padding short lists with (-inf, INT64_MAX).
+__device__ __forceinline__ void topk_write_row(const TopkRowState& st, int r, int lane, float* out_s,
+                                               int64_t* out_i, int64_t base, const int64_t* identifiers) {
+  const int k = st.k, cnt = st.count[r];
+  for (int t = lane; t < k; t += 32) {
+    if (t < cnt) {
+      const int idx = st.list_i[(size_t)r * k + t];
+      out_s[t] = st.list_s[(size_t)r * k + t];
+      out_i[t] = identifiers ? __ldg(identifiers + idx) : base + idx;
+    } else {
+      out_s[t] = -INFINITY;
+      out_i[t] = LLONG_MAX;
+    }
+  }
+}
+
+template <int KU>
+__global__ void __launch_bounds__(256)
+topk_simt_kernel(const float* __restrict__ Q, const float* __restrict__ C, int64_t nq, int64_t nc, int d, int k,
+                 int64_t cand_base, const int64_t* __restrict__ identifiers, int64_t split_len,
+                 float* __restrict__ out_s, int64_t* __restrict__ out_i) {
+  extern __shared__ __align__(16) float smem[];
+  float* Xs_T = smem;
+  float* Ys_T = Xs_T + d * TLD;
+  TopkRowState st = topk_state_carve(Ys_T + d * TLD, TS, k, TS);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, warp = tid >> 5;
+  const int64_t q0 = (int64_t)blockIdx.x * TS;
+  const int64_t c_lo = (int64_t)blockIdx.y * split_len;
+  const int64_t c_hi = min(nc, c_lo + split_len);
+
+  if (tid < TS) { st.count[tid] = 0; st.tau[tid] = -INFINITY; st.pend_n[tid] = 0; }
+  load_tile(Q, q0, nq, d, Xs_T, nullptr);
+
+  for (int64_t y0 = c_lo; y0 < c_hi; y0 += TS) {
+    __syncthreads();
+    load_tile(C, y0, c_hi, d, Ys_T, nullptr);
+    __syncthreads();
+    float acc[4][4];
+    tile_dot(Xs_T, Ys_T, d, tx, ty, acc);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = ty * 4 + i;
+      if (q0 + r >= nq) continue;
+      const float tau = st.tau[r];
+      const bool full = st.count[r] == k;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t ci = y0 + tx * 4 + j;
+        if (ci >= c_hi) continue;
+        const float s = acc[i][j];
+        if (!full || s > tau) {
+          const int slot = atomicAdd(&st.pend_n[r], 1);
+          st.pend_s[r * TS + slot] = s;
+          st.pend_i[r * TS + slot] = (int)ci;
+        }
+      }
+    }
+    __syncthreads();
+    for (int r = warp * 8; r < warp * 8 + 8; ++r) topk_merge_row<KU>(st, r, lane);
+  }
+  __syncthreads();
+  for (int r = warp * 8; r < warp * 8 + 8; ++r) {
+    if (q0 + r >= nq) continue;
+    const size_t o = ((size_t)blockIdx.y * nq + (q0 + r)) * k;
+    topk_write_row(st, r, lane, out_s + o, out_i + o, cand_base, identifiers);
+  }
+}
+
+// L-way merge of sorted lists, one warp per query; lane l walks list l (L <= 32).
+__global__ void __launch_bounds__(256)
+topk_merge_kernel(const float* __restrict__ scores, const int64_t* __restrict__ ids, int L, int64_t nq, int k_in,
+                  int k_out, float* __restrict__ out_s, int64_t* __restrict__ out_i) {
+  const int lane = threadIdx.x & 31;
+  const int64_t qi = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (qi >= nq) return;
+  int head = 0;
+  const float* ls = scores + ((size_t)lane * nq + qi) * k_in;
+  const int64_t* li = ids + ((size_t)lane * nq + qi) * k_in;
+  float hs = -INFINITY; int64_t hi = LLONG_MAX;
+  if (lane < L && k_in > 0) { hs = ls[0]; hi = li[0]; }
+  for (int t = 0; t < k_out; ++t) {
+    float bs = hs; int64_t bi = hi; int bl = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float s2 = __shfl_xor_sync(0xffffffffu, bs, o);
+      const int64_t i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+      const int l2 = __shfl_xor_sync(0xffffffffu, bl, o);
+      const bool take = s2 > bs || (s2 == bs && (i2 < bi || (i2 == bi && l2 < bl)));
+      if (take) { bs = s2; bi = i2; bl = l2; }
+    }
+    if (lane == 0) { out_s[qi * k_out + t] = bs; out_i[qi * k_out + t] = bi; }
+    if (lane == bl) {
+      ++head;
+      if (head < k_in) { hs = ls[head]; hi = li[head]; } else { hs = -INFINITY; hi = LLONG_MAX; }
+    }
+  }
+}
+
+// FactorizedTopK hit counting (score mode / id mode).
+__global__ void __launch_bounds__(256)
+topk_hits_kernel(const float* __restrict__ positive, const float* __restrict__ topk_scores,
+                 const int64_t* __restrict__ topk_ids, const int64_t* __restrict__ true_ids,
+                 const float* __restrict__ w, int64_t nq, int k, const int* __restrict__ ks_dev_unused,
+                 int ks0, int ks1, int ks2, int ks3, int ks4, int ks5, int ks6, int ks7, int num_ks,
+                 float* __restrict__ hits_out, float* __restrict__ weight_out) {
+  const int ks[8] = {ks0, ks1, ks2, ks3, ks4, ks5, ks6, ks7};
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float hit[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) hit[j] = 0.f;
+  float wi = 0.f;
+  if (i < nq) {
+    wi = w ? w[i] : 1.f;
+    if (true_ids == nullptr) {
+      const float p = positive[i];
+      int greater = 0;
+      for (int t = 0; t < k; ++t) greater += topk_scores[i * k + t] > p ? 1 : 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (j < num_ks && greater < ks[j]) hit[j] = wi;
+    } else {
+      const int64_t tid_ = true_ids[i];
+      int first = INT_MAX;
+      for (int t = 0; t < k; ++t) if (topk_ids[i * k + t] == tid_) { first = t; break; }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (j < num_ks && first < ks[j]) hit[j] = wi;
+    }
+  }
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (j >= num_ks) break;
+    float v = warp_sum(hit[j]);
+    if (lane == 0 && v != 0.f) atomicAdd(hits_out + j, v);
+  }
+  float ws = warp_sum(wi);
+  if (lane == 0 && ws != 0.f) atomicAdd(weight_out, ws);
+}
+
+template <typename T> __device__ __forceinline__ float ld_as_float(const T* p, int64_t i);
+template <> __device__ __forceinline__ float ld_as_float<float>(const float* p, int64_t i) { return p[i]; }
+template <> __device__ __forceinline__ float ld_as_float<uint16_t>(const uint16_t* p, int64_t i) { return bf16_bits_to_float(p[i]); }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+rowwise_dot_kernel(const T* __restrict__ q, const T* __restrict__ c, float* __restrict__ out, int64_t n, int64_t d) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n) return;
+  float s = 0.f;
+  for (int64_t k = lane; k < d; k += 32) s = fmaf(ld_as_float(q, r * d + k), ld_as_float(c, r * d + k), s);
+  s = warp_sum(s);
+  if (lane == 0) out[r] = s;
+}
+
+static size_t simt_topk_smem(int d, int k) { return (size_t)2 * d * TLD * 4 + topk_state_bytes(TS, k, TS); }
+
+}  // namespace tt
+
+using namespace tt;
+
+static const size_t kMaxSmem = 227 * 1024;
+
+static int simt_num_splits(int64_t nq, int64_t nc) {
+  const int64_t qtiles = ceil_div(nq, TS);
+  const int64_t target = 2 * (int64_t)num_sms();
+  int64_t s = qtiles >= target ? 1 : ceil_div(target, qtiles);
+  const int64_t max_by_len = std::max<int64_t>(1, nc / 4096);   // keep >= 4096 candidates per split
+  if (s > max_by_len) s = max_by_len;
+  if (s > 32) s = 32;
+  return (int)s;
+}
+
+extern "C" int32_t tt_topk_num_splits(int32_t precision, int64_t nq, int64_t nc, int64_t d, int32_t k) {
+  if (precision == TT_BF16) return tc_topk_num_splits(nq, nc, d, k);
+  return simt_num_splits(nq, nc);
+}
+
+extern "C" int64_t tt_topk_workspace_bytes(int32_t precision, int64_t nq, int64_t nc, int64_t d, int32_t k) {
+  const int s = tt_topk_num_splits(precision, nq, nc, d, k);
+  if (s <= 1) return 256;
+  return round_up((int64_t)s * nq * k * 4, 256) + round_up((int64_t)s * nq * k * 8, 256);
+}
+
+extern "C" int tt_topk_merge(const float* scores, const int64_t* ids, int32_t num_lists, int64_t nq, int32_t k_in,
+                             int32_t k_out, float* out_scores, int64_t* out_ids, void* stream) {
+  TT_REQUIRE(scores && ids && out_scores && out_ids, "tt_topk_merge: null buffer");
+  TT_REQUIRE(num_lists >= 1 && num_lists <= 32, "tt_topk_merge: num_lists must be in [1, 32], got %d", num_lists);
+  TT_REQUIRE(nq >= 0 && k_in >= 1 && k_out >= 1 && k_out <= num_lists * k_in, "tt_topk_merge: bad k (k_in=%d k_out=%d lists=%d)", k_in, k_out, num_lists);
+  if (nq == 0) return TT_OK;
+  topk_merge_kernel<<<(unsigned)ceil_div(nq, 8), 256, 0, (cudaStream_t)stream>>>(scores, ids, num_lists, nq, k_in, k_out, out_scores, out_ids);
+  TT_LAUNCH_OK("topk_merge_kernel");
+  return TT_OK;
+}
+
+extern "C" int tt_topk_bruteforce(int32_t precision, const void* queries, const void* candidates, int64_t nq,
+                                  int64_t nc, int64_t d, int32_t k, int64_t cand_index_base,
+                                  const int64_t* identifiers, float* out_scores, int64_t* out_ids,
+                                  void* workspace, int64_t workspace_bytes, void* stream) {
+  TT_REQUIRE(precision == TT_F32 || precision == TT_BF16, "tt_topk_bruteforce: unknown precision %d", precision);
+  TT_REQUIRE(queries && candidates && out_scores && out_ids, "tt_topk_bruteforce: null buffer");
+  TT_REQUIRE(nq > 0 && nc > 0 && d > 0 && nc < INT_MAX, "tt_topk_bruteforce: bad sizes");
+  TT_REQUIRE(k >= 1 && k <= nc, "tt_topk_bruteforce: k=%d must be in [1, num_candidates=%lld]", k, (long long)nc);
+  TT_REQUIRE(k <= 512, "tt_topk_bruteforce: k=%d exceeds the supported maximum 512", k);
+  TT_REQUIRE(aligned16(queries) && aligned16(candidates), "tt_topk_bruteforce: inputs must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == TT_BF16)
+    return tc_topk(queries, candidates, nq, nc, d, k, cand_index_base, identifiers, out_scores, out_ids, workspace,
+                   workspace_bytes, st);
+  TT_REQUIRE(d % 4 == 0 && d <= 256, "tt_topk_bruteforce: fp32 path needs d %% 4 == 0 and d <= 256");
+  const size_t smem = simt_topk_smem((int)d, k);
+  if (smem > kMaxSmem) return set_error(TT_ERR_UNSUPPORTED, "tt_topk_bruteforce: d=%lld k=%d needs %zu bytes of shared memory (> %zu)", (long long)d, k, smem, kMaxSmem);
+  const int splits = simt_num_splits(nq, nc);
+  float* ps = out_scores; int64_t* pi = out_ids;
+  if (splits > 1) {
+    const int64_t need = tt_topk_workspace_bytes(precision, nq, nc, d, k);
+    if (!workspace || workspace_bytes < need) return set_error(TT_ERR_WORKSPACE, "tt_topk_bruteforce: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
+    ps = (float*)workspace;
+    pi = (int64_t*)((char*)workspace + round_up((int64_t)splits * nq * k * 4, 256));
+  }
+  const int64_t split_len = round_up(ceil_div(nc, splits), TS);
+  dim3 grid((unsigned)ceil_div(nq, TS), (unsigned)splits);
+#define TT_TOPK_LAUNCH(KU)                                                                                  \
+  {                                                                                                         \
+    TT_CUDA_OK(cudaFuncSetAttribute(topk_simt_kernel<KU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    topk_simt_kernel<KU><<<grid, 256, smem, st>>>((const float*)queries, (const float*)candidates, nq, nc, (int)d, k, \
+                                                  cand_index_base, identifiers, split_len, ps, pi);          \
+  }
+  if (k <= 32) TT_TOPK_LAUNCH(1)
+  else if (k <= 64) TT_TOPK_LAUNCH(2)
+  else if (k <= 128) TT_TOPK_LAUNCH(4)
+  else if (k <= 256) TT_TOPK_LAUNCH(8)
+  else TT_TOPK_LAUNCH(16)
+#undef TT_TOPK_LAUNCH
+  TT_LAUNCH_OK("topk_simt_kernel");
+  if (splits > 1) return tt_topk_merge(ps, pi, splits, nq, k, k, out_scores, out_ids, stream);
+  return TT_OK;
+}
+
+extern "C" int tt_topk_hits(const float* positive, const float* topk_scores, const int64_t* topk_ids,
+                            const int64_t* true_ids, const float* sample_weight, int64_t nq, int32_t k,
+                            const int32_t* host_ks, int32_t num_ks, float* hits_out, float* weight_out,
+                            void* stream) {
+  TT_REQUIRE(host_ks && num_ks >= 1 && num_ks <= 8, "tt_topk_hits: num_ks must be in [1, 8]");
+  TT_REQUIRE(hits_out && weight_out, "tt_topk_hits: null output");
+  TT_REQUIRE(true_ids ? (topk_ids != nullptr) : (positive && topk_scores), "tt_topk_hits: missing inputs for the chosen mode");
+  int ks[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < num_ks; ++i) {
+    TT_REQUIRE(host_ks[i] >= 1 && host_ks[i] <= k, "tt_topk_hits: ks[%d]=%d outside [1, k=%d]", i, host_ks[i], k);
+    ks[i] = host_ks[i];
+  }
+  if (nq == 0) return TT_OK;
+  topk_hits_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, (cudaStream_t)stream>>>(
+      positive, topk_scores, topk_ids, true_ids, sample_weight, nq, k, nullptr, ks[0], ks[1], ks[2], ks[3], ks[4],
+      ks[5], ks[6], ks[7], num_ks, hits_out, weight_out);
+  TT_LAUNCH_OK("topk_hits_kernel");
+  return TT_OK;
+}
+
+extern "C" int tt_rowwise_dot(int32_t precision, const void* q, const void* c, float* out, int64_t n, int64_t d,
+                              void* stream) {
+  TT_REQUIRE(q && c && out && n >= 0 && d > 0, "tt_rowwise_dot: bad arguments");
+  if (n == 0) return TT_OK;
+  unsigned blocks = (unsigned)ceil_div(n, 8);
+  if (precision == TT_F32) rowwise_dot_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float*)q, (const float*)c, out, n, d);
+  else if (precision == TT_BF16) rowwise_dot_kernel<uint16_t><<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)q, (const uint16_t*)c, out, n, d);
+  else return set_error(TT_ERR_INVALID_ARG, "tt_rowwise_dot: unknown precision %d", precision);
+  TT_LAUNCH_OK("rowwise_dot_kernel");
+  return TT_OK;
+}

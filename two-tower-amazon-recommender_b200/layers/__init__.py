@@ -1,0 +1,258 @@
+"""Tower layers: Embedding, pooled multi-hot Embedding, Dense, Sequential -- the
+tf.keras.layers surface a TFRS two-tower model is built from (sizes from
+/root/reference/configs/data_config.yaml:55-59, ids from
+/root/reference/src/data/preprocessor.py:481-489)."""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..core import DenseGrad, GradientTape, IndexedSlices, Tensor, Variable, config, device
+
+_layer_counter = [0]
+
+
+def _next_seed() -> int:
+    _layer_counter[0] += 1
+    return config.seed * 1000003 + _layer_counter[0]
+
+
+def _as_ids(x) -> torch.Tensor:
+    if isinstance(x, torch.Tensor):
+        t = x
+    else:
+        t = torch.as_tensor(np.asarray(x))
+    if t.dtype != torch.int64:
+        t = t.to(torch.int64)
+    if not t.is_cuda:
+        t = t.to(device(), non_blocking=True)
+    return t.contiguous()
+
+
+class Layer:
+    name = "layer"
+
+    @property
+    def trainable_variables(self):
+        return []
+
+    @property
+    def losses_l2(self):
+        """[(variable, l2)] pairs contributing l2 * sum(w^2) to model.losses."""
+        return []
+
+
+class Embedding(Layer):
+    """tf.keras.layers.Embedding(input_dim, output_dim): weight [input_dim, output_dim] fp32,
+    initializer "uniform" = U(-0.05, 0.05); forward = gather; gradient = IndexedSlices."""
+
+    combiner = None
+
+    def __init__(self, input_dim: int, output_dim: int, name: Optional[str] = None):
+        self.input_dim, self.output_dim = int(input_dim), int(output_dim)
+        self.name = name or f"embedding_{_layer_counter[0]}"
+        g = torch.Generator(device=device())
+        g.manual_seed(_next_seed())
+        table = torch.empty((self.input_dim, self.output_dim), dtype=torch.float32, device=device())
+        table.uniform_(-0.05, 0.05, generator=g)
+        self.embeddings = Variable(self.name + "/embeddings", table, "table")
+
+    @property
+    def trainable_variables(self):
+        return [self.embeddings]
+
+    def get_weights(self):
+        return [self.embeddings.numpy()]
+
+    def set_weights(self, weights):
+        self.embeddings.assign(weights[0])
+
+    def _feature(self, inputs):
+        return (self.embeddings.value, _as_ids(inputs).reshape(-1), None, "sum")
+
+    def __call__(self, inputs, training: bool = False) -> Tensor:
+        return _tower_input([self], [inputs])
+
+
+class EmbeddingBag(Embedding):
+    """Embedding over a ragged id list reduced over the bag axis: reduce_mean / reduce_sum of a
+    ragged Embedding output == safe_embedding_lookup_sparse(combiner).  Input: (values, offsets)
+    CSR (int64).  Empty bag -> zeros; duplicates inside a bag count each time."""
+
+    def __init__(self, input_dim: int, output_dim: int, combiner: str = "mean", name: Optional[str] = None):
+        super().__init__(input_dim, output_dim, name)
+        if combiner not in ("sum", "mean"):
+            raise ValueError("combiner must be 'sum' or 'mean'")
+        self.combiner = combiner
+
+    def _feature(self, inputs):
+        values, offsets = inputs
+        return (self.embeddings.value, _as_ids(values), _as_ids(offsets), self.combiner)
+
+
+def _tower_input(layers: Sequence[Embedding], inputs: Sequence) -> Tensor:
+    feats = [l._feature(x) for l, x in zip(layers, inputs)]
+    f0 = feats[0]
+    batch = f0[1].numel() if f0[2] is None else f0[2].numel() - 1
+    for f in feats[1:]:
+        b = f[1].numel() if f[2] is None else f[2].numel() - 1
+        if b != batch:
+            raise ValueError(f"features disagree on the batch size ({b} != {batch})")
+    dim = layers[0].output_dim
+    bf16 = config.precision == "bf16"
+    out_f32, out_bf16 = ops.tower_input_fwd(feats, batch, dim, want_f32=not bf16, want_bf16=bf16)
+    out = Tensor(f32=out_f32, bf16=out_bf16, grad_formats=("f32",))
+
+    def backward():
+        if out.grad is None:
+            return
+        rows = out.grad["f32"]
+        for layer, f in zip(layers, feats):
+            if layer.embeddings.grad is not None:
+                raise NotImplementedError("an embedding table used twice in one step is not supported")
+            layer.embeddings.grad = IndexedSlices(values=f[1], offsets=f[2], mode=f[3], rows=rows)
+
+    GradientTape.record(backward)
+    return out
+
+
+class FeatureSum(Layer):
+    """Sum of several (pooled) embeddings of one example, fused into a single gather pass:
+    out = sum_f pool_f(table_f[ids_f]).  ``features`` maps input-dict keys to Embedding /
+    EmbeddingBag layers (cfg3: item id + mean(category) + mean(brand))."""
+
+    def __init__(self, features: Dict[str, Embedding], name: Optional[str] = None):
+        if not 1 <= len(features) <= 8:
+            raise ValueError("FeatureSum takes 1..8 features")
+        dims = {l.output_dim for l in features.values()}
+        if len(dims) != 1:
+            raise ValueError("all features must share output_dim")
+        self.features = dict(features)
+        self.name = name or "feature_sum"
+
+    @property
+    def trainable_variables(self):
+        return [l.embeddings for l in self.features.values()]
+
+    def __call__(self, inputs: dict, training: bool = False) -> Tensor:
+        keys = list(self.features)
+        return _tower_input([self.features[k] for k in keys], [inputs[k] for k in keys])
+
+
+class Dense(Layer):
+    """tf.keras.layers.Dense(units, activation): kernel [in, out] glorot_uniform, bias zeros,
+    optional kernel_regularizer=l2(lam) (lam * sum(w^2) added to the model losses)."""
+
+    def __init__(self, units: int, activation: Optional[str] = None, kernel_regularizer=None,
+                 name: Optional[str] = None):
+        if activation not in (None, "linear", "relu"):
+            raise NotImplementedError(f"activation {activation!r}: only relu / linear are on the hot path")
+        self.units = int(units)
+        self.relu = activation == "relu"
+        self.l2 = float(getattr(kernel_regularizer, "l2", kernel_regularizer) or 0.0)
+        self.name = name or f"dense_{_layer_counter[0]}"
+        self._seed = _next_seed()
+        self.kernel: Optional[Variable] = None
+        self.bias: Optional[Variable] = None
+
+    def build(self, in_dim: int) -> None:
+        rng = np.random.Generator(np.random.PCG64(self._seed))
+        lim = math.sqrt(6.0 / (in_dim + self.units))
+        k = rng.uniform(-lim, lim, size=(in_dim, self.units)).astype(np.float32)
+        dev = device()
+        self.kernel = Variable(self.name + "/kernel", torch.from_numpy(k).to(dev), "kernel", l2=self.l2)
+        self.bias = Variable(self.name + "/bias", torch.zeros(self.units, dtype=torch.float32, device=dev), "bias")
+        if config.precision == "bf16":
+            self.kernel.want_shadows = True
+            self.kernel.refresh_shadows()
+
+    @property
+    def trainable_variables(self):
+        return [] if self.kernel is None else [self.kernel, self.bias]
+
+    @property
+    def losses_l2(self):
+        return [(self.kernel, self.l2)] if (self.kernel is not None and self.l2) else []
+
+    def get_weights(self):
+        return [self.kernel.numpy(), self.bias.numpy()]
+
+    def set_weights(self, weights):
+        if self.kernel is None:
+            self.build(np.asarray(weights[0]).shape[0])
+        self.kernel.assign(weights[0])
+        self.bias.assign(weights[1])
+
+    def __call__(self, x: Tensor, training: bool = False) -> Tensor:
+        in_dim = x.shape[1]
+        if self.kernel is None:
+            self.build(in_dim)
+        prec = config.precision
+        if prec == "fp32":
+            y, _, _ = ops.dense_fwd("fp32", x.f32, self.kernel.value, self.bias.value, self.relu)
+            out = Tensor(f32=y, grad_formats=("f32",))
+        else:
+            if self.kernel.shadow_t is None:
+                self.kernel.want_shadows = True
+                self.kernel.refresh_shadows()
+            y, y_t, _ = ops.dense_fwd("bf16", x.bf16, self.kernel.shadow_t, self.bias.value, self.relu, want_t=True)
+            out = Tensor(bf16=y, bf16_t=y_t, grad_formats=("bf16", "bf16_t"))
+        out.relu_output = self.relu
+
+        def backward():
+            if out.grad is None:
+                return
+            g = out.grad
+            want = x.grad_formats
+            need_dx = x.producer_needs_grad
+            if prec == "fp32":
+                dx, _, _, dk, P, db = ops.dense_bwd("fp32", g["f32"], None, x.f32, None, self.kernel.value,
+                                                    relu_mask_x=x.relu_output, want_dx=need_dx)
+                if need_dx:
+                    x.grad = dict(f32=dx)
+            else:
+                if x.bf16_t is None:
+                    x.bf16_t = ops.transpose_bf16(x.bf16)
+                dx, dx_t, dx_f32, dk, P, db = ops.dense_bwd(
+                    "bf16", g["bf16"], g["bf16_t"], x.bf16, x.bf16_t, self.kernel.shadow,
+                    relu_mask_x=x.relu_output, want_dx=need_dx and "bf16" in want,
+                    want_dx_t=need_dx and "bf16_t" in want, want_dx_f32=need_dx and "f32" in want)
+                if need_dx:
+                    x.grad = dict(f32=dx_f32, bf16=dx, bf16_t=dx_t)
+            self.kernel.grad = DenseGrad(dk, P)
+            self.bias.grad = DenseGrad(db.reshape(1, 1, -1), 1)
+
+        GradientTape.record(backward)
+        return out
+
+
+class Sequential(Layer):
+    """tf.keras.Sequential over the layers above."""
+
+    def __init__(self, layers: Sequence[Layer] = (), name: Optional[str] = None):
+        self.layers = list(layers)
+        self.name = name or "sequential"
+
+    def add(self, layer: Layer) -> None:
+        self.layers.append(layer)
+
+    @property
+    def trainable_variables(self):
+        return [v for l in self.layers for v in l.trainable_variables]
+
+    @property
+    def losses_l2(self):
+        return [p for l in self.layers for p in l.losses_l2]
+
+    def __call__(self, inputs, training: bool = False) -> Tensor:
+        x = inputs
+        for l in self.layers:
+            x = l(x, training=training)
+        return x
+
+
+from . import factorized_top_k  # noqa: E402,F401

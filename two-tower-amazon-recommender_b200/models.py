@@ -1,0 +1,173 @@
+"""tfrs.models.Model: user overrides compute_loss; train_step runs the tape,
+adds the regularization losses, takes gradients and applies them."""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List, Optional
+
+import torch
+
+from . import ops
+from .core import GradientTape, Scalar, Variable
+from .layers import Layer
+
+
+class Model:
+    def __init__(self, name: Optional[str] = None):
+        self.name = name or type(self).__name__
+        self.optimizer = None
+
+    # ---- Keras-ish plumbing ----------------------------------------------------------
+    def compile(self, optimizer=None, **_ignored) -> None:
+        self.optimizer = optimizer
+
+    def _sublayers(self) -> List[Layer]:
+        seen, out = set(), []
+
+        def visit(obj):
+            if id(obj) in seen:
+                return
+            seen.add(id(obj))
+            if isinstance(obj, Layer):
+                out.append(obj)
+                return
+            if isinstance(obj, (list, tuple)):
+                for o in obj:
+                    visit(o)
+            elif isinstance(obj, dict):
+                for o in obj.values():
+                    visit(o)
+
+        for v in self.__dict__.values():
+            visit(v)
+        return out
+
+    @property
+    def trainable_variables(self) -> List[Variable]:
+        seen, out = set(), []
+        for l in self._sublayers():
+            for v in l.trainable_variables:
+                if id(v) not in seen:
+                    seen.add(id(v))
+                    out.append(v)
+        return out
+
+    @property
+    def metrics(self):
+        ms = []
+        for v in self.__dict__.values():
+            fm = getattr(v, "factorized_metrics", None)
+            if fm is not None:
+                ms.append(fm)
+        return ms
+
+    def _regularization_loss(self) -> Optional[torch.Tensor]:
+        pairs = [p for l in self._sublayers() for p in l.losses_l2]
+        if not pairs:
+            return None
+        out = torch.empty(1, dtype=torch.float32, device=pairs[0][0].value.device)
+        for i, (var, lam) in enumerate(pairs):
+            ops.sum_squares(var.value, lam, out, accumulate=i > 0)
+        return out
+
+    # ---- the TFRS contract -----------------------------------------------------------
+    def compute_loss(self, inputs, training: bool = False) -> Scalar:
+        raise NotImplementedError("Implementers must implement the `compute_loss` method.")
+
+    def train_step(self, inputs) -> Dict[str, object]:
+        if self.optimizer is None:
+            raise RuntimeError("call model.compile(optimizer=...) before train_step")
+        with GradientTape() as tape:
+            loss = self.compute_loss(inputs, training=True)
+            reg = self._regularization_loss()
+            variables = self.trainable_variables
+            grads = tape.gradient(loss, variables)
+        self.optimizer.apply_gradients(zip(grads, variables))
+        return self._report(loss, reg)
+
+    def test_step(self, inputs) -> Dict[str, object]:
+        loss = self.compute_loss(inputs, training=False)
+        return self._report(loss, self._regularization_loss())
+
+    def _report(self, loss: Scalar, reg: Optional[torch.Tensor]) -> Dict[str, object]:
+        out = {}
+        for m in self.metrics:
+            out.update(m.result())
+        zero = torch.zeros_like(loss.value) if reg is None else reg
+        out["loss"] = loss.value
+        out["regularization_loss"] = zero
+        out["total_loss"] = loss.value if reg is None else loss.value + reg
+        return out
+
+    def fit(self, dataset: Iterable, epochs: int = 1, verbose: int = 0):
+        history = {"loss": [], "total_loss": []}
+        for _ in range(epochs):
+            last = None
+            for batch in dataset:
+                last = self.train_step(batch)
+            if last is not None:
+                history["loss"].append(float(last["loss"].item()))
+                history["total_loss"].append(float(last["total_loss"].item()))
+        return history
+
+    def evaluate(self, dataset: Iterable, return_dict: bool = True):
+        for m in self.metrics:
+            m.reset_states()
+        last = None
+        for batch in dataset:
+            last = self.test_step(batch)
+        if last is None:
+            return {}
+        return {k: (float(v.item()) if isinstance(v, torch.Tensor) else v) for k, v in last.items()}
+
+    # ---- CUDA-graph replay of the whole step (launch-bound at cfg2) ------------------
+    def make_graphed_train_step(self, example_inputs: Dict[str, torch.Tensor], warmup: int = 3):
+        """Capture train_step into a CUDA graph with static input buffers.  Returns
+        step(inputs) -> dict of device scalars (valid until the next replay)."""
+        return GraphedStep(self, example_inputs, warmup)
+
+
+class GraphedStep:
+    def __init__(self, model: Model, example_inputs, warmup: int):
+        self.model = model
+        self.static_in = _clone_inputs(example_inputs)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                model.train_step(self.static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        before = ops.LAUNCHES
+        with torch.cuda.graph(self.graph):
+            self.static_out = model.train_step(self.static_in)
+        self.launches_per_replay = ops.LAUNCHES - before
+        self.iterations0 = model.optimizer.iterations
+
+    def __call__(self, inputs=None):
+        if inputs is not None:
+            _copy_inputs(self.static_in, inputs)
+        self.graph.replay()
+        ops._count(self.launches_per_replay)
+        return self.static_out
+
+
+def _clone_inputs(x):
+    if isinstance(x, torch.Tensor):
+        return x.clone()
+    if isinstance(x, dict):
+        return {k: _clone_inputs(v) for k, v in x.items()}
+    if isinstance(x, (tuple, list)):
+        return type(x)(_clone_inputs(v) for v in x)
+    return x
+
+
+def _copy_inputs(dst, src):
+    if isinstance(dst, torch.Tensor):
+        dst.copy_(src, non_blocking=True)
+    elif isinstance(dst, dict):
+        for k in dst:
+            _copy_inputs(dst[k], src[k])
+    elif isinstance(dst, (tuple, list)):
+        for d, s in zip(dst, src):
+            _copy_inputs(d, s)

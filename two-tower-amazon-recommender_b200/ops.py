@@ -1,0 +1,377 @@
+"""Thin torch-tensor wrappers over the libtwotower C-ABI.
+
+torch is used for device memory, the current stream and (elsewhere) torch.distributed only;
+every computation below is a kernel of libtwotower.so.  Nothing here falls back to torch ops
+or to the CPU: a missing library or a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import TT_BF16, TT_F32, TT_POOL_MEAN, TT_POOL_SUM, check
+
+# number of libtwotower kernel launches issued through this module (bench.py's gpu_launches)
+LAUNCHES = 0
+
+
+def _count(n: int) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor], dtype=None) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise TypeError("libtwotower operates on CUDA tensors only (no CPU fallback)")
+    if not t.is_contiguous():
+        raise ValueError("libtwotower needs contiguous tensors")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"expected {dtype}, got {t.dtype}")
+    return t.data_ptr()
+
+
+def precision_code(precision: str) -> int:
+    if precision == "fp32":
+        return TT_F32
+    if precision == "bf16":
+        return TT_BF16
+    raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+
+
+def pool_code(mode: str) -> int:
+    if mode == "sum":
+        return TT_POOL_SUM
+    if mode == "mean":
+        return TT_POOL_MEAN
+    raise ValueError(f"combiner must be 'sum' or 'mean', got {mode!r}")
+
+
+def device_check() -> None:
+    check(_lib.load().tt_device_check())
+
+
+# ------------------------------------------------------------------------------------ K1
+def tower_input_fwd(features: Sequence[tuple], batch: int, dim: int, want_f32: bool, want_bf16: bool,
+                    fault_flag: Optional[torch.Tensor] = None):
+    """features: [(table f32 [V,d], values i64, offsets i64 | None, combiner)].  Returns
+    (out_f32 | None, out_bf16 | None), each [batch, dim]."""
+    lib = _lib.load()
+    n = len(features)
+    arr = (_lib.tt_feature * n)()
+    dev = features[0][0].device
+    for i, (table, values, offsets, mode) in enumerate(features):
+        arr[i].table = _ptr(table, torch.float32)
+        arr[i].values = _ptr(values, torch.int64)
+        arr[i].offsets = _ptr(offsets, torch.int64)
+        arr[i].vocab = table.shape[0]
+        arr[i].mode = pool_code(mode)
+        if table.shape[1] != dim:
+            raise ValueError("all features of a tower must share the embedding dimension")
+    out_f32 = torch.empty((batch, dim), dtype=torch.float32, device=dev) if want_f32 else None
+    out_bf16 = torch.empty((batch, dim), dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    check(lib.tt_tower_input_fwd(arr, n, _ptr(out_f32), _ptr(out_bf16), batch, dim,
+                                 _ptr(fault_flag, torch.int32), _stream()))
+    _count(1)
+    return out_f32, out_bf16
+
+
+def embedding_gather(table, ids, out_dtype=torch.float32):
+    lib = _lib.load()
+    out = torch.empty((ids.numel(), table.shape[1]), dtype=out_dtype, device=table.device)
+    fn = lib.tt_embedding_gather_f32 if out_dtype == torch.float32 else lib.tt_embedding_gather_bf16
+    check(fn(_ptr(table, torch.float32), _ptr(ids, torch.int64), _ptr(out), ids.numel(), table.shape[1],
+             table.shape[0], _stream()))
+    _count(1)
+    return out
+
+
+def embedding_bag(table, values, offsets, mode="mean", out_dtype=torch.float32):
+    lib = _lib.load()
+    nb = offsets.numel() - 1
+    out = torch.empty((nb, table.shape[1]), dtype=out_dtype, device=table.device)
+    check(lib.tt_embedding_bag_fwd(_ptr(table, torch.float32), _ptr(values, torch.int64), _ptr(offsets, torch.int64),
+                                   pool_code(mode), _ptr(out), TT_F32 if out_dtype == torch.float32 else TT_BF16,
+                                   nb, table.shape[1], table.shape[0], _stream()))
+    _count(1)
+    return out
+
+
+# ------------------------------------------------------------------------------------ K5
+class SparseWorkspace:
+    """Caller-owned scratch of the sparse optimizer (hash table + accumulation rows)."""
+
+    def __init__(self, nnz: int, dim: int, device):
+        lib = _lib.load()
+        self.nnz, self.dim = int(nnz), int(dim)
+        self.nbytes = int(lib.tt_sparse_workspace_bytes(self.nnz, self.dim))
+        self.buf = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
+        check(lib.tt_sparse_workspace_init(_ptr(self.buf), self.nbytes, self.nnz, self.dim, _stream()))
+        _count(1)
+
+    def fits(self, nnz: int, dim: int) -> bool:
+        return nnz <= self.nnz and dim == self.dim and \
+            int(_lib.load().tt_sparse_workspace_bytes(nnz, dim)) <= self.nbytes
+
+
+def sparse_adagrad_update(table, accum, values, offsets, mode, grad, lr, eps, ws: SparseWorkspace,
+                          first_flag=None):
+    lib = _lib.load()
+    nnz = values.numel()
+    check(lib.tt_sparse_adagrad_update(_ptr(table, torch.float32), _ptr(accum, torch.float32), table.shape[0],
+                                       table.shape[1], _ptr(values, torch.int64), _ptr(offsets, torch.int64),
+                                       pool_code(mode), grad.shape[0], nnz, _ptr(grad, torch.float32), lr, eps,
+                                       _ptr(ws.buf), ws.nbytes, _ptr(first_flag, torch.uint8), _stream()))
+    _count(3 if nnz else 0)
+
+
+def sparse_lazy_adam_update(table, m, v, values, offsets, mode, grad, alpha, beta1, beta2, eps,
+                            ws: SparseWorkspace, first_flag=None):
+    lib = _lib.load()
+    nnz = values.numel()
+    check(lib.tt_sparse_lazy_adam_update(_ptr(table, torch.float32), _ptr(m, torch.float32), _ptr(v, torch.float32),
+                                         table.shape[0], table.shape[1], _ptr(values, torch.int64),
+                                         _ptr(offsets, torch.int64), pool_code(mode), grad.shape[0], nnz,
+                                         _ptr(grad, torch.float32), alpha, beta1, beta2, eps, _ptr(ws.buf),
+                                         ws.nbytes, _ptr(first_flag, torch.uint8), _stream()))
+    _count(3 if nnz else 0)
+
+
+def dense_adagrad_update(w, accum, grad_parts, num_parts, lr, eps, l2=0.0, shadow=None, shadow_t=None):
+    lib = _lib.load()
+    rows, cols = (w.shape[0], w.shape[1]) if w.dim() == 2 else (1, w.numel())
+    check(lib.tt_dense_adagrad_update(_ptr(w, torch.float32), _ptr(accum, torch.float32),
+                                      _ptr(grad_parts, torch.float32), num_parts, rows, cols, lr, eps, l2,
+                                      _ptr(shadow, torch.bfloat16), _ptr(shadow_t, torch.bfloat16), _stream()))
+    _count(1)
+
+
+def dense_adam_update(w, m, v, grad_parts, num_parts, alpha, beta1, beta2, eps, l2=0.0, shadow=None,
+                      shadow_t=None):
+    lib = _lib.load()
+    rows, cols = (w.shape[0], w.shape[1]) if w.dim() == 2 else (1, w.numel())
+    check(lib.tt_dense_adam_update(_ptr(w, torch.float32), _ptr(m, torch.float32), _ptr(v, torch.float32),
+                                   _ptr(grad_parts, torch.float32), num_parts, rows, cols, alpha, beta1, beta2,
+                                   eps, l2, _ptr(shadow, torch.bfloat16), _ptr(shadow_t, torch.bfloat16),
+                                   _stream()))
+    _count(1)
+
+
+def sum_squares(x, scale, out, accumulate):
+    check(_lib.load().tt_sum_squares(_ptr(x, torch.float32), x.numel(), scale, _ptr(out, torch.float32),
+                                     1 if accumulate else 0, _stream()))
+    _count(1)
+
+
+# ------------------------------------------------------------------------------------ K2
+def dense_fwd(precision: str, x, kernel, bias, relu: bool, want_t: bool = False, want_f32: bool = False):
+    """fp32: x f32 [M,in], kernel f32 [in,out] -> y f32.
+    bf16: x bf16 [M,in], kernel = shadow_t bf16 [out,in] -> (y bf16, y_t bf16 | None, y_f32 | None)."""
+    lib = _lib.load()
+    M, in_dim = x.shape
+    if precision == "fp32":
+        out_dim = kernel.shape[1]
+        y = torch.empty((M, out_dim), dtype=torch.float32, device=x.device)
+        check(lib.tt_dense_fwd(TT_F32, _ptr(x, torch.float32), _ptr(kernel, torch.float32),
+                               _ptr(bias, torch.float32), _ptr(y), None, None, M, in_dim, out_dim,
+                               1 if relu else 0, _stream()))
+        _count(1)
+        return y, None, None
+    out_dim = kernel.shape[0]
+    y = torch.empty((M, out_dim), dtype=torch.bfloat16, device=x.device)
+    y_t = torch.empty((out_dim, M), dtype=torch.bfloat16, device=x.device) if want_t else None
+    y_f32 = torch.empty((M, out_dim), dtype=torch.float32, device=x.device) if want_f32 else None
+    check(lib.tt_dense_fwd(TT_BF16, _ptr(x, torch.bfloat16), _ptr(kernel, torch.bfloat16),
+                           _ptr(bias, torch.float32), _ptr(y), _ptr(y_t), _ptr(y_f32), M, in_dim, out_dim,
+                           1 if relu else 0, _stream()))
+    _count(1)
+    return y, y_t, y_f32
+
+
+def dense_bwd_num_parts(precision: str, M: int, in_dim: int, out_dim: int) -> int:
+    return int(_lib.load().tt_dense_bwd_num_parts(precision_code(precision), M, in_dim, out_dim))
+
+
+def dense_bwd(precision: str, dy, dy_t, x, x_t, kernel, relu_mask_x: bool, want_dx: bool, want_dx_t: bool = False,
+              want_dx_f32: bool = False):
+    """Returns (dx, dx_t, dx_f32, dkernel_parts [P,in,out] f32, P, dbias f32 [out])."""
+    lib = _lib.load()
+    M, out_dim = dy.shape
+    in_dim = x.shape[1]
+    dev = dy.device
+    P = dense_bwd_num_parts(precision, M, in_dim, out_dim)
+    dk = torch.empty((P, in_dim, out_dim), dtype=torch.float32, device=dev)
+    db = torch.empty((out_dim,), dtype=torch.float32, device=dev)
+    if precision == "fp32":
+        dx = torch.empty((M, in_dim), dtype=torch.float32, device=dev) if want_dx else None
+        check(lib.tt_dense_bwd(TT_F32, _ptr(dy, torch.float32), None, _ptr(x, torch.float32), None,
+                               _ptr(kernel, torch.float32), _ptr(dx), None, None, _ptr(dk), P, _ptr(db), M,
+                               in_dim, out_dim, 1 if relu_mask_x else 0, _stream()))
+        _count(3 if want_dx else 2)
+        return dx, None, None, dk, P, db
+    dx = torch.empty((M, in_dim), dtype=torch.bfloat16, device=dev) if want_dx else None
+    dx_t = torch.empty((in_dim, M), dtype=torch.bfloat16, device=dev) if want_dx_t else None
+    dx_f32 = torch.empty((M, in_dim), dtype=torch.float32, device=dev) if want_dx_f32 else None
+    check(lib.tt_dense_bwd(TT_BF16, _ptr(dy, torch.bfloat16), _ptr(dy_t, torch.bfloat16), _ptr(x, torch.bfloat16),
+                           _ptr(x_t, torch.bfloat16), _ptr(kernel, torch.bfloat16), _ptr(dx), _ptr(dx_t),
+                           _ptr(dx_f32), _ptr(dk), P, _ptr(db), M, in_dim, out_dim, 1 if relu_mask_x else 0,
+                           _stream()))
+    _count(3)
+    return dx, dx_t, dx_f32, dk, P, db
+
+
+def transpose_bf16(x):
+    rows, cols = x.shape
+    out = torch.empty((cols, rows), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().tt_transpose_bf16(_ptr(x, torch.bfloat16), _ptr(out), rows, cols, _stream()))
+    _count(1)
+    return out
+
+
+def cast_f32_to_bf16(x, want=True, want_t=False):
+    rows, cols = x.shape
+    out = torch.empty((rows, cols), dtype=torch.bfloat16, device=x.device) if want else None
+    out_t = torch.empty((cols, rows), dtype=torch.bfloat16, device=x.device) if want_t else None
+    check(_lib.load().tt_cast_f32_to_bf16(_ptr(x, torch.float32), _ptr(out), _ptr(out_t), rows, cols, _stream()))
+    _count(1)
+    return out, out_t
+
+
+# --------------------------------------------------------------------------------- K3/K4
+_ws_cache = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    """Scratch reused across calls on one device (grown on demand)."""
+    key = (device.type, device.index)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def retrieval_loss_fwd(precision: str, q, c, inv_temperature: float, label_offset: int = 0, sample_weight=None,
+                       cand_log_q=None, cand_ids=None):
+    """Returns (loss [1] f32, row_lse [nq] f32, row_pos [nq] f32)."""
+    lib = _lib.load()
+    pc = precision_code(precision)
+    dt = torch.float32 if precision == "fp32" else torch.bfloat16
+    nq, d = q.shape
+    nc = c.shape[0]
+    dev = q.device
+    lse = torch.empty((nq,), dtype=torch.float32, device=dev)
+    pos = torch.empty((nq,), dtype=torch.float32, device=dev)
+    loss = torch.empty((1,), dtype=torch.float32, device=dev)
+    nbytes = int(lib.tt_retrieval_workspace_bytes(pc, nq, nc, d))
+    ws = _workspace(nbytes, dev)
+    check(lib.tt_retrieval_loss_fwd(pc, _ptr(q, dt), _ptr(c, dt), nq, nc, d, inv_temperature, label_offset,
+                                    _ptr(sample_weight, torch.float32), _ptr(cand_log_q, torch.float32),
+                                    _ptr(cand_ids, torch.int64), _ptr(lse), _ptr(pos), _ptr(loss), _ptr(ws),
+                                    ws.numel(), _stream()))
+    _count(2)
+    return loss, lse, pos
+
+
+def retrieval_loss_bwd(precision: str, q, c, q_t, c_t, inv_temperature: float, row_lse, label_offset: int = 0,
+                       sample_weight=None, cand_log_q=None, cand_ids=None, grad_scale: float = 1.0,
+                       want_bf16=(False, False), want_bf16_t=(False, False)):
+    """Returns dict(dq, dc [f32], dq_bf16, dq_bf16_t, dc_bf16, dc_bf16_t)."""
+    lib = _lib.load()
+    pc = precision_code(precision)
+    dt = torch.float32 if precision == "fp32" else torch.bfloat16
+    nq, d = q.shape
+    nc = c.shape[0]
+    dev = q.device
+    dq = torch.empty((nq, d), dtype=torch.float32, device=dev)
+    dc = torch.empty((nc, d), dtype=torch.float32, device=dev)
+    mk = lambda shape, on: torch.empty(shape, dtype=torch.bfloat16, device=dev) if on else None
+    dq_b, dc_b = mk((nq, d), want_bf16[0]), mk((nc, d), want_bf16[1])
+    dq_bt, dc_bt = mk((d, nq), want_bf16_t[0]), mk((d, nc), want_bf16_t[1])
+    nbytes = int(lib.tt_retrieval_workspace_bytes(pc, nq, nc, d))
+    ws = _workspace(nbytes, dev)
+    check(lib.tt_retrieval_loss_bwd(pc, _ptr(q, dt), _ptr(c, dt), _ptr(q_t), _ptr(c_t), nq, nc, d, inv_temperature,
+                                    label_offset, _ptr(sample_weight, torch.float32),
+                                    _ptr(cand_log_q, torch.float32), _ptr(cand_ids, torch.int64),
+                                    _ptr(row_lse, torch.float32), grad_scale, _ptr(dq), _ptr(dc), _ptr(dq_b),
+                                    _ptr(dq_bt), _ptr(dc_b), _ptr(dc_bt), _ptr(ws), ws.numel(), _stream()))
+    _count(2)
+    return dict(dq=dq, dc=dc, dq_bf16=dq_b, dq_bf16_t=dq_bt, dc_bf16=dc_b, dc_bf16_t=dc_bt)
+
+
+# ------------------------------------------------------------------------------------ K6
+def topk_bruteforce(precision: str, queries, candidates, k: int, cand_index_base: int = 0, identifiers=None):
+    lib = _lib.load()
+    pc = precision_code(precision)
+    dt = torch.float32 if precision == "fp32" else torch.bfloat16
+    nq, d = queries.shape
+    nc = candidates.shape[0]
+    dev = queries.device
+    scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    nbytes = int(lib.tt_topk_workspace_bytes(pc, nq, nc, d, k))
+    ws = _workspace(nbytes, dev)
+    splits = int(lib.tt_topk_num_splits(pc, nq, nc, d, k))
+    check(lib.tt_topk_bruteforce(pc, _ptr(queries, dt), _ptr(candidates, dt), nq, nc, d, k, cand_index_base,
+                                 _ptr(identifiers, torch.int64), _ptr(scores), _ptr(ids), _ptr(ws), ws.numel(),
+                                 _stream()))
+    _count(2 if splits > 1 else 1)
+    return scores, ids
+
+
+def topk_merge(scores, ids, k_out: int):
+    """scores/ids: [L, nq, k_in] -> ([nq, k_out], [nq, k_out])."""
+    L, nq, k_in = scores.shape
+    out_s = torch.empty((nq, k_out), dtype=torch.float32, device=scores.device)
+    out_i = torch.empty((nq, k_out), dtype=torch.int64, device=scores.device)
+    check(_lib.load().tt_topk_merge(_ptr(scores, torch.float32), _ptr(ids, torch.int64), L, nq, k_in, k_out,
+                                    _ptr(out_s), _ptr(out_i), _stream()))
+    _count(1)
+    return out_s, out_i
+
+
+def topk_hits(positive, topk_scores, topk_ids, true_ids, sample_weight, ks, hits_out, weight_out):
+    nq, k = (topk_scores if topk_scores is not None else topk_ids).shape
+    arr = (C.c_int32 * len(ks))(*[int(x) for x in ks])
+    check(_lib.load().tt_topk_hits(_ptr(positive, torch.float32), _ptr(topk_scores, torch.float32),
+                                   _ptr(topk_ids, torch.int64), _ptr(true_ids, torch.int64),
+                                   _ptr(sample_weight, torch.float32), nq, k, arr, len(ks),
+                                   _ptr(hits_out, torch.float32), _ptr(weight_out, torch.float32), _stream()))
+    _count(1)
+
+
+def rowwise_dot(precision: str, q, c):
+    out = torch.empty((q.shape[0],), dtype=torch.float32, device=q.device)
+    check(_lib.load().tt_rowwise_dot(precision_code(precision), _ptr(q), _ptr(c), _ptr(out), q.shape[0], q.shape[1],
+                                     _stream()))
+    _count(1)
+    return out
+
+
+# ------------------------------------------------------------------------ sharding helpers
+def partition_ids(ids, world: int):
+    """Stable partition by owner = id % world.  Returns (send_local_rows [n], perm [n], counts [world])."""
+    n = ids.numel()
+    send = torch.empty((n,), dtype=torch.int64, device=ids.device)
+    perm = torch.empty((n,), dtype=torch.int64, device=ids.device)
+    counts = torch.empty((world,), dtype=torch.int64, device=ids.device)
+    check(_lib.load().tt_partition_ids(_ptr(ids, torch.int64), n, world, _ptr(send), _ptr(perm), _ptr(counts),
+                                       _stream()))
+    _count(1)
+    return send, perm, counts
+
+
+def permute_rows(x, perm, inverse: bool):
+    out = torch.empty_like(x)
+    check(_lib.load().tt_permute_rows_f32(_ptr(x, torch.float32), _ptr(perm, torch.int64), _ptr(out), x.shape[0],
+                                          x.shape[1], 1 if inverse else 0, _stream()))
+    _count(1)
+    return out

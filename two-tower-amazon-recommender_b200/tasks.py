@@ -1,0 +1,115 @@
+"""tfrs.tasks.Retrieval: in-batch softmax retrieval loss, fused forward and
+backward kernels, logits never in HBM."""
+from __future__ import annotations
+
+import math
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ops
+from .core import GradientTape, Scalar, Tensor, config
+
+
+def _as_f32_device(x, dev):
+    if x is None:
+        return None
+    t = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x))
+    return t.to(device=dev, dtype=torch.float32).contiguous()
+
+
+class Retrieval:
+    """tfrs.tasks.Retrieval(loss=None, metrics=None, batch_metrics=None, loss_metrics=None,
+    temperature=None, num_hard_negatives=None, remove_accidental_hits=False).
+
+    Default (and only hot-path) loss: CategoricalCrossentropy(from_logits=True, reduction=SUM)
+    with labels = eye(num_queries, num_candidates).  ``process_group`` (extension, SURVEY.md
+    8e): all-gather the candidate embeddings over the group so negatives span the global
+    batch; the result equals the single-device loss on the concatenated batch.
+    """
+
+    def __init__(self, loss=None, metrics=None, batch_metrics=None, loss_metrics=None,
+                 temperature: Optional[float] = None, num_hard_negatives: Optional[int] = None,
+                 remove_accidental_hits: bool = False, name: Optional[str] = None, process_group=None):
+        if loss is not None:
+            raise NotImplementedError("only the default CategoricalCrossentropy(from_logits=True, reduction=SUM) is built")
+        if num_hard_negatives is not None:
+            raise NotImplementedError("num_hard_negatives is not on the built path yet (SURVEY.md 8f, row f2)")
+        self._factorized_metrics = metrics
+        self._batch_metrics = batch_metrics
+        self._loss_metrics = loss_metrics
+        self._temperature = temperature
+        self._remove_accidental_hits = bool(remove_accidental_hits)
+        self.name = name or "retrieval"
+        self.process_group = process_group
+
+    @property
+    def factorized_metrics(self):
+        return self._factorized_metrics
+
+    @factorized_metrics.setter
+    def factorized_metrics(self, value):
+        self._factorized_metrics = value
+
+    def __call__(self, query_embeddings: Tensor, candidate_embeddings: Tensor, sample_weight=None,
+                 candidate_sampling_probability=None, candidate_ids=None, compute_metrics: bool = True,
+                 compute_batch_metrics: bool = True) -> Scalar:
+        q, c = query_embeddings, candidate_embeddings
+        prec = config.precision
+        dev = (q.f32 if q.f32 is not None else q.bf16).device
+        nq = q.shape[0]
+        inv_t = 1.0 if self._temperature is None else 1.0 / float(self._temperature)
+        w = _as_f32_device(sample_weight, dev)
+        logq = None
+        if candidate_sampling_probability is not None:
+            p = _as_f32_device(candidate_sampling_probability, dev)
+            logq = torch.log(torch.clamp(p, 1e-6, 1.0))      # [nc] input preparation
+        ids = None
+        if self._remove_accidental_hits:
+            if candidate_ids is None:
+                raise ValueError("When accidental hit removal is enabled, candidate ids must be supplied.")
+            ids = candidate_ids if isinstance(candidate_ids, torch.Tensor) else torch.as_tensor(np.asarray(candidate_ids))
+            ids = ids.to(device=dev, dtype=torch.int64).contiguous()
+
+        if self.process_group is not None:
+            from . import parallel
+            return parallel.global_retrieval(self, q, c, inv_t, w, logq, ids)
+
+        if prec == "fp32":
+            qm, cm = q.f32, c.f32
+        else:
+            qm, cm = q.bf16, c.bf16
+        loss, lse, _pos = ops.retrieval_loss_fwd(prec, qm, cm, inv_t, 0, w, logq, ids)
+
+        def backward():
+            q_t = c_t = None
+            if prec == "bf16":
+                if q.bf16_t is None:
+                    q.bf16_t = ops.transpose_bf16(q.bf16)
+                if c.bf16_t is None:
+                    c.bf16_t = ops.transpose_bf16(c.bf16)
+                q_t, c_t = q.bf16_t, c.bf16_t
+            r = ops.retrieval_loss_bwd(
+                prec, qm, cm, q_t, c_t, inv_t, lse, 0, w, logq, ids, 1.0,
+                want_bf16=("bf16" in q.grad_formats and prec == "bf16", "bf16" in c.grad_formats and prec == "bf16"),
+                want_bf16_t=("bf16_t" in q.grad_formats and prec == "bf16", "bf16_t" in c.grad_formats and prec == "bf16"))
+            q.grad = dict(f32=r["dq"], bf16=r["dq_bf16"], bf16_t=r["dq_bf16_t"])
+            c.grad = dict(f32=r["dc"], bf16=r["dc_bf16"], bf16_t=r["dc_bf16_t"])
+
+        GradientTape.record(backward)
+
+        if compute_metrics and self._factorized_metrics is not None:
+            self._factorized_metrics.update_state(q, _first_rows(c, nq),
+                                                  true_candidate_ids=None if candidate_ids is None else candidate_ids,
+                                                  sample_weight=sample_weight)
+        return Scalar(loss)
+
+    call = __call__
+
+
+def _first_rows(c: Tensor, n: int) -> Tensor:
+    if c.shape[0] == n:
+        return c
+    return Tensor(f32=None if c.f32 is None else c.f32[:n].contiguous(),
+                  bf16=None if c.bf16 is None else c.bf16[:n].contiguous())
