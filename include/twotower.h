@@ -66,7 +66,8 @@ typedef struct tt_feature {
 /* out[b,:] = sum_f pool_f(table_f[bag_f(b)]).  Either output may be NULL (not both).
  * `host_feats` is a HOST array of num_feats descriptors (copied into kernel parameters).
  * d % 4 == 0, rows 16-byte aligned.  Ids outside [0, vocab) raise a device-side flag that
- * the next tt_check_id_fault() returns (TF raises on CPU; a GPU kernel cannot). */
+ * sets *id_fault_flag = 1 (a caller-owned device int, nullable) and read as zero rows
+ * (TF raises on CPU; a GPU kernel cannot). */
 int tt_tower_input_fwd(const tt_feature* host_feats, int32_t num_feats, float* out_f32,
                        uint16_t* out_bf16, int64_t B, int64_t d, int32_t* id_fault_flag,
                        void* stream);
@@ -205,10 +206,12 @@ int tt_topk_bruteforce(int32_t precision, const void* queries, const void* candi
                        const int64_t* identifiers, float* out_scores, int64_t* out_ids,
                        void* workspace, int64_t workspace_bytes, void* stream);
 /* Merge `num_lists` sorted top-k lists per query: scores/ids are [num_lists, nq, k_in]
- * (list-major, as written by per-shard searches after an all-gather); ordering rule
- * (score desc, id asc).  Writes [nq, k_out]. */
+ * (list-major, as written by per-shard searches after an all-gather); ids are candidate
+ * INDICES and the ordering rule is (score desc, index asc).  Writes [nq, k_out] with
+ * out_ids = identifiers ? identifiers[index] : index_base + index. */
 int tt_topk_merge(const float* scores, const int64_t* ids, int32_t num_lists, int64_t nq,
-                  int32_t k_in, int32_t k_out, float* out_scores, int64_t* out_ids, void* stream);
+                  int32_t k_in, int32_t k_out, int64_t index_base, const int64_t* identifiers,
+                  float* out_scores, int64_t* out_ids, void* stream);
 /* FactorizedTopK hit counting.  Score mode (true_ids == NULL): hit@k iff
  * fewer than k of topk_scores[i,:] are strictly greater than positive[i].  Id mode: hit@k iff
  * true_ids[i] appears in topk_ids[i,:k].  hits_out[j] += sum_i w_i * hit_{ks[j]}(i);

@@ -252,11 +252,13 @@ def adagrad_dense(w, acc, g, lr=0.001, eps=1e-7):
     return w, acc
 
 
-def adagrad_sparse(table, acc, ids, rows, lr=0.001, eps=1e-7):
+def adagrad_sparse(table, acc, ids, rows, lr=0.001, eps=1e-7, inplace=False):
     """Keras Adagrad on IndexedSlices: dedup, then the row-wise update on touched rows only.
-    Mutates copies; returns (table, acc, unique_ids)."""
-    table = table.copy()
-    acc = acc.copy()
+    Mutates copies unless inplace (the timing baseline updates in place, as TF's
+    ResourceScatter ops do); returns (table, acc, unique_ids)."""
+    if not inplace:
+        table = table.copy()
+        acc = acc.copy()
     u, g, _ = dedup_sparse_grad(ids, rows)
     g = g.astype(table.dtype)
     acc[u] = acc[u] + g * g
@@ -264,11 +266,17 @@ def adagrad_sparse(table, acc, ids, rows, lr=0.001, eps=1e-7):
     return table, acc, u
 
 
+def _one_minus_f32(b):
+    """Keras casts beta to the variable dtype (fp32) before forming 1 - beta, so the factor
+    carries fp32 rounding (1 - 0.999f = 0.00100005): restated exactly."""
+    return float(np.float32(1.0) - np.float32(b))
+
+
 def adam_dense(w, m, v, g, step, lr=0.001, b1=0.9, b2=0.999, eps=1e-7):
     """Keras 2.15 Adam.update_step (dense).  ``step`` is 1-based (iterations + 1)."""
     alpha = lr * np.sqrt(1.0 - b2 ** step) / (1.0 - b1 ** step)
-    m = m + (g - m) * (1 - b1)
-    v = v + (g * g - v) * (1 - b2)
+    m = m + (g - m) * _one_minus_f32(b1)
+    v = v + (g * g - v) * _one_minus_f32(b2)
     w = w - m * alpha / (np.sqrt(v) + eps)
     return w, m, v
 
@@ -289,8 +297,8 @@ def lazy_adam_sparse(table, m, v, ids, rows, step, lr=0.001, b1=0.9, b2=0.999, e
     u, g, _ = dedup_sparse_grad(ids, rows)
     g = g.astype(table.dtype)
     alpha = lr * np.sqrt(1.0 - b2 ** step) / (1.0 - b1 ** step)
-    m[u] = m[u] + (g - m[u]) * (1 - b1)
-    v[u] = v[u] + (g * g - v[u]) * (1 - b2)
+    m[u] = m[u] + (g - m[u]) * _one_minus_f32(b1)
+    v[u] = v[u] + (g * g - v[u]) * _one_minus_f32(b2)
     table[u] = table[u] - m[u] * alpha / (np.sqrt(v[u]) + eps)
     return table, m, v, u
 
@@ -462,7 +470,7 @@ def two_tower_train_step(qspec, cspec, qparams, cparams, qslots, cslots, batch_q
                          temperature=None, lr=0.001, eps=1e-7, l2=0.0, dtype=np.float64,
                          sample_weight=None, candidate_sampling_probability=None,
                          candidate_ids=None, remove_accidental_hits=False,
-                         num_hard_negatives=None, bf16=False):
+                         num_hard_negatives=None, bf16=False, inplace=False):
     """tfrs.models.Model.train_step with Keras Adagrad on every variable:
     loss = task(q, c); reg = sum(model.losses); total = loss + reg; grads of total;
     apply_gradients (sparse for tables, dense for Dense).  Params/slots are updated in place
@@ -493,8 +501,9 @@ def two_tower_train_step(qspec, cspec, qparams, cparams, qslots, cslots, batch_q
             w, a = adagrad_dense(params["biases"][l].astype(dtype), slots["biases"][l].astype(dtype), db[l], lr, eps)
             params["biases"][l], slots["biases"][l] = w, a
         for name, (ids, rows) in sparse.items():
-            t, a, u = adagrad_sparse(params["tables"][name].astype(dtype),
-                                     slots["tables"][name].astype(dtype), ids, rows.astype(dtype), lr, eps)
+            t, a, u = adagrad_sparse(params["tables"][name].astype(dtype, copy=False),
+                                     slots["tables"][name].astype(dtype, copy=False), ids,
+                                     rows.astype(dtype, copy=False), lr, eps, inplace=inplace)
             params["tables"][name], slots["tables"][name] = t, a
             out["unique"][f"{tag}/{name}"] = u
     return out

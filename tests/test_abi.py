@@ -41,7 +41,7 @@ def test_argument_validation_reports_through_last_error(tt):
     rc = lib.tt_topk_bruteforce(0, 16, 16, 4, 8, 8, 9, 0, None, 16, 16, None, 0, None)
     assert rc == -1 and b"k=9" in lib.tt_last_error()                      # k > num candidates
     with pytest.raises(tt.TwoTowerError) as e:
-        tt._lib.check(lib.tt_topk_merge(None, None, 1, 1, 1, 1, None, None, None))
+        tt._lib.check(lib.tt_topk_merge(None, None, 1, 1, 1, 1, 0, None, None, None, None))
     assert e.value.code == -1
 
 

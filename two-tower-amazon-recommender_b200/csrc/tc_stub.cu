@@ -1,9 +1,6 @@
 // TEMPORARY link stubs for the tcgen05 entry points (replaced by dense_tc.cu / retrieval_tc.cu / topk_tc.cu).
 #include "common.cuh"
 namespace tt {
-int tc_dense_fwd(const void*, const void*, const float*, void*, void*, float*, int64_t, int64_t, int64_t, int, cudaStream_t) { return set_error(TT_ERR_UNSUPPORTED, "bf16 dense path not built"); }
-int tc_dense_bwd(const void*, const void*, const void*, const void*, const void*, void*, void*, float*, float*, int, float*, int64_t, int64_t, int64_t, int, cudaStream_t) { return set_error(TT_ERR_UNSUPPORTED, "bf16 dense path not built"); }
-int tc_dense_bwd_num_parts(int64_t, int64_t, int64_t) { return 1; }
 int tc_retrieval_fwd(const void*, const void*, int64_t, int64_t, int64_t, float, int64_t, const float*, const float*, const int64_t*, float*, float*, float*, void*, int64_t, cudaStream_t) { return set_error(TT_ERR_UNSUPPORTED, "bf16 retrieval path not built"); }
 int tc_retrieval_bwd(const void*, const void*, const void*, const void*, int64_t, int64_t, int64_t, float, int64_t, const float*, const float*, const int64_t*, const float*, float, float*, float*, uint16_t*, uint16_t*, uint16_t*, uint16_t*, void*, int64_t, cudaStream_t) { return set_error(TT_ERR_UNSUPPORTED, "bf16 retrieval path not built"); }
 int64_t tc_retrieval_workspace_bytes(int64_t, int64_t, int64_t) { return 256; }

@@ -81,14 +81,15 @@ topk_simt_kernel(const float* __restrict__ Q, const float* __restrict__ C, int64
   for (int r = warp * 8; r < warp * 8 + 8; ++r) {
     if (q0 + r >= nq) continue;
     const size_t o = ((size_t)blockIdx.y * nq + (q0 + r)) * k;
-    topk_write_row(st, r, lane, out_s + o, out_i + o, cand_base, identifiers);
+    topk_write_row(st, r, lane, out_s + o, out_i + o, gridDim.y > 1 ? 0 : cand_base, gridDim.y > 1 ? nullptr : identifiers);
   }
 }
 
 // L-way merge of sorted lists, one warp per query; lane l walks list l (L <= 32).
 __global__ void __launch_bounds__(256)
 topk_merge_kernel(const float* __restrict__ scores, const int64_t* __restrict__ ids, int L, int64_t nq, int k_in,
-                  int k_out, float* __restrict__ out_s, int64_t* __restrict__ out_i) {
+                  int k_out, int64_t base, const int64_t* __restrict__ identifiers, float* __restrict__ out_s,
+                  int64_t* __restrict__ out_i) {
   const int lane = threadIdx.x & 31;
   const int64_t qi = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (qi >= nq) return;
@@ -107,7 +108,10 @@ topk_merge_kernel(const float* __restrict__ scores, const int64_t* __restrict__ 
       const bool take = s2 > bs || (s2 == bs && (i2 < bi || (i2 == bi && l2 < bl)));
       if (take) { bs = s2; bi = i2; bl = l2; }
     }
-    if (lane == 0) { out_s[qi * k_out + t] = bs; out_i[qi * k_out + t] = bi; }
+    if (lane == 0) {
+      out_s[qi * k_out + t] = bs;
+      out_i[qi * k_out + t] = (bi == LLONG_MAX) ? bi : (identifiers ? __ldg(identifiers + bi) : base + bi);
+    }
     if (lane == bl) {
       ++head;
       if (head < k_in) { hs = ls[head]; hi = li[head]; } else { hs = -INFINITY; hi = LLONG_MAX; }
@@ -201,12 +205,13 @@ extern "C" int64_t tt_topk_workspace_bytes(int32_t precision, int64_t nq, int64_
 }
 
 extern "C" int tt_topk_merge(const float* scores, const int64_t* ids, int32_t num_lists, int64_t nq, int32_t k_in,
-                             int32_t k_out, float* out_scores, int64_t* out_ids, void* stream) {
+                             int32_t k_out, int64_t index_base, const int64_t* identifiers, float* out_scores,
+                             int64_t* out_ids, void* stream) {
   TT_REQUIRE(scores && ids && out_scores && out_ids, "tt_topk_merge: null buffer");
   TT_REQUIRE(num_lists >= 1 && num_lists <= 32, "tt_topk_merge: num_lists must be in [1, 32], got %d", num_lists);
   TT_REQUIRE(nq >= 0 && k_in >= 1 && k_out >= 1 && k_out <= num_lists * k_in, "tt_topk_merge: bad k (k_in=%d k_out=%d lists=%d)", k_in, k_out, num_lists);
   if (nq == 0) return TT_OK;
-  topk_merge_kernel<<<(unsigned)ceil_div(nq, 8), 256, 0, (cudaStream_t)stream>>>(scores, ids, num_lists, nq, k_in, k_out, out_scores, out_ids);
+  topk_merge_kernel<<<(unsigned)ceil_div(nq, 8), 256, 0, (cudaStream_t)stream>>>(scores, ids, num_lists, nq, k_in, k_out, index_base, identifiers, out_scores, out_ids);
   TT_LAUNCH_OK("topk_merge_kernel");
   return TT_OK;
 }
@@ -251,7 +256,7 @@ extern "C" int tt_topk_bruteforce(int32_t precision, const void* queries, const 
   else TT_TOPK_LAUNCH(16)
 #undef TT_TOPK_LAUNCH
   TT_LAUNCH_OK("topk_simt_kernel");
-  if (splits > 1) return tt_topk_merge(ps, pi, splits, nq, k, k, out_scores, out_ids, stream);
+  if (splits > 1) return tt_topk_merge(ps, pi, splits, nq, k, k, cand_index_base, identifiers, out_scores, out_ids, stream);
   return TT_OK;
 }
 

@@ -78,6 +78,8 @@ def tower_input_fwd(features: Sequence[tuple], batch: int, dim: int, want_f32: b
             raise ValueError("all features of a tower must share the embedding dimension")
     out_f32 = torch.empty((batch, dim), dtype=torch.float32, device=dev) if want_f32 else None
     out_bf16 = torch.empty((batch, dim), dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    if batch == 0:
+        return out_f32, out_bf16
     check(lib.tt_tower_input_fwd(arr, n, _ptr(out_f32), _ptr(out_bf16), batch, dim,
                                  _ptr(fault_flag, torch.int32), _stream()))
     _count(1)
@@ -87,6 +89,8 @@ def tower_input_fwd(features: Sequence[tuple], batch: int, dim: int, want_f32: b
 def embedding_gather(table, ids, out_dtype=torch.float32):
     lib = _lib.load()
     out = torch.empty((ids.numel(), table.shape[1]), dtype=out_dtype, device=table.device)
+    if ids.numel() == 0:
+        return out
     fn = lib.tt_embedding_gather_f32 if out_dtype == torch.float32 else lib.tt_embedding_gather_bf16
     check(fn(_ptr(table, torch.float32), _ptr(ids, torch.int64), _ptr(out), ids.numel(), table.shape[1],
              table.shape[0], _stream()))
@@ -327,13 +331,13 @@ def topk_bruteforce(precision: str, queries, candidates, k: int, cand_index_base
     return scores, ids
 
 
-def topk_merge(scores, ids, k_out: int):
-    """scores/ids: [L, nq, k_in] -> ([nq, k_out], [nq, k_out])."""
+def topk_merge(scores, ids, k_out: int, index_base: int = 0, identifiers=None):
+    """scores/ids (candidate indices): [L, nq, k_in] -> ([nq, k_out], [nq, k_out])."""
     L, nq, k_in = scores.shape
     out_s = torch.empty((nq, k_out), dtype=torch.float32, device=scores.device)
     out_i = torch.empty((nq, k_out), dtype=torch.int64, device=scores.device)
     check(_lib.load().tt_topk_merge(_ptr(scores, torch.float32), _ptr(ids, torch.int64), L, nq, k_in, k_out,
-                                    _ptr(out_s), _ptr(out_i), _stream()))
+                                    index_base, _ptr(identifiers, torch.int64), _ptr(out_s), _ptr(out_i), _stream()))
     _count(1)
     return out_s, out_i
 
