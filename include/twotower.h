@@ -144,12 +144,17 @@ int tt_dense_fwd(int32_t precision, const void* x, const void* kernel, const flo
  *          [in,out] (the shadow copy); dx bf16 [M,in] (+ dx_t [in,M] nullable);
  *          dkernel_parts fp32 [num_parts, in, out]; dbias fp32 [out].
  * dx may be NULL (first layer: only the embedding gradient dx_f32 is wanted) and dx_f32
- * (nullable) receives an fp32 copy of dx. */
+ * (nullable) receives an fp32 copy of dx.  dbias may be NULL (the caller then takes
+ * tt_colsum_f32 of an fp32 copy of dy: the bias gradient is a cancelling sum, so it is taken
+ * before bf16 rounding whenever an fp32 dy exists). */
 int tt_dense_bwd(int32_t precision, const void* dy, const void* dy_t, const void* x,
                  const void* x_t, const void* kernel, void* dx, void* dx_t, float* dx_f32,
                  float* dkernel_parts, int32_t num_parts, float* dbias, int64_t M,
                  int64_t in_dim, int64_t out_dim, int32_t relu_mask_x, void* stream);
 int32_t tt_dense_bwd_num_parts(int32_t precision, int64_t M, int64_t in_dim, int64_t out_dim);
+
+/* out[c] = sum_r x[r, c] in a fixed order (fp32). */
+int tt_colsum_f32(const float* x, float* out, int64_t rows, int64_t cols, void* stream);
 
 /* bf16 [rows, cols] -> bf16 [cols, rows] */
 int tt_transpose_bf16(const uint16_t* in, uint16_t* out, int64_t rows, int64_t cols, void* stream);

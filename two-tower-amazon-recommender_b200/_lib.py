@@ -48,6 +48,7 @@ SIGNATURES = {
     "tt_dense_fwd": (C.c_int, [_i32, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i32, _p]),
     "tt_dense_bwd": (C.c_int, [_i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _i64, _i64, _i64, _i32, _p]),
     "tt_dense_bwd_num_parts": (_i32, [_i32, _i64, _i64, _i64]),
+    "tt_colsum_f32": (C.c_int, [_p, _p, _i64, _i64, _p]),
     "tt_transpose_bf16": (C.c_int, [_p, _p, _i64, _i64, _p]),
     "tt_cast_f32_to_bf16": (C.c_int, [_p, _p, _p, _i64, _i64, _p]),
     "tt_retrieval_workspace_bytes": (_i64, [_i32, _i64, _i64, _i64]),

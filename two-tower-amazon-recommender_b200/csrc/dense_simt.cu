@@ -162,7 +162,7 @@ extern "C" int tt_dense_bwd(int32_t precision, const void* dy, const void* dy_t,
                             const void* x_t, const void* kernel, void* dx, void* dx_t, float* dx_f32,
                             float* dkernel_parts, int32_t num_parts, float* dbias, int64_t M,
                             int64_t in_dim, int64_t out_dim, int32_t relu_mask_x, void* stream) {
-  TT_REQUIRE(dy && x && kernel && dkernel_parts && dbias, "tt_dense_bwd: null buffer");
+  TT_REQUIRE(dy && x && kernel && dkernel_parts, "tt_dense_bwd: null buffer");
   TT_REQUIRE(M > 0 && in_dim > 0 && out_dim > 0 && M < (1ll << 31), "tt_dense_bwd: bad sizes");
   cudaStream_t st = (cudaStream_t)stream;
   if (precision == TT_F32) {
@@ -178,13 +178,22 @@ extern "C" int tt_dense_bwd(int32_t precision, const void* dy, const void* dy_t,
     rc = sgemm((const float*)x, 1, in_dim, (const float*)dy, out_dim, 1, dkernel_parts, out_dim, in_dim, out_dim,
                M, nullptr, 0, nullptr, st);
     if (rc) return rc;
-    colsum_f32_kernel<<<(unsigned)ceil_div(out_dim, 32), 256, 0, st>>>((const float*)dy, dbias, M, out_dim);
-    TT_LAUNCH_OK("colsum_f32_kernel");
+    if (dbias) {
+      colsum_f32_kernel<<<(unsigned)ceil_div(out_dim, 32), 256, 0, st>>>((const float*)dy, dbias, M, out_dim);
+      TT_LAUNCH_OK("colsum_f32_kernel");
+    }
     return TT_OK;
   }
   TT_REQUIRE(precision == TT_BF16, "tt_dense_bwd: unknown precision %d", precision);
   return tc_dense_bwd(dy, dy_t, x, x_t, kernel, dx, dx_t, dx_f32, dkernel_parts, num_parts, dbias, M, in_dim,
                       out_dim, relu_mask_x, st);
+}
+
+extern "C" int tt_colsum_f32(const float* x, float* out, int64_t rows, int64_t cols, void* stream) {
+  TT_REQUIRE(x && out && rows > 0 && cols > 0, "tt_colsum_f32: bad arguments");
+  colsum_f32_kernel<<<(unsigned)ceil_div(cols, 32), 256, 0, (cudaStream_t)stream>>>(x, out, rows, cols);
+  TT_LAUNCH_OK("colsum_f32_kernel");
+  return TT_OK;
 }
 
 extern "C" int tt_transpose_bf16(const uint16_t* in, uint16_t* out, int64_t rows, int64_t cols, void* stream) {

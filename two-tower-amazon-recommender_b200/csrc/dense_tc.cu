@@ -295,8 +295,10 @@ int tc_dense_bwd(const void* dy, const void* dy_t, const void* x, const void* x_
     rc = launch_gemm_tc(x_t, dy_t, in_dim, out_dim, M, parts, kps, ep, stream);
     if (rc) return rc;
   }
-  rowsum_bf16_kernel<<<(unsigned)ceil_div(out_dim, 8), 256, 0, stream>>>((const uint16_t*)dy_t, dbias, out_dim, M);
-  TT_LAUNCH_OK("rowsum_bf16_kernel");
+  if (dbias) {
+    rowsum_bf16_kernel<<<(unsigned)ceil_div(out_dim, 8), 256, 0, stream>>>((const uint16_t*)dy_t, dbias, out_dim, M);
+    TT_LAUNCH_OK("rowsum_bf16_kernel");
+  }
   return TT_OK;
 }
 

@@ -41,18 +41,15 @@ __device__ __forceinline__ bool topk_precedes(float s1, int i1, float s2, int i2
   return s1 > s2 || (s1 == s2 && i1 < i2);
 }
 
-// Warp-cooperative: fold row r's pending entries into its sorted list.  KU*32 >= k.
+// Warp-cooperative: fold `n` pending (score, index) pairs into one row's sorted list
+// (ls/li: [k], *count entries valid).  KU*32 >= k.  Updates *count and *tau.
 template <int KU>
-__device__ __forceinline__ void topk_merge_row(const TopkRowState& st, int r, int lane) {
-  const int k = st.k;
-  const int n = st.pend_n[r];
-  if (n == 0) return;
-  float* ls = st.list_s + (size_t)r * k;
-  int* li = st.list_i + (size_t)r * k;
-  int cnt = st.count[r];
+__device__ __forceinline__ void topk_fold(float* ls, int* li, int* count, float* tau, int k, const float* pend_s,
+                                          const int* pend_i, int n, int lane) {
+  int cnt = *count;
   for (int e = 0; e < n; ++e) {
-    const float s = st.pend_s[(size_t)r * st.pend_cap + e];
-    const int id = st.pend_i[(size_t)r * st.pend_cap + e];
+    const float s = pend_s[e];
+    const int id = pend_i[e];
     int pos = 0;
     for (int t = lane; t < cnt; t += 32) pos += topk_precedes(ls[t], li[t], s, id) ? 1 : 0;
 #pragma unroll
@@ -76,10 +73,20 @@ __device__ __forceinline__ void topk_merge_row(const TopkRowState& st, int r, in
     cnt = newcnt;
   }
   if (lane == 0) {
-    st.count[r] = cnt;
-    st.tau[r] = (cnt == k) ? ls[k - 1] : -INFINITY;
-    st.pend_n[r] = 0;
+    *count = cnt;
+    *tau = (cnt == k) ? ls[k - 1] : -INFINITY;
   }
+  __syncwarp();
+}
+
+// Fold row r's own pending buffer (fp32 CUDA-core kernel: one pending buffer per row).
+template <int KU>
+__device__ __forceinline__ void topk_merge_row(const TopkRowState& st, int r, int lane) {
+  const int n = st.pend_n[r];
+  if (n == 0) return;
+  topk_fold<KU>(st.list_s + (size_t)r * st.k, st.list_i + (size_t)r * st.k, st.count + r, st.tau + r, st.k,
+                st.pend_s + (size_t)r * st.pend_cap, st.pend_i + (size_t)r * st.pend_cap, n, lane);
+  if (lane == 0) st.pend_n[r] = 0;
   __syncwarp();
 }
 

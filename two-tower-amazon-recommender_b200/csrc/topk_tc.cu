@@ -1,0 +1,276 @@
+// K6 (bf16 precision) -- brute-force scoring on tcgen05 fused with a running top-k
+// (tfrs BruteForce / faiss.IndexFlatIP replacement).
+//
+// A CTA keeps 128 queries resident (shared memory, 128B-swizzled K-major) and streams the
+// candidate range in 128-row tiles through a TMA ring; S = Q C^T goes to TMEM (two buffers so
+// the next tile's MMA overlaps the selection of the current one) and is never written out.
+// Selection warpgroup: thread = one query row.  Per 32-column tcgen05.ld the thread takes the
+// max of its 32 scores and compares it with the row's current k-th best (tau): almost every
+// chunk is rejected with ~1.3 instructions per score.  A hit is handled warp-cooperatively:
+// the row's 32 scores are redistributed over the lanes, the survivors are compacted into a
+// per-warp pending buffer and folded into the row's sorted (score desc, index asc) list kept
+// in shared memory (topk_select.cuh).  Candidate ranges may be split over blockIdx.y for
+// small query batches; partial lists are merged by topk_merge_kernel.
+#include "tc_common.cuh"
+#include "topk_select.cuh"
+#include <limits.h>
+
+namespace tt {
+
+constexpr int TK_BM = 128;
+constexpr int TK_THREADS = 192;   // warp 0 TMA, warp 1 MMA, warps 2-5 selection
+
+struct TopkTcArgs {
+  int nq, nc, d, k;
+  long long cand_base;
+  const long long* identifiers;
+  int tiles_per_split;
+  int stages;
+  int raw_indices;          // partial lists (splits > 1): write raw candidate indices
+  float* out_s;
+  long long* out_i;
+};
+
+struct TopkTcLayout { int q_bytes, y_bytes, list_bytes, stages, total; };
+__host__ __device__ inline TopkTcLayout topk_tc_layout(int d, int k, int TK_BN) {
+  TopkTcLayout L;
+  L.q_bytes = TK_BM * d * 2;
+  L.y_bytes = TK_BN * d * 2;
+  L.list_bytes = TK_BM * k * 8;
+  const int fixed = L.q_bytes + L.list_bytes + 4096;     // tail: barriers, count/tau, per-warp pending
+  L.stages = (227 * 1024 - fixed) / L.y_bytes;
+  if (L.stages > 4) L.stages = 4;
+  L.total = fixed + L.stages * L.y_bytes;
+  return L;
+}
+
+template <int KU, int TK_BN>
+__global__ void __launch_bounds__(TK_THREADS, 1)
+topk_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmC, const TopkTcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  const int d = a.d, nkb = d / 64, k = a.k;
+  const TopkTcLayout L = topk_tc_layout(d, k, TK_BN);
+  const int STAGES = a.stages;
+  uint8_t* sQ = smem;
+  uint8_t* sY = sQ + L.q_bytes;
+  uint8_t* tail = sY + STAGES * L.y_bytes;
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* full = q_full + 1;
+  uint64_t* empty = full + 4;
+  uint64_t* s_full = empty + 4;
+  uint64_t* s_empty = s_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + 2);
+  int* row_count = reinterpret_cast<int*>(tail + 256);            // [128]
+  float* row_tau = reinterpret_cast<float*>(tail + 256 + 512);    // [128]
+  float* pend_s = reinterpret_cast<float*>(tail + 256 + 1024);    // [4 warps][32]
+  int* pend_i = reinterpret_cast<int*>(tail + 256 + 1024 + 512);  // [4 warps][32]
+  float* list_s = reinterpret_cast<float*>(tail + 4096);          // [128][k]
+  int* list_i = reinterpret_cast<int*>(tail + 4096 + TK_BM * k * 4);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * TK_BM;
+  const int tile_begin = blockIdx.y * a.tiles_per_split;
+  const int total_tiles = (a.nc + TK_BN - 1) / TK_BN;
+  const int T = max(0, min(a.tiles_per_split, total_tiles - tile_begin));
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmC);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 4; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * TK_BN);
+  if (threadIdx.x >= 64) { row_count[threadIdx.x - 64] = 0; row_tau[threadIdx.x - 64] = -INFINITY; }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, L.q_bytes);
+      for (int kb = 0; kb < nkb; ++kb) tma_load_2d(sQ + kb * TK_BM * 128, &tmQ, q_full, kb * 64, q0);
+      for (int t = 0; t < T; ++t) {
+        const int s = t % STAGES;
+        mbar_wait(&empty[s], ((t / STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full[s], L.y_bytes);
+        for (int kb = 0; kb < nkb; ++kb)
+          tma_load_2d(sY + s * L.y_bytes + kb * TK_BN * 128, &tmC, &full[s], kb * 64, (tile_begin + t) * TK_BN);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TK_BM, TK_BN);
+      mbar_wait(q_full, 0);
+      for (int t = 0; t < T; ++t) {
+        const int s = t % STAGES, b = t & 1;
+        mbar_wait(&full[s], (t / STAGES) & 1);
+        mbar_wait(&s_empty[b], ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < nkb; ++kb) {
+          const uint64_t da = umma_desc_k_sw128(smem_u32(sQ + kb * TK_BM * 128));
+          const uint64_t db = umma_desc_k_sw128(smem_u32(sY + s * L.y_bytes + kb * TK_BN * 128));
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(tmem_base + b * TK_BN, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0);
+        }
+        umma_commit(&s_full[b]);
+        umma_commit(&empty[s]);
+      }
+    }
+  } else {
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;                  // this thread's query row in the tile
+    const int wslot = warp - 2;                    // pending buffer of this warp
+    float tau = -INFINITY;
+    bool fullk = false;
+    if ((long long)q0 + r >= a.nq) { tau = INFINITY; fullk = true; }    // padding rows never select
+    for (int t = 0; t < T; ++t) {
+      const int b = t & 1;
+      const int c_tile = (tile_begin + t) * TK_BN;
+      mbar_wait(&s_full[b], (t >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < TK_BN; c0 += 32) {
+        if (c_tile + c0 >= a.nc) break;            // uniform: chunk entirely past the candidates
+        uint32_t rr[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(qd * 32) << 16) + b * TK_BN + c0, rr);
+        tmem_ld_wait();
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(rr[j]);
+        if (c_tile + c0 + 32 > a.nc) {             // uniform: ragged last chunk
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (c_tile + c0 + j >= a.nc) x[j] = -INFINITY;
+        }
+        float mx = x[0];
+#pragma unroll
+        for (int j = 1; j < 32; ++j) mx = fmaxf(mx, x[j]);
+        const bool hit = !fullk || mx > tau;
+        unsigned hits = __ballot_sync(0xffffffffu, hit);
+        while (hits) {
+          const int src = __ffs(hits) - 1;
+          hits &= hits - 1;
+          // lane j receives score j of lane src's row
+          float mine = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float v = __shfl_sync(0xffffffffu, x[j], src);
+            if (lane == j) mine = v;
+          }
+          const float src_tau = __shfl_sync(0xffffffffu, tau, src);
+          const int src_full = __shfl_sync(0xffffffffu, (int)fullk, src);
+          const bool pass = (c_tile + c0 + lane < a.nc) && (!src_full || mine > src_tau);
+          const unsigned pm = __ballot_sync(0xffffffffu, pass);
+          if (pass) {
+            const int slot = __popc(pm & ((1u << lane) - 1));
+            pend_s[wslot * 32 + slot] = mine;
+            pend_i[wslot * 32 + slot] = c_tile + c0 + lane;
+          }
+          __syncwarp();
+          const int row = qd * 32 + src;
+          topk_fold<KU>(list_s + (size_t)row * k, list_i + (size_t)row * k, row_count + row, row_tau + row, k,
+                        pend_s + wslot * 32, pend_i + wslot * 32, __popc(pm), lane);
+        }
+        if (hit) { tau = row_tau[r]; fullk = row_count[r] == k; }
+      }
+      tc_fence_before();
+      mbar_arrive(&s_empty[b]);
+    }
+    // write this warp's 32 rows
+    __syncwarp();
+    for (int rr2 = 0; rr2 < 32; ++rr2) {
+      const int row = qd * 32 + rr2;
+      const long long qi = (long long)q0 + row;
+      if (qi >= a.nq) break;
+      const int cnt = row_count[row];
+      const size_t o = ((size_t)blockIdx.y * a.nq + qi) * k;
+      for (int t2 = lane; t2 < k; t2 += 32) {
+        if (t2 < cnt) {
+          const int idx = list_i[(size_t)row * k + t2];
+          a.out_s[o + t2] = list_s[(size_t)row * k + t2];
+          a.out_i[o + t2] = a.raw_indices ? (long long)idx : (a.identifiers ? a.identifiers[idx] : a.cand_base + idx);
+        } else {
+          a.out_s[o + t2] = -INFINITY;
+          a.out_i[o + t2] = LLONG_MAX;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * TK_BN);
+}
+
+static int tk_bn_for(int64_t d) { return d <= 128 ? 128 : 64; }
+
+// splits are planned in 128-candidate granules (independent of the tile width)
+static int tc_topk_splits(int64_t nq, int64_t nc, int bn, int* tiles_per_split) {
+  const int64_t q_tiles = ceil_div(nq, TK_BM), y128 = ceil_div(nc, 128);
+  int64_t s = std::max<int64_t>(1, num_sms() / q_tiles);
+  const int64_t max_by_len = std::max<int64_t>(1, y128 / 32);     // >= 4096 candidates per split
+  if (s > max_by_len) s = max_by_len;
+  if (s > 32) s = 32;
+  const int64_t per128 = ceil_div(y128, s);
+  *tiles_per_split = (int)(per128 * (128 / bn));
+  return (int)ceil_div(y128, per128);
+}
+
+int tc_topk_num_splits(int64_t nq, int64_t nc, int64_t d, int k) {
+  int tps;
+  return tc_topk_splits(nq, nc, tk_bn_for(d), &tps);
+}
+
+extern "C" int tt_topk_merge(const float*, const int64_t*, int32_t, int64_t, int32_t, int32_t, int64_t, const int64_t*,
+                             float*, int64_t*, void*);
+
+int tc_topk(const void* queries, const void* candidates, int64_t nq, int64_t nc, int64_t d, int k,
+            int64_t cand_index_base, const int64_t* identifiers, float* out_scores, int64_t* out_ids, void* ws,
+            int64_t ws_bytes, cudaStream_t st) {
+  TT_REQUIRE(d % 64 == 0 && d >= 64 && d <= 256, "tt_topk_bruteforce(bf16): d must be 64, 128, 192 or 256 (got %lld)", (long long)d);
+  const int bn = tk_bn_for(d);
+  const TopkTcLayout L = topk_tc_layout((int)d, k, bn);
+  if (L.stages < 2)
+    return set_error(TT_ERR_UNSUPPORTED, "tt_topk_bruteforce(bf16): d=%lld k=%d does not fit the shared-memory pipeline", (long long)d, k);
+  int tps;
+  const int splits = tc_topk_splits(nq, nc, bn, &tps);
+  float* ps = out_scores; int64_t* pi = out_ids;
+  if (splits > 1) {
+    const int64_t need = round_up((int64_t)splits * nq * k * 4, 256) + round_up((int64_t)splits * nq * k * 8, 256);
+    if (!ws || ws_bytes < need) return set_error(TT_ERR_WORKSPACE, "tt_topk_bruteforce(bf16): workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)need);
+    ps = (float*)ws;
+    pi = (int64_t*)((char*)ws + round_up((int64_t)splits * nq * k * 4, 256));
+  }
+  CUtensorMap tmQ, tmC;
+  int rc = make_tmap_bf16_2d(&tmQ, queries, (uint64_t)d, (uint64_t)nq, (uint64_t)d * 2, 64, TK_BM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tmC, candidates, (uint64_t)d, (uint64_t)nc, (uint64_t)d * 2, 64, (uint32_t)bn);
+  if (rc) return rc;
+  TopkTcArgs a{};
+  a.nq = (int)nq; a.nc = (int)nc; a.d = (int)d; a.k = k;
+  a.cand_base = cand_index_base; a.identifiers = (const long long*)identifiers;
+  a.tiles_per_split = tps; a.stages = L.stages; a.raw_indices = splits > 1;
+  a.out_s = ps; a.out_i = (long long*)pi;
+  dim3 grid((unsigned)ceil_div(nq, TK_BM), (unsigned)splits);
+#define TT_TK2(KU, BNV)                                                                                            \
+  {                                                                                                                \
+    TT_CUDA_OK(cudaFuncSetAttribute(topk_tc_kernel<KU, BNV>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total)); \
+    topk_tc_kernel<KU, BNV><<<grid, TK_THREADS, L.total, st>>>(tmQ, tmC, a);                                       \
+  }
+#define TT_TK(KU) { if (bn == 128) TT_TK2(KU, 128) else TT_TK2(KU, 64) }
+  if (k <= 32) TT_TK(1)
+  else if (k <= 64) TT_TK(2)
+  else if (k <= 128) TT_TK(4)
+  else if (k <= 256) TT_TK(8)
+  else TT_TK(16)
+#undef TT_TK
+#undef TT_TK2
+  TT_LAUNCH_OK("topk_tc_kernel");
+  if (splits > 1) return tt_topk_merge(ps, pi, splits, nq, k, k, cand_index_base, identifiers, out_scores, out_ids, st);
+  return TT_OK;
+}
+
+}  // namespace tt

@@ -217,10 +217,14 @@ class Dense(Layer):
             else:
                 if x.bf16_t is None:
                     x.bf16_t = ops.transpose_bf16(x.bf16)
+                dy_f32 = g.get("f32")
                 dx, dx_t, dx_f32, dk, P, db = ops.dense_bwd(
                     "bf16", g["bf16"], g["bf16_t"], x.bf16, x.bf16_t, self.kernel.shadow,
                     relu_mask_x=x.relu_output, want_dx=need_dx and "bf16" in want,
-                    want_dx_t=need_dx and "bf16_t" in want, want_dx_f32=need_dx and "f32" in want)
+                    want_dx_t=need_dx and "bf16_t" in want, want_dx_f32=need_dx and "f32" in want,
+                    want_dbias=dy_f32 is None)
+                if dy_f32 is not None:      # bias gradient from the un-rounded upstream gradient
+                    db = ops.colsum_f32(dy_f32)
                 if need_dx:
                     x.grad = dict(f32=dx_f32, bf16=dx, bf16_t=dx_t)
             self.kernel.grad = DenseGrad(dk, P)

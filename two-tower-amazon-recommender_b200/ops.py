@@ -204,22 +204,29 @@ def dense_bwd_num_parts(precision: str, M: int, in_dim: int, out_dim: int) -> in
     return int(_lib.load().tt_dense_bwd_num_parts(precision_code(precision), M, in_dim, out_dim))
 
 
+def colsum_f32(x):
+    out = torch.empty((x.shape[1],), dtype=torch.float32, device=x.device)
+    check(_lib.load().tt_colsum_f32(_ptr(x, torch.float32), _ptr(out), x.shape[0], x.shape[1], _stream()))
+    _count(1)
+    return out
+
+
 def dense_bwd(precision: str, dy, dy_t, x, x_t, kernel, relu_mask_x: bool, want_dx: bool, want_dx_t: bool = False,
-              want_dx_f32: bool = False):
-    """Returns (dx, dx_t, dx_f32, dkernel_parts [P,in,out] f32, P, dbias f32 [out])."""
+              want_dx_f32: bool = False, want_dbias: bool = True):
+    """Returns (dx, dx_t, dx_f32, dkernel_parts [P,in,out] f32, P, dbias f32 [out] | None)."""
     lib = _lib.load()
     M, out_dim = dy.shape
     in_dim = x.shape[1]
     dev = dy.device
     P = dense_bwd_num_parts(precision, M, in_dim, out_dim)
     dk = torch.empty((P, in_dim, out_dim), dtype=torch.float32, device=dev)
-    db = torch.empty((out_dim,), dtype=torch.float32, device=dev)
+    db = torch.empty((out_dim,), dtype=torch.float32, device=dev) if want_dbias else None
     if precision == "fp32":
         dx = torch.empty((M, in_dim), dtype=torch.float32, device=dev) if want_dx else None
         check(lib.tt_dense_bwd(TT_F32, _ptr(dy, torch.float32), None, _ptr(x, torch.float32), None,
                                _ptr(kernel, torch.float32), _ptr(dx), None, None, _ptr(dk), P, _ptr(db), M,
                                in_dim, out_dim, 1 if relu_mask_x else 0, _stream()))
-        _count(3 if want_dx else 2)
+        _count(1 + int(want_dx) + int(want_dbias))
         return dx, None, None, dk, P, db
     dx = torch.empty((M, in_dim), dtype=torch.bfloat16, device=dev) if want_dx else None
     dx_t = torch.empty((in_dim, M), dtype=torch.bfloat16, device=dev) if want_dx_t else None
@@ -228,7 +235,7 @@ def dense_bwd(precision: str, dy, dy_t, x, x_t, kernel, relu_mask_x: bool, want_
                            _ptr(x_t, torch.bfloat16), _ptr(kernel, torch.bfloat16), _ptr(dx), _ptr(dx_t),
                            _ptr(dx_f32), _ptr(dk), P, _ptr(db), M, in_dim, out_dim, 1 if relu_mask_x else 0,
                            _stream()))
-    _count(3)
+    _count(1 + int(want_dx or want_dx_t or want_dx_f32) + int(want_dbias))
     return dx, dx_t, dx_f32, dk, P, db
 
 
