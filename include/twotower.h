@@ -46,6 +46,13 @@ const char* tt_last_error(void);
 /* 0 when the current CUDA device is compute capability 10.x, TT_ERR_UNSUPPORTED otherwise. */
 int tt_device_check(void);
 
+/* Per-kernel timing for bench.py: while enabled, every kernel the library launches outside a
+ * CUDA-graph capture is bracketed by a cudaEvent pair on its own stream.  tt_profile_collect
+ * synchronises and writes "kernel_name launches total_ms\n" lines into host_buf; returns the
+ * buffer size needed.  tt_profile_enable(0/1) also clears the records. */
+int tt_profile_enable(int32_t on);
+int64_t tt_profile_collect(char* host_buf, int64_t buf_len);
+
 /* ---------------------------------------------------------------------------------------
  * K1  tower input: Embedding gather and multi-hot sum/mean pooling.
  * Replaces tf.keras.layers.Embedding -> tf.nn.embedding_lookup and
@@ -153,8 +160,12 @@ int tt_dense_bwd(int32_t precision, const void* dy, const void* dy_t, const void
                  int64_t in_dim, int64_t out_dim, int32_t relu_mask_x, void* stream);
 int32_t tt_dense_bwd_num_parts(int32_t precision, int64_t M, int64_t in_dim, int64_t out_dim);
 
-/* out[c] = sum_r x[r, c] in a fixed order (fp32). */
-int tt_colsum_f32(const float* x, float* out, int64_t rows, int64_t cols, void* stream);
+/* out_parts[p, c] = sum over the p-th slice of rows of x[r, c], fixed order (fp32); the
+ * num_parts partial rows feed tt_dense_*_update's grad_parts.  tt_sum_parts_f32 folds
+ * stacked partials [num_parts, n] into one (before an all-reduce). */
+int tt_colsum_f32(const float* x, float* out_parts, int64_t rows, int64_t cols, int32_t num_parts,
+                  void* stream);
+int tt_sum_parts_f32(const float* parts, int32_t num_parts, int64_t n, float* out, void* stream);
 
 /* bf16 [rows, cols] -> bf16 [cols, rows] */
 int tt_transpose_bf16(const uint16_t* in, uint16_t* out, int64_t rows, int64_t cols, void* stream);
@@ -232,15 +243,20 @@ int tt_rowwise_dot(int32_t precision, const void* q, const void* c, float* out, 
 /* ---------------------------------------------------------------------------------------
  * Row-sharded tables across ranks: stable partition of ids by owner.
  * owner(id) = id % world (cyclic).  Outputs: perm [n] (position of entry j in the
- * owner-major send buffer), send_ids [n] = local row (id / world) in owner-major order,
+ * owner-major send buffer), send_ids = local row (id / world) in owner-major order,
  * counts [world].  Stable: entries of one owner keep their batch order, so per-owner
- * buckets are bit-reproducible.
+ * buckets are bit-reproducible.  capacity == 0: buckets are packed (send_ids [n]);
+ * capacity > 0: bucket o starts at o * capacity (send_ids [world * capacity], unused slots
+ * -1) so the all-to-all has static shapes; an entry that does not fit gets perm = -1 and
+ * *overflow_flag = 1 (nullable).
  * ------------------------------------------------------------------------------------- */
-int tt_partition_ids(const int64_t* ids, int64_t n, int32_t world, int64_t* send_ids,
-                     int64_t* perm, int64_t* counts, void* stream);
-/* out[perm[j], :] = in[j, :]  (inverse = 0)   or   out[j, :] = in[perm[j], :]  (inverse = 1) */
-int tt_permute_rows_f32(const float* in, const int64_t* perm, float* out, int64_t n, int64_t d,
-                        int32_t inverse, void* stream);
+int tt_partition_ids(const int64_t* ids, int64_t n, int32_t world, int64_t capacity,
+                     int64_t* send_ids, int64_t* perm, int64_t* counts, int32_t* overflow_flag,
+                     void* stream);
+/* Rows of row_bytes (multiple of 16): out[perm[j]] = in[j] (inverse = 0) or out[j] = in[perm[j]]
+ * (inverse = 1); entries with perm[j] < 0 are skipped. */
+int tt_permute_rows(const void* in, const int64_t* perm, void* out, int64_t n, int64_t row_bytes,
+                    int32_t inverse, void* stream);
 
 #ifdef __cplusplus
 }

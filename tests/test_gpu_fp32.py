@@ -434,3 +434,18 @@ class TestShardingHelpers:
             y = ops.permute_rows(dev(x), perm, inverse=False)
             assert np.array_equal(y.cpu().numpy(), x[order])
             assert np.array_equal(ops.permute_rows(y, perm, inverse=True).cpu().numpy(), x)
+            # padded buckets (static all-to-all shapes): bucket o starts at o * cap, padding = -1
+            cap = int(np.bincount(owner, minlength=world).max()) + 3
+            flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+            send_p, perm_p, _ = ops.partition_ids(dev(ids), world, cap, flag)
+            ref = np.full(world * cap, -1, np.int64)
+            starts = np.concatenate([[0], np.cumsum(np.bincount(owner, minlength=world))[:-1]])
+            pos = np.arange(n) - starts[owner[order]] + owner[order] * cap
+            ref[pos] = (ids // world)[order]
+            assert np.array_equal(send_p.cpu().numpy(), ref) and int(flag.item()) == 0
+            xb = torch.as_tensor(x).cuda().to(torch.bfloat16)
+            yb = ops.permute_rows(xb, perm_p, inverse=False, out_rows=world * cap, zero_fill=True)
+            assert np.array_equal(ops.permute_rows(yb, perm_p, inverse=True).float().cpu().numpy(), xb.float().cpu().numpy())
+            if world > 1 and n > 100:
+                ops.partition_ids(dev(ids), world, 8, flag)
+                assert int(flag.item()) == 1                      # a bucket larger than the capacity is reported

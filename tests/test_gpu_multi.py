@@ -1,0 +1,93 @@
+"""2-GPU NCCL test of the sharded path (skipped on a single-GPU box): row-sharded tables with
+all-to-all lookups/gradients + all-gathered candidates must reproduce the oracle's step on the
+concatenated global batch."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+pytestmark = pytest.mark.gpu
+WORLD = 2
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, port, precision, results):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=WORLD, device_id=torch.device("cuda", rank))
+    try:
+        import oracle
+        import two_tower_b200 as tt
+        from two_tower_b200 import parallel, synth
+        tt.set_precision(precision)
+        tol = 1e-5 if precision == "fp32" else 2e-2
+        cfg = synth.Config("tiny", 77, 256, 64, 3001, 2003, (128, 64), 0.5)
+        model = parallel.build_sharded_two_tower(cfg, dist.group.WORLD, lr=0.05, capacity_factor=None)
+        batches = [synth.make_batch(cfg, 10 + r) for r in range(WORLD)]
+        model.test_step(batches[rank])                                  # builds the Dense layers
+        # one global set of weights: full tables from a common seed, Dense weights from rank 0
+        rng = synth.rng_for(5)
+        U = oracle.keras_uniform(rng, (cfg.v_user, cfg.dim)); I = oracle.keras_uniform(rng, (cfg.v_item, cfg.dim))
+        model.user_model.layers[0].load_full_table(U); model.item_model.layers[0].load_full_table(I)
+        qs = oracle.TowerSpec([("user_id_encoded", "id", cfg.v_user, None)], cfg.dim, cfg.mlp)
+        cs = oracle.TowerSpec([("item_id_encoded", "id", cfg.v_item, None)], cfg.dim, cfg.mlp)
+        def dense_params(seq):
+            ks, bs = [], []
+            for l in seq.layers[1:]:
+                for v in (l.kernel, l.bias):
+                    dist.broadcast(v.value, src=0)
+                    v.refresh_shadows()
+                ks.append(l.kernel.numpy().astype(np.float64)); bs.append(l.bias.numpy().astype(np.float64))
+            return ks, bs
+        qk, qb = dense_params(model.user_model); ck, cb = dense_params(model.item_model)
+        qp = {"tables": {"user_id_encoded": U.astype(np.float64)}, "kernels": qk, "biases": qb}
+        cp = {"tables": {"item_id_encoded": I.astype(np.float64)}, "kernels": ck, "biases": cb}
+        mk = lambda p: {"tables": {k: np.full(v.shape, 0.1) for k, v in p["tables"].items()},
+                        "kernels": [np.full(k.shape, 0.1) for k in p["kernels"]], "biases": [np.full(x.shape, 0.1) for x in p["biases"]]}
+        out = model.train_step(batches[rank])
+        gq = {"user_id_encoded": np.concatenate([b["user_id_encoded"] for b in batches])}
+        gc = {"item_id_encoded": np.concatenate([b["item_id_encoded"] for b in batches])}
+        ref = oracle.two_tower_train_step(qs, cs, qp, cp, mk(qp), mk(cp), gq, gc, temperature=cfg.temperature, lr=0.05,
+                                          bf16=precision == "bf16")
+        assert abs(float(out["loss"].item()) - ref["loss"]) <= tol * abs(ref["loss"]), (float(out["loss"].item()), ref["loss"])
+        shard = model.user_model.layers[0].embeddings.numpy()
+        want = qp["tables"]["user_id_encoded"][rank::WORLD]
+        touched = np.unique(gq["user_id_encoded"]); mine = touched[touched % WORLD == rank] // WORLD
+        rest = np.setdiff1d(np.arange(want.shape[0]), mine)
+        assert np.array_equal(shard[rest], U[rank::WORLD][rest])                      # gradient row set exact per shard
+        assert (np.abs(shard[mine] - U[rank::WORLD][mine]).max(axis=1) > 0).all()
+        if precision == "fp32":
+            err = np.abs(shard[:want.shape[0]] - want).max() / np.abs(want).max()
+            assert err < 10 * tol, err
+            k0 = model.user_model.layers[1].kernel.numpy()
+            assert np.abs(k0 - qp["kernels"][0]).max() / np.abs(qp["kernels"][0]).max() < 10 * tol
+        results[rank] = "ok"
+    except Exception:
+        import traceback
+        results[rank] = traceback.format_exc()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_sharded_two_tower_matches_global_batch_oracle(precision):
+    if torch.cuda.device_count() < WORLD:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker, args=(_free_port(), precision, results), nprocs=WORLD, join=True)
+    for r in range(WORLD):
+        assert results.get(r) == "ok", results.get(r)

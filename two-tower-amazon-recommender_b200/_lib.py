@@ -34,6 +34,8 @@ SIGNATURES = {
     "tt_version": (C.c_int, []),
     "tt_last_error": (C.c_char_p, []),
     "tt_device_check": (C.c_int, []),
+    "tt_profile_enable": (C.c_int, [_i32]),
+    "tt_profile_collect": (_i64, [C.c_char_p, _i64]),
     "tt_tower_input_fwd": (C.c_int, [C.POINTER(tt_feature), _i32, _p, _p, _i64, _i64, _p, _p]),
     "tt_embedding_gather_f32": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _p]),
     "tt_embedding_gather_bf16": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _p]),
@@ -48,7 +50,8 @@ SIGNATURES = {
     "tt_dense_fwd": (C.c_int, [_i32, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i32, _p]),
     "tt_dense_bwd": (C.c_int, [_i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _i64, _i64, _i64, _i32, _p]),
     "tt_dense_bwd_num_parts": (_i32, [_i32, _i64, _i64, _i64]),
-    "tt_colsum_f32": (C.c_int, [_p, _p, _i64, _i64, _p]),
+    "tt_colsum_f32": (C.c_int, [_p, _p, _i64, _i64, _i32, _p]),
+    "tt_sum_parts_f32": (C.c_int, [_p, _i32, _i64, _p, _p]),
     "tt_transpose_bf16": (C.c_int, [_p, _p, _i64, _i64, _p]),
     "tt_cast_f32_to_bf16": (C.c_int, [_p, _p, _p, _i64, _i64, _p]),
     "tt_retrieval_workspace_bytes": (_i64, [_i32, _i64, _i64, _i64]),
@@ -61,8 +64,8 @@ SIGNATURES = {
     "tt_topk_merge": (C.c_int, [_p, _p, _i32, _i64, _i32, _i32, _i64, _p, _p, _p, _p]),
     "tt_topk_hits": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, C.POINTER(_i32), _i32, _p, _p, _p]),
     "tt_rowwise_dot": (C.c_int, [_i32, _p, _p, _p, _i64, _i64, _p]),
-    "tt_partition_ids": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p]),
-    "tt_permute_rows_f32": (C.c_int, [_p, _p, _p, _i64, _i64, _i32, _p]),
+    "tt_partition_ids": (C.c_int, [_p, _i64, _i32, _i64, _p, _p, _p, _p, _p]),
+    "tt_permute_rows": (C.c_int, [_p, _p, _p, _i64, _i64, _i32, _p]),
 }
 
 _lib = None

@@ -32,7 +32,14 @@ int set_error(int code, const char* fmt, ...);
     if (_e != cudaSuccess)                                                                 \
       return ::tt::set_error(TT_ERR_CUDA, "launch of %s failed: %s", name,                 \
                              cudaGetErrorString(_e));                                      \
+    ::tt::prof_end();                                                                      \
   } while (0)
+
+// Optional per-kernel timing (tt_profile_enable): a CUDA event pair around a launch on its own
+// stream.  TT_PROF(name, stream) goes immediately before the <<<>>>; TT_LAUNCH_OK closes it.
+void prof_begin(const char* name, cudaStream_t st);
+void prof_end();
+#define TT_PROF(name, st) ::tt::prof_begin(name, st)
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

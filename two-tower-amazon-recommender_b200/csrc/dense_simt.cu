@@ -77,23 +77,35 @@ sgemm_kernel(const float* __restrict__ A, int64_t sa_m, int64_t sa_k, const floa
   }
 }
 
-// out[n] = sum_m X[m, n] in fixed order (deterministic): one thread column, 8 row groups.
+// out[p][n] = sum over the p-th row slice of X[m, n], fixed order (deterministic).
+// grid (ceil(N/32), num_parts); 256 threads = 32 columns x 8 row groups.
 __global__ void __launch_bounds__(256)
-colsum_f32_kernel(const float* __restrict__ X, float* __restrict__ out, int64_t M, int64_t N) {
+colsum_f32_kernel(const float* __restrict__ X, float* __restrict__ out, int64_t M, int64_t N, int64_t rows_per_part) {
   __shared__ float part[8][32];
   const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int64_t n = (int64_t)blockIdx.x * 32 + c;
+  const int64_t m_lo = (int64_t)blockIdx.y * rows_per_part, m_hi = min(M, m_lo + rows_per_part);
   float s = 0.f;
   if (n < N)
-    for (int64_t m = g; m < M; m += 8) s += X[m * N + n];
+    for (int64_t m = m_lo + g; m < m_hi; m += 8) s += X[m * N + n];
   part[g][c] = s;
   __syncthreads();
   if (g == 0 && n < N) {
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += part[i][c];
-    out[n] = t;
+    out[(int64_t)blockIdx.y * N + n] = t;
   }
+}
+
+// out[i] = sum_p parts[p][i]
+__global__ void __launch_bounds__(256)
+sum_parts_kernel(const float* __restrict__ parts, int num_parts, int64_t n, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int p = 0; p < num_parts; ++p) s += parts[(int64_t)p * n + i];
+  out[i] = s;
 }
 
 __global__ void __launch_bounds__(256)
@@ -130,6 +142,7 @@ static int sgemm(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int
                  float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias, int relu,
                  const float* mask, cudaStream_t stream) {
   dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, BM));
+  TT_PROF("sgemm_kernel", stream);
   sgemm_kernel<<<grid, 256, 0, stream>>>(A, sa_m, sa_k, B, sb_k, sb_n, C, ldc, (int)M, (int)N, (int)K, bias, relu, mask);
   TT_LAUNCH_OK("sgemm_kernel");
   return TT_OK;
@@ -179,7 +192,8 @@ extern "C" int tt_dense_bwd(int32_t precision, const void* dy, const void* dy_t,
                M, nullptr, 0, nullptr, st);
     if (rc) return rc;
     if (dbias) {
-      colsum_f32_kernel<<<(unsigned)ceil_div(out_dim, 32), 256, 0, st>>>((const float*)dy, dbias, M, out_dim);
+      TT_PROF("colsum_f32_kernel", st);
+      colsum_f32_kernel<<<(unsigned)ceil_div(out_dim, 32), 256, 0, st>>>((const float*)dy, dbias, M, out_dim, M);
       TT_LAUNCH_OK("colsum_f32_kernel");
     }
     return TT_OK;
@@ -189,16 +203,29 @@ extern "C" int tt_dense_bwd(int32_t precision, const void* dy, const void* dy_t,
                       out_dim, relu_mask_x, st);
 }
 
-extern "C" int tt_colsum_f32(const float* x, float* out, int64_t rows, int64_t cols, void* stream) {
-  TT_REQUIRE(x && out && rows > 0 && cols > 0, "tt_colsum_f32: bad arguments");
-  colsum_f32_kernel<<<(unsigned)ceil_div(cols, 32), 256, 0, (cudaStream_t)stream>>>(x, out, rows, cols);
+extern "C" int tt_colsum_f32(const float* x, float* out_parts, int64_t rows, int64_t cols, int32_t num_parts,
+                             void* stream) {
+  TT_REQUIRE(x && out_parts && rows > 0 && cols > 0 && num_parts >= 1, "tt_colsum_f32: bad arguments");
+  const int64_t rpp = ceil_div(rows, num_parts);
+  dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)num_parts);
+  TT_PROF("colsum_f32_kernel", (cudaStream_t)stream);
+  colsum_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, out_parts, rows, cols, rpp);
   TT_LAUNCH_OK("colsum_f32_kernel");
+  return TT_OK;
+}
+
+extern "C" int tt_sum_parts_f32(const float* parts, int32_t num_parts, int64_t n, float* out, void* stream) {
+  TT_REQUIRE(parts && out && num_parts >= 1 && n > 0, "tt_sum_parts_f32: bad arguments");
+  TT_PROF("sum_parts_kernel", (cudaStream_t)stream);
+  sum_parts_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(parts, num_parts, n, out);
+  TT_LAUNCH_OK("sum_parts_kernel");
   return TT_OK;
 }
 
 extern "C" int tt_transpose_bf16(const uint16_t* in, uint16_t* out, int64_t rows, int64_t cols, void* stream) {
   TT_REQUIRE(in && out && rows > 0 && cols > 0, "tt_transpose_bf16: bad arguments");
   dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32));
+  TT_PROF("transpose_bf16_kernel", (cudaStream_t)stream);
   transpose_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, rows, cols);
   TT_LAUNCH_OK("transpose_bf16_kernel");
   return TT_OK;
@@ -208,6 +235,7 @@ extern "C" int tt_cast_f32_to_bf16(const float* in, uint16_t* out, uint16_t* out
                                    int64_t cols, void* stream) {
   TT_REQUIRE(in && (out || out_t) && rows > 0 && cols > 0, "tt_cast_f32_to_bf16: bad arguments");
   dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32));
+  TT_PROF("cast_bf16_kernel", (cudaStream_t)stream);
   cast_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, out_t, rows, cols);
   TT_LAUNCH_OK("cast_bf16_kernel");
   return TT_OK;

@@ -245,6 +245,7 @@ int launch_gemm_tc(const void* A, const void* B, int64_t M, int64_t N, int64_t K
   dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, GEMM_BM), (unsigned)splits);
   const int smem = GemmSmem<BN>::TOTAL;
   TT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  TT_PROF("gemm_tc_kernel", st);
   gemm_tc_kernel<BN><<<grid, 192, smem, st>>>(tmA, tmB, ep);
   TT_LAUNCH_OK("gemm_tc_kernel");
   return TT_OK;
@@ -296,6 +297,7 @@ int tc_dense_bwd(const void* dy, const void* dy_t, const void* x, const void* x_
     if (rc) return rc;
   }
   if (dbias) {
+    TT_PROF("rowsum_bf16_kernel", stream);
     rowsum_bf16_kernel<<<(unsigned)ceil_div(out_dim, 8), 256, 0, stream>>>((const uint16_t*)dy_t, dbias, out_dim, M);
     TT_LAUNCH_OK("rowsum_bf16_kernel");
   }

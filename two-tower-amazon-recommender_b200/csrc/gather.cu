@@ -45,8 +45,8 @@ tower_input_kernel(const FeatureParams p, float* __restrict__ out_f32, uint16_t*
 
       if (ft.offsets == nullptr) {
         int64_t id = __ldg(ft.values + b);
-        if (id < 0 || id >= ft.vocab) {
-          if (lane == 0 && fault) atomicExch(fault, 1);
+        if (id < 0 || id >= ft.vocab) {      // id == -1 is padding (zero row); anything else is a fault
+          if (lane == 0 && fault && id != -1) atomicExch(fault, 1);
         } else {
 #pragma unroll
           for (int c = 0; c < CH; ++c) {
@@ -142,10 +142,10 @@ int launch_tower_input(const tt_feature* feats, int n, float* out_f32, uint16_t*
   if (blocks > cap) blocks = cap;
   dim3 grid((unsigned)blocks), block(256);
   const int64_t chunks = d / 4;
-  if (chunks <= 32) tower_input_kernel<1><<<grid, block, 0, stream>>>(p, out_f32, out_bf16, B, d, fault);
-  else if (chunks <= 64) tower_input_kernel<2><<<grid, block, 0, stream>>>(p, out_f32, out_bf16, B, d, fault);
-  else if (chunks <= 128) tower_input_kernel<4><<<grid, block, 0, stream>>>(p, out_f32, out_bf16, B, d, fault);
-  else tower_input_kernel<8><<<grid, block, 0, stream>>>(p, out_f32, out_bf16, B, d, fault);
+  if (chunks <= 32) TT_PROF("tower_input_kernel", stream), tower_input_kernel<1><<<grid, block, 0, stream>>>(p, out_f32, out_bf16, B, d, fault);
+  else if (chunks <= 64) TT_PROF("tower_input_kernel", stream), tower_input_kernel<2><<<grid, block, 0, stream>>>(p, out_f32, out_bf16, B, d, fault);
+  else if (chunks <= 128) TT_PROF("tower_input_kernel", stream), tower_input_kernel<4><<<grid, block, 0, stream>>>(p, out_f32, out_bf16, B, d, fault);
+  else TT_PROF("tower_input_kernel", stream), tower_input_kernel<8><<<grid, block, 0, stream>>>(p, out_f32, out_bf16, B, d, fault);
   TT_LAUNCH_OK("tower_input_kernel");
   return TT_OK;
 }
@@ -155,9 +155,9 @@ int launch_tower_input(const tt_feature* feats, int n, float* out_f32, uint16_t*
 // (<= 64K), so one CTA walks the batch in 1024-entry strips and keeps running per-owner
 // cursors -> stable and deterministic.  Two passes: count, then place.
 __global__ void __launch_bounds__(1024)
-partition_ids_kernel(const int64_t* __restrict__ ids, int64_t n, int world,
+partition_ids_kernel(const int64_t* __restrict__ ids, int64_t n, int world, int64_t capacity,
                      int64_t* __restrict__ send_ids, int64_t* __restrict__ perm,
-                     int64_t* __restrict__ counts) {
+                     int64_t* __restrict__ counts, int* __restrict__ overflow) {
   __shared__ int s_warp_cnt[32][8];   // per warp, per owner (world <= 8)
   __shared__ int64_t s_base[8];       // running start of each owner's bucket
   __shared__ int64_t s_total[8];
@@ -185,8 +185,16 @@ partition_ids_kernel(const int64_t* __restrict__ ids, int64_t n, int world,
   __syncthreads();
   if (tid == 0) {
     int64_t run = 0;
-    for (int o = 0; o < world; ++o) { s_base[o] = run; run += s_total[o]; counts[o] = s_total[o]; }
+    for (int o = 0; o < world; ++o) {
+      s_base[o] = capacity > 0 ? o * capacity : run;
+      run += s_total[o];
+      counts[o] = s_total[o];
+      if (capacity > 0 && s_total[o] > capacity && overflow) *overflow = 1;
+    }
   }
+  __syncthreads();
+  if (capacity > 0)      // padded layout: unused slots carry -1
+    for (int64_t j = tid; j < capacity * world; j += blockDim.x) send_ids[j] = -1;
   __syncthreads();
 
   // pass 2: stable placement, strip by strip
@@ -207,8 +215,9 @@ partition_ids_kernel(const int64_t* __restrict__ ids, int64_t n, int world,
       int before = 0;
       for (int ww = 0; ww < w; ++ww) before += s_warp_cnt[ww][o];
       int64_t pos = s_base[o] + before + rank_in_warp;
-      perm[j] = pos;
-      send_ids[pos] = id / world;
+      const bool fits = capacity <= 0 || pos < (int64_t)(o + 1) * capacity;
+      perm[j] = fits ? pos : -1;
+      if (fits) send_ids[pos] = id / world;
     }
     __syncthreads();
     if (tid < world) {
@@ -220,15 +229,17 @@ partition_ids_kernel(const int64_t* __restrict__ ids, int64_t n, int world,
   }
 }
 
-__global__ void permute_rows_kernel(const float* __restrict__ in, const int64_t* __restrict__ perm,
-                                    float* __restrict__ out, int64_t n, int64_t d, int inverse) {
+// rows are `chunks` 16-byte units wide (fp32 d/4, bf16 d/8); perm[j] < 0 entries are skipped
+__global__ void permute_rows_kernel(const uint4* __restrict__ in, const int64_t* __restrict__ perm,
+                                    uint4* __restrict__ out, int64_t n, int64_t chunks, int inverse) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
   const int64_t p = perm[row];
-  const float4* src = reinterpret_cast<const float4*>(in + (inverse ? p : row) * d);
-  float4* dst = reinterpret_cast<float4*>(out + (inverse ? row : p) * d);
-  for (int c = lane; c < (int)(d >> 2); c += 32) dst[c] = src[c];
+  if (p < 0) return;
+  const uint4* src = in + (inverse ? p : row) * chunks;
+  uint4* dst = out + (inverse ? row : p) * chunks;
+  for (int c = lane; c < (int)chunks; c += 32) dst[c] = src[c];
 }
 
 }  // namespace tt
@@ -275,22 +286,25 @@ extern "C" int tt_embedding_bag_fwd(const float* table, const int64_t* values, c
                             out_dtype == TT_BF16 ? (uint16_t*)out : nullptr, num_bags, d, nullptr, stream);
 }
 
-extern "C" int tt_partition_ids(const int64_t* ids, int64_t n, int32_t world, int64_t* send_ids,
-                                int64_t* perm, int64_t* counts, void* stream) {
+extern "C" int tt_partition_ids(const int64_t* ids, int64_t n, int32_t world, int64_t capacity,
+                                int64_t* send_ids, int64_t* perm, int64_t* counts, int32_t* overflow_flag,
+                                void* stream) {
   TT_REQUIRE(world >= 1 && world <= 8, "tt_partition_ids: world must be in [1, 8], got %d", world);
-  TT_REQUIRE(n >= 0 && (n == 0 || (ids && send_ids && perm)) && counts, "tt_partition_ids: null buffer");
-  partition_ids_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(ids, n, world, send_ids, perm, counts);
+  TT_REQUIRE(n >= 0 && capacity >= 0 && (n == 0 || (ids && send_ids && perm)) && counts, "tt_partition_ids: bad arguments");
+  TT_PROF("partition_ids_kernel", (cudaStream_t)stream);
+  partition_ids_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(ids, n, world, capacity, send_ids, perm, counts, overflow_flag);
   TT_LAUNCH_OK("partition_ids_kernel");
   return TT_OK;
 }
 
-extern "C" int tt_permute_rows_f32(const float* in, const int64_t* perm, float* out, int64_t n,
-                                   int64_t d, int32_t inverse, void* stream) {
-  TT_REQUIRE(d > 0 && d % 4 == 0, "tt_permute_rows_f32: d must be a multiple of 4");
-  TT_REQUIRE(n == 0 || (in && perm && out), "tt_permute_rows_f32: null buffer");
-  TT_REQUIRE(aligned16(in) && aligned16(out), "tt_permute_rows_f32: buffers must be 16-byte aligned");
+extern "C" int tt_permute_rows(const void* in, const int64_t* perm, void* out, int64_t n,
+                               int64_t row_bytes, int32_t inverse, void* stream) {
+  TT_REQUIRE(row_bytes > 0 && row_bytes % 16 == 0, "tt_permute_rows: row_bytes must be a multiple of 16");
+  TT_REQUIRE(n == 0 || (in && perm && out), "tt_permute_rows: null buffer");
+  TT_REQUIRE(aligned16(in) && aligned16(out), "tt_permute_rows: buffers must be 16-byte aligned");
   if (n == 0) return TT_OK;
-  permute_rows_kernel<<<(unsigned)ceil_div(n, 8), 256, 0, (cudaStream_t)stream>>>(in, perm, out, n, d, inverse);
+  TT_PROF("permute_rows_kernel", (cudaStream_t)stream);
+  permute_rows_kernel<<<(unsigned)ceil_div(n, 8), 256, 0, (cudaStream_t)stream>>>((const uint4*)in, perm, (uint4*)out, n, row_bytes / 16, inverse);
   TT_LAUNCH_OK("permute_rows_kernel");
   return TT_OK;
 }

@@ -213,6 +213,7 @@ loss_reduce_kernel(const float* __restrict__ lse, const float* __restrict__ pos,
 }
 
 int launch_loss_reduce(const float* lse, const float* pos, const float* w, int64_t n, float* loss, cudaStream_t st) {
+  TT_PROF("loss_reduce_kernel", st);
   loss_reduce_kernel<<<1, 1024, 0, st>>>(lse, pos, w, n, loss);
   TT_LAUNCH_OK("loss_reduce_kernel");
   return TT_OK;
@@ -229,7 +230,7 @@ static int launch_retrieval(const RetrievalArgs& a, cudaStream_t st) {
 #define TT_RL(DJV)                                                                                       \
   {                                                                                                      \
     TT_CUDA_OK(cudaFuncSetAttribute(retrieval_kernel<MODE, DJV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    retrieval_kernel<MODE, DJV><<<grid, 256, smem, st>>>(a);                                             \
+    TT_PROF("retrieval_kernel", st), retrieval_kernel<MODE, DJV><<<grid, 256, smem, st>>>(a);                                             \
   }
   if (MODE == 0) TT_RL(1)
   else if (dj == 1) TT_RL(1)

@@ -584,12 +584,15 @@ int tc_retrieval_fwd(const void* q, const void* c, int64_t nq, int64_t nc, int64
   dim3 grid((unsigned)ceil_div(nq, RT_BM), (unsigned)splits);
   if (logq || cand_ids) {
     TT_CUDA_OK(cudaFuncSetAttribute(retrieval_fwd_tc_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TT_PROF("retrieval_fwd_tc_kernel", st);
     retrieval_fwd_tc_kernel<BN, true><<<grid, RT_THREADS, smem, st>>>(tmQ, tmC, a);
   } else {
     TT_CUDA_OK(cudaFuncSetAttribute(retrieval_fwd_tc_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TT_PROF("retrieval_fwd_tc_kernel", st);
     retrieval_fwd_tc_kernel<BN, false><<<grid, RT_THREADS, smem, st>>>(tmQ, tmC, a);
   }
   TT_LAUNCH_OK("retrieval_fwd_tc_kernel");
+  TT_PROF("retrieval_fwd_finalize_kernel", st);
   retrieval_fwd_finalize_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, st>>>((const float2*)ws, splits, (int)nq, row_lse);
   TT_LAUNCH_OK("retrieval_fwd_finalize_kernel");
   return launch_loss_reduce(row_lse, row_pos, w, nq, loss, st);
@@ -617,7 +620,7 @@ static int launch_bwd(const void* x, const void* y, const void* y_t, int64_t nX,
 #define TT_BWD_LAUNCH(EX)                                                                                     \
   {                                                                                                           \
     TT_CUDA_OK(cudaFuncSetAttribute(retrieval_bwd_tc_kernel<BN, TRANSPOSED, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total)); \
-    retrieval_bwd_tc_kernel<BN, TRANSPOSED, EX><<<grid, RT_THREADS, L.total, st>>>(tmX, tmY, tmYT, a);        \
+    TT_PROF("retrieval_bwd_tc_kernel", st), retrieval_bwd_tc_kernel<BN, TRANSPOSED, EX><<<grid, RT_THREADS, L.total, st>>>(tmX, tmY, tmYT, a);        \
   }
   if (extras) TT_BWD_LAUNCH(true) else TT_BWD_LAUNCH(false)
 #undef TT_BWD_LAUNCH
@@ -655,8 +658,10 @@ int tc_retrieval_bwd(const void* q, const void* c, const void* q_t, const void* 
     rc = launch_bwd<64, true>(c, q, q_t, nc, nq, a, part_c, &sc, st);
   }
   if (rc) return rc;
+  TT_PROF("combine_partials_kernel", st);
   combine_partials_kernel<<<(unsigned)ceil_div(nq, 8), 256, 0, st>>>(part_q, sq, nq, (int)d, dq, dq_bf16, dq_bf16_t);
   TT_LAUNCH_OK("combine_partials_kernel");
+  TT_PROF("combine_partials_kernel", st);
   combine_partials_kernel<<<(unsigned)ceil_div(nc, 8), 256, 0, st>>>(part_c, sc, nc, (int)d, dc, dc_bf16, dc_bf16_t);
   TT_LAUNCH_OK("combine_partials_kernel");
   return TT_OK;

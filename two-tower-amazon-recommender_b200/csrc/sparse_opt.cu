@@ -192,10 +192,13 @@ static int run_sparse(const char* name, Rule rule, float* table, int64_t vocab, 
   if (nnz == 0) return TT_OK;
   SparseWs ws;
   ws_layout(nnz, d, workspace, &ws);
+  TT_PROF("sparse_insert_kernel", stream);
   sparse_insert_kernel<<<(unsigned)ceil_div(nnz, 256), 256, 0, stream>>>(ws, values, offsets, num_rows, nnz, vocab);
   TT_LAUNCH_OK("sparse_insert_kernel");
+  TT_PROF("sparse_accumulate_kernel", stream);
   sparse_accumulate_kernel<<<(unsigned)ceil_div(nnz, 8), 256, 0, stream>>>(ws, offsets, mode, nnz, d, grad);
   TT_LAUNCH_OK("sparse_accumulate_kernel");
+  TT_PROF("sparse_apply_kernel", stream);
   sparse_apply_kernel<Rule><<<(unsigned)ceil_div(nnz, 8), 256, 0, stream>>>(ws, rule, table, nnz, d, first_flag);
   TT_LAUNCH_OK("sparse_apply_kernel");
   return TT_OK;
@@ -251,6 +254,7 @@ using namespace tt;
 
 extern "C" int tt_sum_squares(const float* x, int64_t n, float scale, float* out, int32_t accumulate, void* stream) {
   TT_REQUIRE(x && out && n >= 0, "tt_sum_squares: bad arguments");
+  TT_PROF("sum_squares_kernel", (cudaStream_t)stream);
   sum_squares_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, n, scale, out, accumulate);
   TT_LAUNCH_OK("sum_squares_kernel");
   return TT_OK;
@@ -269,6 +273,7 @@ extern "C" int tt_sparse_workspace_init(void* workspace, int64_t workspace_bytes
     return set_error(TT_ERR_WORKSPACE, "tt_sparse_workspace_init: workspace too small");
   SparseWs ws;
   ws_layout(nnz, d, workspace, &ws);
+  TT_PROF("sparse_ws_init_kernel", (cudaStream_t)stream);
   sparse_ws_init_kernel<<<num_sms() * 4, 256, 0, (cudaStream_t)stream>>>(ws, nnz, d);
   TT_LAUNCH_OK("sparse_ws_init_kernel");
   return TT_OK;
@@ -303,8 +308,8 @@ static int dense_opt(bool adam, float* w, float* s0, float* s1, const float* par
   TT_REQUIRE(rows > 0 && cols > 0 && num_parts >= 1, "dense optimizer: bad sizes");
   const int64_t n = rows * cols;
   unsigned blocks = (unsigned)ceil_div(n, 256);
-  if (adam) dense_opt_kernel<true><<<blocks, 256, 0, stream>>>(w, s0, s1, parts, num_parts, rows, cols, lr, b1, b2, eps, l2, shadow, shadow_t);
-  else dense_opt_kernel<false><<<blocks, 256, 0, stream>>>(w, s0, s1, parts, num_parts, rows, cols, lr, b1, b2, eps, l2, shadow, shadow_t);
+  if (adam) TT_PROF("dense_opt_kernel", stream), dense_opt_kernel<true><<<blocks, 256, 0, stream>>>(w, s0, s1, parts, num_parts, rows, cols, lr, b1, b2, eps, l2, shadow, shadow_t);
+  else TT_PROF("dense_opt_kernel", stream), dense_opt_kernel<false><<<blocks, 256, 0, stream>>>(w, s0, s1, parts, num_parts, rows, cols, lr, b1, b2, eps, l2, shadow, shadow_t);
   TT_LAUNCH_OK("dense_opt_kernel");
   return TT_OK;
 }

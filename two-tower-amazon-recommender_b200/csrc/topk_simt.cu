@@ -211,6 +211,7 @@ extern "C" int tt_topk_merge(const float* scores, const int64_t* ids, int32_t nu
   TT_REQUIRE(num_lists >= 1 && num_lists <= 32, "tt_topk_merge: num_lists must be in [1, 32], got %d", num_lists);
   TT_REQUIRE(nq >= 0 && k_in >= 1 && k_out >= 1 && k_out <= num_lists * k_in, "tt_topk_merge: bad k (k_in=%d k_out=%d lists=%d)", k_in, k_out, num_lists);
   if (nq == 0) return TT_OK;
+  TT_PROF("topk_merge_kernel", (cudaStream_t)stream);
   topk_merge_kernel<<<(unsigned)ceil_div(nq, 8), 256, 0, (cudaStream_t)stream>>>(scores, ids, num_lists, nq, k_in, k_out, index_base, identifiers, out_scores, out_ids);
   TT_LAUNCH_OK("topk_merge_kernel");
   return TT_OK;
@@ -246,7 +247,7 @@ extern "C" int tt_topk_bruteforce(int32_t precision, const void* queries, const 
 #define TT_TOPK_LAUNCH(KU)                                                                                  \
   {                                                                                                         \
     TT_CUDA_OK(cudaFuncSetAttribute(topk_simt_kernel<KU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    topk_simt_kernel<KU><<<grid, 256, smem, st>>>((const float*)queries, (const float*)candidates, nq, nc, (int)d, k, \
+    TT_PROF("topk_simt_kernel", st), topk_simt_kernel<KU><<<grid, 256, smem, st>>>((const float*)queries, (const float*)candidates, nq, nc, (int)d, k, \
                                                   cand_index_base, identifiers, split_len, ps, pi);          \
   }
   if (k <= 32) TT_TOPK_LAUNCH(1)
@@ -273,6 +274,7 @@ extern "C" int tt_topk_hits(const float* positive, const float* topk_scores, con
     ks[i] = host_ks[i];
   }
   if (nq == 0) return TT_OK;
+  TT_PROF("topk_hits_kernel", (cudaStream_t)stream);
   topk_hits_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, (cudaStream_t)stream>>>(
       positive, topk_scores, topk_ids, true_ids, sample_weight, nq, k, nullptr, ks[0], ks[1], ks[2], ks[3], ks[4],
       ks[5], ks[6], ks[7], num_ks, hits_out, weight_out);
@@ -285,8 +287,8 @@ extern "C" int tt_rowwise_dot(int32_t precision, const void* q, const void* c, f
   TT_REQUIRE(q && c && out && n >= 0 && d > 0, "tt_rowwise_dot: bad arguments");
   if (n == 0) return TT_OK;
   unsigned blocks = (unsigned)ceil_div(n, 8);
-  if (precision == TT_F32) rowwise_dot_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float*)q, (const float*)c, out, n, d);
-  else if (precision == TT_BF16) rowwise_dot_kernel<uint16_t><<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)q, (const uint16_t*)c, out, n, d);
+  if (precision == TT_F32) TT_PROF("rowwise_dot_kernel", (cudaStream_t)stream), rowwise_dot_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float*)q, (const float*)c, out, n, d);
+  else if (precision == TT_BF16) TT_PROF("rowwise_dot_kernel", (cudaStream_t)stream), rowwise_dot_kernel<uint16_t><<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)q, (const uint16_t*)c, out, n, d);
   else return set_error(TT_ERR_INVALID_ARG, "tt_rowwise_dot: unknown precision %d", precision);
   TT_LAUNCH_OK("rowwise_dot_kernel");
   return TT_OK;

@@ -258,7 +258,7 @@ int tc_topk(const void* queries, const void* candidates, int64_t nq, int64_t nc,
 #define TT_TK2(KU, BNV)                                                                                            \
   {                                                                                                                \
     TT_CUDA_OK(cudaFuncSetAttribute(topk_tc_kernel<KU, BNV>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total)); \
-    topk_tc_kernel<KU, BNV><<<grid, TK_THREADS, L.total, st>>>(tmQ, tmC, a);                                       \
+    TT_PROF("topk_tc_kernel", st), topk_tc_kernel<KU, BNV><<<grid, TK_THREADS, L.total, st>>>(tmQ, tmC, a);                                       \
   }
 #define TT_TK(KU) { if (bn == 128) TT_TK2(KU, 128) else TT_TK2(KU, 64) }
   if (k <= 32) TT_TK(1)

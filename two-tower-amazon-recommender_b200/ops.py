@@ -204,9 +204,21 @@ def dense_bwd_num_parts(precision: str, M: int, in_dim: int, out_dim: int) -> in
     return int(_lib.load().tt_dense_bwd_num_parts(precision_code(precision), M, in_dim, out_dim))
 
 
-def colsum_f32(x):
-    out = torch.empty((x.shape[1],), dtype=torch.float32, device=x.device)
-    check(_lib.load().tt_colsum_f32(_ptr(x, torch.float32), _ptr(out), x.shape[0], x.shape[1], _stream()))
+def colsum_f32(x, num_parts: int = 0):
+    """Column sums as `num_parts` stacked partial rows [P, cols] (summed later, in order, by the optimizer)."""
+    rows, cols = x.shape
+    P = num_parts or max(1, min(64, rows // 64))
+    out = torch.empty((P, cols), dtype=torch.float32, device=x.device)
+    check(_lib.load().tt_colsum_f32(_ptr(x, torch.float32), _ptr(out), rows, cols, P, _stream()))
+    _count(1)
+    return out
+
+
+def sum_parts(parts, num_parts: int):
+    """[P, ...] -> [...] (fixed order)."""
+    n = parts[0].numel()
+    out = torch.empty_like(parts[0])
+    check(_lib.load().tt_sum_parts_f32(_ptr(parts, torch.float32), num_parts, n, _ptr(out), _stream()))
     _count(1)
     return out
 
@@ -368,21 +380,26 @@ def rowwise_dot(precision: str, q, c):
 
 
 # ------------------------------------------------------------------------ sharding helpers
-def partition_ids(ids, world: int):
-    """Stable partition by owner = id % world.  Returns (send_local_rows [n], perm [n], counts [world])."""
+def partition_ids(ids, world: int, capacity: int = 0, overflow_flag=None):
+    """Stable partition by owner = id % world.  Returns (send_local_rows, perm [n], counts [world]);
+    send_local_rows is [n] packed (capacity == 0) or [world * capacity] padded with -1."""
     n = ids.numel()
-    send = torch.empty((n,), dtype=torch.int64, device=ids.device)
+    send = torch.empty((world * capacity if capacity else n,), dtype=torch.int64, device=ids.device)
     perm = torch.empty((n,), dtype=torch.int64, device=ids.device)
     counts = torch.empty((world,), dtype=torch.int64, device=ids.device)
-    check(_lib.load().tt_partition_ids(_ptr(ids, torch.int64), n, world, _ptr(send), _ptr(perm), _ptr(counts),
-                                       _stream()))
+    check(_lib.load().tt_partition_ids(_ptr(ids, torch.int64), n, world, capacity, _ptr(send), _ptr(perm),
+                                       _ptr(counts), _ptr(overflow_flag, torch.int32), _stream()))
     _count(1)
     return send, perm, counts
 
 
-def permute_rows(x, perm, inverse: bool):
-    out = torch.empty_like(x)
-    check(_lib.load().tt_permute_rows_f32(_ptr(x, torch.float32), _ptr(perm, torch.int64), _ptr(out), x.shape[0],
-                                          x.shape[1], 1 if inverse else 0, _stream()))
+def permute_rows(x, perm, inverse: bool, out_rows: int = 0, zero_fill: bool = False):
+    """inverse=False: out[perm[j]] = x[j] (out has out_rows rows); inverse=True: out[j] = x[perm[j]]."""
+    n = perm.numel()
+    rows = out_rows or n
+    shape = (rows, x.shape[1])
+    out = torch.zeros(shape, dtype=x.dtype, device=x.device) if zero_fill else torch.empty(shape, dtype=x.dtype, device=x.device)
+    check(_lib.load().tt_permute_rows(_ptr(x), _ptr(perm, torch.int64), _ptr(out), n, x.shape[1] * x.element_size(),
+                                      1 if inverse else 0, _stream()))
     _count(1)
     return out

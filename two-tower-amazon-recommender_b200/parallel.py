@@ -1,0 +1,245 @@
+"""One process per GPU: embedding tables row-sharded over the ranks with
+all-to-all lookups and gradient returns, data-parallel tower MLPs (all-reduced dense
+gradients), and candidate embeddings all-gathered so the in-batch negatives span the GLOBAL
+batch.  The result equals the single-device TFRS loss / update on the concatenated batch.
+
+torch.distributed (NCCL over NVLink on the box, gloo in the CPU tests) is the plumbing; every
+local computation goes through ``prim`` -- the libtwotower wrappers (``ops``) in the product.
+The CPU tests inject their own ``prim`` (built on the oracle) to exercise the routing logic
+under gloo; this module never falls back to one by itself.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops as _cuda_ops
+from .core import DenseGrad, GradientTape, IndexedSlices, Scalar, Tensor, Variable, config
+from .layers import Dense, Layer, Sequential, _as_ids
+from .models import Model
+
+
+# ------------------------------------------------------------------------- collectives
+class Collectives:
+    """Static-shape collectives over one process group; hides backend gaps (gloo has no
+    all_to_all / reduce_scatter on CPU tensors: emulated with all_gather / all_reduce)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.native = dist.get_backend(group) == "nccl"
+
+    def all_to_all(self, x: torch.Tensor) -> torch.Tensor:
+        """x [world * n, ...] -> y with y[r*n:(r+1)*n] = rank r's x[me*n:(me+1)*n]."""
+        out = torch.empty_like(x)
+        if self.native:
+            dist.all_to_all_single(out, x, group=self.group)
+            return out
+        n = x.shape[0] // self.world
+        bufs = [torch.empty_like(x) for _ in range(self.world)]
+        dist.all_gather(bufs, x, group=self.group)
+        for r in range(self.world):
+            out[r * n:(r + 1) * n] = bufs[r][self.rank * n:(self.rank + 1) * n]
+        return out
+
+    def all_gather(self, x: torch.Tensor) -> torch.Tensor:
+        out = torch.empty((self.world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(out, x.contiguous(), group=self.group)
+        return out
+
+    def reduce_scatter(self, x: torch.Tensor) -> torch.Tensor:
+        """x [world * n, ...] summed over ranks; this rank keeps rows [me*n, (me+1)*n)."""
+        n = x.shape[0] // self.world
+        if self.native:
+            out = torch.empty((n,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+            dist.reduce_scatter_tensor(out, x.contiguous(), group=self.group)
+            return out
+        y = x.clone()
+        dist.all_reduce(y, group=self.group)
+        return y[self.rank * n:(self.rank + 1) * n].contiguous()
+
+    def all_reduce_(self, x: torch.Tensor) -> torch.Tensor:
+        dist.all_reduce(x, group=self.group)
+        return x
+
+
+# ------------------------------------------------------------------ row-sharded lookups
+def bucket_capacity(batch: int, world: int, capacity_factor: Optional[float]) -> int:
+    """Slots per owner in the static-shape all-to-all.  None -> batch (can never overflow)."""
+    if capacity_factor is None or world == 1:
+        return batch
+    return min(batch, int(-(-batch * capacity_factor // world)) + 8)
+
+
+def exchange_lookup(prim, coll: Collectives, table_shard: torch.Tensor, ids: torch.Tensor, capacity: int,
+                    out_dtype, overflow_flag=None):
+    """Rows table[ids] of a table sharded cyclically (owner = id % world, local row = id // world).
+    ids [b] int64 -> (rows [b, d], ctx).  Stable partition => bit-reproducible per-owner buckets."""
+    send, perm, _counts = prim.partition_ids(ids, coll.world, capacity, overflow_flag)
+    recv = coll.all_to_all(send)                               # local rows wanted from me (-1 = padding)
+    rows = prim.embedding_gather(table_shard, recv, out_dtype) # padding -> zero rows
+    back = coll.all_to_all(rows)
+    out = prim.permute_rows(back, perm, inverse=True)
+    return out, (recv, perm)
+
+
+def exchange_grads(prim, coll: Collectives, ctx, grad_rows: torch.Tensor, capacity: int):
+    """Route d(loss)/d(rows) [b, d] back to the owners.  Returns (local_rows [world*cap] with -1
+    padding, grads [world*cap, d]) == the IndexedSlices of this rank's shard."""
+    recv_ids, perm = ctx
+    send = prim.permute_rows(grad_rows, perm, inverse=False, out_rows=coll.world * capacity, zero_fill=True)
+    recv = coll.all_to_all(send)
+    return recv_ids, recv
+
+
+class ShardedEmbedding(Layer):
+    """tf.keras.layers.Embedding whose [input_dim, d] table is row-sharded over the group."""
+
+    def __init__(self, input_dim: int, output_dim: int, group=None, capacity_factor: Optional[float] = None,
+                 name: Optional[str] = None, prim=None, seed: int = 0):
+        self.coll = Collectives(group)
+        self.prim = prim or _cuda_ops
+        self.input_dim, self.output_dim = int(input_dim), int(output_dim)
+        self.capacity_factor = capacity_factor
+        self.name = name or "sharded_embedding"
+        rows = -(-self.input_dim // self.coll.world)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        g = torch.Generator(device=dev)
+        g.manual_seed(config.seed * 7919 + seed * 8 + self.coll.rank)
+        shard = torch.empty((rows, self.output_dim), dtype=torch.float32, device=dev)
+        shard.uniform_(-0.05, 0.05, generator=g)
+        self.embeddings = Variable(f"{self.name}/embeddings_shard{self.coll.rank}", shard, "table")
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    @property
+    def trainable_variables(self):
+        return [self.embeddings]
+
+    def load_full_table(self, table) -> None:
+        """Keep rows owned by this rank (row r of the full table lives on rank r % world at r // world)."""
+        t = torch.as_tensor(table, dtype=torch.float32)
+        mine = t[self.coll.rank::self.coll.world]
+        self.embeddings.value[:mine.shape[0]].copy_(mine.to(self.embeddings.value.device))
+
+    def __call__(self, inputs, training: bool = False) -> Tensor:
+        ids = _as_ids(inputs).reshape(-1)
+        b = ids.numel()
+        cap = bucket_capacity(b, self.coll.world, self.capacity_factor)
+        bf16 = config.precision == "bf16"
+        rows, ctx = exchange_lookup(self.prim, self.coll, self.embeddings.value, ids, cap,
+                                    torch.bfloat16 if bf16 else torch.float32, self.overflow)
+        out = Tensor(f32=None if bf16 else rows, bf16=rows if bf16 else None, grad_formats=("f32",))
+
+        def backward():
+            if out.grad is None:
+                return
+            local_ids, grads = exchange_grads(self.prim, self.coll, ctx, out.grad["f32"], cap)
+            self.embeddings.grad = IndexedSlices(values=local_ids, offsets=None, mode="sum", rows=grads)
+
+        GradientTape.record(backward)
+        return out
+
+    def check_overflow(self) -> None:
+        if int(self.overflow.item()) != 0:
+            raise RuntimeError(f"{self.name}: an owner bucket exceeded capacity_factor={self.capacity_factor}; "
+                               "rerun with capacity_factor=None")
+
+
+# ------------------------------------------------------------------- global negatives
+def global_retrieval(task, q: Tensor, c: Tensor, inv_t: float, w, logq, ids, prim=None) -> Scalar:
+    """tfrs.tasks.Retrieval with the candidates all-gathered over task.process_group: rank r's
+    queries score against all world*b candidates, positives at columns [r*b, (r+1)*b).
+    Loss reported = this rank's share; sum over ranks == single-device loss on the global batch."""
+    prim = prim or _cuda_ops
+    coll = Collectives(task.process_group)
+    prec = config.precision
+    qm = q.f32 if prec == "fp32" else q.bf16
+    cm = c.f32 if prec == "fp32" else c.bf16
+    nq = qm.shape[0]
+    c_all = coll.all_gather(cm)                                   # [world*b, d]
+    label_offset = coll.rank * nq
+    logq_all = None if logq is None else coll.all_gather(logq)
+    ids_all = None if ids is None else coll.all_gather(ids)
+    loss, lse, _pos = prim.retrieval_loss_fwd(prec, qm, c_all, inv_t, label_offset, w, logq_all, ids_all)
+
+    def backward():
+        q_t = c_all_t = None
+        if prec == "bf16":
+            if q.bf16_t is None:
+                q.bf16_t = prim.transpose_bf16(q.bf16)
+            q_t, c_all_t = q.bf16_t, prim.transpose_bf16(c_all)
+        r = prim.retrieval_loss_bwd(prec, qm, c_all, q_t, c_all_t, inv_t, lse, label_offset, w, logq_all, ids_all, 1.0,
+                                    want_bf16=("bf16" in q.grad_formats and prec == "bf16", False),
+                                    want_bf16_t=("bf16_t" in q.grad_formats and prec == "bf16", False))
+        q.grad = dict(f32=r["dq"], bf16=r["dq_bf16"], bf16_t=r["dq_bf16_t"])
+        dc = coll.reduce_scatter(r["dc"])                         # every rank's partial for my candidates
+        dc_b = dc_bt = None
+        if prec == "bf16" and ("bf16" in c.grad_formats or "bf16_t" in c.grad_formats):
+            dc_b, dc_bt = prim.cast_f32_to_bf16(dc, want=True, want_t=True)
+        c.grad = dict(f32=dc, bf16=dc_b, bf16_t=dc_bt)
+
+    GradientTape.record(backward)
+    return Scalar(loss)
+
+
+class DataParallelModel(Model):
+    """tfrs.models.Model whose Dense gradients are summed over the group before the update (the
+    tables are sharded, their gradients were already routed to the owners)."""
+
+    def __init__(self, group=None, name: Optional[str] = None):
+        super().__init__(name)
+        self.process_group = group
+        self._coll = Collectives(group)
+
+    def train_step(self, inputs):
+        if self.optimizer is None:
+            raise RuntimeError("call model.compile(optimizer=...) before train_step")
+        with GradientTape() as tape:
+            loss = self.compute_loss(inputs, training=True)
+            variables = self.trainable_variables
+            grads = tape.gradient(loss, variables)
+        flat = []
+        for i, g in enumerate(grads):
+            if isinstance(g, DenseGrad):
+                summed = _cuda_ops.sum_parts(g.parts, g.num_parts) if g.num_parts > 1 else g.parts[0]
+                flat.append((i, summed))
+        if flat:
+            # one bucket for every dense gradient: a single latency-bound all-reduce per step
+            bucket = torch.cat([t.reshape(-1) for _, t in flat])
+            self._coll.all_reduce_(bucket)
+            off = 0
+            for i, t in flat:
+                n = t.numel()
+                grads[i] = DenseGrad(bucket[off:off + n].reshape((1,) + tuple(t.shape)), 1)
+                off += n
+        self.optimizer.apply_gradients(zip(grads, variables))
+        total = loss.value.clone()
+        self._coll.all_reduce_(total)
+        return {"loss": total, "local_loss": loss.value, "regularization_loss": torch.zeros_like(total), "total_loss": total}
+
+
+def build_sharded_two_tower(cfg, group, lr: float = 0.001, capacity_factor: Optional[float] = 2.0):
+    """The bench model at N > 1: ID-only two-tower of `cfg`, tables row-sharded, global negatives."""
+    from . import optimizers, tasks
+
+    class ShardedTwoTower(DataParallelModel):
+        def __init__(self):
+            super().__init__(group)
+            def tower(vocab, seed):
+                layers = [ShardedEmbedding(vocab, cfg.dim, group, capacity_factor, seed=seed)]
+                for j, u in enumerate(cfg.mlp):
+                    layers.append(Dense(u, "relu" if j < len(cfg.mlp) - 1 else None))
+                return Sequential(layers)
+            self.user_model = tower(cfg.v_user, 1)
+            self.item_model = tower(cfg.v_item, 2)
+            self.task = tasks.Retrieval(temperature=cfg.temperature, process_group=group)
+
+        def compute_loss(self, features, training=False):
+            return self.task(self.user_model(features["user_id_encoded"]), self.item_model(features["item_id_encoded"]))
+
+    model = ShardedTwoTower()
+    model.compile(optimizer=optimizers.Adagrad(learning_rate=lr))
+    return model
