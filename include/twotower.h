@@ -117,14 +117,14 @@ int tt_sparse_lazy_adam_update(float* table, float* m, float* v, int64_t vocab, 
 /* Dense Keras Adagrad / Adam on a [rows, cols] variable.  grad_parts holds `num_parts`
  * stacked partial gradients [num_parts, rows, cols] (split-K partials of the wgrad GEMM) that
  * are summed in index order (deterministic).  l2 adds 2*l2*w (kernel_regularizer=l2,
- * /root/reference/configs/data_config.yaml:59).  Optional bf16 shadow copies of the updated
- * variable: shadow [rows, cols] and shadow_t [cols, rows]. */
+ * /root/reference/configs/data_config.yaml:59).  shadow (nullable): bf16 copy [rows, cols] of
+ * the updated variable, the operand the tensor-core kernels read. */
 int tt_dense_adagrad_update(float* w, float* accum, const float* grad_parts, int32_t num_parts,
                             int64_t rows, int64_t cols, float lr, float eps, float l2,
-                            uint16_t* shadow, uint16_t* shadow_t, void* stream);
+                            uint16_t* shadow, void* stream);
 int tt_dense_adam_update(float* w, float* m, float* v, const float* grad_parts, int32_t num_parts,
                          int64_t rows, int64_t cols, float alpha, float beta1, float beta2,
-                         float eps, float l2, uint16_t* shadow, uint16_t* shadow_t, void* stream);
+                         float eps, float l2, uint16_t* shadow, void* stream);
 
 /* out[0] (+)= scale * sum(x^2) in a fixed order: the kernel_regularizer=l2 term of
  * tfrs.models.Model.train_step's regularization_loss (sum(model.losses)). */
@@ -133,31 +133,29 @@ int tt_sum_squares(const float* x, int64_t n, float scale, float* out, int32_t a
 
 /* ---------------------------------------------------------------------------------------
  * K2  tower MLP: tf.keras.layers.Dense forward / backward (layer sizes
- * /root/reference/configs/data_config.yaml:56-57).  kernel is the Keras layout [in, out].
+ * /root/reference/configs/data_config.yaml:56-57).  kernel is ALWAYS the Keras layout
+ * [in, out]; no transposed copy of any operand is needed (the tcgen05 descriptors read
+ * K-major or MN-major shared-memory tiles as required).
  *
  * precision TT_F32 : x, kernel, y fp32 (CUDA-core FFMA path, 1e-5 parity).
- * precision TT_BF16: x bf16 [M,in], kernel_t bf16 [out,in] (the shadow_t copy), fp32
- *                    accumulation on tcgen05; y bf16 [M,out]; y_t (nullable) bf16 [out,M]
- *                    transposed copy (the wgrad operand); y_f32 (nullable) fp32 copy.
+ * precision TT_BF16: x bf16 [M,in], kernel bf16 [in,out] (the shadow copy), fp32 accumulation
+ *                    on tcgen05; y bf16 [M,out]; y_f32 (nullable) fp32 copy.
  * ------------------------------------------------------------------------------------- */
 int tt_dense_fwd(int32_t precision, const void* x, const void* kernel, const float* bias,
-                 void* y, void* y_t, float* y_f32, int64_t M, int64_t in_dim, int64_t out_dim,
+                 void* y, float* y_f32, int64_t M, int64_t in_dim, int64_t out_dim,
                  int32_t relu, void* stream);
 /* dx = (dy @ kernel^T) [* (x > 0) when relu_mask_x != 0: x is the relu OUTPUT of the previous
  * layer, so the mask applies the previous layer's activation gradient];
- * dkernel_parts[p] partial x^T @ dy over the p-th M-slice; dbias = colsum(dy).
+ * dkernel_parts[p] = partial x^T @ dy over the p-th M-slice; dbias_parts[p] = colsum(dy) over
+ * the same slice (nullable: the caller then takes tt_colsum_f32 of an fp32 copy of dy -- the
+ * bias gradient is a cancelling sum, so it is taken before bf16 rounding whenever possible).
  * TT_F32 : everything fp32, num_parts must be 1.
- * TT_BF16: dy bf16 [M,out] + dy_t bf16 [out,M]; x bf16 [M,in] + x_t bf16 [in,M]; kernel bf16
- *          [in,out] (the shadow copy); dx bf16 [M,in] (+ dx_t [in,M] nullable);
- *          dkernel_parts fp32 [num_parts, in, out]; dbias fp32 [out].
- * dx may be NULL (first layer: only the embedding gradient dx_f32 is wanted) and dx_f32
- * (nullable) receives an fp32 copy of dx.  dbias may be NULL (the caller then takes
- * tt_colsum_f32 of an fp32 copy of dy: the bias gradient is a cancelling sum, so it is taken
- * before bf16 rounding whenever an fp32 dy exists). */
-int tt_dense_bwd(int32_t precision, const void* dy, const void* dy_t, const void* x,
-                 const void* x_t, const void* kernel, void* dx, void* dx_t, float* dx_f32,
-                 float* dkernel_parts, int32_t num_parts, float* dbias, int64_t M,
-                 int64_t in_dim, int64_t out_dim, int32_t relu_mask_x, void* stream);
+ * TT_BF16: dy bf16 [M,out], x bf16 [M,in], kernel bf16 [in,out]; dx bf16 [M,in] (nullable);
+ *          dx_f32 (nullable) fp32 copy of dx (the embedding gradient of the first layer);
+ *          dkernel_parts fp32 [num_parts, in, out]; dbias_parts fp32 [num_parts, out]. */
+int tt_dense_bwd(int32_t precision, const void* dy, const void* x, const void* kernel, void* dx,
+                 float* dx_f32, float* dkernel_parts, int32_t num_parts, float* dbias_parts,
+                 int64_t M, int64_t in_dim, int64_t out_dim, int32_t relu_mask_x, void* stream);
 int32_t tt_dense_bwd_num_parts(int32_t precision, int64_t M, int64_t in_dim, int64_t out_dim);
 
 /* out_parts[p, c] = sum over the p-th slice of rows of x[r, c], fixed order (fp32); the
@@ -167,10 +165,12 @@ int tt_colsum_f32(const float* x, float* out_parts, int64_t rows, int64_t cols, 
                   void* stream);
 int tt_sum_parts_f32(const float* parts, int32_t num_parts, int64_t n, float* out, void* stream);
 
-/* bf16 [rows, cols] -> bf16 [cols, rows] */
-int tt_transpose_bf16(const uint16_t* in, uint16_t* out, int64_t rows, int64_t cols, void* stream);
-int tt_cast_f32_to_bf16(const float* in, uint16_t* out, uint16_t* out_t, int64_t rows,
-                        int64_t cols, void* stream);
+/* Test hook: D[M,N] (fp32) = A * B with bf16 operands in either storage order
+ * (a_mn = 0: A is [M,K]; 1: A is [K,M].  b_mn = 0: B is [N,K]; 1: B is [K,N]). */
+int tt_debug_gemm_bf16(const void* A, int32_t a_mn, const void* B, int32_t b_mn, int64_t M,
+                       int64_t N, int64_t K, float* out, void* stream);
+
+int tt_cast_f32_to_bf16(const float* in, uint16_t* out, int64_t n, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * K3/K4  tfrs.tasks.Retrieval: in-batch softmax cross-entropy, logits never written to HBM.
@@ -193,17 +193,14 @@ int tt_retrieval_loss_fwd(int32_t precision, const void* q, const void* c, int64
                           const int64_t* cand_ids, float* row_lse, float* row_pos, float* loss,
                           void* workspace, int64_t workspace_bytes, void* stream);
 /* dq [nq, d] fp32, dc [nc, d] fp32 (this rank's partial when candidates are all-gathered).
- * TT_BF16 additionally takes q_t [d, nq] and c_t [d, nc] bf16 transposed copies and can emit
- * bf16 copies dq_bf16 [nq,d], dq_bf16_t [d,nq], dc_bf16, dc_bf16_t (each nullable) for the
- * MLP backward that follows. grad_scale multiplies the upstream gradient (1.0 for SUM). */
-int tt_retrieval_loss_bwd(int32_t precision, const void* q, const void* c, const void* q_t,
-                          const void* c_t, int64_t nq, int64_t nc, int64_t d,
-                          float inv_temperature, int64_t label_offset,
+ * TT_BF16 can also emit bf16 copies dq_bf16 [nq,d] / dc_bf16 [nc,d] (nullable) for the MLP
+ * backward that follows.  grad_scale multiplies the upstream gradient (1.0 for SUM). */
+int tt_retrieval_loss_bwd(int32_t precision, const void* q, const void* c, int64_t nq, int64_t nc,
+                          int64_t d, float inv_temperature, int64_t label_offset,
                           const float* sample_weight, const float* cand_log_q,
                           const int64_t* cand_ids, const float* row_lse, float grad_scale,
-                          float* dq, float* dc, uint16_t* dq_bf16, uint16_t* dq_bf16_t,
-                          uint16_t* dc_bf16, uint16_t* dc_bf16_t, void* workspace,
-                          int64_t workspace_bytes, void* stream);
+                          float* dq, float* dc, uint16_t* dq_bf16, uint16_t* dc_bf16,
+                          void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * K6  brute-force scoring + top-k.

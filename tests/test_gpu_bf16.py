@@ -41,12 +41,11 @@ class TestDenseTensorCore:
         rng = synth.rng_for(M + i + o)
         x = synth.exact_matrix(rng, M, i, 4); k = synth.exact_matrix(rng, i, o, 4)
         b = synth.exact_matrix(rng, 1, o, 4)[0]
-        y, y_t, y_f = ops.dense_fwd("bf16", bf(x), bf(k.T.copy()), dev(b), relu=False, want_t=True, want_f32=True)
+        y, y_f = ops.dense_fwd("bf16", bf(x), bf(k), dev(b), relu=False, want_f32=True)
         ref = x.astype(np.float64) @ k + b
         assert np.array_equal(y_f.cpu().numpy().astype(np.float64), ref)
         assert np.array_equal(y.float().cpu().numpy(), oracle.bf16_round(ref.astype(np.float32)))
-        assert np.array_equal(y_t.float().cpu().numpy(), oracle.bf16_round(ref.astype(np.float32)).T)
-        y2, _, _ = ops.dense_fwd("bf16", bf(x), bf(k.T.copy()), dev(b), relu=True)
+        y2, _ = ops.dense_fwd("bf16", bf(x), bf(k), dev(b), relu=True)
         assert np.array_equal(y2.float().cpu().numpy(), oracle.bf16_round(np.maximum(ref, 0).astype(np.float32)))
 
     @pytest.mark.parametrize("M,i,o", [(256, 128, 256), (8192, 128, 256), (8192, 256, 128), (1000, 64, 48)])
@@ -54,21 +53,19 @@ class TestDenseTensorCore:
         rng = synth.rng_for(M * 3 + i + o)
         x = np.maximum(synth.exact_matrix(rng, M, i, 4), 0); k = synth.exact_matrix(rng, i, o, 2)
         dy = synth.exact_matrix(rng, M, o, 2)
-        dx, dx_t, dx_f, dk, P, db = ops.dense_bwd("bf16", bf(dy), bf(dy.T.copy()), bf(x), bf(x.T.copy()), bf(k),
-                                                  relu_mask_x=True, want_dx=True, want_dx_t=True, want_dx_f32=True)
+        dx, dx_f, dk, P, db = ops.dense_bwd("bf16", bf(dy), bf(x), bf(k), relu_mask_x=True, want_dx=True, want_dx_f32=True)
         ref_dx = (dy.astype(np.float64) @ k.T) * (x > 0)
         assert np.array_equal(dx_f.cpu().numpy().astype(np.float64), ref_dx)
         assert np.array_equal(dx.float().cpu().numpy(), oracle.bf16_round(ref_dx.astype(np.float32)))
-        assert np.array_equal(dx_t.float().cpu().numpy(), oracle.bf16_round(ref_dx.astype(np.float32)).T)
-        assert P == dk.shape[0] and P >= 1
+        assert P == dk.shape[0] == db.shape[0] and P >= 1
         assert np.array_equal(dk.sum(0).cpu().numpy().astype(np.float64), x.astype(np.float64).T @ dy)
-        assert np.array_equal(db.cpu().numpy().astype(np.float64), dy.astype(np.float64).sum(0))
+        assert np.array_equal(db.sum(0).cpu().numpy().astype(np.float64), dy.astype(np.float64).sum(0))
 
     def test_gaussian_within_bf16_tolerance(self, ops):
         rng = synth.rng_for(12)
         M, i, o = 4096, 128, 256
         x = rng.normal(size=(M, i)).astype(np.float32); k = oracle.glorot_uniform(rng, i, o); b = rng.normal(size=o).astype(np.float32)
-        y, _, _ = ops.dense_fwd("bf16", bf(x), bf(k.T.copy()), dev(b), relu=True)
+        y, _ = ops.dense_fwd("bf16", bf(x), bf(k), dev(b), relu=True)
         ref = oracle.dense_forward(x.astype(np.float64), k, b, "relu")
         assert rel_err(y.float().cpu().numpy(), ref) < BF16_RTOL
 
@@ -99,16 +96,15 @@ class TestRetrievalTensorCore:
         # inputs are bf16-exact, so the forward differs from fp64 only by fp32 accumulation + ex2.approx
         assert float(loss.item()) == pytest.approx(r["loss"], rel=2e-4)
         assert rel_err(lse.cpu().numpy(), r["lse"]) < 2e-4 and rel_err(pos.cpu().numpy(), r["pos"]) < 2e-4
-        g = ops.retrieval_loss_bwd("bf16", qb, cb, ops.transpose_bf16(qb), ops.transpose_bf16(cb), inv_t, lse, label_offset,
-                                   w_d, logq, ids_d, want_bf16=(True, True), want_bf16_t=(True, True))
+        g = ops.retrieval_loss_bwd("bf16", qb, cb, inv_t, lse, label_offset, w_d, logq, ids_d, want_bf16=(True, True))
         dc_ref = np.empty_like(r["dc"]); dc_ref[perm] = r["dc"]
         assert rel_err(g["dq"].cpu().numpy(), r["dq"]) < BF16_RTOL
         assert rel_err(g["dc"].cpu().numpy(), dc_ref) < BF16_RTOL
         assert np.array_equal(g["dq_bf16"].float().cpu().numpy(), oracle.bf16_round(g["dq"].cpu().numpy()))
-        assert np.array_equal(g["dc_bf16_t"].float().cpu().numpy(), oracle.bf16_round(g["dc"].cpu().numpy()).T)
+        assert np.array_equal(g["dc_bf16"].float().cpu().numpy(), oracle.bf16_round(g["dc"].cpu().numpy()))
         return r
 
-    @pytest.mark.parametrize("nq,nc,d,off", [(128, 128, 64, 0), (256, 256, 128, 0), (1000, 1000, 128, 0), (8, 8, 64, 0),
+    @pytest.mark.parametrize("nq,nc,d,off", [(128, 128, 64, 0), (256, 256, 128, 0), (1000, 1000, 128, 0), (8, 8, 64, 0), (77, 203, 64, 100),
                                              (520, 1304, 256, 264), (384, 2048, 192, 1024), (4096, 4096, 128, 0)])
     def test_shapes_splits_and_label_offset(self, ops, nq, nc, d, off):
         _, q, c = self._inputs(nq, nc, d, nq + nc + d)
@@ -133,7 +129,7 @@ class TestRetrievalTensorCore:
         qb, cb = bf(U[g["uid"]]), bf(I[g["iid"]])
         loss, lse, _ = ops.retrieval_loss_fwd("bf16", qb, cb, 1.0 / cfg.temperature)
         assert float(loss.item()) == pytest.approx(float(g["temp_loss"]), rel=BF16_RTOL)
-        r = ops.retrieval_loss_bwd("bf16", qb, cb, ops.transpose_bf16(qb), ops.transpose_bf16(cb), 1.0 / cfg.temperature, lse)
+        r = ops.retrieval_loss_bwd("bf16", qb, cb, 1.0 / cfg.temperature, lse)
         assert rel_err(r["dq"].cpu().numpy(), g["temp_dq"]) < BF16_RTOL
         assert rel_err(r["dc"].cpu().numpy(), g["temp_dc"]) < BF16_RTOL
 
@@ -142,7 +138,7 @@ class TestRetrievalTensorCore:
         q = torch.full((B, d), 0.0625, device="cuda", dtype=torch.bfloat16); c = q.clone()
         loss, lse, _ = ops.retrieval_loss_fwd("bf16", q, c, 10.0)
         assert float(loss.item()) == pytest.approx(B * np.log(B), rel=1e-4)
-        g = ops.retrieval_loss_bwd("bf16", q, c, ops.transpose_bf16(q), ops.transpose_bf16(c), 10.0, lse)
+        g = ops.retrieval_loss_bwd("bf16", q, c, 10.0, lse)
         assert float(g["dq"].abs().max().item()) < 1e-3 and float(g["dc"].abs().max().item()) < 1e-3
 
 
@@ -297,3 +293,19 @@ class TestTopKTensorCore:
         m.update_state(torch.as_tensor(q).cuda(), torch.as_tensor(cands[true_idx]).cuda())
         o.update_state(q, cands[true_idx])
         assert m.result() == pytest.approx(o.result())
+
+
+class TestOperandMajorness:
+    """tcgen05 shared-memory descriptors: K-major and MN-major operands (both 128B-swizzled) must
+    give the same exact product, so no kernel needs a transposed copy of its input."""
+
+    @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+    @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 128, 128), (1000, 136, 200), (128, 256, 8192)])
+    def test_gemm_all_layouts_exact(self, tt, a_mn, b_mn, M, N, K):
+        rng = synth.rng_for(M + N + K)
+        A = synth.exact_matrix(rng, M, K, 3); B = synth.exact_matrix(rng, N, K, 3)
+        a_dev = bf(A.T.copy() if a_mn else A); b_dev = bf(B.T.copy() if b_mn else B)
+        out = torch.empty((M, N), dtype=torch.float32, device="cuda")
+        tt._lib.check(tt._lib.load().tt_debug_gemm_bf16(a_dev.data_ptr(), a_mn, b_dev.data_ptr(), b_mn, M, N, K,
+                                                         out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        assert np.array_equal(out.cpu().numpy().astype(np.float64), A.astype(np.float64) @ B.astype(np.float64).T)

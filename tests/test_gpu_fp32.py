@@ -162,13 +162,12 @@ class TestSparseOptimizer:
         rng = synth.rng_for(6)
         w = rng.normal(size=(24, 40)).astype(np.float32); parts = rng.normal(size=(3, 24, 40)).astype(np.float32)
         w_d, a_d = dev(w), dev(np.full_like(w, 0.1))
-        sh = torch.empty((24, 40), dtype=torch.bfloat16, device="cuda"); sht = torch.empty((40, 24), dtype=torch.bfloat16, device="cuda")
-        ops.dense_adagrad_update(w_d, a_d, dev(parts), 3, 0.05, 1e-7, 1e-3, sh, sht)
+        sh = torch.empty((24, 40), dtype=torch.bfloat16, device="cuda")
+        ops.dense_adagrad_update(w_d, a_d, dev(parts), 3, 0.05, 1e-7, 1e-3, sh)
         g = parts.astype(np.float64).sum(0) + 2e-3 * w
         w_ref, a_ref = oracle.adagrad_dense(w.astype(np.float64), np.full(w.shape, 0.1), g, 0.05, 1e-7)
         assert rel_err(w_d.cpu().numpy(), w_ref) < RTOL and rel_err(a_d.cpu().numpy(), a_ref) < RTOL
         assert np.array_equal(sh.float().cpu().numpy(), oracle.bf16_round(w_d.cpu().numpy()))
-        assert np.array_equal(sht.float().cpu().numpy(), oracle.bf16_round(w_d.cpu().numpy()).T)
         m_d, v_d, w2 = dev(np.zeros_like(w)), dev(np.zeros_like(w)), dev(w)
         alpha = 0.001 * np.sqrt(1 - 0.999) / (1 - 0.9)
         ops.dense_adam_update(w2, m_d, v_d, dev(parts[:1]), 1, float(alpha), 0.9, 0.999, 1e-7)
@@ -183,15 +182,15 @@ class TestDenseFp32:
         rng = synth.rng_for(M)
         x = np.maximum(rng.normal(size=(M, i)), 0).astype(np.float32)     # looks like a relu output
         k = oracle.glorot_uniform(rng, i, o); b = rng.normal(size=o).astype(np.float32) * 0.1
-        y, _, _ = ops.dense_fwd("fp32", dev(x), dev(k), dev(b), relu=True)
+        y, _ = ops.dense_fwd("fp32", dev(x), dev(k), dev(b), relu=True)
         ref = oracle.dense_forward(x.astype(np.float64), k, b, "relu")
         assert rel_err(y.cpu().numpy(), ref) < RTOL
         dy = rng.normal(size=(M, o)).astype(np.float32)
-        dx, _, _, dk, P, db = ops.dense_bwd("fp32", dev(dy), None, dev(x), None, dev(k), relu_mask_x=True, want_dx=True)
+        dx, _, dk, P, db = ops.dense_bwd("fp32", dev(dy), dev(x), dev(k), relu_mask_x=True, want_dx=True)
         assert P == 1
         assert rel_err(dx.cpu().numpy(), (dy.astype(np.float64) @ k.T) * (x > 0)) < RTOL
         assert rel_err(dk[0].cpu().numpy(), x.astype(np.float64).T @ dy) < RTOL
-        assert rel_err(db.cpu().numpy(), dy.astype(np.float64).sum(0)) < RTOL
+        assert rel_err(db.sum(0).cpu().numpy(), dy.astype(np.float64).sum(0)) < RTOL
 
 
 # ------------------------------------------------------------------------------- K3/K4
@@ -214,7 +213,7 @@ class TestRetrievalFp32:
         loss, lse, pos = ops.retrieval_loss_fwd("fp32", dev(q), dev(c), inv_t, label_offset, w_d, logq, ids_d)
         assert float(loss.item()) == pytest.approx(r["loss"], rel=RTOL)
         assert rel_err(lse.cpu().numpy(), r["lse"]) < RTOL and rel_err(pos.cpu().numpy(), r["pos"]) < RTOL
-        g = ops.retrieval_loss_bwd("fp32", dev(q), dev(c), None, None, inv_t, lse, label_offset, w_d, logq, ids_d)
+        g = ops.retrieval_loss_bwd("fp32", dev(q), dev(c), inv_t, lse, label_offset, w_d, logq, ids_d)
         dc_ref = np.empty_like(r["dc"]); dc_ref[perm] = r["dc"]
         assert rel_err(g["dq"].cpu().numpy(), r["dq"]) < RTOL
         assert rel_err(g["dc"].cpu().numpy(), dc_ref) < RTOL
@@ -243,7 +242,7 @@ class TestRetrievalFp32:
         q = torch.full((B, d), 0.05, device="cuda"); c = torch.full((B, d), 0.05, device="cuda")
         loss, lse, _ = ops.retrieval_loss_fwd("fp32", q, c, 10.0)
         assert float(loss.item()) == pytest.approx(B * np.log(B), rel=1e-5)
-        g = ops.retrieval_loss_bwd("fp32", q, c, None, None, 10.0, lse)
+        g = ops.retrieval_loss_bwd("fp32", q, c, 10.0, lse)
         assert float(g["dq"].abs().max().item()) < 1e-6
         assert float(g["dc"].abs().max().item()) < 1e-5    # each column of (softmax - eye) sums to 0
 

@@ -72,13 +72,13 @@ class CpuPrims:
         return torch.tensor([r["loss"]], dtype=torch.float64), torch.from_numpy(r["lse"]), torch.from_numpy(r["pos"])
 
     @classmethod
-    def retrieval_loss_bwd(cls, prec, q, c, q_t, c_t, inv_t, lse, label_offset=0, w=None, logq=None, ids=None,
-                           grad_scale=1.0, want_bf16=(False, False), want_bf16_t=(False, False)):
+    def retrieval_loss_bwd(cls, prec, q, c, inv_t, lse, label_offset=0, w=None, logq=None, ids=None,
+                           grad_scale=1.0, want_bf16=(False, False)):
         import oracle
         perm = cls._rot(q.shape[0], c.shape[0], label_offset)
         r = oracle.retrieval_loss_and_grads(q.numpy().astype(np.float64), c.numpy().astype(np.float64)[perm], temperature=1.0 / inv_t)
         dc = np.empty_like(r["dc"]); dc[perm] = r["dc"]
-        return dict(dq=torch.from_numpy(r["dq"]), dc=torch.from_numpy(dc), dq_bf16=None, dq_bf16_t=None, dc_bf16=None, dc_bf16_t=None)
+        return dict(dq=torch.from_numpy(r["dq"]), dc=torch.from_numpy(dc), dq_bf16=None, dc_bf16=None)
 
 
 def _free_port():

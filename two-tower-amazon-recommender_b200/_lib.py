@@ -44,20 +44,20 @@ SIGNATURES = {
     "tt_sparse_workspace_init": (C.c_int, [_p, _i64, _i64, _i64, _p]),
     "tt_sparse_adagrad_update": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _i32, _i64, _i64, _p, _f, _f, _p, _i64, _p, _p]),
     "tt_sparse_lazy_adam_update": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _p, _i32, _i64, _i64, _p, _f, _f, _f, _f, _p, _i64, _p, _p]),
-    "tt_dense_adagrad_update": (C.c_int, [_p, _p, _p, _i32, _i64, _i64, _f, _f, _f, _p, _p, _p]),
-    "tt_dense_adam_update": (C.c_int, [_p, _p, _p, _p, _i32, _i64, _i64, _f, _f, _f, _f, _f, _p, _p, _p]),
+    "tt_dense_adagrad_update": (C.c_int, [_p, _p, _p, _i32, _i64, _i64, _f, _f, _f, _p, _p]),
+    "tt_dense_adam_update": (C.c_int, [_p, _p, _p, _p, _i32, _i64, _i64, _f, _f, _f, _f, _f, _p, _p]),
     "tt_sum_squares": (C.c_int, [_p, _i64, _f, _p, _i32, _p]),
-    "tt_dense_fwd": (C.c_int, [_i32, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i32, _p]),
-    "tt_dense_bwd": (C.c_int, [_i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _i64, _i64, _i64, _i32, _p]),
+    "tt_dense_fwd": (C.c_int, [_i32, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i32, _p]),
+    "tt_dense_bwd": (C.c_int, [_i32, _p, _p, _p, _p, _p, _p, _i32, _p, _i64, _i64, _i64, _i32, _p]),
     "tt_dense_bwd_num_parts": (_i32, [_i32, _i64, _i64, _i64]),
     "tt_colsum_f32": (C.c_int, [_p, _p, _i64, _i64, _i32, _p]),
     "tt_sum_parts_f32": (C.c_int, [_p, _i32, _i64, _p, _p]),
-    "tt_transpose_bf16": (C.c_int, [_p, _p, _i64, _i64, _p]),
-    "tt_cast_f32_to_bf16": (C.c_int, [_p, _p, _p, _i64, _i64, _p]),
+    "tt_debug_gemm_bf16": (C.c_int, [_p, _i32, _p, _i32, _i64, _i64, _i64, _p, _p]),
+    "tt_cast_f32_to_bf16": (C.c_int, [_p, _p, _i64, _p]),
     "tt_retrieval_workspace_bytes": (_i64, [_i32, _i64, _i64, _i64]),
     "tt_retrieval_loss_fwd": (C.c_int, [_i32, _p, _p, _i64, _i64, _i64, _f, _i64, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
-    "tt_retrieval_loss_bwd": (C.c_int, [_i32, _p, _p, _p, _p, _i64, _i64, _i64, _f, _i64, _p, _p, _p, _p, _f,
-                                         _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
+    "tt_retrieval_loss_bwd": (C.c_int, [_i32, _p, _p, _i64, _i64, _i64, _f, _i64, _p, _p, _p, _p, _f,
+                                         _p, _p, _p, _p, _p, _i64, _p]),
     "tt_topk_num_splits": (_i32, [_i32, _i64, _i64, _i64, _i32]),
     "tt_topk_workspace_bytes": (_i64, [_i32, _i64, _i64, _i64, _i32]),
     "tt_topk_bruteforce": (C.c_int, [_i32, _p, _p, _i64, _i64, _i64, _i32, _i64, _p, _p, _p, _p, _i64, _p]),

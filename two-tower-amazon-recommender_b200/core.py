@@ -38,16 +38,15 @@ def device() -> torch.device:
 
 
 class Tensor:
-    """Activations of one layer: any of an fp32 copy, a bf16 copy and a transposed bf16 copy.
+    """Activations of one layer: an fp32 copy and/or a bf16 copy.
     ``grad_formats`` tells the consumer which gradient representations the producer needs."""
 
-    def __init__(self, f32=None, bf16=None, bf16_t=None, grad_formats=("f32",), producer=None):
+    def __init__(self, f32=None, bf16=None, grad_formats=("f32",), producer=None):
         self.f32: Optional[torch.Tensor] = f32
         self.bf16: Optional[torch.Tensor] = bf16
-        self.bf16_t: Optional[torch.Tensor] = bf16_t
         self.grad_formats = tuple(grad_formats)
         self.producer = producer
-        self.grad = None          # dict(f32=..., bf16=..., bf16_t=...) set by the consumer's backward
+        self.grad = None          # dict(f32=..., bf16=...) set by the consumer's backward
         self.relu_output = False  # True when this is the output of a relu Dense
         self.producer_needs_grad = True   # False for constants fed in by the user
 
@@ -99,9 +98,8 @@ class Variable:
         self.value = value            # fp32 master copy
         self.kind = kind              # "table" | "kernel" | "bias"
         self.l2 = float(l2)
-        self.want_shadows = False     # keep bf16 copies of the value in step with it
+        self.want_shadows = False     # keep a bf16 copy of the value in step with it
         self.shadow = None            # bf16 [rows, cols]   (kernel only, bf16 precision)
-        self.shadow_t = None          # bf16 [cols, rows]
         self.grad = None
         self.slots = {}               # optimizer state
 
@@ -123,7 +121,7 @@ class Variable:
     def refresh_shadows(self) -> None:
         from . import ops
         if self.want_shadows:
-            self.shadow, self.shadow_t = ops.cast_f32_to_bf16(self.value, want=True, want_t=True)
+            self.shadow = ops.cast_f32_to_bf16(self.value)
 
 
 class GradientTape:

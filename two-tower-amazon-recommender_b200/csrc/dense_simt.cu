@@ -7,11 +7,11 @@
 
 namespace tt {
 
-int tc_dense_fwd(const void* x, const void* kernel_t, const float* bias, void* y, void* y_t, float* y_f32,
+int tc_dense_fwd(const void* x, const void* kernel, const float* bias, void* y, float* y_f32,
                  int64_t M, int64_t in_dim, int64_t out_dim, int relu, cudaStream_t stream);
-int tc_dense_bwd(const void* dy, const void* dy_t, const void* x, const void* x_t, const void* kernel,
-                 void* dx, void* dx_t, float* dx_f32, float* dkernel_parts, int num_parts, float* dbias,
-                 int64_t M, int64_t in_dim, int64_t out_dim, int relu_mask_x, cudaStream_t stream);
+int tc_dense_bwd(const void* dy, const void* x, const void* kernel, void* dx, float* dx_f32,
+                 float* dkernel_parts, int num_parts, float* dbias_parts, int64_t M, int64_t in_dim,
+                 int64_t out_dim, int relu_mask_x, cudaStream_t stream);
 int tc_dense_bwd_num_parts(int64_t M, int64_t in_dim, int64_t out_dim);
 
 constexpr int BM = 64, BN = 64, BK = 16;
@@ -109,33 +109,14 @@ sum_parts_kernel(const float* __restrict__ parts, int num_parts, int64_t n, floa
 }
 
 __global__ void __launch_bounds__(256)
-transpose_bf16_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int64_t rows, int64_t cols) {
-  __shared__ uint16_t tile[32][34];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
-  for (int i = ty; i < 32; i += 8)
-    if (r0 + i < rows && c0 + tx < cols) tile[i][tx] = in[(r0 + i) * cols + c0 + tx];
-  __syncthreads();
-  for (int i = ty; i < 32; i += 8)
-    if (c0 + i < cols && r0 + tx < rows) out[(c0 + i) * rows + r0 + tx] = tile[tx][i];
-}
-
-__global__ void __launch_bounds__(256)
-cast_bf16_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, uint16_t* __restrict__ out_t,
-                 int64_t rows, int64_t cols) {
-  __shared__ uint16_t tile[32][34];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
-  for (int i = ty; i < 32; i += 8)
-    if (r0 + i < rows && c0 + tx < cols) {
-      uint16_t b = float_to_bf16_bits(in[(r0 + i) * cols + c0 + tx]);
-      tile[i][tx] = b;
-      if (out) out[(r0 + i) * cols + c0 + tx] = b;
-    }
-  __syncthreads();
-  if (out_t)
-    for (int i = ty; i < 32; i += 8)
-      if (c0 + i < cols && r0 + tx < rows) out_t[(c0 + i) * rows + r0 + tx] = tile[tx][i];
+cast_bf16_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, int64_t n) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(in + i);
+    *reinterpret_cast<uint2*>(out + i) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  } else {
+    for (int64_t k = i; k < n; ++k) out[k] = float_to_bf16_bits(in[k]);
+  }
 }
 
 static int sgemm(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k, int64_t sb_n,
@@ -153,17 +134,17 @@ static int sgemm(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int
 using namespace tt;
 
 extern "C" int tt_dense_fwd(int32_t precision, const void* x, const void* kernel, const float* bias,
-                            void* y, void* y_t, float* y_f32, int64_t M, int64_t in_dim, int64_t out_dim,
+                            void* y, float* y_f32, int64_t M, int64_t in_dim, int64_t out_dim,
                             int32_t relu, void* stream) {
   TT_REQUIRE(x && kernel && y, "tt_dense_fwd: null buffer");
   TT_REQUIRE(M > 0 && in_dim > 0 && out_dim > 0 && M < (1ll << 31), "tt_dense_fwd: bad sizes");
   if (precision == TT_F32) {
-    TT_REQUIRE(y_t == nullptr && y_f32 == nullptr, "tt_dense_fwd: y_t / y_f32 are bf16-path outputs");
+    TT_REQUIRE(y_f32 == nullptr, "tt_dense_fwd: y_f32 is a bf16-path output");
     return sgemm((const float*)x, in_dim, 1, (const float*)kernel, out_dim, 1, (float*)y, out_dim, M, out_dim,
                  in_dim, bias, relu, nullptr, (cudaStream_t)stream);
   }
   TT_REQUIRE(precision == TT_BF16, "tt_dense_fwd: unknown precision %d", precision);
-  return tc_dense_fwd(x, kernel, bias, y, y_t, y_f32, M, in_dim, out_dim, relu, (cudaStream_t)stream);
+  return tc_dense_fwd(x, kernel, bias, y, y_f32, M, in_dim, out_dim, relu, (cudaStream_t)stream);
 }
 
 extern "C" int32_t tt_dense_bwd_num_parts(int32_t precision, int64_t M, int64_t in_dim, int64_t out_dim) {
@@ -171,16 +152,15 @@ extern "C" int32_t tt_dense_bwd_num_parts(int32_t precision, int64_t M, int64_t 
   return tc_dense_bwd_num_parts(M, in_dim, out_dim);
 }
 
-extern "C" int tt_dense_bwd(int32_t precision, const void* dy, const void* dy_t, const void* x,
-                            const void* x_t, const void* kernel, void* dx, void* dx_t, float* dx_f32,
-                            float* dkernel_parts, int32_t num_parts, float* dbias, int64_t M,
-                            int64_t in_dim, int64_t out_dim, int32_t relu_mask_x, void* stream) {
+extern "C" int tt_dense_bwd(int32_t precision, const void* dy, const void* x, const void* kernel, void* dx,
+                            float* dx_f32, float* dkernel_parts, int32_t num_parts, float* dbias_parts,
+                            int64_t M, int64_t in_dim, int64_t out_dim, int32_t relu_mask_x, void* stream) {
   TT_REQUIRE(dy && x && kernel && dkernel_parts, "tt_dense_bwd: null buffer");
   TT_REQUIRE(M > 0 && in_dim > 0 && out_dim > 0 && M < (1ll << 31), "tt_dense_bwd: bad sizes");
   cudaStream_t st = (cudaStream_t)stream;
   if (precision == TT_F32) {
     TT_REQUIRE(num_parts == 1, "tt_dense_bwd: fp32 path writes a single gradient part");
-    TT_REQUIRE(dx_t == nullptr && dx_f32 == nullptr, "tt_dense_bwd: dx_t / dx_f32 are bf16-path outputs");
+    TT_REQUIRE(dx_f32 == nullptr, "tt_dense_bwd: dx_f32 is a bf16-path output");
     int rc;
     if (dx) {   // dx = dy[M,out] @ kernel[in,out]^T  (* relu mask of x)
       rc = sgemm((const float*)dy, out_dim, 1, (const float*)kernel, 1, out_dim, (float*)dx, in_dim, M, in_dim,
@@ -191,16 +171,16 @@ extern "C" int tt_dense_bwd(int32_t precision, const void* dy, const void* dy_t,
     rc = sgemm((const float*)x, 1, in_dim, (const float*)dy, out_dim, 1, dkernel_parts, out_dim, in_dim, out_dim,
                M, nullptr, 0, nullptr, st);
     if (rc) return rc;
-    if (dbias) {
+    if (dbias_parts) {
       TT_PROF("colsum_f32_kernel", st);
-      colsum_f32_kernel<<<(unsigned)ceil_div(out_dim, 32), 256, 0, st>>>((const float*)dy, dbias, M, out_dim, M);
+      colsum_f32_kernel<<<(unsigned)ceil_div(out_dim, 32), 256, 0, st>>>((const float*)dy, dbias_parts, M, out_dim, M);
       TT_LAUNCH_OK("colsum_f32_kernel");
     }
     return TT_OK;
   }
   TT_REQUIRE(precision == TT_BF16, "tt_dense_bwd: unknown precision %d", precision);
-  return tc_dense_bwd(dy, dy_t, x, x_t, kernel, dx, dx_t, dx_f32, dkernel_parts, num_parts, dbias, M, in_dim,
-                      out_dim, relu_mask_x, st);
+  return tc_dense_bwd(dy, x, kernel, dx, dx_f32, dkernel_parts, num_parts, dbias_parts, M, in_dim, out_dim,
+                      relu_mask_x, st);
 }
 
 extern "C" int tt_colsum_f32(const float* x, float* out_parts, int64_t rows, int64_t cols, int32_t num_parts,
@@ -222,21 +202,11 @@ extern "C" int tt_sum_parts_f32(const float* parts, int32_t num_parts, int64_t n
   return TT_OK;
 }
 
-extern "C" int tt_transpose_bf16(const uint16_t* in, uint16_t* out, int64_t rows, int64_t cols, void* stream) {
-  TT_REQUIRE(in && out && rows > 0 && cols > 0, "tt_transpose_bf16: bad arguments");
-  dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32));
-  TT_PROF("transpose_bf16_kernel", (cudaStream_t)stream);
-  transpose_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, rows, cols);
-  TT_LAUNCH_OK("transpose_bf16_kernel");
-  return TT_OK;
-}
-
-extern "C" int tt_cast_f32_to_bf16(const float* in, uint16_t* out, uint16_t* out_t, int64_t rows,
-                                   int64_t cols, void* stream) {
-  TT_REQUIRE(in && (out || out_t) && rows > 0 && cols > 0, "tt_cast_f32_to_bf16: bad arguments");
-  dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32));
+extern "C" int tt_cast_f32_to_bf16(const float* in, uint16_t* out, int64_t n, void* stream) {
+  TT_REQUIRE(in && out && n > 0, "tt_cast_f32_to_bf16: bad arguments");
+  TT_REQUIRE(aligned16(in) && (reinterpret_cast<uintptr_t>(out) & 7u) == 0, "tt_cast_f32_to_bf16: unaligned buffers");
   TT_PROF("cast_bf16_kernel", (cudaStream_t)stream);
-  cast_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, out_t, rows, cols);
+  cast_bf16_kernel<<<(unsigned)ceil_div(ceil_div(n, 4), 256), 256, 0, (cudaStream_t)stream>>>(in, out, n);
   TT_LAUNCH_OK("cast_bf16_kernel");
   return TT_OK;
 }

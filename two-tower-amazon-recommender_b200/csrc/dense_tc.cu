@@ -21,7 +21,6 @@ struct GemmEpilogue {
   const float* bias;       // [N] or null
   const uint16_t* mask;    // bf16 [M, N]: output zeroed where mask <= 0 (ReLU gradient) or null
   uint16_t* out_bf16;      // [M, N] or null
-  uint16_t* out_bf16_t;    // [N, M] or null
   float* out_f32;          // [splits, M, N] or null
   int M, N, K;
   int k_per_split;         // multiple of 64
@@ -38,7 +37,9 @@ struct GemmSmem {
   static constexpr int TOTAL = BAR_OFF + (2 * GEMM_STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
 };
 
-template <int BN>
+// A_MN / B_MN: that operand is stored with its M (resp. N) dimension contiguous, i.e. global
+// A is [K, M] (resp. B is [K, N]) row-major; otherwise [M, K] (resp. [N, K]).
+template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmEpilogue ep) {
   using L = GemmSmem<BN>;
@@ -80,23 +81,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&full[s], L::A_BYTES + L::B_BYTES);
         const int k = k_begin + kb * GEMM_BK;
-        tma_load_2d(sA + s * L::A_BYTES, &tmA, &full[s], k, m0);
-        tma_load_2d(sB + s * L::B_BYTES, &tmB, &full[s], k, n0);
+        if (A_MN) {
+          for (int c = 0; c < GEMM_BM / 64; ++c) tma_load_2d(sA + s * L::A_BYTES + c * 8192, &tmA, &full[s], m0 + 64 * c, k);
+        } else {
+          tma_load_2d(sA + s * L::A_BYTES, &tmA, &full[s], k, m0);
+        }
+        if (B_MN) {
+          for (int c = 0; c < BN / 64; ++c) tma_load_2d(sB + s * L::B_BYTES + c * 8192, &tmB, &full[s], n0 + 64 * c, k);
+        } else {
+          tma_load_2d(sB + s * L::B_BYTES, &tmB, &full[s], k, n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % GEMM_STAGES;
         const uint32_t ph = (kb / GEMM_STAGES) & 1;
         mbar_wait(&full[s], ph);
         tc_fence_after();
-        const uint64_t da = umma_desc_k_sw128(smem_u32(sA + s * L::A_BYTES));
-        const uint64_t db = umma_desc_k_sw128(smem_u32(sB + s * L::B_BYTES));
+        const uint64_t da = A_MN ? umma_desc_mn_sw128(smem_u32(sA + s * L::A_BYTES), 8192) : umma_desc_k_sw128(smem_u32(sA + s * L::A_BYTES));
+        const uint64_t db = B_MN ? umma_desc_mn_sw128(smem_u32(sB + s * L::B_BYTES), 8192) : umma_desc_k_sw128(smem_u32(sB + s * L::B_BYTES));
 #pragma unroll
         for (int k = 0; k < GEMM_BK / 16; ++k)
-          umma_bf16_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          umma_bf16_ss(tmem_base, da + (A_MN ? 128 : 2) * k, db + (B_MN ? 128 : 2) * k, idesc, (kb | k) != 0);
         umma_commit(&empty[s]);
       }
       umma_commit(tmem_full);
@@ -164,11 +173,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int g = 0; g < 8; ++g)
             if (col0 + g * 4 < ep.N) op[g] = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
         }
-        if (ep.out_bf16_t) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < ep.N) ep.out_bf16_t[(size_t)(col0 + j) * ep.M + row] = float_to_bf16_bits(v[j]);
-        }
       }
     }
   }
@@ -177,22 +181,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// row sums of a bf16 [rows, cols] matrix in fp32 (dbias = colsum(dy) read from dy_t)
+// out[p][n] = sum over the p-th row slice of a bf16 [M, N] matrix, fp32, fixed order
+// (dbias = colsum(dy) for hidden layers).  grid (ceil(N/64), parts); 256 threads = 32 column
+// pairs x 8 row groups.
 __global__ void __launch_bounds__(256)
-rowsum_bf16_kernel(const uint16_t* __restrict__ x, float* __restrict__ out, int64_t rows, int64_t cols) {
-  const int lane = threadIdx.x & 31;
-  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= rows) return;
-  const uint16_t* p = x + r * cols;
-  float s = 0.f;
-  for (int64_t c = lane * 8; c < cols; c += 256) {     // cols % 8 == 0
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p + c));
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+colsum_bf16_kernel(const uint16_t* __restrict__ X, float* __restrict__ out, int64_t M, int64_t N, int64_t rows_per_part) {
+  __shared__ float part[8][64];
+  const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int64_t n = (int64_t)blockIdx.x * 64 + 2 * c;
+  const int64_t m_lo = (int64_t)blockIdx.y * rows_per_part, m_hi = min(M, m_lo + rows_per_part);
+  float s0 = 0.f, s1 = 0.f;
+  if (n < N)
+    for (int64_t m = m_lo + g; m < m_hi; m += 8) {
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(X + m * N + n);
+      s0 += __uint_as_float(w << 16);
+      s1 += __uint_as_float(w & 0xffff0000u);
+    }
+  part[g][2 * c] = s0; part[g][2 * c + 1] = s1;
+  __syncthreads();
+  if (g == 0 && n < N) {
+    float t0 = 0.f, t1 = 0.f;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) s += __uint_as_float(w[t] << 16) + __uint_as_float(w[t] & 0xffff0000u);
+    for (int i = 0; i < 8; ++i) { t0 += part[i][2 * c]; t1 += part[i][2 * c + 1]; }
+    out[(int64_t)blockIdx.y * N + n] = t0;
+    out[(int64_t)blockIdx.y * N + n + 1] = t1;
   }
-  s = warp_sum(s);
-  if (lane == 0) out[r] = s;
 }
 
 // ---- host ----------------------------------------------------------------------------
@@ -230,38 +243,60 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64
   return TT_OK;
 }
 
-// D[M,N] = A[M,K] * B[N,K]^T (+ epilogue); splits over K write out_f32[z].
-int launch_gemm_tc(const void* A, const void* B, int64_t M, int64_t N, int64_t K, int splits, int k_per_split,
-                   GemmEpilogue ep, cudaStream_t st) {
-  TT_REQUIRE(K % 8 == 0 && N % 8 == 0, "bf16 GEMM needs K %% 8 == 0 and N %% 8 == 0 (got K=%lld N=%lld)", (long long)K, (long long)N);
+// D[M,N] = A * B^T-or-B (+ epilogue); splits over K write out_f32[z].
+// a_mn == 0: A is [M, K] row-major; a_mn == 1: A is [K, M] row-major (M contiguous).
+// b_mn == 0: B is [N, K] row-major; b_mn == 1: B is [K, N] row-major (N contiguous).
+int launch_gemm_tc(const void* A, int a_mn, const void* B, int b_mn, int64_t M, int64_t N, int64_t K, int splits,
+                   int k_per_split, GemmEpilogue ep, cudaStream_t st) {
+  TT_REQUIRE(K % 8 == 0 && N % 8 == 0 && (!a_mn || M % 8 == 0), "bf16 GEMM needs M, N, K multiples of 8 (got M=%lld N=%lld K=%lld)", (long long)M, (long long)N, (long long)K);
   TT_REQUIRE(aligned16(A) && aligned16(B), "bf16 GEMM operands must be 16-byte aligned");
   constexpr int BN = 128;
   CUtensorMap tmA, tmB;
-  int rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, GEMM_BK, GEMM_BM);
+  int rc = a_mn ? make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)M * 2, 64, GEMM_BK)
+                : make_tmap_bf16_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, GEMM_BK, GEMM_BM);
   if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, GEMM_BK, BN);
+  rc = b_mn ? make_tmap_bf16_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)N * 2, 64, GEMM_BK)
+            : make_tmap_bf16_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, GEMM_BK, BN);
   if (rc) return rc;
   ep.M = (int)M; ep.N = (int)N; ep.K = (int)K; ep.k_per_split = k_per_split;
   dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, GEMM_BM), (unsigned)splits);
   const int smem = GemmSmem<BN>::TOTAL;
-  TT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  TT_PROF("gemm_tc_kernel", st);
-  gemm_tc_kernel<BN><<<grid, 192, smem, st>>>(tmA, tmB, ep);
+#define TT_GEMM(AMN, BMN)                                                                                          \
+  {                                                                                                                \
+    TT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, AMN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    TT_PROF("gemm_tc_kernel", st), gemm_tc_kernel<BN, AMN, BMN><<<grid, 192, smem, st>>>(tmA, tmB, ep);            \
+  }
+  if (a_mn && b_mn) TT_GEMM(true, true) else if (a_mn) TT_GEMM(true, false) else if (b_mn) TT_GEMM(false, true) else TT_GEMM(false, false)
+#undef TT_GEMM
   TT_LAUNCH_OK("gemm_tc_kernel");
   return TT_OK;
 }
 
-int tc_dense_fwd(const void* x, const void* kernel_t, const float* bias, void* y, void* y_t, float* y_f32,
+}  // namespace tt
+
+// Test hook (tests/test_gpu_bf16.py): plain bf16 GEMM in every operand-major combination, fp32 out.
+extern "C" int tt_debug_gemm_bf16(const void* A, int32_t a_mn, const void* B, int32_t b_mn, int64_t M, int64_t N, int64_t K,
+                                  float* out, void* stream) {
+  tt::GemmEpilogue ep{};
+  ep.out_f32 = out;
+  return tt::launch_gemm_tc(A, a_mn, B, b_mn, M, N, K, 1, (int)tt::round_up(K, tt::GEMM_BK), ep, (cudaStream_t)stream);
+}
+
+namespace tt {
+
+int tc_dense_fwd(const void* x, const void* kernel, const float* bias, void* y, float* y_f32,
                  int64_t M, int64_t in_dim, int64_t out_dim, int relu, cudaStream_t stream) {
   GemmEpilogue ep{};
   ep.bias = bias; ep.relu = relu;
-  ep.out_bf16 = (uint16_t*)y; ep.out_bf16_t = (uint16_t*)y_t; ep.out_f32 = y_f32;
-  return launch_gemm_tc(x, kernel_t, M, out_dim, in_dim, 1, (int)round_up(in_dim, GEMM_BK), ep, stream);
+  ep.out_bf16 = (uint16_t*)y; ep.out_f32 = y_f32;
+  // y[M,out] = x[M,in] * kernel[in,out]: B is the Keras-layout kernel itself (N contiguous)
+  return launch_gemm_tc(x, 0, kernel, 1, M, out_dim, in_dim, 1, (int)round_up(in_dim, GEMM_BK), ep, stream);
 }
 
 static void wgrad_split(int64_t M, int64_t in_dim, int64_t out_dim, int* parts, int* k_per_split) {
   const int64_t tiles = ceil_div(in_dim, GEMM_BM) * ceil_div(out_dim, 128);
   int64_t want = std::max<int64_t>(1, num_sms() / tiles);
+  if (want > 32) want = 32;
   int64_t kps = round_up(ceil_div(M, want), GEMM_BK);
   if (kps < 2 * GEMM_BK) kps = 2 * GEMM_BK;
   *k_per_split = (int)kps;
@@ -274,32 +309,33 @@ int tc_dense_bwd_num_parts(int64_t M, int64_t in_dim, int64_t out_dim) {
   return parts;
 }
 
-int tc_dense_bwd(const void* dy, const void* dy_t, const void* x, const void* x_t, const void* kernel,
-                 void* dx, void* dx_t, float* dx_f32, float* dkernel_parts, int num_parts, float* dbias,
-                 int64_t M, int64_t in_dim, int64_t out_dim, int relu_mask_x, cudaStream_t stream) {
-  TT_REQUIRE(dy_t && x_t, "tt_dense_bwd(bf16): the transposed copies dy_t and x_t are required");
+int tc_dense_bwd(const void* dy, const void* x, const void* kernel, void* dx, float* dx_f32,
+                 float* dkernel_parts, int num_parts, float* dbias_parts, int64_t M, int64_t in_dim,
+                 int64_t out_dim, int relu_mask_x, cudaStream_t stream) {
   TT_REQUIRE(M % 8 == 0, "tt_dense_bwd(bf16): batch must be a multiple of 8 (got %lld)", (long long)M);
+  TT_REQUIRE(out_dim % 2 == 0, "tt_dense_bwd(bf16): out_dim must be even");
   int parts, kps;
   wgrad_split(M, in_dim, out_dim, &parts, &kps);
   TT_REQUIRE(num_parts == parts, "tt_dense_bwd(bf16): num_parts=%d, expected tt_dense_bwd_num_parts()=%d", num_parts, parts);
   int rc;
-  if (dx || dx_t || dx_f32) {      // dx[M,in] = dy[M,out] * kernel[in,out]^T
+  if (dx || dx_f32) {              // dx[M,in] = dy[M,out] * kernel[in,out]^T  (kernel is [N=in, K=out]: K-major)
     GemmEpilogue ep{};
     ep.mask = relu_mask_x ? (const uint16_t*)x : nullptr;
-    ep.out_bf16 = (uint16_t*)dx; ep.out_bf16_t = (uint16_t*)dx_t; ep.out_f32 = dx_f32;
-    rc = launch_gemm_tc(dy, kernel, M, in_dim, out_dim, 1, (int)round_up(out_dim, GEMM_BK), ep, stream);
+    ep.out_bf16 = (uint16_t*)dx; ep.out_f32 = dx_f32;
+    rc = launch_gemm_tc(dy, 0, kernel, 0, M, in_dim, out_dim, 1, (int)round_up(out_dim, GEMM_BK), ep, stream);
     if (rc) return rc;
   }
-  {                                // dkernel[in,out] = x_t[in,M] * dy_t[out,M]^T, split over M
+  {                                // dkernel[in,out] = x[M,in]^T * dy[M,out]: both operands MN-major, split over M
     GemmEpilogue ep{};
     ep.out_f32 = dkernel_parts;
-    rc = launch_gemm_tc(x_t, dy_t, in_dim, out_dim, M, parts, kps, ep, stream);
+    rc = launch_gemm_tc(x, 1, dy, 1, in_dim, out_dim, M, parts, kps, ep, stream);
     if (rc) return rc;
   }
-  if (dbias) {
-    TT_PROF("rowsum_bf16_kernel", stream);
-    rowsum_bf16_kernel<<<(unsigned)ceil_div(out_dim, 8), 256, 0, stream>>>((const uint16_t*)dy_t, dbias, out_dim, M);
-    TT_LAUNCH_OK("rowsum_bf16_kernel");
+  if (dbias_parts) {               // [num_parts, out]: same row slices as the wgrad split
+    dim3 grid((unsigned)ceil_div(out_dim, 64), (unsigned)parts);
+    TT_PROF("colsum_bf16_kernel", stream);
+    colsum_bf16_kernel<<<grid, 256, 0, stream>>>((const uint16_t*)dy, dbias_parts, M, out_dim, kps);
+    TT_LAUNCH_OK("colsum_bf16_kernel");
   }
   return TT_OK;
 }

@@ -15,11 +15,10 @@ namespace tt {
 int tc_retrieval_fwd(const void* q, const void* c, int64_t nq, int64_t nc, int64_t d, float inv_temp,
                      int64_t label_offset, const float* w, const float* logq, const int64_t* cand_ids,
                      float* row_lse, float* row_pos, float* loss, void* ws, int64_t ws_bytes, cudaStream_t st);
-int tc_retrieval_bwd(const void* q, const void* c, const void* q_t, const void* c_t, int64_t nq, int64_t nc,
+int tc_retrieval_bwd(const void* q, const void* c, int64_t nq, int64_t nc,
                      int64_t d, float inv_temp, int64_t label_offset, const float* w, const float* logq,
                      const int64_t* cand_ids, const float* row_lse, float grad_scale, float* dq, float* dc,
-                     uint16_t* dq_bf16, uint16_t* dq_bf16_t, uint16_t* dc_bf16, uint16_t* dc_bf16_t, void* ws,
-                     int64_t ws_bytes, cudaStream_t st);
+                     uint16_t* dq_bf16, uint16_t* dc_bf16, void* ws, int64_t ws_bytes, cudaStream_t st);
 int64_t tc_retrieval_workspace_bytes(int64_t nq, int64_t nc, int64_t d);
 
 struct RetrievalArgs {
@@ -282,24 +281,21 @@ extern "C" int tt_retrieval_loss_fwd(int32_t precision, const void* q, const voi
   return launch_loss_reduce(row_lse, row_pos, sample_weight, nq, loss, st);
 }
 
-extern "C" int tt_retrieval_loss_bwd(int32_t precision, const void* q, const void* c, const void* q_t,
-                                     const void* c_t, int64_t nq, int64_t nc, int64_t d,
-                                     float inv_temperature, int64_t label_offset,
+extern "C" int tt_retrieval_loss_bwd(int32_t precision, const void* q, const void* c, int64_t nq, int64_t nc,
+                                     int64_t d, float inv_temperature, int64_t label_offset,
                                      const float* sample_weight, const float* cand_log_q,
                                      const int64_t* cand_ids, const float* row_lse, float grad_scale,
-                                     float* dq, float* dc, uint16_t* dq_bf16, uint16_t* dq_bf16_t,
-                                     uint16_t* dc_bf16, uint16_t* dc_bf16_t, void* workspace,
-                                     int64_t workspace_bytes, void* stream) {
+                                     float* dq, float* dc, uint16_t* dq_bf16, uint16_t* dc_bf16,
+                                     void* workspace, int64_t workspace_bytes, void* stream) {
   int rc = check_retrieval_common("tt_retrieval_loss_bwd", precision, q, c, nq, nc, d, label_offset);
   if (rc) return rc;
   TT_REQUIRE(row_lse && dq && dc, "tt_retrieval_loss_bwd: null buffer");
   TT_REQUIRE(aligned16(dq) && aligned16(dc), "tt_retrieval_loss_bwd: gradients must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   if (precision == TT_BF16)
-    return tc_retrieval_bwd(q, c, q_t, c_t, nq, nc, d, inv_temperature, label_offset, sample_weight, cand_log_q,
-                            cand_ids, row_lse, grad_scale, dq, dc, dq_bf16, dq_bf16_t, dc_bf16, dc_bf16_t,
-                            workspace, workspace_bytes, st);
-  TT_REQUIRE(!dq_bf16 && !dq_bf16_t && !dc_bf16 && !dc_bf16_t, "tt_retrieval_loss_bwd: bf16 copies are bf16-path outputs");
+    return tc_retrieval_bwd(q, c, nq, nc, d, inv_temperature, label_offset, sample_weight, cand_log_q,
+                            cand_ids, row_lse, grad_scale, dq, dc, dq_bf16, dc_bf16, workspace, workspace_bytes, st);
+  TT_REQUIRE(!dq_bf16 && !dc_bf16, "tt_retrieval_loss_bwd: bf16 copies are bf16-path outputs");
   RetrievalArgs a{(const float*)q, (const float*)c, nq, nc, (int)d, inv_temperature, label_offset, sample_weight,
                   cand_log_q, cand_ids, row_lse, grad_scale, nullptr, nullptr, dq};
   rc = launch_retrieval<1>(a, st);

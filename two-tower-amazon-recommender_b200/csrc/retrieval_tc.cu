@@ -11,7 +11,8 @@
 // backward (retrieval_bwd_tc_kernel<TRANSPOSED>): the same streaming structure, plus a second
 //   GEMM per tile.  The softmax warps turn S into dS = softmax - eye (bf16) and store it to
 //   shared memory in the 128B-swizzled K-major layout; the MMA thread then accumulates
-//   dX[128, d] += dS[128, BN] * Y^T-tile into a TMEM accumulator.  TRANSPOSED = false keeps
+//   dX[128, d] += dS[128, BN] * Y-tile into a TMEM accumulator, reading the SAME shared-memory Y
+//   tile as an MN-major B operand (no transposed copy is loaded or kept in HBM).  TRANSPOSED = false keeps
 //   query rows stationary (dQ); TRANSPOSED = true keeps candidate rows stationary and streams
 //   queries (dC).  S is recomputed in each pass (5 GEMM units for 3 algorithmic ones).
 //
@@ -240,7 +241,7 @@ retrieval_fwd_finalize_kernel(const float2* __restrict__ partial, int splits, in
 // backward
 // ---------------------------------------------------------------------------------------
 struct BwdLayout {
-  int x_bytes, y_bytes, yt_bytes, ds_bytes, stage_bytes, stages, total;
+  int x_bytes, y_bytes, ds_bytes, stage_bytes, stages, total;
 };
 // tail = barriers (256 B) + per-column lse/weight vectors (2 KB) + per-column ids (2 KB)
 __host__ __device__ inline int bwd_tail_bytes(bool transposed, bool extras) {
@@ -250,9 +251,8 @@ __host__ __device__ inline BwdLayout bwd_layout(int d, int BN, int tail_bytes) {
   BwdLayout L;
   L.x_bytes = RT_BM * d * 2;
   L.y_bytes = BN * d * 2;
-  L.yt_bytes = d * BN * 2;
   L.ds_bytes = RT_BM * BN * 2;
-  L.stage_bytes = L.y_bytes + L.yt_bytes;
+  L.stage_bytes = L.y_bytes;
   const int budget = 227 * 1024 - tail_bytes - L.x_bytes - 2 * L.ds_bytes;
   L.stages = budget / L.stage_bytes;
   if (L.stages > 4) L.stages = 4;
@@ -263,7 +263,7 @@ __host__ __device__ inline BwdLayout bwd_layout(int d, int BN, int tail_bytes) {
 template <int BN, bool TRANSPOSED, bool EXTRAS>
 __global__ void __launch_bounds__(RT_THREADS, 1)
 retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
-                        const __grid_constant__ CUtensorMap tmYT, const RetrievalTcArgs a) {
+                        const RetrievalTcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;      // no slack: the swizzled tiles need the 1024-byte alignment the declaration asks for
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
@@ -272,7 +272,7 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   const int STAGES = L.stages;
   uint8_t* sX = smem;
   uint8_t* sDS = sX + L.x_bytes;                      // [2][BN/64][128 x 64] bf16, SW128
-  uint8_t* sY = sDS + 2 * L.ds_bytes;                 // per stage: Y tile then Y^T tile
+  uint8_t* sY = sDS + 2 * L.ds_bytes;                 // per stage: Y tile [d/64][BN x 64], SW128
   uint8_t* tail = sY + STAGES * L.stage_bytes;
   uint64_t* x_full = reinterpret_cast<uint64_t*>(tail);
   uint64_t* full = x_full + 1;
@@ -298,7 +298,7 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   const uint32_t ACC_COL = 2 * BN;                    // TMEM: [S0 | S1 | acc(d)]
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmY); tma_prefetch_desc(&tmYT);
+    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmY);
     mbar_init(x_full, 1);
     for (int s = 0; s < 4; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) {
@@ -325,13 +325,12 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         uint8_t* base = sY + s * L.stage_bytes;
         const int y0 = (tile_begin + t) * BN;
         for (int kb = 0; kb < nkb; ++kb) tma_load_2d(base + kb * BN * 128, &tmY, &full[s], kb * 64, y0);
-        for (int jb = 0; jb < BN / 64; ++jb) tma_load_2d(base + L.y_bytes + jb * d * 128, &tmYT, &full[s], y0 + jb * 64, 0);
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && T > 0) {
       constexpr uint32_t idesc1 = umma_idesc_bf16(RT_BM, BN);
-      const uint32_t idesc2 = umma_idesc_bf16(RT_BM, d);
+      const uint32_t idesc2 = umma_idesc_bf16(RT_BM, d, 0, 1);     // B = Y tile read MN-major (N = d contiguous)
       mbar_wait(x_full, 0);
       auto issue_mma1 = [&](int t) {
         const int s = t % STAGES, b = t & 1;
@@ -352,11 +351,14 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         const int s = t % STAGES, b = t & 1;
         mbar_wait(&ds_full[b], (t >> 1) & 1);
         tc_fence_after();
+        // K = the BN streamed rows: 16 rows (2048 B) per MMA; the d/64 column chunks of the Y tile
+        // are BN*128 bytes apart (LBO)
+        const uint64_t db0 = umma_desc_mn_sw128(smem_u32(sY + s * L.stage_bytes), BN * 128);
         for (int jb = 0; jb < BN / 64; ++jb) {
           const uint64_t da = umma_desc_k_sw128(smem_u32(sDS + b * L.ds_bytes + jb * RT_BM * 128));
-          const uint64_t db = umma_desc_k_sw128(smem_u32(sY + s * L.stage_bytes + L.y_bytes + jb * d * 128));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + ACC_COL, da + 2 * k, db + 2 * k, idesc2, (t | jb | k) != 0);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ss(tmem_base + ACC_COL, da + 2 * k, db0 + 128 * (jb * 4 + k), idesc2, (t | jb | k) != 0);
         }
         umma_commit(&ds_empty[b]);
         umma_commit(&empty[s]);
@@ -498,10 +500,10 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-// out = sum_s partial[s]; optional bf16 and transposed bf16 copies.  One warp per row.
+// out = sum_s partial[s]; optional bf16 copy.  One warp per row.
 __global__ void __launch_bounds__(256)
 combine_partials_kernel(const float* __restrict__ partial, int splits, int64_t rows, int d, float* __restrict__ out_f32,
-                        uint16_t* __restrict__ out_bf16, uint16_t* __restrict__ out_bf16_t) {
+                        uint16_t* __restrict__ out_bf16) {
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -513,12 +515,6 @@ combine_partials_kernel(const float* __restrict__ partial, int splits, int64_t r
     }
     if (out_f32) *reinterpret_cast<float4*>(out_f32 + r * d + c) = s;
     if (out_bf16) *reinterpret_cast<uint2*>(out_bf16 + r * d + c) = make_uint2(pack_bf16x2(s.x, s.y), pack_bf16x2(s.z, s.w));
-    if (out_bf16_t) {
-      out_bf16_t[(size_t)(c + 0) * rows + r] = float_to_bf16_bits(s.x);
-      out_bf16_t[(size_t)(c + 1) * rows + r] = float_to_bf16_bits(s.y);
-      out_bf16_t[(size_t)(c + 2) * rows + r] = float_to_bf16_bits(s.z);
-      out_bf16_t[(size_t)(c + 3) * rows + r] = float_to_bf16_bits(s.w);
-    }
   }
 }
 
@@ -599,18 +595,16 @@ int tc_retrieval_fwd(const void* q, const void* c, int64_t nq, int64_t nc, int64
 }
 
 template <int BN, bool TRANSPOSED>
-static int launch_bwd(const void* x, const void* y, const void* y_t, int64_t nX, int64_t nY, RetrievalTcArgs a,
+static int launch_bwd(const void* x, const void* y, int64_t nX, int64_t nY, RetrievalTcArgs a,
                       float* partial, int* splits_out, cudaStream_t st) {
   const int d = a.d;
   int splits, tps;
   split_plan(nX, nY, BN, &splits, &tps);
   *splits_out = splits;
-  CUtensorMap tmX, tmY, tmYT;
+  CUtensorMap tmX, tmY;
   int rc = make_tmap_bf16_2d(&tmX, x, (uint64_t)d, (uint64_t)nX, (uint64_t)d * 2, 64, RT_BM);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmY, y, (uint64_t)d, (uint64_t)nY, (uint64_t)d * 2, 64, BN);
-  if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tmYT, y_t, (uint64_t)nY, (uint64_t)d, (uint64_t)nY * 2, 64, (uint32_t)d);
   if (rc) return rc;
   a.partial_out = partial; a.tiles_per_split = tps;
   const bool extras = a.logq || a.cand_ids;
@@ -620,7 +614,7 @@ static int launch_bwd(const void* x, const void* y, const void* y_t, int64_t nX,
 #define TT_BWD_LAUNCH(EX)                                                                                     \
   {                                                                                                           \
     TT_CUDA_OK(cudaFuncSetAttribute(retrieval_bwd_tc_kernel<BN, TRANSPOSED, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total)); \
-    TT_PROF("retrieval_bwd_tc_kernel", st), retrieval_bwd_tc_kernel<BN, TRANSPOSED, EX><<<grid, RT_THREADS, L.total, st>>>(tmX, tmY, tmYT, a);        \
+    TT_PROF("retrieval_bwd_tc_kernel", st), retrieval_bwd_tc_kernel<BN, TRANSPOSED, EX><<<grid, RT_THREADS, L.total, st>>>(tmX, tmY, a);        \
   }
   if (extras) TT_BWD_LAUNCH(true) else TT_BWD_LAUNCH(false)
 #undef TT_BWD_LAUNCH
@@ -628,15 +622,12 @@ static int launch_bwd(const void* x, const void* y, const void* y_t, int64_t nX,
   return TT_OK;
 }
 
-int tc_retrieval_bwd(const void* q, const void* c, const void* q_t, const void* c_t, int64_t nq, int64_t nc,
+int tc_retrieval_bwd(const void* q, const void* c, int64_t nq, int64_t nc,
                      int64_t d, float inv_temp, int64_t label_offset, const float* w, const float* logq,
                      const int64_t* cand_ids, const float* row_lse, float grad_scale, float* dq, float* dc,
-                     uint16_t* dq_bf16, uint16_t* dq_bf16_t, uint16_t* dc_bf16, uint16_t* dc_bf16_t, void* ws,
-                     int64_t ws_bytes, cudaStream_t st) {
+                     uint16_t* dq_bf16, uint16_t* dc_bf16, void* ws, int64_t ws_bytes, cudaStream_t st) {
   int rc = check_tc_dims("tt_retrieval_loss_bwd", nq, nc, d);
   if (rc) return rc;
-  TT_REQUIRE(q_t && c_t, "tt_retrieval_loss_bwd(bf16): transposed copies q_t [d,nq] and c_t [d,nc] are required");
-  TT_REQUIRE(nq % 8 == 0 && nc % 8 == 0, "tt_retrieval_loss_bwd(bf16): nq and nc must be multiples of 8");
   if (!ws || ws_bytes < tc_retrieval_workspace_bytes(nq, nc, d))
     return set_error(TT_ERR_WORKSPACE, "tt_retrieval_loss_bwd(bf16): workspace too small");
   RetrievalTcArgs a{};
@@ -649,20 +640,20 @@ int tc_retrieval_bwd(const void* q, const void* c, const void* q_t, const void* 
   float* part_c = (float*)((char*)ws + plan.off_c);
   int sq = 1, sc = 1;
   if (BN == 128) {
-    rc = launch_bwd<128, false>(q, c, c_t, nq, nc, a, part_q, &sq, st);
+    rc = launch_bwd<128, false>(q, c, nq, nc, a, part_q, &sq, st);
     if (rc) return rc;
-    rc = launch_bwd<128, true>(c, q, q_t, nc, nq, a, part_c, &sc, st);
+    rc = launch_bwd<128, true>(c, q, nc, nq, a, part_c, &sc, st);
   } else {
-    rc = launch_bwd<64, false>(q, c, c_t, nq, nc, a, part_q, &sq, st);
+    rc = launch_bwd<64, false>(q, c, nq, nc, a, part_q, &sq, st);
     if (rc) return rc;
-    rc = launch_bwd<64, true>(c, q, q_t, nc, nq, a, part_c, &sc, st);
+    rc = launch_bwd<64, true>(c, q, nc, nq, a, part_c, &sc, st);
   }
   if (rc) return rc;
   TT_PROF("combine_partials_kernel", st);
-  combine_partials_kernel<<<(unsigned)ceil_div(nq, 8), 256, 0, st>>>(part_q, sq, nq, (int)d, dq, dq_bf16, dq_bf16_t);
+  combine_partials_kernel<<<(unsigned)ceil_div(nq, 8), 256, 0, st>>>(part_q, sq, nq, (int)d, dq, dq_bf16);
   TT_LAUNCH_OK("combine_partials_kernel");
   TT_PROF("combine_partials_kernel", st);
-  combine_partials_kernel<<<(unsigned)ceil_div(nc, 8), 256, 0, st>>>(part_c, sc, nc, (int)d, dc, dc_bf16, dc_bf16_t);
+  combine_partials_kernel<<<(unsigned)ceil_div(nc, 8), 256, 0, st>>>(part_c, sc, nc, (int)d, dc, dc_bf16);
   TT_LAUNCH_OK("combine_partials_kernel");
   return TT_OK;
 }

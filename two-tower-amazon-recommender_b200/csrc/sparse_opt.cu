@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(256)
 dense_opt_kernel(float* __restrict__ w, float* __restrict__ s0, float* __restrict__ s1,
                  const float* __restrict__ parts, int num_parts, int64_t rows, int64_t cols,
                  float lr_or_alpha, float b1, float b2, float eps, float l2,
-                 uint16_t* __restrict__ shadow, uint16_t* __restrict__ shadow_t) {
+                 uint16_t* __restrict__ shadow) {
   const int64_t n = rows * cols;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -231,7 +231,6 @@ dense_opt_kernel(float* __restrict__ w, float* __restrict__ s0, float* __restric
   }
   w[i] = wv;
   if (shadow) shadow[i] = float_to_bf16_bits(wv);
-  if (shadow_t) { int64_t r = i / cols, c = i % cols; shadow_t[c * rows + r] = float_to_bf16_bits(wv); }
 }
 
 __global__ void __launch_bounds__(1024)
@@ -303,27 +302,27 @@ extern "C" int tt_sparse_lazy_adam_update(float* table, float* m, float* v, int6
 
 static int dense_opt(bool adam, float* w, float* s0, float* s1, const float* parts, int num_parts,
                      int64_t rows, int64_t cols, float lr, float b1, float b2, float eps, float l2,
-                     uint16_t* shadow, uint16_t* shadow_t, cudaStream_t stream) {
+                     uint16_t* shadow, cudaStream_t stream) {
   TT_REQUIRE(w && s0 && parts && (!adam || s1), "dense optimizer: null buffer");
   TT_REQUIRE(rows > 0 && cols > 0 && num_parts >= 1, "dense optimizer: bad sizes");
   const int64_t n = rows * cols;
   unsigned blocks = (unsigned)ceil_div(n, 256);
-  if (adam) TT_PROF("dense_opt_kernel", stream), dense_opt_kernel<true><<<blocks, 256, 0, stream>>>(w, s0, s1, parts, num_parts, rows, cols, lr, b1, b2, eps, l2, shadow, shadow_t);
-  else TT_PROF("dense_opt_kernel", stream), dense_opt_kernel<false><<<blocks, 256, 0, stream>>>(w, s0, s1, parts, num_parts, rows, cols, lr, b1, b2, eps, l2, shadow, shadow_t);
+  if (adam) TT_PROF("dense_opt_kernel", stream), dense_opt_kernel<true><<<blocks, 256, 0, stream>>>(w, s0, s1, parts, num_parts, rows, cols, lr, b1, b2, eps, l2, shadow);
+  else TT_PROF("dense_opt_kernel", stream), dense_opt_kernel<false><<<blocks, 256, 0, stream>>>(w, s0, s1, parts, num_parts, rows, cols, lr, b1, b2, eps, l2, shadow);
   TT_LAUNCH_OK("dense_opt_kernel");
   return TT_OK;
 }
 
 extern "C" int tt_dense_adagrad_update(float* w, float* accum, const float* grad_parts, int32_t num_parts,
                                        int64_t rows, int64_t cols, float lr, float eps, float l2,
-                                       uint16_t* shadow, uint16_t* shadow_t, void* stream) {
+                                       uint16_t* shadow, void* stream) {
   return dense_opt(false, w, accum, nullptr, grad_parts, num_parts, rows, cols, lr, 0.f, 0.f, eps, l2,
-                   shadow, shadow_t, (cudaStream_t)stream);
+                   shadow, (cudaStream_t)stream);
 }
 
 extern "C" int tt_dense_adam_update(float* w, float* m, float* v, const float* grad_parts, int32_t num_parts,
                                     int64_t rows, int64_t cols, float alpha, float beta1, float beta2,
-                                    float eps, float l2, uint16_t* shadow, uint16_t* shadow_t, void* stream) {
+                                    float eps, float l2, uint16_t* shadow, void* stream) {
   return dense_opt(true, w, m, v, grad_parts, num_parts, rows, cols, alpha, beta1, beta2, eps, l2,
-                   shadow, shadow_t, (cudaStream_t)stream);
+                   shadow, (cudaStream_t)stream);
 }

@@ -104,9 +104,23 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                               // layout_type = SWIZZLE_128B
   return d;
 }
-// Instruction descriptor: kind::f16, A = B = bf16 (K-major), D = fp32, shape M x N x 16.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// MN-major operand (the M or N dimension is the contiguous one), SWIZZLE_128B: the tile is
+// [K rows][64 elements = 128 B] per 64-wide MN chunk, chunks `lbo_bytes` apart, 8-row K groups
+// 1024 B apart.  One MMA (K=16) consumes 16 rows, so successive k-steps advance by 2048 B.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;     // LBO: stride between 64-element MN chunks
+  d |= (uint64_t)(1024 >> 4) << 32;                     // SBO: stride between 8-row K groups
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor: kind::f16, A = B = bf16, D = fp32, shape M x N x 16.
+// a_mn / b_mn = 1 when that operand is MN-major (bits 15 / 16).
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn = 0, int b_mn = 0) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // D[tmem] (+)= A[smem] * B[smem]^T; issued by ONE thread.
 __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {

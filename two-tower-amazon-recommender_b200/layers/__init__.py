@@ -193,14 +193,14 @@ class Dense(Layer):
             self.build(in_dim)
         prec = config.precision
         if prec == "fp32":
-            y, _, _ = ops.dense_fwd("fp32", x.f32, self.kernel.value, self.bias.value, self.relu)
+            y, _ = ops.dense_fwd("fp32", x.f32, self.kernel.value, self.bias.value, self.relu)
             out = Tensor(f32=y, grad_formats=("f32",))
         else:
-            if self.kernel.shadow_t is None:
+            if self.kernel.shadow is None:
                 self.kernel.want_shadows = True
                 self.kernel.refresh_shadows()
-            y, y_t, _ = ops.dense_fwd("bf16", x.bf16, self.kernel.shadow_t, self.bias.value, self.relu, want_t=True)
-            out = Tensor(bf16=y, bf16_t=y_t, grad_formats=("bf16", "bf16_t"))
+            y, _ = ops.dense_fwd("bf16", x.bf16, self.kernel.shadow, self.bias.value, self.relu)
+            out = Tensor(bf16=y, grad_formats=("bf16",))
         out.relu_output = self.relu
 
         def backward():
@@ -210,25 +210,23 @@ class Dense(Layer):
             want = x.grad_formats
             need_dx = x.producer_needs_grad
             if prec == "fp32":
-                dx, _, _, dk, P, db = ops.dense_bwd("fp32", g["f32"], None, x.f32, None, self.kernel.value,
-                                                    relu_mask_x=x.relu_output, want_dx=need_dx)
+                dx, _, dk, P, db = ops.dense_bwd("fp32", g["f32"], x.f32, self.kernel.value,
+                                                 relu_mask_x=x.relu_output, want_dx=need_dx)
                 if need_dx:
                     x.grad = dict(f32=dx)
             else:
-                if x.bf16_t is None:
-                    x.bf16_t = ops.transpose_bf16(x.bf16)
                 dy_f32 = g.get("f32")
-                dx, dx_t, dx_f32, dk, P, db = ops.dense_bwd(
-                    "bf16", g["bf16"], g["bf16_t"], x.bf16, x.bf16_t, self.kernel.shadow,
-                    relu_mask_x=x.relu_output, want_dx=need_dx and "bf16" in want,
-                    want_dx_t=need_dx and "bf16_t" in want, want_dx_f32=need_dx and "f32" in want,
+                dx, dx_f32, dk, P, db = ops.dense_bwd(
+                    "bf16", g["bf16"], x.bf16, self.kernel.shadow, relu_mask_x=x.relu_output,
+                    want_dx=need_dx and "bf16" in want, want_dx_f32=need_dx and "f32" in want,
                     want_dbias=dy_f32 is None)
+                if need_dx:
+                    x.grad = dict(f32=dx_f32, bf16=dx)
                 if dy_f32 is not None:      # bias gradient from the un-rounded upstream gradient
                     db = ops.colsum_f32(dy_f32)
-                if need_dx:
-                    x.grad = dict(f32=dx_f32, bf16=dx, bf16_t=dx_t)
             self.kernel.grad = DenseGrad(dk, P)
-            self.bias.grad = DenseGrad(db.reshape(1, 1, -1), 1)
+            db = db.reshape(-1, 1, self.units)
+            self.bias.grad = DenseGrad(db, db.shape[0])
 
         GradientTape.record(backward)
         return out

@@ -15,7 +15,7 @@ from ..core import Tensor, config, device
 def _to_device_matrix(x, precision: str) -> torch.Tensor:
     if isinstance(x, Tensor):
         if precision == "bf16":
-            return x.bf16 if x.bf16 is not None else ops.cast_f32_to_bf16(x.f32)[0]
+            return x.bf16 if x.bf16 is not None else ops.cast_f32_to_bf16(x.f32)
         return x.f32 if x.f32 is not None else x.bf16.float()
     t = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x))
     if not t.is_cuda:
@@ -23,7 +23,7 @@ def _to_device_matrix(x, precision: str) -> torch.Tensor:
     if precision == "bf16":
         if t.dtype == torch.bfloat16:
             return t.contiguous()
-        return ops.cast_f32_to_bf16(t.float().contiguous())[0]
+        return ops.cast_f32_to_bf16(t.float().contiguous())
     return t.float().contiguous()
 
 

@@ -149,23 +149,21 @@ def sparse_lazy_adam_update(table, m, v, values, offsets, mode, grad, alpha, bet
     _count(3 if nnz else 0)
 
 
-def dense_adagrad_update(w, accum, grad_parts, num_parts, lr, eps, l2=0.0, shadow=None, shadow_t=None):
+def dense_adagrad_update(w, accum, grad_parts, num_parts, lr, eps, l2=0.0, shadow=None):
     lib = _lib.load()
     rows, cols = (w.shape[0], w.shape[1]) if w.dim() == 2 else (1, w.numel())
     check(lib.tt_dense_adagrad_update(_ptr(w, torch.float32), _ptr(accum, torch.float32),
                                       _ptr(grad_parts, torch.float32), num_parts, rows, cols, lr, eps, l2,
-                                      _ptr(shadow, torch.bfloat16), _ptr(shadow_t, torch.bfloat16), _stream()))
+                                      _ptr(shadow, torch.bfloat16), _stream()))
     _count(1)
 
 
-def dense_adam_update(w, m, v, grad_parts, num_parts, alpha, beta1, beta2, eps, l2=0.0, shadow=None,
-                      shadow_t=None):
+def dense_adam_update(w, m, v, grad_parts, num_parts, alpha, beta1, beta2, eps, l2=0.0, shadow=None):
     lib = _lib.load()
     rows, cols = (w.shape[0], w.shape[1]) if w.dim() == 2 else (1, w.numel())
     check(lib.tt_dense_adam_update(_ptr(w, torch.float32), _ptr(m, torch.float32), _ptr(v, torch.float32),
                                    _ptr(grad_parts, torch.float32), num_parts, rows, cols, alpha, beta1, beta2,
-                                   eps, l2, _ptr(shadow, torch.bfloat16), _ptr(shadow_t, torch.bfloat16),
-                                   _stream()))
+                                   eps, l2, _ptr(shadow, torch.bfloat16), _stream()))
     _count(1)
 
 
@@ -176,28 +174,26 @@ def sum_squares(x, scale, out, accumulate):
 
 
 # ------------------------------------------------------------------------------------ K2
-def dense_fwd(precision: str, x, kernel, bias, relu: bool, want_t: bool = False, want_f32: bool = False):
-    """fp32: x f32 [M,in], kernel f32 [in,out] -> y f32.
-    bf16: x bf16 [M,in], kernel = shadow_t bf16 [out,in] -> (y bf16, y_t bf16 | None, y_f32 | None)."""
+def dense_fwd(precision: str, x, kernel, bias, relu: bool, want_f32: bool = False):
+    """y = act(x @ kernel + bias), kernel in the Keras layout [in, out].
+    fp32: fp32 tensors -> (y f32, None).  bf16: x bf16, kernel bf16 (shadow) -> (y bf16, y_f32 | None)."""
     lib = _lib.load()
     M, in_dim = x.shape
+    out_dim = kernel.shape[1]
     if precision == "fp32":
-        out_dim = kernel.shape[1]
         y = torch.empty((M, out_dim), dtype=torch.float32, device=x.device)
         check(lib.tt_dense_fwd(TT_F32, _ptr(x, torch.float32), _ptr(kernel, torch.float32),
-                               _ptr(bias, torch.float32), _ptr(y), None, None, M, in_dim, out_dim,
+                               _ptr(bias, torch.float32), _ptr(y), None, M, in_dim, out_dim,
                                1 if relu else 0, _stream()))
         _count(1)
-        return y, None, None
-    out_dim = kernel.shape[0]
+        return y, None
     y = torch.empty((M, out_dim), dtype=torch.bfloat16, device=x.device)
-    y_t = torch.empty((out_dim, M), dtype=torch.bfloat16, device=x.device) if want_t else None
     y_f32 = torch.empty((M, out_dim), dtype=torch.float32, device=x.device) if want_f32 else None
     check(lib.tt_dense_fwd(TT_BF16, _ptr(x, torch.bfloat16), _ptr(kernel, torch.bfloat16),
-                           _ptr(bias, torch.float32), _ptr(y), _ptr(y_t), _ptr(y_f32), M, in_dim, out_dim,
+                           _ptr(bias, torch.float32), _ptr(y), _ptr(y_f32), M, in_dim, out_dim,
                            1 if relu else 0, _stream()))
     _count(1)
-    return y, y_t, y_f32
+    return y, y_f32
 
 
 def dense_bwd_num_parts(precision: str, M: int, in_dim: int, out_dim: int) -> int:
@@ -223,49 +219,37 @@ def sum_parts(parts, num_parts: int):
     return out
 
 
-def dense_bwd(precision: str, dy, dy_t, x, x_t, kernel, relu_mask_x: bool, want_dx: bool, want_dx_t: bool = False,
-              want_dx_f32: bool = False, want_dbias: bool = True):
-    """Returns (dx, dx_t, dx_f32, dkernel_parts [P,in,out] f32, P, dbias f32 [out] | None)."""
+def dense_bwd(precision: str, dy, x, kernel, relu_mask_x: bool, want_dx: bool, want_dx_f32: bool = False,
+              want_dbias: bool = True):
+    """Returns (dx, dx_f32, dkernel_parts [P,in,out] f32, P, dbias_parts [P,out] f32 | None)."""
     lib = _lib.load()
     M, out_dim = dy.shape
     in_dim = x.shape[1]
     dev = dy.device
     P = dense_bwd_num_parts(precision, M, in_dim, out_dim)
     dk = torch.empty((P, in_dim, out_dim), dtype=torch.float32, device=dev)
-    db = torch.empty((out_dim,), dtype=torch.float32, device=dev) if want_dbias else None
+    db = torch.empty((P, out_dim), dtype=torch.float32, device=dev) if want_dbias else None
     if precision == "fp32":
         dx = torch.empty((M, in_dim), dtype=torch.float32, device=dev) if want_dx else None
-        check(lib.tt_dense_bwd(TT_F32, _ptr(dy, torch.float32), None, _ptr(x, torch.float32), None,
-                               _ptr(kernel, torch.float32), _ptr(dx), None, None, _ptr(dk), P, _ptr(db), M,
-                               in_dim, out_dim, 1 if relu_mask_x else 0, _stream()))
+        check(lib.tt_dense_bwd(TT_F32, _ptr(dy, torch.float32), _ptr(x, torch.float32), _ptr(kernel, torch.float32),
+                               _ptr(dx), None, _ptr(dk), P, _ptr(db), M, in_dim, out_dim,
+                               1 if relu_mask_x else 0, _stream()))
         _count(1 + int(want_dx) + int(want_dbias))
-        return dx, None, None, dk, P, db
+        return dx, None, dk, P, db
     dx = torch.empty((M, in_dim), dtype=torch.bfloat16, device=dev) if want_dx else None
-    dx_t = torch.empty((in_dim, M), dtype=torch.bfloat16, device=dev) if want_dx_t else None
     dx_f32 = torch.empty((M, in_dim), dtype=torch.float32, device=dev) if want_dx_f32 else None
-    check(lib.tt_dense_bwd(TT_BF16, _ptr(dy, torch.bfloat16), _ptr(dy_t, torch.bfloat16), _ptr(x, torch.bfloat16),
-                           _ptr(x_t, torch.bfloat16), _ptr(kernel, torch.bfloat16), _ptr(dx), _ptr(dx_t),
-                           _ptr(dx_f32), _ptr(dk), P, _ptr(db), M, in_dim, out_dim, 1 if relu_mask_x else 0,
-                           _stream()))
-    _count(1 + int(want_dx or want_dx_t or want_dx_f32) + int(want_dbias))
-    return dx, dx_t, dx_f32, dk, P, db
+    check(lib.tt_dense_bwd(TT_BF16, _ptr(dy, torch.bfloat16), _ptr(x, torch.bfloat16), _ptr(kernel, torch.bfloat16),
+                           _ptr(dx), _ptr(dx_f32), _ptr(dk), P, _ptr(db), M, in_dim, out_dim,
+                           1 if relu_mask_x else 0, _stream()))
+    _count(1 + int(want_dx or want_dx_f32) + int(want_dbias))
+    return dx, dx_f32, dk, P, db
 
 
-def transpose_bf16(x):
-    rows, cols = x.shape
-    out = torch.empty((cols, rows), dtype=torch.bfloat16, device=x.device)
-    check(_lib.load().tt_transpose_bf16(_ptr(x, torch.bfloat16), _ptr(out), rows, cols, _stream()))
+def cast_f32_to_bf16(x):
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().tt_cast_f32_to_bf16(_ptr(x, torch.float32), _ptr(out), x.numel(), _stream()))
     _count(1)
     return out
-
-
-def cast_f32_to_bf16(x, want=True, want_t=False):
-    rows, cols = x.shape
-    out = torch.empty((rows, cols), dtype=torch.bfloat16, device=x.device) if want else None
-    out_t = torch.empty((cols, rows), dtype=torch.bfloat16, device=x.device) if want_t else None
-    check(_lib.load().tt_cast_f32_to_bf16(_ptr(x, torch.float32), _ptr(out), _ptr(out_t), rows, cols, _stream()))
-    _count(1)
-    return out, out_t
 
 
 # --------------------------------------------------------------------------------- K3/K4
@@ -300,14 +284,14 @@ def retrieval_loss_fwd(precision: str, q, c, inv_temperature: float, label_offse
                                     _ptr(sample_weight, torch.float32), _ptr(cand_log_q, torch.float32),
                                     _ptr(cand_ids, torch.int64), _ptr(lse), _ptr(pos), _ptr(loss), _ptr(ws),
                                     ws.numel(), _stream()))
-    _count(2)
+    _count(3 if precision == "bf16" else 2)
     return loss, lse, pos
 
 
-def retrieval_loss_bwd(precision: str, q, c, q_t, c_t, inv_temperature: float, row_lse, label_offset: int = 0,
+def retrieval_loss_bwd(precision: str, q, c, inv_temperature: float, row_lse, label_offset: int = 0,
                        sample_weight=None, cand_log_q=None, cand_ids=None, grad_scale: float = 1.0,
-                       want_bf16=(False, False), want_bf16_t=(False, False)):
-    """Returns dict(dq, dc [f32], dq_bf16, dq_bf16_t, dc_bf16, dc_bf16_t)."""
+                       want_bf16=(False, False)):
+    """Returns dict(dq, dc [f32], dq_bf16, dc_bf16)."""
     lib = _lib.load()
     pc = precision_code(precision)
     dt = torch.float32 if precision == "fp32" else torch.bfloat16
@@ -318,16 +302,15 @@ def retrieval_loss_bwd(precision: str, q, c, q_t, c_t, inv_temperature: float, r
     dc = torch.empty((nc, d), dtype=torch.float32, device=dev)
     mk = lambda shape, on: torch.empty(shape, dtype=torch.bfloat16, device=dev) if on else None
     dq_b, dc_b = mk((nq, d), want_bf16[0]), mk((nc, d), want_bf16[1])
-    dq_bt, dc_bt = mk((d, nq), want_bf16_t[0]), mk((d, nc), want_bf16_t[1])
     nbytes = int(lib.tt_retrieval_workspace_bytes(pc, nq, nc, d))
     ws = _workspace(nbytes, dev)
-    check(lib.tt_retrieval_loss_bwd(pc, _ptr(q, dt), _ptr(c, dt), _ptr(q_t), _ptr(c_t), nq, nc, d, inv_temperature,
+    check(lib.tt_retrieval_loss_bwd(pc, _ptr(q, dt), _ptr(c, dt), nq, nc, d, inv_temperature,
                                     label_offset, _ptr(sample_weight, torch.float32),
                                     _ptr(cand_log_q, torch.float32), _ptr(cand_ids, torch.int64),
                                     _ptr(row_lse, torch.float32), grad_scale, _ptr(dq), _ptr(dc), _ptr(dq_b),
-                                    _ptr(dq_bt), _ptr(dc_b), _ptr(dc_bt), _ptr(ws), ws.numel(), _stream()))
-    _count(2)
-    return dict(dq=dq, dc=dc, dq_bf16=dq_b, dq_bf16_t=dq_bt, dc_bf16=dc_b, dc_bf16_t=dc_bt)
+                                    _ptr(dc_b), _ptr(ws), ws.numel(), _stream()))
+    _count(4 if precision == "bf16" else 2)
+    return dict(dq=dq, dc=dc, dq_bf16=dq_b, dc_bf16=dc_b)
 
 
 # ------------------------------------------------------------------------------------ K6

@@ -63,8 +63,7 @@ class Adagrad(Optimizer):
 
     def _apply_dense(self, g: DenseGrad, var: Variable) -> None:
         ops.dense_adagrad_update(var.value, self._acc(var), g.parts, g.num_parts, self.learning_rate,
-                                 self.epsilon, var.l2, var.shadow if var.want_shadows else None,
-                                 var.shadow_t if var.want_shadows else None)
+                                 self.epsilon, var.l2, var.shadow if var.want_shadows else None)
 
 
 class Adam(Optimizer):
@@ -91,8 +90,7 @@ class Adam(Optimizer):
     def _apply_dense(self, g: DenseGrad, var: Variable) -> None:
         m, v = self._mv(var)
         ops.dense_adam_update(var.value, m, v, g.parts, g.num_parts, self._alpha(), self.beta_1, self.beta_2,
-                              self.epsilon, var.l2, var.shadow if var.want_shadows else None,
-                              var.shadow_t if var.want_shadows else None)
+                              self.epsilon, var.l2, var.shadow if var.want_shadows else None)
 
     def _apply_sparse(self, g: IndexedSlices, var: Variable) -> None:
         if not self.lazy:

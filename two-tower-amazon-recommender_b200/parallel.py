@@ -166,20 +166,13 @@ def global_retrieval(task, q: Tensor, c: Tensor, inv_t: float, w, logq, ids, pri
     loss, lse, _pos = prim.retrieval_loss_fwd(prec, qm, c_all, inv_t, label_offset, w, logq_all, ids_all)
 
     def backward():
-        q_t = c_all_t = None
-        if prec == "bf16":
-            if q.bf16_t is None:
-                q.bf16_t = prim.transpose_bf16(q.bf16)
-            q_t, c_all_t = q.bf16_t, prim.transpose_bf16(c_all)
-        r = prim.retrieval_loss_bwd(prec, qm, c_all, q_t, c_all_t, inv_t, lse, label_offset, w, logq_all, ids_all, 1.0,
-                                    want_bf16=("bf16" in q.grad_formats and prec == "bf16", False),
-                                    want_bf16_t=("bf16_t" in q.grad_formats and prec == "bf16", False))
-        q.grad = dict(f32=r["dq"], bf16=r["dq_bf16"], bf16_t=r["dq_bf16_t"])
+        bf = prec == "bf16"
+        r = prim.retrieval_loss_bwd(prec, qm, c_all, inv_t, lse, label_offset, w, logq_all, ids_all, 1.0,
+                                    want_bf16=(bf and "bf16" in q.grad_formats, False))
+        q.grad = dict(f32=r["dq"], bf16=r["dq_bf16"])
         dc = coll.reduce_scatter(r["dc"])                         # every rank's partial for my candidates
-        dc_b = dc_bt = None
-        if prec == "bf16" and ("bf16" in c.grad_formats or "bf16_t" in c.grad_formats):
-            dc_b, dc_bt = prim.cast_f32_to_bf16(dc, want=True, want_t=True)
-        c.grad = dict(f32=dc, bf16=dc_b, bf16_t=dc_bt)
+        dc_b = prim.cast_f32_to_bf16(dc) if (bf and "bf16" in c.grad_formats) else None
+        c.grad = dict(f32=dc, bf16=dc_b)
 
     GradientTape.record(backward)
     return Scalar(loss)

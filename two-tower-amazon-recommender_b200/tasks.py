@@ -83,19 +83,11 @@ class Retrieval:
         loss, lse, _pos = ops.retrieval_loss_fwd(prec, qm, cm, inv_t, 0, w, logq, ids)
 
         def backward():
-            q_t = c_t = None
-            if prec == "bf16":
-                if q.bf16_t is None:
-                    q.bf16_t = ops.transpose_bf16(q.bf16)
-                if c.bf16_t is None:
-                    c.bf16_t = ops.transpose_bf16(c.bf16)
-                q_t, c_t = q.bf16_t, c.bf16_t
-            r = ops.retrieval_loss_bwd(
-                prec, qm, cm, q_t, c_t, inv_t, lse, 0, w, logq, ids, 1.0,
-                want_bf16=("bf16" in q.grad_formats and prec == "bf16", "bf16" in c.grad_formats and prec == "bf16"),
-                want_bf16_t=("bf16_t" in q.grad_formats and prec == "bf16", "bf16_t" in c.grad_formats and prec == "bf16"))
-            q.grad = dict(f32=r["dq"], bf16=r["dq_bf16"], bf16_t=r["dq_bf16_t"])
-            c.grad = dict(f32=r["dc"], bf16=r["dc_bf16"], bf16_t=r["dc_bf16_t"])
+            bf = prec == "bf16"
+            r = ops.retrieval_loss_bwd(prec, qm, cm, inv_t, lse, 0, w, logq, ids, 1.0,
+                                       want_bf16=(bf and "bf16" in q.grad_formats, bf and "bf16" in c.grad_formats))
+            q.grad = dict(f32=r["dq"], bf16=r["dq_bf16"])
+            c.grad = dict(f32=r["dc"], bf16=r["dc_bf16"])
 
         GradientTape.record(backward)
 
