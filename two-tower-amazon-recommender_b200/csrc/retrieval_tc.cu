@@ -163,48 +163,70 @@ retrieval_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       }
       mbar_wait(&s_full[b], (t >> 1) & 1);
       tc_fence_after();
-      const bool edge = c_tile + BN > a.nc;
-      const bool has_label = label >= c_tile && label < c_tile + BN;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t rr[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(qd * 32) << 16) + b * BN + c0, rr);
-        tmem_ld_wait();
-        float x[32];
+      // whole row of the tile into registers, then hand the TMEM buffer back at once so the
+      // next tile's MMA overlaps the exponentials
+      uint32_t rr[BN];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(rr[j]) * a.k2;
-        if (EXTRAS) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            x[j] -= col_logq2[b * BN + c0 + j];
-            const long long ci = c_tile + c0 + j;
-            if (col_id[b * BN + c0 + j] == pos_id && ci != label) x[j] += TT_MIN_FLOAT;
-          }
-        }
-        if (has_label && label >= c_tile + c0 && label < c_tile + c0 + 32) {
-          const int jj = (int)(label - c_tile - c0);
-          float p = 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) if (j == jj) p = x[j];
-          if (qi < a.nq) a.row_pos[qi] = p * kLn2;
-        }
-        if (edge) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) if (c_tile + c0 + j >= a.nc) x[j] = -INFINITY;
-        }
-        float cmax = x[0];
-#pragma unroll
-        for (int j = 1; j < 32; ++j) cmax = fmaxf(cmax, x[j]);
-        if (cmax > m2) { l *= ex2_approx(m2 - cmax); m2 = cmax; }
-        if (m2 > -INFINITY) {
-          float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) { acc0 += ex2_approx(x[j] - m2); acc1 += ex2_approx(x[j + 1] - m2); }
-          l += acc0 + acc1;
-        }
-      }
+      for (int c = 0; c < BN / 32; ++c) tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + b * BN + c * 32, rr + c * 32);
+      tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&s_empty[b]);
+      const bool edge = c_tile + BN > a.nc;
+      const bool has_label = label >= c_tile && label < c_tile + BN;
+      if (!EXTRAS && !edge && !has_label) {
+        // fast path: max on the raw accumulators (k2 > 0), then one FFMA + ex2 + add per logit
+        float cmax = fmax3(__uint_as_float(rr[0]), __uint_as_float(rr[1]), __uint_as_float(rr[2]));
+#pragma unroll
+        for (int j = 3; j + 1 < BN; j += 2) cmax = fmax3(cmax, __uint_as_float(rr[j]), __uint_as_float(rr[j + 1]));
+        cmax = fmaxf(cmax, __uint_as_float(rr[BN - 1])) * a.k2;
+        if (cmax > m2) { l *= ex2_approx(m2 - cmax); m2 = cmax; }
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+        const float nm = -m2;
+#pragma unroll
+        for (int j = 0; j < BN; j += 4) {
+          acc0 += ex2_approx(fmaf(__uint_as_float(rr[j]), a.k2, nm));
+          acc1 += ex2_approx(fmaf(__uint_as_float(rr[j + 1]), a.k2, nm));
+          acc2 += ex2_approx(fmaf(__uint_as_float(rr[j + 2]), a.k2, nm));
+          acc3 += ex2_approx(fmaf(__uint_as_float(rr[j + 3]), a.k2, nm));
+        }
+        l += (acc0 + acc1) + (acc2 + acc3);
+      } else {
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          float x[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(rr[c0 + j]) * a.k2;
+          if (EXTRAS) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              x[j] -= col_logq2[b * BN + c0 + j];
+              const long long ci = c_tile + c0 + j;
+              if (col_id[b * BN + c0 + j] == pos_id && ci != label) x[j] += TT_MIN_FLOAT;
+            }
+          }
+          if (has_label && label >= c_tile + c0 && label < c_tile + c0 + 32) {
+            const int jj = (int)(label - c_tile - c0);
+            float p = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j == jj) p = x[j];
+            if (qi < a.nq) a.row_pos[qi] = p * kLn2;
+          }
+          if (edge) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (c_tile + c0 + j >= a.nc) x[j] = -INFINITY;
+          }
+          float cmax = x[0];
+#pragma unroll
+          for (int j = 1; j < 32; ++j) cmax = fmaxf(cmax, x[j]);
+          if (cmax > m2) { l *= ex2_approx(m2 - cmax); m2 = cmax; }
+          if (m2 > -INFINITY) {
+            float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) { acc0 += ex2_approx(x[j] - m2); acc1 += ex2_approx(x[j + 1] - m2); }
+            l += acc0 + acc1;
+          }
+        }
+      }
     }
     // merge the two warpgroups' partials, write one (max, sum) per row and split
     if (g == 1) wg_ml[r] = make_float2(m2, l);
@@ -405,23 +427,26 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
       }
       mbar_wait(&s_full[b], (t >> 1) & 1);
-      mbar_wait(&ds_empty[b], ((t >> 1) & 1) ^ 1);
       tc_fence_after();
+      uint32_t rr[BN];
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + b * BN + c * 32, rr + c * 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_empty[b]);                      // S buffer free: the MMA of tile t+2 may start
+      mbar_wait(&ds_empty[b], ((t >> 1) & 1) ^ 1);   // dS buffer free (MMA2 of tile t-2 done)
       // label column (dQ) / label row (dC) intersects this tile?
-      const long long lab_lo = TRANSPOSED ? y_tile + a.label_offset : y_tile - a.label_offset;
       // dQ: element (xi, y) is the positive when y == label_offset + xi  <=>  xi == y - label_offset
       // dC: element (xi, y) is the positive when xi == label_offset + y
-      const bool diag = TRANSPOSED ? (xi >= lab_lo && xi < lab_lo + BN) : (xi >= lab_lo && xi < lab_lo + BN);
+      const long long lab_lo = TRANSPOSED ? y_tile + a.label_offset : y_tile - a.label_offset;
+      const bool diag = xi >= lab_lo && xi < lab_lo + BN;
       uint8_t* ds_base = sDS + b * L.ds_bytes;
-#pragma unroll 1
+#pragma unroll
       for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t rr[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(qd * 32) << 16) + b * BN + c0, rr);
-        tmem_ld_wait();
         float p[32];
         if (!TRANSPOSED) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) p[j] = fmaf(__uint_as_float(rr[j]), a.k2, -row_lse2);
+          for (int j = 0; j < 32; ++j) p[j] = fmaf(__uint_as_float(rr[c0 + j]), a.k2, -row_lse2);
           if (EXTRAS) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -433,10 +458,10 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 l4 = *reinterpret_cast<const float4*>(col_a + b * BN + c0 + j);
-            p[j] = fmaf(__uint_as_float(rr[j]), a.k2, -l4.x - row_logq2);
-            p[j + 1] = fmaf(__uint_as_float(rr[j + 1]), a.k2, -l4.y - row_logq2);
-            p[j + 2] = fmaf(__uint_as_float(rr[j + 2]), a.k2, -l4.z - row_logq2);
-            p[j + 3] = fmaf(__uint_as_float(rr[j + 3]), a.k2, -l4.w - row_logq2);
+            p[j] = fmaf(__uint_as_float(rr[c0 + j]), a.k2, -l4.x - row_logq2);
+            p[j + 1] = fmaf(__uint_as_float(rr[c0 + j + 1]), a.k2, -l4.y - row_logq2);
+            p[j + 2] = fmaf(__uint_as_float(rr[c0 + j + 2]), a.k2, -l4.z - row_logq2);
+            p[j + 3] = fmaf(__uint_as_float(rr[c0 + j + 3]), a.k2, -l4.w - row_logq2);
           }
           if (EXTRAS) {
 #pragma unroll
@@ -464,8 +489,6 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           *reinterpret_cast<uint4*>(sub + sw128_offset(r, ((c0 & 63) >> 3) + g8)) = v;
         }
       }
-      tc_fence_before();
-      mbar_arrive(&s_empty[b]);
       fence_proxy_async();
       mbar_arrive(&ds_full[b]);
     }
