@@ -301,6 +301,10 @@ def run_ours(args):
     lib.tt_profile_enable(1)
     prof_steps = min(args.steps, 20)
     for i in range(prof_steps):
+        # keep the GPU busy while the host enqueues the step, so that every event pair brackets a kernel
+        # that starts back to back with its predecessor (otherwise the interval also holds the host's
+        # launch latency, several us per launch in eager mode)
+        torch.cuda._sleep(4_000_000)
         model.train_step(dev_pool[i % n_pool])
     import ctypes
     buf = ctypes.create_string_buffer(1 << 16)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TT_VERSION 100 /* 0.1.0 */
+#define TT_VERSION 110 /* 0.1.1 */
 
 enum tt_status {
   TT_OK = 0,
@@ -131,6 +131,58 @@ int tt_dense_adam_update(float* w, float* m, float* v, const float* grad_parts, 
 int tt_sum_squares(const float* x, int64_t n, float scale, float* out, int32_t accumulate,
                    void* stream);
 
+/* The same updates for several variables in ONE launch each (the whole optimizer step of a
+ * two-tower model is launch-bound at the BASELINE sizes).  host_vars: HOST arrays. */
+#define TT_MAX_DENSE_VARS 16
+#define TT_MAX_SPARSE_VARS 8
+typedef struct tt_dense_var {
+  float* w;
+  float* slot0;             /* Adagrad accumulator / Adam m */
+  float* slot1;             /* Adam v (NULL for Adagrad) */
+  const float* grad_parts;  /* [num_parts, n] */
+  int64_t n;                /* rows * cols */
+  int32_t num_parts;
+  float l2;
+  uint16_t* shadow;         /* nullable bf16 copy */
+} tt_dense_var;
+int tt_dense_adagrad_update_multi(const tt_dense_var* host_vars, int32_t num_vars, float lr, float eps,
+                                  void* stream);
+int tt_dense_adam_update_multi(const tt_dense_var* host_vars, int32_t num_vars, float alpha, float beta1,
+                               float beta2, float eps, void* stream);
+typedef struct tt_sparse_var {
+  float* table;
+  float* slot0;             /* Adagrad accumulator / LazyAdam m */
+  float* slot1;             /* LazyAdam v (NULL for Adagrad) */
+  int64_t vocab, d;
+  const int64_t* values;
+  const int64_t* offsets;   /* nullable */
+  int64_t num_rows, nnz;
+  const float* grad;        /* [num_rows, d] */
+  void* workspace;
+  int64_t workspace_bytes;
+  uint8_t* first_flag;      /* nullable */
+  int32_t mode;
+  int32_t reserved;
+} tt_sparse_var;
+int tt_sparse_adagrad_update_multi(const tt_sparse_var* host_vars, int32_t num_vars, float lr, float eps,
+                                   void* stream);
+int tt_sparse_lazy_adam_update_multi(const tt_sparse_var* host_vars, int32_t num_vars, float alpha,
+                                     float beta1, float beta2, float eps, void* stream);
+
+/* The whole optimizer step in two launches.  tt_optimizer_prepare_sparse needs only the ids (table,
+ * values, offsets, sizes, workspace of each tt_sparse_var): enqueue it when the lookup happens, on a
+ * side stream, and it overlaps the forward pass.  tt_adagrad_step / tt_lazy_adam_step then update ALL
+ * dense variables and ALL tables in one launch: an id that occurs once is applied straight from its
+ * gradient row; duplicates are reduced into the first occurrence's accumulation row and the last arriver
+ * applies (same results as tt_sparse_*_update: exact row set, fp32 sum order of duplicates not fixed).
+ * Dense variables (Adam arithmetic for tt_lazy_adam_step) as tt_dense_*_update_multi.  The prepare call
+ * must have completed (stream order / event) on the SAME workspaces before the step. */
+int tt_optimizer_prepare_sparse(const tt_sparse_var* host_vars, int32_t num_vars, void* stream);
+int tt_adagrad_step(const tt_dense_var* host_dense, int32_t num_dense, const tt_sparse_var* host_sparse,
+                    int32_t num_sparse, float lr, float eps, void* stream);
+int tt_lazy_adam_step(const tt_dense_var* host_dense, int32_t num_dense, const tt_sparse_var* host_sparse,
+                      int32_t num_sparse, float alpha, float beta1, float beta2, float eps, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * K2  tower MLP: tf.keras.layers.Dense forward / backward (layer sizes
  * /root/reference/configs/data_config.yaml:56-57).  kernel is ALWAYS the Keras layout
@@ -172,6 +224,59 @@ int tt_debug_gemm_bf16(const void* A, int32_t a_mn, const void* B, int32_t b_mn,
 
 int tt_cast_f32_to_bf16(const float* in, uint16_t* out, int64_t n, void* stream);
 
+/* Tuning hook: device buffer of 3 * (16 * 64 + 16) + 3 * 4 * 256 int64 that receives clock64() stamps of
+ * the software pipeline of CTA (0,0) of the bf16 loss forward / dQ / dC kernels and per-CTA
+ * {entry, setup done, exit, smid} globaltimer records (grids up to 256 CTAs); NULL = off. */
+int tt_debug_trace_buffer(long long* device_buf);
+
+/* ---------------------------------------------------------------------------------------
+ * K1+K2 fused  tower forward / backward for the two-layer tower of the BASELINE configs
+ * (Embedding [+ pooled multi-hot Embeddings] -> Dense(relu) -> Dense(linear); sizes
+ * /root/reference/configs/data_config.yaml:55-57, ids /root/reference/src/data/preprocessor.py:481-489).
+ * One launch covers up to TT_MAX_TOWERS towers (query + candidate): a CTA owns 128 batch rows of
+ * one tower, gathers / pools them straight into the swizzled shared-memory A tile, and runs both
+ * Dense layers on tcgen05 with the hidden activations kept on chip.  bf16 operands, fp32
+ * accumulation (TT_BF16 precision of tt_dense_*).  Same arithmetic as tt_tower_input_fwd ->
+ * tt_dense_fwd(relu) -> tt_dense_fwd, so the same oracle checks it.
+ *
+ * forward : x [B,d_in] = pooled tower input (bf16, saved for the backward),
+ *           h [B,d_hid] = relu(x w1 + b1) (bf16, saved), y [B,d_out] = h w2 + b2 (bf16).
+ * backward: dy = sum of `dy_splits` stacked fp32 partials [dy_splits, B, d_out] (the split
+ *           partials tt_retrieval_loss_bwd_parts leaves, or any fp32 gradient with splits = 1),
+ *           dx [B,d_in] fp32 = the embedding-row gradient, and per 128-row slice p of the batch
+ *           (num_parts = ceil(B / 128)): dw1_parts [P,d_in,d_hid], dw2_parts [P,d_hid,d_out],
+ *           db1_parts [P,d_hid], db2_parts [P,d_out] (fp32; db2 from the un-rounded dy), to be
+ *           summed in index order by tt_dense_*_update[_multi].
+ * Supported shapes: tt_tower_mlp2_supported(d_in, d_hid, d_out) != 0 (d_in = 128, d_hid in
+ * {128, 256}, d_out in {64, 128}); other shapes use the per-layer entry points.
+ * ------------------------------------------------------------------------------------- */
+#define TT_MAX_TOWERS 4
+typedef struct tt_tower_mlp2 {
+  tt_feature feats[TT_MAX_FEATURES];
+  int32_t num_feats;
+  int32_t d_in, d_hid, d_out;
+  int64_t batch;
+  const uint16_t* w1;   /* bf16 [d_in, d_hid]  (Keras layout) */
+  const float* b1;      /* [d_hid] */
+  const uint16_t* w2;   /* bf16 [d_hid, d_out] */
+  const float* b2;      /* [d_out] */
+  uint16_t* x;          /* bf16 [B, d_in] : forward output, backward input */
+  uint16_t* h;          /* bf16 [B, d_hid]: forward output, backward input */
+  uint16_t* y;          /* bf16 [B, d_out]: forward output */
+  const float* dy_parts; /* backward: fp32 [dy_splits, B, d_out] */
+  int32_t dy_splits;
+  int32_t reserved;
+  float* dx;            /* backward outputs */
+  float* dw1_parts;
+  float* dw2_parts;
+  float* db1_parts;
+  float* db2_parts;
+} tt_tower_mlp2;
+int32_t tt_tower_mlp2_supported(int32_t d_in, int32_t d_hid, int32_t d_out);
+int tt_tower_mlp2_fwd(const tt_tower_mlp2* host_towers, int32_t num_towers, int32_t* id_fault_flag,
+                      void* stream);
+int tt_tower_mlp2_bwd(const tt_tower_mlp2* host_towers, int32_t num_towers, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * K3/K4  tfrs.tasks.Retrieval: in-batch softmax cross-entropy, logits never written to HBM.
  * Replaces matmul(q, c, transpose_b) [/ temperature] [- log clip(p)] [accidental-hit mask]
@@ -187,6 +292,12 @@ int tt_cast_f32_to_bf16(const float* in, uint16_t* out, int64_t n, void* stream)
  * sum_i w_i (lse_i - pos_i) reduced in a fixed order.
  * ------------------------------------------------------------------------------------- */
 int64_t tt_retrieval_workspace_bytes(int32_t precision, int64_t nq, int64_t nc, int64_t d);
+/* TT_BF16: the head of the workspace holds arrival tickets (the forward's last CTA per row block
+ * folds the candidate splits and the loss in-kernel).  Call this ONCE after allocating a workspace
+ * (it zeroes the tickets; equivalently zero-fill the buffer); every launch leaves them zero again.
+ * A workspace must not be shared by launches that may run concurrently. */
+int tt_retrieval_workspace_init(int32_t precision, void* workspace, int64_t workspace_bytes, int64_t nq,
+                                int64_t nc, int64_t d, void* stream);
 int tt_retrieval_loss_fwd(int32_t precision, const void* q, const void* c, int64_t nq, int64_t nc,
                           int64_t d, float inv_temperature, int64_t label_offset,
                           const float* sample_weight, const float* cand_log_q,
@@ -201,6 +312,21 @@ int tt_retrieval_loss_bwd(int32_t precision, const void* q, const void* c, int64
                           const int64_t* cand_ids, const float* row_lse, float grad_scale,
                           float* dq, float* dc, uint16_t* dq_bf16, uint16_t* dc_bf16,
                           void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Split form of the backward for a consumer that folds the partial sums itself
+ * (tt_tower_mlp2_bwd): the dQ pass leaves *dq_splits stacked fp32 partials [dq_splits, nq, d] in
+ * dq_parts, the dC pass [dc_splits, nc, d] in dc_parts; dq = sum over splits in index order.
+ * Buffers are caller-owned, sized with tt_retrieval_bwd_num_splits.  TT_BF16 only.
+ * tt_combine_parts_f32 is that ordered sum as a stand-alone kernel (fp32 and/or bf16 output). */
+int tt_retrieval_bwd_num_splits(int32_t precision, int64_t nq, int64_t nc, int64_t d, int32_t* dq_splits,
+                                int32_t* dc_splits);
+int tt_retrieval_loss_bwd_parts(int32_t precision, const void* q, const void* c, int64_t nq, int64_t nc,
+                                int64_t d, float inv_temperature, int64_t label_offset,
+                                const float* sample_weight, const float* cand_log_q,
+                                const int64_t* cand_ids, const float* row_lse, float grad_scale,
+                                float* dq_parts, float* dc_parts, void* stream);
+int tt_combine_parts_f32(const float* parts, int32_t num_parts, int64_t rows, int64_t d, float* out_f32,
+                         uint16_t* out_bf16, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * K6  brute-force scoring + top-k.

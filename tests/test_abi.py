@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(tt):
         assert hasattr(lib, name), f"{name} declared in twotower.h but not exported"
         assert name in tt._lib.SIGNATURES, f"{name} has no ctypes signature"
     assert set(tt._lib.SIGNATURES) == set(declared_symbols())
-    assert lib.tt_version() == 100
+    assert lib.tt_version() == 110
 
 
 def test_argument_validation_reports_through_last_error(tt):

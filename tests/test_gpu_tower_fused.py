@@ -1,0 +1,387 @@
+"""GPU parity of the fused tower kernels (tt_tower_mlp2_fwd / tt_tower_mlp2_bwd), the split form of
+the loss backward and the multi-variable optimizer launches, through the C-ABI.
+
+On exact-arithmetic inputs (dyadic tables / kernels / gradients: every product and partial sum is
+representable) each stage must equal the numpy restatement EXACTLY, with bf16 rounding applied at
+the same points (x, h, dh) -- this pins the shared-memory layouts, UMMA descriptors and TMEM column
+re-use of the fused kernels.  On Gaussian data the usual 2e-2 bf16 bound applies."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from two_tower_b200 import synth
+
+pytestmark = pytest.mark.gpu
+BF16_RTOL = 2e-2
+
+
+def dev(x, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(x))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda().contiguous()
+
+
+def bf(x):
+    return dev(x, torch.bfloat16)
+
+
+def r16(x):
+    return oracle.bf16_round(np.asarray(x, dtype=np.float32)).astype(np.float64)
+
+
+@pytest.fixture(scope="module")
+def ops(tt):
+    tt.ops.device_check()
+    return tt.ops
+
+
+def make_tower(rng, B, d_in, d_hid, d_out, with_bag):
+    V = 997
+    table = synth.exact_matrix(rng, V, d_in, 2)
+    ids = rng.integers(0, V, size=B, dtype=np.int64)
+    feats_np = [(table, ids, None, "sum")]
+    x = table[ids].astype(np.float64)
+    if with_bag:
+        Vb = 211
+        tb = synth.exact_matrix(rng, Vb, d_in, 1)
+        values, offsets = synth.draw_bags(rng, B, Vb, 0, 3)
+        feats_np.append((tb, values, offsets, "sum"))
+        x = x + oracle.embedding_bag(tb.astype(np.float64), values, offsets, "sum")
+    w1 = synth.exact_matrix(rng, d_in, d_hid, 2); b1 = synth.exact_matrix(rng, 1, d_hid, 4)[0]
+    w2 = synth.exact_matrix(rng, d_hid, d_out, 2); b2 = synth.exact_matrix(rng, 1, d_out, 4)[0]
+    spec = dict(features=[(dev(t), dev(v), None if o is None else dev(o), m) for t, v, o, m in feats_np],
+                batch=B, w1=bf(w1), b1=dev(b1), w2=bf(w2), b2=dev(b2))
+    return spec, dict(x=x, w1=w1.astype(np.float64), b1=b1.astype(np.float64), w2=w2.astype(np.float64), b2=b2.astype(np.float64))
+
+
+def ref_forward(n):
+    x = r16(n["x"])
+    h = r16(np.maximum(x @ n["w1"] + n["b1"], 0))
+    y = h @ n["w2"] + n["b2"]
+    return x, h, y
+
+
+SHAPES = [(300, 128, 256, 128, True), (128, 128, 128, 64, False), (1000, 128, 256, 64, True), (77, 128, 128, 128, False)]
+
+
+class TestFusedTowerExact:
+    def test_supported_shapes(self, ops):
+        assert ops.tower_mlp2_supported(128, 256, 128) and ops.tower_mlp2_supported(128, 128, 64)
+        assert not ops.tower_mlp2_supported(64, 128, 64) and not ops.tower_mlp2_supported(128, 512, 128)
+
+    @pytest.mark.parametrize("B,d_in,d_hid,d_out,bag", SHAPES)
+    def test_forward(self, ops, B, d_in, d_hid, d_out, bag):
+        rng = synth.rng_for(B + d_hid + d_out)
+        spec, n = make_tower(rng, B, d_in, d_hid, d_out, bag)
+        (x, h, y), = ops.tower_mlp2_fwd([spec])
+        rx, rh, ry = ref_forward(n)
+        assert np.array_equal(x.float().cpu().numpy(), rx)
+        assert np.array_equal(h.float().cpu().numpy(), rh)
+        assert np.array_equal(y.float().cpu().numpy(), r16(ry))
+
+    @pytest.mark.parametrize("B,d_in,d_hid,d_out,bag", SHAPES)
+    @pytest.mark.parametrize("splits", [1, 3])
+    def test_backward(self, ops, B, d_in, d_hid, d_out, bag, splits):
+        rng = synth.rng_for(7 * B + d_hid + d_out + splits)
+        spec, n = make_tower(rng, B, d_in, d_hid, d_out, bag)
+        (x, h, y), = ops.tower_mlp2_fwd([spec])
+        parts = np.stack([synth.exact_matrix(rng, B, d_out, 1) for _ in range(splits)])
+        dy = parts.astype(np.float64).sum(0)                       # multiples of 1/8, |.| <= 3/8: exact in bf16
+        o, = ops.tower_mlp2_bwd([dict(spec, x=x, h=h, dy_parts=dev(parts), dy_splits=splits)])
+        rx, rh, _ = ref_forward(n)
+        dh = r16((dy @ n["w2"].T) * (rh > 0))
+        P = (B + 127) // 128
+        assert o["P"] == P and tuple(o["dw1"].shape) == (P, d_in, d_hid)
+        assert np.array_equal(o["dx"].cpu().numpy().astype(np.float64), dh @ n["w1"].T)
+        assert np.array_equal(o["dw2"].sum(0).cpu().numpy().astype(np.float64), rh.T @ dy)
+        assert np.array_equal(o["dw1"].sum(0).cpu().numpy().astype(np.float64), rx.T @ dh)
+        assert np.array_equal(o["db2"].sum(0).cpu().numpy().astype(np.float64), dy.sum(0))
+        assert np.array_equal(o["db1"].sum(0).cpu().numpy().astype(np.float64), dh.sum(0))
+        # per-slice partials: slice p covers rows [128p, 128p+128)
+        p = P - 1
+        sl = slice(128 * p, min(B, 128 * p + 128))
+        assert np.array_equal(o["dw2"][p].cpu().numpy().astype(np.float64), rh[sl].T @ dy[sl])
+
+    def test_two_towers_one_launch_full_batch(self, ops):
+        rng = synth.rng_for(8192)
+        sa, na = make_tower(rng, 8192, 128, 256, 128, False)
+        sb, nb = make_tower(rng, 8192, 128, 256, 128, True)
+        before = ops.LAUNCHES
+        (xa, ha, ya), (xb, hb, yb) = ops.tower_mlp2_fwd([sa, sb])
+        assert ops.LAUNCHES - before == 1
+        for n, y in ((na, ya), (nb, yb)):
+            assert np.array_equal(y.float().cpu().numpy(), r16(ref_forward(n)[2]))
+        pa, pb = synth.exact_matrix(rng, 8192, 128, 1)[None], synth.exact_matrix(rng, 8192, 128, 1)[None]
+        oa, ob = ops.tower_mlp2_bwd([dict(sa, x=xa, h=ha, dy_parts=dev(pa), dy_splits=1),
+                                     dict(sb, x=xb, h=hb, dy_parts=dev(pb), dy_splits=1)])
+        for n, o, p in ((na, oa, pa), (nb, ob, pb)):
+            rx, rh, _ = ref_forward(n)
+            dy = p[0].astype(np.float64)
+            dh = r16((dy @ n["w2"].T) * (rh > 0))
+            assert np.array_equal(o["dx"].cpu().numpy().astype(np.float64), dh @ n["w1"].T)
+            assert np.array_equal(o["dw1"].sum(0).cpu().numpy().astype(np.float64), rx.T @ dh)
+            assert np.array_equal(o["dw2"].sum(0).cpu().numpy().astype(np.float64), rh.T @ dy)
+
+    def test_matches_the_per_layer_kernels_on_gaussian_data(self, ops):
+        rng = synth.rng_for(55)
+        B, d_in, d_hid, d_out = 1024, 128, 256, 128
+        table = oracle.keras_uniform(rng, (5000, d_in)); ids = rng.integers(0, 5000, B, dtype=np.int64)
+        w1 = oracle.glorot_uniform(rng, d_in, d_hid); w2 = oracle.glorot_uniform(rng, d_hid, d_out)
+        b1 = (rng.normal(size=d_hid) * 0.1).astype(np.float32); b2 = (rng.normal(size=d_out) * 0.1).astype(np.float32)
+        spec = dict(features=[(dev(table), dev(ids), None, "sum")], batch=B, w1=bf(w1), b1=dev(b1), w2=bf(w2), b2=dev(b2))
+        (x, h, y), = ops.tower_mlp2_fwd([spec])
+        _, x2 = ops.tower_input_fwd(spec["features"], B, d_in, want_f32=False, want_bf16=True)
+        h2, _ = ops.dense_fwd("bf16", x2, spec["w1"], spec["b1"], relu=True)
+        y2, _ = ops.dense_fwd("bf16", h2, spec["w2"], spec["b2"], relu=False)
+        assert torch.equal(x, x2) and torch.equal(h, h2) and torch.equal(y, y2)   # same arithmetic, same bits
+        ref = oracle.mlp_forward(table[ids].astype(np.float64), [w1, w2], [b1, b2], bf16=True)[0]
+        err = np.abs(y.float().cpu().numpy() - ref).max() / np.abs(ref).max()
+        assert err < BF16_RTOL
+
+
+class TestSplitLossBackward:
+    @pytest.mark.parametrize("nq,nc,d", [(512, 512, 128), (8192, 8192, 128), (300, 1000, 64)])
+    def test_parts_sum_to_the_combined_gradients(self, ops, nq, nc, d):
+        rng = synth.rng_for(nq + nc + d)
+        q = bf(rng.normal(size=(nq, d)).astype(np.float32) * 0.3); c = bf(rng.normal(size=(nc, d)).astype(np.float32) * 0.3)
+        loss, lse, _ = ops.retrieval_loss_fwd("bf16", q, c, 2.0)
+        r = ops.retrieval_loss_bwd("bf16", q, c, 2.0, lse, want_bf16=(True, True))
+        dq_parts, dc_parts = ops.retrieval_loss_bwd_parts(q, c, 2.0, lse)
+        sq, sc = ops.retrieval_bwd_num_splits(nq, nc, d)
+        assert dq_parts.shape == (sq, nq, d) and dc_parts.shape == (sc, nc, d)
+        f, b = ops.combine_parts(dq_parts, True, True)
+        assert torch.equal(f, r["dq"]) and torch.equal(b, r["dq_bf16"])
+        f, b = ops.combine_parts(dc_parts, True, True)
+        assert torch.equal(f, r["dc"]) and torch.equal(b, r["dc_bf16"])
+
+
+class TestMultiVariableOptimizer:
+    def test_dense_multi_equals_single(self, ops):
+        rng = synth.rng_for(91)
+        shapes = [(128, 256), (256, 128), (1, 256), (1, 130), (7, 9)]
+        mk = lambda: [(dev(rng.normal(size=s).astype(np.float32)), dev(np.full(s, 0.1, np.float32)),
+                       dev(rng.normal(size=(5, *s)).astype(np.float32))) for s in shapes]
+        vars_a = mk()
+        vars_b = [(w.clone(), a.clone(), g.clone()) for w, a, g in vars_a]
+        shadows_a = [torch.empty(w.shape, dtype=torch.bfloat16, device="cuda") for w, _, _ in vars_a]
+        shadows_b = [torch.empty_like(s) for s in shadows_a]
+        for (w, a, g), sh in zip(vars_a, shadows_a):
+            ops.dense_adagrad_update(w, a, g, 5, 0.05, 1e-7, 1e-3, sh)
+        before = ops.LAUNCHES
+        ops.dense_update_multi("adagrad", [(w, a, None, g, 5, 1e-3, sh) for (w, a, g), sh in zip(vars_b, shadows_b)], (0.05, 1e-7))
+        assert ops.LAUNCHES - before == 1
+        for (wa, aa, _), (wb, ab, _), sa, sb in zip(vars_a, vars_b, shadows_a, shadows_b):
+            assert torch.equal(wa, wb) and torch.equal(aa, ab) and torch.equal(sa, sb)
+
+    def test_dense_adam_multi_equals_single(self, ops):
+        rng = synth.rng_for(92)
+        shapes = [(64, 64), (1, 64)]
+        A = [(dev(rng.normal(size=s).astype(np.float32)), dev(np.zeros(s, np.float32)), dev(np.zeros(s, np.float32)),
+              dev(rng.normal(size=(3, *s)).astype(np.float32))) for s in shapes]
+        Bv = [tuple(t.clone() for t in v) for v in A]
+        for w, m, v, g in A:
+            ops.dense_adam_update(w, m, v, g, 3, 0.01, 0.9, 0.999, 1e-7, 0.0, None)
+        ops.dense_update_multi("adam", [(w, m, v, g, 3, 0.0, None) for w, m, v, g in Bv], (0.01, 0.9, 0.999, 1e-7))
+        for a, b in zip(A, Bv):
+            assert all(torch.equal(x, y) for x, y in zip(a[:3], b[:3]))
+
+    def test_sparse_multi_equals_oracle_and_single(self, ops):
+        rng = synth.rng_for(93)
+        d = 128
+        cases = []
+        for V, nnz, zipf in ((5000, 1024, 1.2), (300, 700, None)):
+            table = rng.normal(size=(V, d)).astype(np.float32)
+            ids = synth.draw_ids(rng, nnz, V, zipf)
+            grad = synth.exact_matrix(rng, nnz, d, 4)          # dyadic: duplicate sums are order-independent
+            cases.append((table, ids, grad))
+        items, flags = [], []
+        for table, ids, grad in cases:
+            t = dev(table); acc = dev(np.full(table.shape, 0.1, np.float32))
+            ws = ops.SparseWorkspace(len(ids), d, t.device)
+            ff = torch.zeros(len(ids), dtype=torch.uint8, device="cuda")
+            items.append((t, acc, None, dev(ids), None, "sum", dev(grad), ws, ff)); flags.append(ff)
+        before = ops.LAUNCHES
+        ops.sparse_update_multi("adagrad", items, (0.05, 1e-7))
+        assert ops.LAUNCHES - before == 3
+        for (table, ids, grad), it, ff in zip(cases, items, flags):
+            uniq, summed, _ = oracle.dedup_sparse_grad(ids, grad.astype(np.float64))
+            assert np.array_equal(ids[ff.cpu().numpy().astype(bool)], uniq)                  # tf.unique order, bit-exact
+            t2, a2, _ = oracle.adagrad_sparse(table.astype(np.float64), np.full(table.shape, 0.1), ids, grad.astype(np.float64), lr=0.05)
+            got = it[0].cpu().numpy()
+            assert np.abs(got - t2).max() <= 1e-5 * np.abs(t2).max()
+            untouched = np.setdiff1d(np.arange(table.shape[0]), uniq)
+            assert np.array_equal(got[untouched], table[untouched])
+        # the workspace is left clean: a second update with the same items works and moves the rows again
+        snap = items[0][0].clone()
+        ops.sparse_update_multi("adagrad", items, (0.05, 1e-7))
+        assert not torch.equal(snap, items[0][0])
+
+
+class TestFusedOptimizerStep:
+    """tt_optimizer_prepare_sparse + tt_adagrad_step / tt_lazy_adam_step: one launch for every dense variable and
+    every table; unique ids applied straight from their gradient row, duplicates reduced then applied by the last arriver."""
+
+    def _tables(self, ops, rng, d=128, bag_mode="mean"):
+        cases = []
+        for V, nnz, zipf in ((5000, 1024, 1.2), (300, 700, None), (100000, 4096, None)):
+            table = rng.normal(size=(V, d)).astype(np.float32)
+            ids = synth.draw_ids(rng, nnz, V, zipf)
+            ids[5] = -1                                           # padding id: dropped
+            grad = synth.exact_matrix(rng, nnz, d, 4)             # dyadic: duplicate sums are order-independent
+            cases.append((table, ids, None, "sum", grad))
+        # a mean-pooled bag feature: entry j belongs to bag(j), gradient scaled by 1 / len(bag)
+        V, B = 2000, 512
+        values, offsets = synth.draw_bags(rng, B, V, 0, 4)
+        cases.append((rng.normal(size=(V, d)).astype(np.float32), values, offsets, bag_mode, synth.exact_matrix(rng, B, d, 4)))
+        return cases
+
+    def _expand(self, ids, offsets, mode, grad):
+        if offsets is None:
+            return grad.astype(np.float64)
+        lens = np.diff(offsets)
+        bag = np.repeat(np.arange(len(lens)), lens)
+        rows = grad[bag].astype(np.float64)
+        if mode == "mean":
+            rows = (grad[bag] / lens[bag][:, None].astype(np.float32)).astype(np.float64)   # fp32 division as the kernel does
+        return rows
+
+    @pytest.mark.parametrize("kind", ["adagrad", "lazy_adam"])
+    def test_tables_and_dense_in_one_launch(self, ops, kind):
+        rng = synth.rng_for(97)
+        # Adam's first step is ~ alpha * sign(g): a duplicate sum that cancels to 0 exactly in the oracle but to 1e-8
+        # on the device would flip it, so the Adam case keeps every sum exact (dyadic rows, sum pooling)
+        cases = self._tables(ops, rng, bag_mode="mean" if kind == "adagrad" else "sum")
+        sparse_items, flags = [], []
+        for table, ids, offsets, mode, grad in cases:
+            t = dev(table)
+            s0 = dev(np.full(table.shape, 0.1 if kind == "adagrad" else 0.0, np.float32))
+            s1 = None if kind == "adagrad" else dev(np.zeros(table.shape, np.float32))
+            ws = ops.SparseWorkspace(len(ids), table.shape[1], t.device)
+            ff = torch.zeros(len(ids), dtype=torch.uint8, device="cuda")
+            sparse_items.append((t, s0, s1, dev(ids), None if offsets is None else dev(offsets), mode, dev(grad), ws, ff))
+            flags.append(ff)
+        shapes = [(128, 256), (1, 256), (7, 9)]
+        dense_np = [(rng.normal(size=sh).astype(np.float32), rng.normal(size=(5, *sh)).astype(np.float32)) for sh in shapes]
+        dense_items = [(dev(w), dev(np.full(w.shape, 0.1 if kind == "adagrad" else 0.0, np.float32)),
+                        None if kind == "adagrad" else dev(np.zeros(w.shape, np.float32)), dev(g), 5, 0.0, None) for w, g in dense_np]
+        hyper = (0.05, 1e-7) if kind == "adagrad" else (0.01, 0.9, 0.999, 1e-7)
+        before = ops.LAUNCHES
+        ops.sparse_prepare(sparse_items)
+        ops.optimizer_step(kind, dense_items, sparse_items, hyper)
+        assert ops.LAUNCHES - before == 2
+        for (table, ids, offsets, mode, grad), it, ff in zip(cases, sparse_items, flags):
+            rows = self._expand(ids, offsets, mode, grad)
+            ok = ids >= 0
+            uniq, summed, _ = oracle.dedup_sparse_grad(ids[ok], rows[ok])
+            first = np.zeros(len(ids), bool); first[np.flatnonzero(ok)[np.unique(ids[ok], return_index=True)[1]]] = True
+            assert np.array_equal(ff.cpu().numpy().astype(bool), first)                      # tf.unique positions, bit-exact
+            if kind == "adagrad":
+                ref, _, _ = oracle.adagrad_sparse(table.astype(np.float64), np.full(table.shape, 0.1), ids[ok], rows[ok], lr=0.05)
+            else:
+                ref, _, _, _ = oracle.lazy_adam_sparse(table.astype(np.float64), np.zeros(table.shape), np.zeros(table.shape), ids[ok], rows[ok],
+                                                    step=1, lr=0.01 / (np.sqrt(1 - 0.999) / (1 - 0.9)))
+            got = it[0].cpu().numpy()
+            assert np.abs(got - ref).max() <= 2e-5 * np.abs(ref).max()
+            untouched = np.setdiff1d(np.arange(table.shape[0]), uniq)
+            assert np.array_equal(got[untouched], table[untouched])                          # gradient row set exact
+        for (w, g), it in zip(dense_np, dense_items):
+            gs = g.astype(np.float64).sum(0)
+            if kind == "adagrad":
+                ref, _ = oracle.adagrad_dense(w.astype(np.float64), np.full(w.shape, 0.1), gs, lr=0.05)
+            else:
+                ref = oracle.adam_dense(w.astype(np.float64), np.zeros(w.shape), np.zeros(w.shape), gs, 1, lr=0.01 / (np.sqrt(1 - 0.999) / (1 - 0.9)))[0]
+            assert np.abs(it[0].cpu().numpy() - ref).max() <= 2e-5 * np.abs(ref).max()
+        # workspaces are clean again: the same step can be repeated and moves the rows again
+        snap = sparse_items[0][0].clone()
+        ops.sparse_prepare(sparse_items)
+        ops.optimizer_step(kind, dense_items, sparse_items, hyper)
+        assert not torch.equal(snap, sparse_items[0][0])
+        # ... and the multi-launch form still works on the same workspaces afterwards
+        if kind == "adagrad":
+            ops.sparse_update_multi("adagrad", sparse_items, hyper)
+
+
+class TestFusedTrainStep:
+    """Model-level: the TFRS-shaped surface picks the fused kernels for a 128-256-128 tower and the
+    step still tracks the oracle."""
+
+    def _model(self, tt, vu, vi, d, mlp, T, lr, fuse=True):
+        tt.set_precision("bf16")
+
+        class TwoTower(tt.models.Model):
+            def __init__(s):
+                super().__init__()
+                s.user_model = tt.Sequential([tt.layers.Embedding(vu, d), tt.layers.Dense(mlp[0], "relu"), tt.layers.Dense(mlp[1])])
+                s.item_model = tt.Sequential([tt.layers.Embedding(vi, d), tt.layers.Dense(mlp[0], "relu"), tt.layers.Dense(mlp[1])])
+                s.user_model.fuse = s.item_model.fuse = fuse
+                s.task = tt.tasks.Retrieval(temperature=T)
+
+            def compute_loss(s, f, training=False):
+                return s.task(s.user_model(f["user_id_encoded"]), s.item_model(f["item_id_encoded"]))
+
+        model = TwoTower(); model.compile(optimizer=tt.optimizers.Adagrad(lr))
+        return model
+
+    def test_launch_count_and_fused_equals_unfused(self, tt):
+        vu, vi, d, mlp, B, T, lr = 3000, 2500, 128, (256, 128), 640, 0.5, 0.05
+        tt.set_seed(5)
+        a = self._model(tt, vu, vi, d, mlp, T, lr, fuse=True)
+        b = self._model(tt, vu, vi, d, mlp, T, lr, fuse=False)
+        rng = synth.rng_for(41)
+        batch = {"user_id_encoded": synth.draw_ids(rng, B, vu, 1.3), "item_id_encoded": synth.draw_ids(rng, B, vi, 1.3)}
+        a.test_step(batch); b.test_step(batch)
+        for la, lb in zip(a.user_model.layers + a.item_model.layers, b.user_model.layers + b.item_model.layers):
+            lb.set_weights(la.get_weights())
+        oa = a.train_step(batch)
+        ob = b.train_step(batch)
+        assert float(oa["loss"].item()) == pytest.approx(float(ob["loss"].item()), rel=1e-6)
+        for la, lb in zip(a.user_model.layers + a.item_model.layers, b.user_model.layers + b.item_model.layers):
+            for wa, wb in zip(la.get_weights(), lb.get_weights()):
+                # same products; the weight-gradient partial sums are grouped differently (fp32 rounding only)
+                assert np.abs(wa - wb).max() <= 2e-3 * max(np.abs(wb).max(), 1e-6)
+        # steady state (sparse workspaces exist): fwd towers 1 + loss 1 + loss bwd 2 + bwd towers 1 + id dedup 1 (side stream) + optimizer 1
+        before = tt.ops.LAUNCHES
+        a.train_step(batch)
+        assert tt.ops.LAUNCHES - before == 7
+
+    def test_three_steps_track_the_oracle(self, tt):
+        vu, vi, d, mlp, B, T, lr = 2000, 1500, 128, (256, 128), 512, 0.5, 0.05
+        model = self._model(tt, vu, vi, d, mlp, T, lr)
+        rng = synth.rng_for(32)
+        mkb = lambda: {"user_id_encoded": synth.draw_ids(rng, B, vu, 1.3), "item_id_encoded": synth.draw_ids(rng, B, vi, 1.3)}
+        model.test_step(mkb())
+        qs = oracle.TowerSpec([("user_id_encoded", "id", vu, None)], d, mlp)
+        cs = oracle.TowerSpec([("item_id_encoded", "id", vi, None)], d, mlp)
+        get = lambda seq, name: {"tables": {name: seq.layers[0].get_weights()[0].astype(np.float64)},
+                                 "kernels": [l.get_weights()[0].astype(np.float64) for l in seq.layers[1:]],
+                                 "biases": [l.get_weights()[1].astype(np.float64) for l in seq.layers[1:]]}
+        qp, cp = get(model.user_model, "user_id_encoded"), get(model.item_model, "item_id_encoded")
+        tab0 = qp["tables"]["user_id_encoded"].copy()
+        k0 = [k.copy() for k in qp["kernels"]]
+        mk = lambda p: {"tables": {k: np.full(v.shape, 0.1) for k, v in p["tables"].items()},
+                        "kernels": [np.full(k.shape, 0.1) for k in p["kernels"]], "biases": [np.full(x.shape, 0.1) for x in p["biases"]]}
+        qsl, csl = mk(qp), mk(cp)
+        touched = set()
+        for _ in range(3):
+            b = mkb()
+            out = model.train_step(b)
+            ref = oracle.two_tower_train_step(qs, cs, qp, cp, qsl, csl, {"user_id_encoded": b["user_id_encoded"]},
+                                              {"item_id_encoded": b["item_id_encoded"]}, temperature=T, lr=lr, bf16=True)
+            assert float(out["loss"].item()) == pytest.approx(ref["loss"], rel=BF16_RTOL)
+            touched |= set(ref["unique"]["q/user_id_encoded"].tolist())
+        tab = model.user_model.layers[0].get_weights()[0].astype(np.float64)
+        rows = np.array(sorted(touched)); rest = np.setdiff1d(np.arange(vu), rows)
+        assert np.array_equal(tab[rest], tab0[rest])
+        assert (np.abs(tab[rows] - tab0[rows]).max(axis=1) > 0).all()
+        du, dr = (tab - tab0)[rows].ravel(), (qp["tables"]["user_id_encoded"] - tab0)[rows].ravel()
+        assert float(du @ dr / (np.linalg.norm(du) * np.linalg.norm(dr))) > 0.98
+        assert np.linalg.norm(du) == pytest.approx(np.linalg.norm(dr), rel=5e-2)
+        # Dense kernels: same criterion (Adagrad's g/sqrt(acc+g^2) amplifies the bf16 noise of near-cancelling
+        # weight-gradient sums, so the UPDATE is compared by direction and size)
+        for j, layer in enumerate(model.user_model.layers[1:]):
+            du = (layer.get_weights()[0].astype(np.float64) - k0[j]).ravel()
+            dr = (qp["kernels"][j] - k0[j]).ravel()
+            assert float(du @ dr / (np.linalg.norm(du) * np.linalg.norm(dr))) > 0.98
+            assert np.linalg.norm(du) == pytest.approx(np.linalg.norm(dr), rel=5e-2)

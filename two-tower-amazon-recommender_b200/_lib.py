@@ -27,6 +27,32 @@ class tt_feature(C.Structure):
                 ("vocab", C.c_int64), ("mode", C.c_int32), ("reserved", C.c_int32)]
 
 
+TT_MAX_TOWERS, TT_MAX_DENSE_VARS, TT_MAX_SPARSE_VARS = 4, 16, 8
+
+
+class tt_tower_mlp2(C.Structure):
+    _fields_ = [("feats", tt_feature * TT_MAX_FEATURES), ("num_feats", C.c_int32), ("d_in", C.c_int32),
+                ("d_hid", C.c_int32), ("d_out", C.c_int32), ("batch", C.c_int64),
+                ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+                ("x", C.c_void_p), ("h", C.c_void_p), ("y", C.c_void_p),
+                ("dy_parts", C.c_void_p), ("dy_splits", C.c_int32), ("reserved", C.c_int32),
+                ("dx", C.c_void_p), ("dw1_parts", C.c_void_p), ("dw2_parts", C.c_void_p),
+                ("db1_parts", C.c_void_p), ("db2_parts", C.c_void_p)]
+
+
+class tt_dense_var(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("slot0", C.c_void_p), ("slot1", C.c_void_p), ("grad_parts", C.c_void_p),
+                ("n", C.c_int64), ("num_parts", C.c_int32), ("l2", C.c_float), ("shadow", C.c_void_p)]
+
+
+class tt_sparse_var(C.Structure):
+    _fields_ = [("table", C.c_void_p), ("slot0", C.c_void_p), ("slot1", C.c_void_p),
+                ("vocab", C.c_int64), ("d", C.c_int64), ("values", C.c_void_p), ("offsets", C.c_void_p),
+                ("num_rows", C.c_int64), ("nnz", C.c_int64), ("grad", C.c_void_p), ("workspace", C.c_void_p),
+                ("workspace_bytes", C.c_int64), ("first_flag", C.c_void_p), ("mode", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 _p, _i64, _i32, _f = C.c_void_p, C.c_int64, C.c_int32, C.c_float
 
 # symbol -> (restype, argtypes); mirrors include/twotower.h one to one
@@ -47,6 +73,19 @@ SIGNATURES = {
     "tt_dense_adagrad_update": (C.c_int, [_p, _p, _p, _i32, _i64, _i64, _f, _f, _f, _p, _p]),
     "tt_dense_adam_update": (C.c_int, [_p, _p, _p, _p, _i32, _i64, _i64, _f, _f, _f, _f, _f, _p, _p]),
     "tt_sum_squares": (C.c_int, [_p, _i64, _f, _p, _i32, _p]),
+    "tt_dense_adagrad_update_multi": (C.c_int, [C.POINTER(tt_dense_var), _i32, _f, _f, _p]),
+    "tt_dense_adam_update_multi": (C.c_int, [C.POINTER(tt_dense_var), _i32, _f, _f, _f, _f, _p]),
+    "tt_sparse_adagrad_update_multi": (C.c_int, [C.POINTER(tt_sparse_var), _i32, _f, _f, _p]),
+    "tt_sparse_lazy_adam_update_multi": (C.c_int, [C.POINTER(tt_sparse_var), _i32, _f, _f, _f, _f, _p]),
+    "tt_optimizer_prepare_sparse": (C.c_int, [C.POINTER(tt_sparse_var), _i32, _p]),
+    "tt_adagrad_step": (C.c_int, [C.POINTER(tt_dense_var), _i32, C.POINTER(tt_sparse_var), _i32, _f, _f, _p]),
+    "tt_lazy_adam_step": (C.c_int, [C.POINTER(tt_dense_var), _i32, C.POINTER(tt_sparse_var), _i32, _f, _f, _f, _f, _p]),
+    "tt_tower_mlp2_supported": (_i32, [_i32, _i32, _i32]),
+    "tt_tower_mlp2_fwd": (C.c_int, [C.POINTER(tt_tower_mlp2), _i32, _p, _p]),
+    "tt_tower_mlp2_bwd": (C.c_int, [C.POINTER(tt_tower_mlp2), _i32, _p]),
+    "tt_retrieval_bwd_num_splits": (C.c_int, [_i32, _i64, _i64, _i64, C.POINTER(_i32), C.POINTER(_i32)]),
+    "tt_retrieval_loss_bwd_parts": (C.c_int, [_i32, _p, _p, _i64, _i64, _i64, _f, _i64, _p, _p, _p, _p, _f, _p, _p, _p]),
+    "tt_combine_parts_f32": (C.c_int, [_p, _i32, _i64, _i64, _p, _p, _p]),
     "tt_dense_fwd": (C.c_int, [_i32, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i32, _p]),
     "tt_dense_bwd": (C.c_int, [_i32, _p, _p, _p, _p, _p, _p, _i32, _p, _i64, _i64, _i64, _i32, _p]),
     "tt_dense_bwd_num_parts": (_i32, [_i32, _i64, _i64, _i64]),
@@ -54,7 +93,9 @@ SIGNATURES = {
     "tt_sum_parts_f32": (C.c_int, [_p, _i32, _i64, _p, _p]),
     "tt_debug_gemm_bf16": (C.c_int, [_p, _i32, _p, _i32, _i64, _i64, _i64, _p, _p]),
     "tt_cast_f32_to_bf16": (C.c_int, [_p, _p, _i64, _p]),
+    "tt_debug_trace_buffer": (C.c_int, [_p]),
     "tt_retrieval_workspace_bytes": (_i64, [_i32, _i64, _i64, _i64]),
+    "tt_retrieval_workspace_init": (C.c_int, [_i32, _p, _i64, _i64, _i64, _i64, _p]),
     "tt_retrieval_loss_fwd": (C.c_int, [_i32, _p, _p, _i64, _i64, _i64, _f, _i64, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "tt_retrieval_loss_bwd": (C.c_int, [_i32, _p, _p, _i64, _i64, _i64, _f, _i64, _p, _p, _p, _p, _f,
                                          _p, _p, _p, _p, _p, _i64, _p]),

@@ -39,20 +39,49 @@ def device() -> torch.device:
 
 class Tensor:
     """Activations of one layer: an fp32 copy and/or a bf16 copy.
-    ``grad_formats`` tells the consumer which gradient representations the producer needs."""
+    ``grad_formats`` tells the consumer which gradient representations the producer needs
+    ("f32", "bf16", or "parts" = stacked fp32 split partials the producer folds itself).
+    A tensor may be *pending*: its buffers are produced on first access, together with every
+    other pending tower output, by one fused launch (layers.PendingTowers)."""
 
-    def __init__(self, f32=None, bf16=None, grad_formats=("f32",), producer=None):
-        self.f32: Optional[torch.Tensor] = f32
-        self.bf16: Optional[torch.Tensor] = bf16
+    def __init__(self, f32=None, bf16=None, grad_formats=("f32",), producer=None, pending=None, shape=None):
+        self._f32: Optional[torch.Tensor] = f32
+        self._bf16: Optional[torch.Tensor] = bf16
+        self._pending = pending
+        self._shape = shape
         self.grad_formats = tuple(grad_formats)
         self.producer = producer
-        self.grad = None          # dict(f32=..., bf16=...) set by the consumer's backward
+        self.grad = None          # dict(f32=..., bf16=..., parts=...) set by the consumer's backward
         self.relu_output = False  # True when this is the output of a relu Dense
         self.producer_needs_grad = True   # False for constants fed in by the user
 
+    def _force(self):
+        if self._pending is not None:
+            self._pending.flush()
+
+    @property
+    def f32(self) -> Optional[torch.Tensor]:
+        self._force()
+        return self._f32
+
+    @f32.setter
+    def f32(self, v):
+        self._f32 = v
+
+    @property
+    def bf16(self) -> Optional[torch.Tensor]:
+        self._force()
+        return self._bf16
+
+    @bf16.setter
+    def bf16(self, v):
+        self._bf16 = v
+
     @property
     def shape(self):
-        t = self.f32 if self.f32 is not None else self.bf16
+        if self._pending is not None:
+            return tuple(self._shape)
+        t = self._f32 if self._f32 is not None else self._bf16
         return tuple(t.shape)
 
     def torch(self) -> torch.Tensor:
@@ -129,6 +158,9 @@ class GradientTape:
 
     def __init__(self):
         self.nodes: List[Callable[[], None]] = []
+        # called as on_sparse_lookup([(variable, values, offsets, mode)]) whenever embedding tables are read
+        # under this tape: lets the optimizer start the id dedup while the forward pass is still running
+        self.on_sparse_lookup: Optional[Callable] = None
 
     def __enter__(self):
         GradientTape._stack.append(self)
@@ -141,6 +173,12 @@ class GradientTape:
     @staticmethod
     def current() -> Optional["GradientTape"]:
         return GradientTape._stack[-1] if GradientTape._stack else None
+
+    @staticmethod
+    def note_sparse_lookup(lookups) -> None:
+        t = GradientTape.current()
+        if t is not None and t.on_sparse_lookup is not None:
+            t.on_sparse_lookup(lookups)
 
     @staticmethod
     def record(fn: Callable[[], None]) -> None:

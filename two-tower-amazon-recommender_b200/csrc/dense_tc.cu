@@ -74,7 +74,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % GEMM_STAGES;
         const uint32_t ph = (kb / GEMM_STAGES) & 1;
@@ -94,7 +94,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % GEMM_STAGES;

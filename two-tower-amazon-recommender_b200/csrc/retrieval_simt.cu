@@ -20,6 +20,12 @@ int tc_retrieval_bwd(const void* q, const void* c, int64_t nq, int64_t nc,
                      const int64_t* cand_ids, const float* row_lse, float grad_scale, float* dq, float* dc,
                      uint16_t* dq_bf16, uint16_t* dc_bf16, void* ws, int64_t ws_bytes, cudaStream_t st);
 int64_t tc_retrieval_workspace_bytes(int64_t nq, int64_t nc, int64_t d);
+int64_t tc_retrieval_sync_bytes(int64_t nq, int64_t nc, int64_t d);
+void tc_retrieval_bwd_num_splits(int64_t nq, int64_t nc, int64_t d, int* sq, int* sc);
+int tc_retrieval_bwd_parts(const void* q, const void* c, int64_t nq, int64_t nc, int64_t d, float inv_temp,
+                           int64_t label_offset, const float* w, const float* logq, const int64_t* cand_ids,
+                           const float* row_lse, float grad_scale, float* part_q, float* part_c, cudaStream_t st);
+int tc_combine_parts(const float* parts, int splits, int64_t rows, int64_t d, float* out_f32, uint16_t* out_bf16, cudaStream_t st);
 
 struct RetrievalArgs {
   const float* q; const float* c;
@@ -302,4 +308,42 @@ extern "C" int tt_retrieval_loss_bwd(int32_t precision, const void* q, const voi
   if (rc) return rc;
   a.dout = dc;
   return launch_retrieval<2>(a, st);
+}
+
+extern "C" int tt_retrieval_bwd_num_splits(int32_t precision, int64_t nq, int64_t nc, int64_t d, int32_t* dq_splits,
+                                           int32_t* dc_splits) {
+  TT_REQUIRE(precision == TT_BF16, "tt_retrieval_bwd_num_splits: the split form exists for TT_BF16 only");
+  TT_REQUIRE(dq_splits && dc_splits && nq > 0 && nc > 0 && d > 0, "tt_retrieval_bwd_num_splits: bad arguments");
+  int sq, sc;
+  tc_retrieval_bwd_num_splits(nq, nc, d, &sq, &sc);
+  *dq_splits = sq; *dc_splits = sc;
+  return TT_OK;
+}
+
+extern "C" int tt_retrieval_loss_bwd_parts(int32_t precision, const void* q, const void* c, int64_t nq, int64_t nc,
+                                           int64_t d, float inv_temperature, int64_t label_offset,
+                                           const float* sample_weight, const float* cand_log_q,
+                                           const int64_t* cand_ids, const float* row_lse, float grad_scale,
+                                           float* dq_parts, float* dc_parts, void* stream) {
+  TT_REQUIRE(precision == TT_BF16, "tt_retrieval_loss_bwd_parts: the split form exists for TT_BF16 only");
+  int rc = check_retrieval_common("tt_retrieval_loss_bwd_parts", precision, q, c, nq, nc, d, label_offset);
+  if (rc) return rc;
+  TT_REQUIRE(row_lse, "tt_retrieval_loss_bwd_parts: null row_lse");
+  return tc_retrieval_bwd_parts(q, c, nq, nc, d, inv_temperature, label_offset, sample_weight, cand_log_q, cand_ids,
+                                row_lse, grad_scale, dq_parts, dc_parts, (cudaStream_t)stream);
+}
+
+extern "C" int tt_combine_parts_f32(const float* parts, int32_t num_parts, int64_t rows, int64_t d, float* out_f32,
+                                    uint16_t* out_bf16, void* stream) {
+  return tc_combine_parts(parts, num_parts, rows, d, out_f32, out_bf16, (cudaStream_t)stream);
+}
+
+extern "C" int tt_retrieval_workspace_init(int32_t precision, void* workspace, int64_t workspace_bytes, int64_t nq,
+                                           int64_t nc, int64_t d, void* stream) {
+  TT_REQUIRE(workspace && nq > 0 && nc > 0 && d > 0, "tt_retrieval_workspace_init: bad arguments");
+  if (precision != TT_BF16) return TT_OK;
+  if (workspace_bytes < tc_retrieval_workspace_bytes(nq, nc, d))
+    return set_error(TT_ERR_WORKSPACE, "tt_retrieval_workspace_init: workspace too small");
+  TT_CUDA_OK(cudaMemsetAsync(workspace, 0, (size_t)tc_retrieval_sync_bytes(nq, nc, d), (cudaStream_t)stream));
+  return TT_OK;
 }

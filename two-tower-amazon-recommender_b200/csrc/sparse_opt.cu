@@ -21,6 +21,7 @@
 // order over duplicates is not fixed (same as TF's GPU unsorted_segment_sum).
 #include "common.cuh"
 #include <limits.h>
+#include <algorithm>
 
 namespace tt {
 
@@ -29,6 +30,8 @@ static constexpr unsigned long long kEmpty = 0xFFFFFFFFFFFFFFFFull;
 struct SparseWs {
   unsigned long long* keys;  // [cap]
   int* first;                // [cap]
+  int* cnt;                  // [cap] occurrences of the key in this batch (fused step)
+  int* done;                 // [cap] arrival tickets of the duplicates (fused step)
   int* hpos;                 // [nnz]
   int* bag_of;               // [nnz]
   float* accum;              // [nnz, d]
@@ -45,12 +48,14 @@ static int64_t ws_layout(int64_t nnz, int64_t d, void* base, SparseWs* ws) {
   const int64_t cap = hash_capacity(nnz);
   int64_t off = 0;
   auto take = [&](int64_t bytes) { int64_t o = off; off += round_up(bytes, 256); return o; };
-  int64_t o_keys = take(cap * 8), o_first = take(cap * 4), o_hpos = take(nnz * 4),
-          o_bag = take(nnz * 4), o_acc = take(nnz * d * 4);
+  int64_t o_keys = take(cap * 8), o_first = take(cap * 4), o_cnt = take(cap * 4), o_done = take(cap * 4),
+          o_hpos = take(nnz * 4), o_bag = take(nnz * 4), o_acc = take(nnz * d * 4);
   if (ws) {
     char* b = (char*)base;
     ws->keys = (unsigned long long*)(b + o_keys);
     ws->first = (int*)(b + o_first);
+    ws->cnt = (int*)(b + o_cnt);
+    ws->done = (int*)(b + o_done);
     ws->hpos = (int*)(b + o_hpos);
     ws->bag_of = (int*)(b + o_bag);
     ws->accum = (float*)(b + o_acc);
@@ -67,7 +72,7 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
 __global__ void sparse_ws_init_kernel(SparseWs ws, int64_t nnz, int64_t d) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t k = i; k < ws.cap; k += stride) { ws.keys[k] = kEmpty; ws.first[k] = INT_MAX; }
+  for (int64_t k = i; k < ws.cap; k += stride) { ws.keys[k] = kEmpty; ws.first[k] = INT_MAX; ws.cnt[k] = 0; ws.done[k] = 0; }
   for (int64_t k = i; k < nnz * d; k += stride) ws.accum[k] = 0.f;
 }
 
@@ -233,6 +238,459 @@ dense_opt_kernel(float* __restrict__ w, float* __restrict__ s0, float* __restric
   if (shadow) shadow[i] = float_to_bf16_bits(wv);
 }
 
+// ---- multi-variable forms: one launch per stage for all tables / all dense variables ------
+struct SparseMultiVar {
+  SparseWs ws;
+  float* table; float* s0; float* s1;
+  const int64_t* values; const int64_t* offsets;
+  const float* grad;
+  uint8_t* first_flag;
+  int64_t num_rows, nnz, vocab, d;
+  int mode;
+};
+struct SparseMultiArgs { SparseMultiVar v[TT_MAX_SPARSE_VARS]; };
+
+__global__ void __launch_bounds__(256) sparse_insert_multi_kernel(const __grid_constant__ SparseMultiArgs a) {
+  const SparseMultiVar& V = a.v[blockIdx.y];
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= V.nnz) return;
+  const int64_t id = V.values[j];
+  if (id < 0 || id >= V.vocab) { V.ws.hpos[j] = -1; return; }
+  const uint64_t mask = (uint64_t)V.ws.cap - 1;
+  uint64_t h = mix64((uint64_t)id) & mask;
+  while (true) {
+    unsigned long long prev = atomicCAS(&V.ws.keys[h], kEmpty, (unsigned long long)id);
+    if (prev == kEmpty || prev == (unsigned long long)id) break;
+    h = (h + 1) & mask;
+  }
+  V.ws.hpos[j] = (int)h;
+  atomicMin(&V.ws.first[h], (int)j);
+  if (V.offsets) {
+    int64_t lo = 0, hi = V.num_rows;
+    while (hi - lo > 1) {
+      int64_t mid = (lo + hi) >> 1;
+      if (V.offsets[mid] <= j) lo = mid; else hi = mid;
+    }
+    V.ws.bag_of[j] = (int)lo;
+  }
+}
+
+__global__ void __launch_bounds__(256) sparse_accumulate_multi_kernel(const __grid_constant__ SparseMultiArgs a) {
+  const SparseMultiVar& V = a.v[blockIdx.y];
+  const int lane = threadIdx.x & 31;
+  const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= V.nnz) return;
+  const int h = V.ws.hpos[j];
+  if (h < 0) return;
+  const int leader = V.ws.first[h];
+  int64_t row = j;
+  float L = 1.f;
+  if (V.offsets) {
+    row = V.ws.bag_of[j];
+    if (V.mode == TT_POOL_MEAN) L = (float)(V.offsets[row + 1] - V.offsets[row]);
+  }
+  const float4* g = reinterpret_cast<const float4*>(V.grad + row * V.d);
+  float4* acc = reinterpret_cast<float4*>(V.ws.accum + (int64_t)leader * V.d);
+  for (int c = lane; c < (int)(V.d >> 2); c += 32) {
+    float4 v = __ldg(g + c);
+    if (L != 1.f) { v.x = __fdiv_rn(v.x, L); v.y = __fdiv_rn(v.y, L); v.z = __fdiv_rn(v.z, L); v.w = __fdiv_rn(v.w, L); }
+    atomicAdd(acc + c, v);
+  }
+}
+
+template <bool ADAM>
+__global__ void __launch_bounds__(256)
+sparse_apply_multi_kernel(const __grid_constant__ SparseMultiArgs a, float lr_or_alpha, float b1, float b2, float eps) {
+  const SparseMultiVar& V = a.v[blockIdx.y];
+  const int lane = threadIdx.x & 31;
+  const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= V.nnz) return;
+  const int h = V.ws.hpos[j];
+  const bool is_first = (h >= 0) && (V.ws.first[h] == (int)j);
+  if (V.first_flag && lane == 0) V.first_flag[j] = is_first ? 1 : 0;
+  if (!is_first) return;
+  const int64_t id = (int64_t)V.ws.keys[h];
+  float4* acc = reinterpret_cast<float4*>(V.ws.accum + j * V.d);
+  for (int c = lane; c < (int)(V.d >> 2); c += 32) {
+    const float4 g = acc[c];
+    acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ADAM) {
+      LazyAdamRule rule{V.s0, V.s1, lr_or_alpha, b1, b2, eps};
+      rule.apply(V.table + id * V.d, id * V.d, c, g);
+    } else {
+      AdagradRule rule{V.s0, lr_or_alpha, eps};
+      rule.apply(V.table + id * V.d, id * V.d, c, g);
+    }
+  }
+  __syncwarp();
+  if (lane == 0) { V.ws.keys[h] = kEmpty; V.ws.first[h] = INT_MAX; }
+}
+
+static int run_sparse_multi(const char* name, bool adam, const tt_sparse_var* vars, int n, float lr_or_alpha,
+                            float b1, float b2, float eps, cudaStream_t stream) {
+  TT_REQUIRE(vars && n >= 1 && n <= TT_MAX_SPARSE_VARS, "%s: num_vars must be in [1, %d]", name, TT_MAX_SPARSE_VARS);
+  static thread_local SparseMultiArgs args;
+  int64_t max_nnz = 0;
+  for (int i = 0; i < n; ++i) {
+    const tt_sparse_var& s = vars[i];
+    TT_REQUIRE(s.table && s.slot0 && (!adam || s.slot1) && s.values && s.grad && s.workspace, "%s: variable %d has a null buffer", name, i);
+    TT_REQUIRE(s.d > 0 && s.d % 4 == 0, "%s: d must be a multiple of 4, got %lld", name, (long long)s.d);
+    TT_REQUIRE(aligned16(s.table) && aligned16(s.slot0) && aligned16(s.grad) && aligned16(s.workspace), "%s: buffers must be 16-byte aligned", name);
+    TT_REQUIRE(s.nnz >= 0 && s.nnz < INT_MAX && s.num_rows >= 0, "%s: bad sizes", name);
+    TT_REQUIRE(s.offsets != nullptr || s.nnz == s.num_rows, "%s: without offsets nnz must equal num_rows", name);
+    TT_REQUIRE(s.mode == TT_POOL_SUM || s.mode == TT_POOL_MEAN, "%s: bad pooling mode", name);
+    if (s.workspace_bytes < ws_layout(s.nnz, s.d, nullptr, nullptr))
+      return set_error(TT_ERR_WORKSPACE, "%s: workspace of variable %d too small", name, i);
+    SparseMultiVar& v = args.v[i];
+    ws_layout(s.nnz, s.d, s.workspace, &v.ws);
+    v.table = s.table; v.s0 = s.slot0; v.s1 = s.slot1; v.values = s.values; v.offsets = s.offsets; v.grad = s.grad;
+    v.first_flag = s.first_flag; v.num_rows = s.num_rows; v.nnz = s.nnz; v.vocab = s.vocab; v.d = s.d; v.mode = s.mode;
+    max_nnz = std::max<int64_t>(max_nnz, s.nnz);
+  }
+  if (max_nnz == 0) return TT_OK;
+  TT_PROF("sparse_insert_kernel", stream);
+  sparse_insert_multi_kernel<<<dim3((unsigned)ceil_div(max_nnz, 256), n), 256, 0, stream>>>(args);
+  TT_LAUNCH_OK("sparse_insert_multi_kernel");
+  TT_PROF("sparse_accumulate_kernel", stream);
+  sparse_accumulate_multi_kernel<<<dim3((unsigned)ceil_div(max_nnz, 8), n), 256, 0, stream>>>(args);
+  TT_LAUNCH_OK("sparse_accumulate_multi_kernel");
+  TT_PROF("sparse_apply_kernel", stream);
+  if (adam) sparse_apply_multi_kernel<true><<<dim3((unsigned)ceil_div(max_nnz, 8), n), 256, 0, stream>>>(args, lr_or_alpha, b1, b2, eps);
+  else sparse_apply_multi_kernel<false><<<dim3((unsigned)ceil_div(max_nnz, 8), n), 256, 0, stream>>>(args, lr_or_alpha, b1, b2, eps);
+  TT_LAUNCH_OK("sparse_apply_multi_kernel");
+  return TT_OK;
+}
+
+struct DenseMultiVar {
+  float* w; float* s0; float* s1; const float* parts; uint16_t* shadow;
+  int64_t n; int num_parts; float l2;
+};
+struct DenseMultiArgs { DenseMultiVar v[TT_MAX_DENSE_VARS]; };
+
+// thread = 4 consecutive weights (n % 4 == 0) or one weight; the partial sums are read as
+// num_parts strided, coalesced float4 streams (L2-resident) and added in index order
+template <bool ADAM>
+__global__ void __launch_bounds__(256)
+dense_opt_multi_kernel(const __grid_constant__ DenseMultiArgs a, float lr_or_alpha, float b1, float b2, float eps) {
+  const DenseMultiVar& V = a.v[blockIdx.y];
+  const bool vec = (V.n & 3) == 0;
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * (vec ? 4 : 1);
+  if (i0 >= V.n) return;
+  float g[4] = {0.f, 0.f, 0.f, 0.f};
+  if (vec) {
+    const float4* pp = reinterpret_cast<const float4*>(V.parts + i0);
+    const int64_t stride4 = V.n >> 2;
+    int p = 0;
+    for (; p + 8 <= V.num_parts; p += 8) {
+      float4 t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = __ldg(pp + (int64_t)(p + u) * stride4);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        g[0] = __fadd_rn(g[0], t[u].x); g[1] = __fadd_rn(g[1], t[u].y); g[2] = __fadd_rn(g[2], t[u].z); g[3] = __fadd_rn(g[3], t[u].w);
+      }
+    }
+    for (; p < V.num_parts; ++p) {
+      const float4 t = __ldg(pp + (int64_t)p * stride4);
+      g[0] = __fadd_rn(g[0], t.x); g[1] = __fadd_rn(g[1], t.y); g[2] = __fadd_rn(g[2], t.z); g[3] = __fadd_rn(g[3], t.w);
+    }
+  } else {
+    for (int p = 0; p < V.num_parts; ++p) g[0] = __fadd_rn(g[0], V.parts[(int64_t)p * V.n + i0]);
+  }
+  const int cnt = vec ? 4 : 1;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if (e >= cnt) break;
+    const int64_t i = i0 + e;
+    float wv = V.w[i], gv = g[e];
+    if (V.l2 != 0.f) gv = __fadd_rn(gv, __fmul_rn(2.f * V.l2, wv));
+    if (ADAM) {
+      float m = V.s0[i], v = V.s1[i];
+      m = __fadd_rn(m, __fmul_rn(__fsub_rn(gv, m), 1.f - b1));
+      v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(gv, gv), v), 1.f - b2));
+      wv = __fsub_rn(wv, __fdiv_rn(__fmul_rn(m, lr_or_alpha), __fadd_rn(__fsqrt_rn(v), eps)));
+      V.s0[i] = m; V.s1[i] = v;
+    } else {
+      const float acc = __fadd_rn(V.s0[i], __fmul_rn(gv, gv));
+      wv = __fsub_rn(wv, __fdiv_rn(__fmul_rn(lr_or_alpha, gv), __fsqrt_rn(__fadd_rn(acc, eps))));
+      V.s0[i] = acc;
+    }
+    V.w[i] = wv;
+    if (V.shadow) V.shadow[i] = float_to_bf16_bits(wv);
+  }
+}
+
+static int run_dense_multi(const char* name, bool adam, const tt_dense_var* vars, int n, float lr_or_alpha,
+                           float b1, float b2, float eps, cudaStream_t stream) {
+  TT_REQUIRE(vars && n >= 1 && n <= TT_MAX_DENSE_VARS, "%s: num_vars must be in [1, %d]", name, TT_MAX_DENSE_VARS);
+  static thread_local DenseMultiArgs args;
+  int64_t max_threads = 0;
+  for (int i = 0; i < n; ++i) {
+    const tt_dense_var& s = vars[i];
+    TT_REQUIRE(s.w && s.slot0 && s.grad_parts && (!adam || s.slot1), "%s: variable %d has a null buffer", name, i);
+    TT_REQUIRE(s.n > 0 && s.num_parts >= 1, "%s: variable %d has bad sizes", name, i);
+    TT_REQUIRE((s.n & 3) != 0 || aligned16(s.grad_parts), "%s: grad_parts of variable %d must be 16-byte aligned", name, i);
+    DenseMultiVar& v = args.v[i];
+    v.w = s.w; v.s0 = s.slot0; v.s1 = s.slot1; v.parts = s.grad_parts; v.shadow = s.shadow;
+    v.n = s.n; v.num_parts = s.num_parts; v.l2 = s.l2;
+    max_threads = std::max<int64_t>(max_threads, (s.n & 3) == 0 ? s.n / 4 : s.n);
+  }
+  dim3 grid((unsigned)ceil_div(max_threads, 256), (unsigned)n);
+  TT_PROF("dense_opt_kernel", stream);
+  if (adam) dense_opt_multi_kernel<true><<<grid, 256, 0, stream>>>(args, lr_or_alpha, b1, b2, eps);
+  else dense_opt_multi_kernel<false><<<grid, 256, 0, stream>>>(args, lr_or_alpha, b1, b2, eps);
+  TT_LAUNCH_OK("dense_opt_multi_kernel");
+  return TT_OK;
+}
+
+// ---- fused optimizer step ---------------------------------------------------------------------
+// (1) sparse_prepare_kernel: the hash insert alone; it needs only the ids, so the host enqueues it on a
+//     side stream at lookup time and it overlaps the forward pass.  Besides the slot and the first
+//     occurrence it counts the occurrences of every key.
+// (2) optimizer_step_kernel: ONE launch for all dense variables and all tables.
+//     Table entries: a key that occurs once (the common case) is applied straight from its gradient row:
+//     no accumulation traffic at all.  Duplicates add their rows into the accumulation row of the first
+//     occurrence with 128-bit reductions and take a ticket; the LAST arriver applies the update and
+//     cleans the slot ("last block done", per key).  Dense variables: 4 lanes share a float4 of weights
+//     and each folds a quarter of the split-K partials (fixed association: deterministic).
+__global__ void __launch_bounds__(256) sparse_prepare_kernel(const __grid_constant__ SparseMultiArgs a) {
+  const SparseMultiVar& V = a.v[blockIdx.y];
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= V.nnz) return;
+  const int64_t id = V.values[j];
+  if (id < 0 || id >= V.vocab) { V.ws.hpos[j] = -1; return; }
+  const uint64_t mask = (uint64_t)V.ws.cap - 1;
+  uint64_t h = mix64((uint64_t)id) & mask;
+  while (true) {
+    unsigned long long prev = atomicCAS(&V.ws.keys[h], kEmpty, (unsigned long long)id);
+    if (prev == kEmpty || prev == (unsigned long long)id) break;
+    h = (h + 1) & mask;
+  }
+  V.ws.hpos[j] = (int)h;
+  atomicMin(&V.ws.first[h], (int)j);
+  atomicAdd(&V.ws.cnt[h], 1);
+  if (V.offsets) {
+    int64_t lo = 0, hi = V.num_rows;
+    while (hi - lo > 1) {
+      int64_t mid = (lo + hi) >> 1;
+      if (V.offsets[mid] <= j) lo = mid; else hi = mid;
+    }
+    V.ws.bag_of[j] = (int)lo;
+  }
+}
+
+struct StepArgs {
+  DenseMultiArgs dense;
+  SparseMultiArgs sparse;
+  int dense_blocks[TT_MAX_DENSE_VARS + 1];    // prefix sums of the blocks of each dense variable
+  int sparse_blocks[TT_MAX_SPARSE_VARS + 1];  // prefix sums (after the dense blocks)
+  int n_dense, n_sparse;
+};
+
+template <bool ADAM>
+__device__ __forceinline__ void apply_row(const SparseMultiVar& V, int64_t id, int c, float4 g, float lr_or_alpha,
+                                          float b1, float b2, float eps) {
+  if (ADAM) {
+    LazyAdamRule rule{V.s0, V.s1, lr_or_alpha, b1, b2, eps};
+    rule.apply(V.table + id * V.d, id * V.d, c, g);
+  } else {
+    AdagradRule rule{V.s0, lr_or_alpha, eps};
+    rule.apply(V.table + id * V.d, id * V.d, c, g);
+  }
+}
+
+template <bool ADAM>
+__global__ void __launch_bounds__(256)
+optimizer_step_kernel(const __grid_constant__ StepArgs a, float lr_or_alpha, float b1, float b2, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int bid = blockIdx.x;
+  if (bid < a.dense_blocks[a.n_dense]) {
+    // ---------------- dense variable: 4 lanes per float4 of weights, each folds partials q, q+4, ...
+    int vi = 0;
+    while (bid >= a.dense_blocks[vi + 1]) ++vi;
+    const DenseMultiVar& V = a.dense.v[vi];
+    const bool vec = (V.n & 3) == 0;
+    const int64_t item = (int64_t)(bid - a.dense_blocks[vi]) * 64 + (threadIdx.x >> 2);   // 64 items per block
+    const int q = threadIdx.x & 3;
+    const int64_t i0 = item * (vec ? 4 : 1);
+    const bool live = i0 < V.n;
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+    if (live) {
+      if (vec) {
+        const float4* pp = reinterpret_cast<const float4*>(V.parts + i0);
+        const int64_t stride4 = V.n >> 2;
+        int p = q;
+        for (; p + 12 < V.num_parts; p += 16) {
+          float4 t[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) t[u] = __ldg(pp + (int64_t)(p + 4 * u) * stride4);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            g[0] = __fadd_rn(g[0], t[u].x); g[1] = __fadd_rn(g[1], t[u].y); g[2] = __fadd_rn(g[2], t[u].z); g[3] = __fadd_rn(g[3], t[u].w);
+          }
+        }
+        for (; p < V.num_parts; p += 4) {
+          const float4 t = __ldg(pp + (int64_t)p * stride4);
+          g[0] = __fadd_rn(g[0], t.x); g[1] = __fadd_rn(g[1], t.y); g[2] = __fadd_rn(g[2], t.z); g[3] = __fadd_rn(g[3], t.w);
+        }
+      } else {
+        for (int p = q; p < V.num_parts; p += 4) g[0] = __fadd_rn(g[0], V.parts[(int64_t)p * V.n + i0]);
+      }
+    }
+    // (q0 + q1) + (q2 + q3): fixed order
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      g[e] = __fadd_rn(g[e], __shfl_xor_sync(0xffffffffu, g[e], 1));
+      g[e] = __fadd_rn(g[e], __shfl_xor_sync(0xffffffffu, g[e], 2));
+    }
+    if (!live) return;
+    // lane q of the group updates element q of the float4 (scalar variables: lane 0 only)
+    if (!vec && q != 0) return;
+    const int64_t i = i0 + (vec ? q : 0);
+    float gv = vec ? (q == 0 ? g[0] : q == 1 ? g[1] : q == 2 ? g[2] : g[3]) : g[0];
+    float wv = V.w[i];
+    if (V.l2 != 0.f) gv = __fadd_rn(gv, __fmul_rn(2.f * V.l2, wv));
+    if (ADAM) {
+      float m = V.s0[i], v = V.s1[i];
+      m = __fadd_rn(m, __fmul_rn(__fsub_rn(gv, m), 1.f - b1));
+      v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(gv, gv), v), 1.f - b2));
+      wv = __fsub_rn(wv, __fdiv_rn(__fmul_rn(m, lr_or_alpha), __fadd_rn(__fsqrt_rn(v), eps)));
+      V.s0[i] = m; V.s1[i] = v;
+    } else {
+      const float acc = __fadd_rn(V.s0[i], __fmul_rn(gv, gv));
+      wv = __fsub_rn(wv, __fdiv_rn(__fmul_rn(lr_or_alpha, gv), __fsqrt_rn(__fadd_rn(acc, eps))));
+      V.s0[i] = acc;
+    }
+    V.w[i] = wv;
+    if (V.shadow) V.shadow[i] = float_to_bf16_bits(wv);
+    return;
+  }
+  // ---------------- table entries: warp per entry
+  int vi = 0;
+  while (vi + 1 < a.n_sparse && bid >= a.sparse_blocks[vi + 1]) ++vi;
+  const SparseMultiVar& V = a.sparse.v[vi];
+  const int64_t j = (int64_t)(bid - a.sparse_blocks[vi]) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= V.nnz) return;
+  const int h = V.ws.hpos[j];
+  if (h < 0) { if (V.first_flag && lane == 0) V.first_flag[j] = 0; return; }
+  const int leader = V.ws.first[h];
+  const int count = V.ws.cnt[h];
+  if (V.first_flag && lane == 0) V.first_flag[j] = leader == (int)j ? 1 : 0;
+  const int64_t id = (int64_t)V.ws.keys[h];
+  int64_t row = j;
+  float L = 1.f;
+  if (V.offsets) {
+    row = V.ws.bag_of[j];
+    if (V.mode == TT_POOL_MEAN) L = (float)(V.offsets[row + 1] - V.offsets[row]);
+  }
+  const float4* gp = reinterpret_cast<const float4*>(V.grad + row * V.d);
+  const int nch = (int)(V.d >> 2);
+  if (count == 1) {
+    for (int c = lane; c < nch; c += 32) {
+      float4 g = __ldg(gp + c);
+      if (L != 1.f) { g.x = __fdiv_rn(g.x, L); g.y = __fdiv_rn(g.y, L); g.z = __fdiv_rn(g.z, L); g.w = __fdiv_rn(g.w, L); }
+      apply_row<ADAM>(V, id, c, g, lr_or_alpha, b1, b2, eps);
+    }
+    if (lane == 0) { V.ws.keys[h] = kEmpty; V.ws.first[h] = INT_MAX; V.ws.cnt[h] = 0; }
+    return;
+  }
+  float4* acc = reinterpret_cast<float4*>(V.ws.accum + (int64_t)leader * V.d);
+  for (int c = lane; c < nch; c += 32) {
+    float4 g = __ldg(gp + c);
+    if (L != 1.f) { g.x = __fdiv_rn(g.x, L); g.y = __fdiv_rn(g.y, L); g.z = __fdiv_rn(g.z, L); g.w = __fdiv_rn(g.w, L); }
+    atomicAdd(acc + c, g);
+  }
+  __threadfence();
+  __syncwarp();
+  int ticket = 0;
+  if (lane == 0) ticket = atomicAdd(&V.ws.done[h], 1);
+  ticket = __shfl_sync(0xffffffffu, ticket, 0);
+  if (ticket != count - 1) return;
+  __threadfence();
+  for (int c = lane; c < nch; c += 32) {
+    const float4 g = __ldcg(acc + c);
+    acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    apply_row<ADAM>(V, id, c, g, lr_or_alpha, b1, b2, eps);
+  }
+  if (lane == 0) { V.ws.keys[h] = kEmpty; V.ws.first[h] = INT_MAX; V.ws.cnt[h] = 0; V.ws.done[h] = 0; }
+}
+
+static int fill_sparse(const char* name, bool adam, const tt_sparse_var* vars, int n, SparseMultiArgs* args, int64_t* max_nnz) {
+  TT_REQUIRE(n == 0 || vars, "%s: null variable array", name);
+  TT_REQUIRE(n >= 0 && n <= TT_MAX_SPARSE_VARS, "%s: at most %d tables per call", name, TT_MAX_SPARSE_VARS);
+  *max_nnz = 0;
+  for (int i = 0; i < n; ++i) {
+    const tt_sparse_var& s = vars[i];
+    TT_REQUIRE(s.table && s.values && s.workspace, "%s: table %d has a null buffer", name, i);
+    TT_REQUIRE(s.d > 0 && s.d % 4 == 0, "%s: d must be a multiple of 4, got %lld", name, (long long)s.d);
+    TT_REQUIRE(aligned16(s.table) && aligned16(s.workspace), "%s: buffers must be 16-byte aligned", name);
+    TT_REQUIRE(s.nnz >= 0 && s.nnz < INT_MAX && s.num_rows >= 0, "%s: bad sizes", name);
+    TT_REQUIRE(s.offsets != nullptr || s.nnz == s.num_rows, "%s: without offsets nnz must equal num_rows", name);
+    TT_REQUIRE(s.mode == TT_POOL_SUM || s.mode == TT_POOL_MEAN, "%s: bad pooling mode", name);
+    if (s.workspace_bytes < ws_layout(s.nnz, s.d, nullptr, nullptr))
+      return set_error(TT_ERR_WORKSPACE, "%s: workspace of table %d too small", name, i);
+    SparseMultiVar& v = args->v[i];
+    ws_layout(s.nnz, s.d, s.workspace, &v.ws);
+    v.table = s.table; v.s0 = s.slot0; v.s1 = s.slot1; v.values = s.values; v.offsets = s.offsets; v.grad = s.grad;
+    v.first_flag = s.first_flag; v.num_rows = s.num_rows; v.nnz = s.nnz; v.vocab = s.vocab; v.d = s.d; v.mode = s.mode;
+    *max_nnz = std::max<int64_t>(*max_nnz, s.nnz);
+  }
+  (void)adam;
+  return TT_OK;
+}
+
+static int run_prepare(const tt_sparse_var* vars, int n, cudaStream_t stream) {
+  static thread_local SparseMultiArgs args;
+  int64_t max_nnz;
+  int rc = fill_sparse("tt_optimizer_prepare_sparse", false, vars, n, &args, &max_nnz);
+  if (rc) return rc;
+  if (n == 0 || max_nnz == 0) return TT_OK;
+  TT_PROF("sparse_prepare_kernel", stream);
+  sparse_prepare_kernel<<<dim3((unsigned)ceil_div(max_nnz, 256), n), 256, 0, stream>>>(args);
+  TT_LAUNCH_OK("sparse_prepare_kernel");
+  return TT_OK;
+}
+
+static int run_step(const char* name, bool adam, const tt_dense_var* dense, int nd, const tt_sparse_var* sparse, int ns,
+                    float lr_or_alpha, float b1, float b2, float eps, cudaStream_t stream) {
+  TT_REQUIRE(nd >= 0 && nd <= TT_MAX_DENSE_VARS && (nd == 0 || dense), "%s: at most %d dense variables per call", name, TT_MAX_DENSE_VARS);
+  static thread_local StepArgs args;
+  int64_t max_nnz;
+  int rc = fill_sparse(name, adam, sparse, ns, &args.sparse, &max_nnz);
+  if (rc) return rc;
+  for (int i = 0; i < ns; ++i)
+    TT_REQUIRE(sparse[i].slot0 && sparse[i].grad && aligned16(sparse[i].slot0) && aligned16(sparse[i].grad) && (!adam || sparse[i].slot1),
+               "%s: table %d has a null or unaligned slot / gradient", name, i);
+  int blocks = 0;
+  args.dense_blocks[0] = 0;
+  for (int i = 0; i < nd; ++i) {
+    const tt_dense_var& s = dense[i];
+    TT_REQUIRE(s.w && s.slot0 && s.grad_parts && (!adam || s.slot1), "%s: dense variable %d has a null buffer", name, i);
+    TT_REQUIRE(s.n > 0 && s.num_parts >= 1, "%s: dense variable %d has bad sizes", name, i);
+    TT_REQUIRE((s.n & 3) != 0 || aligned16(s.grad_parts), "%s: grad_parts of variable %d must be 16-byte aligned", name, i);
+    DenseMultiVar& v = args.dense.v[i];
+    v.w = s.w; v.s0 = s.slot0; v.s1 = s.slot1; v.parts = s.grad_parts; v.shadow = s.shadow;
+    v.n = s.n; v.num_parts = s.num_parts; v.l2 = s.l2;
+    const int64_t items = (s.n & 3) == 0 ? s.n / 4 : s.n;
+    blocks += (int)ceil_div(items, 64);
+    args.dense_blocks[i + 1] = blocks;
+  }
+  for (int i = nd; i < TT_MAX_DENSE_VARS; ++i) args.dense_blocks[i + 1] = blocks;
+  args.sparse_blocks[0] = blocks;
+  for (int i = 0; i < ns; ++i) {
+    blocks += (int)ceil_div(sparse[i].nnz, 8);
+    args.sparse_blocks[i + 1] = blocks;
+  }
+  for (int i = ns; i < TT_MAX_SPARSE_VARS; ++i) args.sparse_blocks[i + 1] = blocks;
+  args.n_dense = nd; args.n_sparse = ns;
+  if (blocks == 0) return TT_OK;
+  TT_PROF("optimizer_step_kernel", stream);
+  if (adam) optimizer_step_kernel<true><<<blocks, 256, 0, stream>>>(args, lr_or_alpha, b1, b2, eps);
+  else optimizer_step_kernel<false><<<blocks, 256, 0, stream>>>(args, lr_or_alpha, b1, b2, eps);
+  TT_LAUNCH_OK("optimizer_step_kernel");
+  return TT_OK;
+}
+
 __global__ void __launch_bounds__(1024)
 sum_squares_kernel(const float* __restrict__ x, int64_t n, float scale, float* __restrict__ out, int accumulate) {
   __shared__ float part[1024];
@@ -325,4 +783,38 @@ extern "C" int tt_dense_adam_update(float* w, float* m, float* v, const float* g
                                     float eps, float l2, uint16_t* shadow, void* stream) {
   return dense_opt(true, w, m, v, grad_parts, num_parts, rows, cols, alpha, beta1, beta2, eps, l2,
                    shadow, (cudaStream_t)stream);
+}
+
+extern "C" int tt_sparse_adagrad_update_multi(const tt_sparse_var* host_vars, int32_t num_vars, float lr, float eps,
+                                              void* stream) {
+  return run_sparse_multi("tt_sparse_adagrad_update_multi", false, host_vars, num_vars, lr, 0.f, 0.f, eps, (cudaStream_t)stream);
+}
+
+extern "C" int tt_sparse_lazy_adam_update_multi(const tt_sparse_var* host_vars, int32_t num_vars, float alpha,
+                                                float beta1, float beta2, float eps, void* stream) {
+  return run_sparse_multi("tt_sparse_lazy_adam_update_multi", true, host_vars, num_vars, alpha, beta1, beta2, eps, (cudaStream_t)stream);
+}
+
+extern "C" int tt_dense_adagrad_update_multi(const tt_dense_var* host_vars, int32_t num_vars, float lr, float eps,
+                                             void* stream) {
+  return run_dense_multi("tt_dense_adagrad_update_multi", false, host_vars, num_vars, lr, 0.f, 0.f, eps, (cudaStream_t)stream);
+}
+
+extern "C" int tt_dense_adam_update_multi(const tt_dense_var* host_vars, int32_t num_vars, float alpha, float beta1,
+                                          float beta2, float eps, void* stream) {
+  return run_dense_multi("tt_dense_adam_update_multi", true, host_vars, num_vars, alpha, beta1, beta2, eps, (cudaStream_t)stream);
+}
+
+extern "C" int tt_optimizer_prepare_sparse(const tt_sparse_var* host_vars, int32_t num_vars, void* stream) {
+  return run_prepare(host_vars, num_vars, (cudaStream_t)stream);
+}
+
+extern "C" int tt_adagrad_step(const tt_dense_var* host_dense, int32_t num_dense, const tt_sparse_var* host_sparse,
+                               int32_t num_sparse, float lr, float eps, void* stream) {
+  return run_step("tt_adagrad_step", false, host_dense, num_dense, host_sparse, num_sparse, lr, 0.f, 0.f, eps, (cudaStream_t)stream);
+}
+
+extern "C" int tt_lazy_adam_step(const tt_dense_var* host_dense, int32_t num_dense, const tt_sparse_var* host_sparse,
+                                 int32_t num_sparse, float alpha, float beta1, float beta2, float eps, void* stream) {
+  return run_step("tt_lazy_adam_step", true, host_dense, num_dense, host_sparse, num_sparse, alpha, beta1, beta2, eps, (cudaStream_t)stream);
 }

@@ -91,7 +91,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_arrive_expect_tx(q_full, L.q_bytes);
       for (int kb = 0; kb < nkb; ++kb) tma_load_2d(sQ + kb * TK_BM * 128, &tmQ, q_full, kb * 64, q0);
       for (int t = 0; t < T; ++t) {
@@ -103,7 +103,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       constexpr uint32_t idesc = umma_idesc_bf16(TK_BM, TK_BN);
       mbar_wait(q_full, 0);
       for (int t = 0; t < T; ++t) {

@@ -1,0 +1,663 @@
+// K1+K2 fused (bf16 precision) -- a whole two-layer tower in one kernel, forward and backward.
+//
+//   forward : gather/pool 128 batch rows (fp32 tables, sequential fp32 sums) straight into the
+//             swizzled shared-memory A tile, D1 = x W1 on tcgen05 (TMEM), epilogue +b1, relu ->
+//             bf16 h back into shared memory (over the dead W1 tile) and to HBM for the backward,
+//             D2 = h W2 on tcgen05, epilogue +b2 -> bf16 y.  W1/W2 arrive by TMA in the Keras
+//             [in, out] layout and are read as MN-major B operands: no transposed copy exists.
+//   backward: dy = ordered sum of the fp32 split partials of the loss backward (rounded to bf16
+//             once, db2 taken before rounding), then four GEMMs on the same 128 rows:
+//               dh_pre = dy W2^T           (A = dy K-major,  B = W2 K-major)
+//               dW2_p  = h^T dy            (A = h MN-major,  B = dy MN-major)
+//               dx     = dh W1^T           (A = dh K-major,  B = W1 K-major)
+//               dW1_p  = x^T dh            (A = x MN-major,  B = dh MN-major)
+//             with dh = dh_pre * (h > 0) produced by the epilogue warps directly into shared memory,
+//             where ONE copy serves as the K-major A of the third and the MN-major B of the fourth.
+//             Shared memory and TMEM are re-used as operands die (see the region table below).
+//
+// One CTA = 128 rows of one tower, 256 threads; blockIdx.y selects the tower so query and candidate
+// towers share a launch.  Both kernels are latency-bound at the BASELINE sizes (a tower is
+// 0.5 GFLOP forward): what matters is that the gather, four/two GEMMs and all epilogues cost ONE
+// launch and no HBM round trips for x / h / dh.
+#include "tc_common.cuh"
+#include "gather_row.cuh"
+
+namespace tt {
+
+constexpr int TW_BM = 128;
+constexpr int TW_THREADS = 256;
+constexpr int TW_BLK = TW_BM * 128;          // bytes of one [128 rows][64 bf16] swizzled block
+
+struct TowerDev {
+  FeatureParams feats;
+  int64_t B;
+  int d_in, d_hid, d_out;
+  const float* b1;
+  const float* b2;
+  uint16_t* x;
+  uint16_t* h;
+  uint16_t* y;
+};
+
+struct TowerFwdArgs {
+  CUtensorMap tmW1[TT_MAX_TOWERS];   // W1 [d_in, d_hid]: box {64, d_in}
+  CUtensorMap tmW2[TT_MAX_TOWERS];   // W2 [d_hid, d_out]: box {64, d_hid}
+  TowerDev t[TT_MAX_TOWERS];
+  int* fault;
+};
+
+struct TowerBwdDev {
+  int64_t B;
+  int d_in, d_hid, d_out;
+  const float* dy_parts;
+  int dy_splits;
+  float* dx;
+  float* dw1_parts;
+  float* dw2_parts;
+  float* db1_parts;
+  float* db2_parts;
+};
+
+struct TowerBwdArgs {
+  CUtensorMap tmX[TT_MAX_TOWERS];    // x [B, d_in]:  box {64, 128}
+  CUtensorMap tmH[TT_MAX_TOWERS];    // h [B, d_hid]: box {64, 128}
+  CUtensorMap tmW2[TT_MAX_TOWERS];   // W2 [d_hid, d_out] read K-major (N = d_hid rows): box {64, d_hid}
+  CUtensorMap tmW1[TT_MAX_TOWERS];   // W1 [d_in, d_hid]  read K-major (N = d_in rows):  box {64, d_in}
+  TowerBwdDev t[TT_MAX_TOWERS];
+};
+
+__host__ __device__ inline int imax(int a, int b) { return a > b ? a : b; }
+
+// 16-byte-chunk store of 8 bf16 into a K-major swizzled tile made of [128][64] blocks
+__device__ __forceinline__ void st_tile_chunk(uint8_t* tile, int r, int col, uint4 v) {
+  *reinterpret_cast<uint4*>(tile + (col >> 6) * TW_BLK + sw128_offset(r, (col & 63) >> 3)) = v;
+}
+
+// ---------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------
+struct FwdLayout {
+  int x_bytes, r1_bytes, w1_bytes, w2_bytes, off_r1, off_w2, off_tail, total;
+};
+__host__ __device__ inline FwdLayout fwd_layout(int d_in, int d_hid, int d_out) {
+  FwdLayout L;
+  L.x_bytes = TW_BM * d_in * 2;
+  L.w1_bytes = d_in * d_hid * 2;
+  L.w2_bytes = d_hid * d_out * 2;
+  L.r1_bytes = imax(L.w1_bytes, TW_BM * d_hid * 2);   // W1, then h
+  L.off_r1 = L.x_bytes;
+  L.off_w2 = L.off_r1 + L.r1_bytes;
+  L.off_tail = L.off_w2 + L.w2_bytes;
+  L.total = L.off_tail + 64 + (d_hid + d_out) * 4;
+  return L;
+}
+
+__global__ void __launch_bounds__(TW_THREADS, 1)
+tower_mlp2_fwd_kernel(const __grid_constant__ TowerFwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  const int tw = blockIdx.y;
+  const TowerDev& P = a.t[tw];
+  const int64_t m0 = (int64_t)blockIdx.x * TW_BM;
+  if (m0 >= P.B) return;
+  const int d_in = P.d_in, d_hid = P.d_hid, d_out = P.d_out;
+  const FwdLayout L = fwd_layout(d_in, d_hid, d_out);
+  uint8_t* sX = smem;
+  uint8_t* sR1 = smem + L.off_r1;                 // W1 (MN-major chunks [d_in][64]) then h (K-major blocks)
+  uint8_t* sW2 = smem + L.off_w2;                 // MN-major chunks [d_hid][64]
+  uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + L.off_tail);
+  uint64_t* mma1_done = w_full + 1;
+  uint64_t* mma2_done = w_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 3);
+  float* sB1 = reinterpret_cast<float*>(smem + L.off_tail + 64);
+  float* sB2 = sB1 + d_hid;
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&a.tmW1[tw]);
+    tma_prefetch_desc(&a.tmW2[tw]);
+    mbar_init(w_full, 1); mbar_init(mma1_done, 1); mbar_init(mma2_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && elect_one_sync()) {            // weights: L2-resident after the first CTA
+    mbar_arrive_expect_tx(w_full, L.w1_bytes + L.w2_bytes);
+    for (int j = 0; j < d_hid / 64; ++j) tma_load_2d(sR1 + j * d_in * 128, &a.tmW1[tw], w_full, 64 * j, 0);
+    for (int j = 0; j < d_out / 64; ++j) tma_load_2d(sW2 + j * d_hid * 128, &a.tmW2[tw], w_full, 64 * j, 0);
+  }
+  for (int i = threadIdx.x; i < d_hid; i += TW_THREADS) sB1[i] = P.b1[i];
+  for (int i = threadIdx.x; i < d_out; i += TW_THREADS) sB2[i] = P.b2[i];
+
+  // ---- gather / pool the 128 rows: lane l owns columns 4l..4l+3 of the row (d_in == 128)
+  {
+    const int nchunks = d_in >> 2;
+    const int col = 4 * lane;
+    auto put_row = [&](int r, int64_t b, const float4& v) {
+      if (lane < nchunks) {
+        const uint2 pk = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+        *reinterpret_cast<uint2*>(sX + (col >> 6) * TW_BLK + sw128_offset(r, (col & 63) >> 3) + (lane & 1) * 8) = pk;
+        if (b < P.B && P.x) *reinterpret_cast<uint2*>(P.x + b * d_in + col) = pk;
+      }
+    };
+    if (P.feats.n == 1 && P.feats.f[0].offsets == nullptr) {
+      // ID-only tower: the warp's 16 ids in one load, then 16 independent row loads in flight per lane
+      const tt_feature& ft = P.feats.f[0];
+      int64_t my_id = -1;
+      if (lane < TW_BM / 8) {
+        const int64_t b = m0 + warp + 8 * lane;
+        if (b < P.B) {
+          my_id = __ldg(ft.values + b);
+          if (my_id < 0 || my_id >= ft.vocab) {
+            if (a.fault && my_id != -1) atomicExch(a.fault, 1);
+            my_id = -1;
+          }
+        }
+      }
+      float4 v[TW_BM / 8];
+#pragma unroll
+      for (int i = 0; i < TW_BM / 8; ++i) {
+        const int64_t id = __shfl_sync(0xffffffffu, my_id, i);
+        v[i] = (id >= 0 && lane < nchunks) ? ldg_row_chunk(ft.table, id, d_in, lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < TW_BM / 8; ++i) put_row(warp + 8 * i, m0 + warp + 8 * i, v[i]);
+    } else {
+#pragma unroll 4
+      for (int i = 0; i < TW_BM / 8; ++i) {
+        const int r = warp + 8 * i;
+        const int64_t b = m0 + r;
+        float4 v[1];
+        v[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b < P.B) gather_row<1>(P.feats, b, d_in, lane, nchunks, a.fault, v);
+        put_row(r, b, v[0]);
+      }
+    }
+  }
+  fence_proxy_async();
+  __syncthreads();
+
+  // the whole warp waits, one lane issues (no spinning lanes beside a working one)
+  if (warp == 0) {
+    mbar_wait(w_full, 0);
+    tc_fence_after();
+    if (elect_one_sync()) {
+      const uint32_t idesc = umma_idesc_bf16(TW_BM, d_hid, 0, 1);
+      const uint64_t db0 = umma_desc_mn_sw128(smem_u32(sR1), d_in * 128);
+      for (int kk = 0; kk < d_in / 16; ++kk) {
+        const uint64_t da = umma_desc_k_sw128(smem_u32(sX + (kk >> 2) * TW_BLK)) + 2 * (kk & 3);
+        umma_bf16_ss(tmem_base, da, db0 + 128 * kk, idesc, kk != 0);
+      }
+      umma_commit(mma1_done);
+    }
+    __syncwarp();
+  }
+
+  const int q = warp & 3, hf = warp >> 2;
+  const int r = q * 32 + lane;
+  const int64_t row = m0 + r;
+  const bool row_ok = row < P.B;
+  const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+
+  // ---- epilogue 1: h = relu(D1 + b1) -> bf16, into shared memory (over W1) and HBM
+  mbar_wait(mma1_done, 0);
+  tc_fence_after();
+  {
+    const int ncol = d_hid / 2;
+#pragma unroll 1
+    for (int c0 = hf * ncol; c0 < (hf + 1) * ncol; c0 += 32) {
+      uint32_t rr[32];
+      tmem_ld_32x32b_x32(lane_addr + c0, rr);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(__uint_as_float(rr[g * 8 + j]) + sB1[c0 + g * 8 + j], 0.f);
+        const uint4 pk = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        st_tile_chunk(sR1, r, c0 + g * 8, pk);
+        if (row_ok && P.h) *reinterpret_cast<uint4*>(P.h + row * d_hid + c0 + g * 8) = pk;
+      }
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+
+  if (warp == 0) {
+    tc_fence_after();
+    if (elect_one_sync()) {
+      const uint32_t idesc = umma_idesc_bf16(TW_BM, d_out, 0, 1);
+      const uint64_t db0 = umma_desc_mn_sw128(smem_u32(sW2), d_hid * 128);
+      for (int kk = 0; kk < d_hid / 16; ++kk) {
+        const uint64_t da = umma_desc_k_sw128(smem_u32(sR1 + (kk >> 2) * TW_BLK)) + 2 * (kk & 3);
+        umma_bf16_ss(tmem_base + 256, da, db0 + 128 * kk, idesc, kk != 0);
+      }
+      umma_commit(mma2_done);
+    }
+    __syncwarp();
+  }
+
+  // ---- epilogue 2: y = D2 + b2 -> bf16
+  mbar_wait(mma2_done, 0);
+  tc_fence_after();
+  {
+    const int ncol = d_out / 2;
+#pragma unroll 1
+    for (int c0 = hf * ncol; c0 < (hf + 1) * ncol; c0 += 32) {
+      uint32_t rr[32];
+      tmem_ld_32x32b_x32(lane_addr + 256 + c0, rr);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(rr[g * 8 + j]) + sB2[c0 + g * 8 + j];
+          *reinterpret_cast<uint4*>(P.y + row * d_out + c0 + g * 8) =
+              make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------
+// Shared-memory regions and their successive tenants (cfg2: 32 + 64 + 64 + 32 KB):
+//   R_dy : dy tile [128][d_out] (K-major blocks)      -> second half of the W1 k-blocks
+//   R_h  : h tile  [128][d_hid]                        -> x tile [128][d_in]
+//   R_w2 : W2 k-blocks [d_hid][64] x d_out/64          -> dh tile [128][d_hid]
+//   R_w1 : first half of the W1 k-blocks [d_in][64]
+// TMEM columns: dh_pre [0, d_hid) -> dx [0, d_in); dW2 [256, 256 + d_hid/128 * d_out);
+//               dW1 [d_in, d_in + d_hid) once dW2 has been drained.
+struct BwdTLayout {
+  int dy_bytes, h_bytes, w2r_bytes, w1blk, w1lo_blocks, nk1;
+  int off_h, off_w2, off_w1, off_tail, total;
+};
+__host__ __device__ inline BwdTLayout bwdt_layout(int d_in, int d_hid, int d_out) {
+  BwdTLayout L;
+  L.dy_bytes = TW_BM * d_out * 2;
+  L.h_bytes = TW_BM * d_hid * 2;
+  L.w2r_bytes = imax(d_hid * d_out * 2, TW_BM * d_hid * 2);
+  L.w1blk = d_in * 128;
+  L.nk1 = d_hid / 64;
+  L.w1lo_blocks = L.nk1 - L.dy_bytes / L.w1blk < 0 ? 0 : L.nk1 - L.dy_bytes / L.w1blk;   // blocks that do not fit R_dy
+  if (L.w1lo_blocks < L.nk1 / 2) L.w1lo_blocks = L.nk1 / 2;
+  L.off_h = L.dy_bytes;
+  L.off_w2 = L.off_h + L.h_bytes;
+  L.off_w1 = L.off_w2 + L.w2r_bytes;
+  L.off_tail = L.off_w1 + L.w1lo_blocks * L.w1blk;
+  L.total = L.off_tail + 128 + (8 * d_out + d_hid) * 4;
+  return L;
+}
+
+__global__ void __launch_bounds__(TW_THREADS, 1)
+tower_mlp2_bwd_kernel(const __grid_constant__ TowerBwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  const int tw = blockIdx.y;
+  const TowerBwdDev& P = a.t[tw];
+  const int64_t m0 = (int64_t)blockIdx.x * TW_BM;
+  if (m0 >= P.B) return;
+  const int d_in = P.d_in, d_hid = P.d_hid, d_out = P.d_out;
+  const BwdTLayout L = bwdt_layout(d_in, d_hid, d_out);
+  uint8_t* rDY = smem;
+  uint8_t* rH = smem + L.off_h;
+  uint8_t* rW2 = smem + L.off_w2;
+  uint8_t* rW1 = smem + L.off_w1;
+  uint64_t* ld_full = reinterpret_cast<uint64_t*>(smem + L.off_tail);
+  uint64_t* mma_ab_done = ld_full + 1;
+  uint64_t* w1hi_full = ld_full + 2;
+  uint64_t* x_full = ld_full + 3;
+  uint64_t* mma_c_done = ld_full + 4;
+  uint64_t* mma_d_done = ld_full + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ld_full + 6);
+  float* s_db2 = reinterpret_cast<float*>(smem + L.off_tail + 128);   // [8][d_out]
+  const int p = blockIdx.x;                        // partial index of this 128-row slice
+  const int n_hi = L.nk1 - L.w1lo_blocks;          // W1 k-blocks that move into R_dy later
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&a.tmX[tw]); tma_prefetch_desc(&a.tmH[tw]);
+    tma_prefetch_desc(&a.tmW2[tw]); tma_prefetch_desc(&a.tmW1[tw]);
+    for (int i = 0; i < 6; ++i) mbar_init(ld_full + i, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && elect_one_sync()) {
+    mbar_arrive_expect_tx(ld_full, L.h_bytes + d_hid * d_out * 2 + L.w1lo_blocks * L.w1blk);
+    for (int j = 0; j < d_hid / 64; ++j) tma_load_2d(rH + j * TW_BLK, &a.tmH[tw], ld_full, 64 * j, (int)m0);
+    for (int j = 0; j < d_out / 64; ++j) tma_load_2d(rW2 + j * d_hid * 128, &a.tmW2[tw], ld_full, 64 * j, 0);
+    for (int j = 0; j < L.w1lo_blocks; ++j) tma_load_2d(rW1 + j * L.w1blk, &a.tmW1[tw], ld_full, 64 * j, 0);
+  }
+
+  // ---- dy = ordered sum of the split partials; db2 from the fp32 sums; bf16 tile into R_dy
+  {
+    const int nchunks = d_out >> 2;                // float4 chunks per row (<= 32)
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int col = 4 * lane;
+#pragma unroll 4
+    for (int i = 0; i < TW_BM / 8; ++i) {
+      const int r = warp + 8 * i;
+      const int64_t b = m0 + r;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (b < P.B && lane < nchunks) {
+        v = __ldg(reinterpret_cast<const float4*>(P.dy_parts + b * d_out) + lane);
+        for (int s = 1; s < P.dy_splits; ++s) {
+          const float4 u = __ldg(reinterpret_cast<const float4*>(P.dy_parts + ((int64_t)s * P.B + b) * d_out) + lane);
+          v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+        }
+      }
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      if (lane < nchunks)
+        *reinterpret_cast<uint2*>(rDY + (col >> 6) * TW_BLK + sw128_offset(r, (col & 63) >> 3) + (lane & 1) * 8) =
+            make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+    if (lane < nchunks) *reinterpret_cast<float4*>(s_db2 + warp * d_out + col) = acc;
+  }
+  fence_proxy_async();
+  __syncthreads();
+  if (threadIdx.x < d_out) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += s_db2[w * d_out + threadIdx.x];
+    P.db2_parts[(int64_t)p * d_out + threadIdx.x] = s;
+  }
+
+  mbar_wait(ld_full, 0);                           // every thread: h is also read with generic loads below
+  if (warp == 0) {
+    tc_fence_after();
+    if (elect_one_sync()) {
+      {  // dh_pre[128, d_hid] = dy W2^T
+        const uint32_t idesc = umma_idesc_bf16(TW_BM, d_hid, 0, 0);
+        for (int kk = 0; kk < d_out / 16; ++kk) {
+          const uint64_t da = umma_desc_k_sw128(smem_u32(rDY + (kk >> 2) * TW_BLK)) + 2 * (kk & 3);
+          const uint64_t db = umma_desc_k_sw128(smem_u32(rW2 + (kk >> 2) * d_hid * 128)) + 2 * (kk & 3);
+          umma_bf16_ss(tmem_base, da, db, idesc, kk != 0);
+        }
+      }
+      {  // dW2[m-th 128 rows of d_hid, d_out] = h^T dy  (K = the 128 batch rows)
+        const uint32_t idesc = umma_idesc_bf16(128, d_out, 1, 1);
+        const uint64_t db0 = umma_desc_mn_sw128(smem_u32(rDY), TW_BLK);
+        for (int m = 0; m < d_hid / 128; ++m) {
+          const uint64_t da0 = umma_desc_mn_sw128(smem_u32(rH + 2 * m * TW_BLK), TW_BLK);
+          for (int kk = 0; kk < TW_BM / 16; ++kk)
+            umma_bf16_ss(tmem_base + 256 + m * d_out, da0 + 128 * kk, db0 + 128 * kk, idesc, kk != 0);
+        }
+      }
+      umma_commit(mma_ab_done);
+    }
+    __syncwarp();
+    mbar_wait(mma_ab_done, 0);
+    if (n_hi > 0 && elect_one_sync()) {                   // dy is dead once both GEMMs are done: bring in the rest of W1
+      mbar_arrive_expect_tx(w1hi_full, n_hi * L.w1blk);
+      for (int j = 0; j < n_hi; ++j) tma_load_2d(rDY + j * L.w1blk, &a.tmW1[tw], w1hi_full, 64 * (L.w1lo_blocks + j), 0);
+    }
+    __syncwarp();
+  }
+
+  const int q = warp & 3, hf = warp >> 2;
+  const int r = q * 32 + lane;
+  const int64_t row = m0 + r;
+  const bool row_ok = row < P.B;
+  const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+
+  // ---- epilogue a: dh = dh_pre * (h > 0) -> bf16 tile over the dead W2
+  mbar_wait(mma_ab_done, 0);
+  tc_fence_after();
+  {
+    const int ncol = d_hid / 2;
+#pragma unroll 1
+    for (int c0 = hf * ncol; c0 < (hf + 1) * ncol; c0 += 32) {
+      uint32_t rr[32];
+      tmem_ld_32x32b_x32(lane_addr + c0, rr);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int col = c0 + g * 8;
+        const uint4 hv = *reinterpret_cast<const uint4*>(rH + (col >> 6) * TW_BLK + sw128_offset(r, (col & 63) >> 3));
+        const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+        float v[8];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float lo = __uint_as_float(hw[t] << 16), hi = __uint_as_float(hw[t] & 0xffff0000u);
+          v[2 * t] = lo > 0.f ? __uint_as_float(rr[g * 8 + 2 * t]) : 0.f;
+          v[2 * t + 1] = hi > 0.f ? __uint_as_float(rr[g * 8 + 2 * t + 1]) : 0.f;
+        }
+        st_tile_chunk(rW2, r, col, make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
+      }
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+
+  if (warp == 0) {
+    tc_fence_after();
+    if (elect_one_sync()) {
+      // h is dead (dW2 done, mask applied): x takes its place for the last GEMM
+      mbar_arrive_expect_tx(x_full, TW_BM * d_in * 2);
+      for (int j = 0; j < d_in / 64; ++j) tma_load_2d(rH + j * TW_BLK, &a.tmX[tw], x_full, 64 * j, (int)m0);
+    }
+    __syncwarp();
+    if (n_hi > 0) { mbar_wait(w1hi_full, 0); tc_fence_after(); }
+    if (elect_one_sync()) {
+      // dx[128, d_in] = dh W1^T
+      const uint32_t idesc = umma_idesc_bf16(TW_BM, d_in, 0, 0);
+      for (int kk = 0; kk < d_hid / 16; ++kk) {
+        const int kb = kk >> 2;
+        const uint8_t* wblk = kb < L.w1lo_blocks ? rW1 + kb * L.w1blk : rDY + (kb - L.w1lo_blocks) * L.w1blk;
+        const uint64_t da = umma_desc_k_sw128(smem_u32(rW2 + kb * TW_BLK)) + 2 * (kk & 3);
+        const uint64_t db = umma_desc_k_sw128(smem_u32(wblk)) + 2 * (kk & 3);
+        umma_bf16_ss(tmem_base, da, db, idesc, kk != 0);
+      }
+      umma_commit(mma_c_done);
+    }
+    __syncwarp();
+  }
+
+  // ---- dW2 partial -> HBM (rows = d_hid index, TMEM lanes), while dx runs on the tensor pipe
+  {
+    const int C = (d_hid / 128) * d_out;           // concatenated columns of the dW2 tiles
+    float* out = P.dw2_parts + (int64_t)p * d_hid * d_out;
+#pragma unroll 1
+    for (int cc = hf * (C / 2); cc < (hf + 1) * (C / 2); cc += 32) {
+      uint32_t rr[32];
+      tmem_ld_32x32b_x32(lane_addr + 256 + cc, rr);
+      tmem_ld_wait();
+      const int m = cc / d_out, n0 = cc % d_out;
+      float4* dst = reinterpret_cast<float4*>(out + (int64_t)(m * 128 + r) * d_out + n0);
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        dst[g] = make_float4(__uint_as_float(rr[4 * g]), __uint_as_float(rr[4 * g + 1]), __uint_as_float(rr[4 * g + 2]), __uint_as_float(rr[4 * g + 3]));
+    }
+  }
+  // ---- db1 partial = column sums of the bf16 dh tile (thread = column)
+  if (threadIdx.x < d_hid) {
+    const int col = threadIdx.x;
+    const uint8_t* base = rW2 + (col >> 6) * TW_BLK + (col & 7) * 2;
+    const int ch = (col & 63) >> 3;
+    float s = 0.f;
+#pragma unroll 8
+    for (int rr = 0; rr < TW_BM; ++rr)
+      s += bf16_bits_to_float(*reinterpret_cast<const uint16_t*>(base + sw128_offset(rr, ch)));
+    P.db1_parts[(int64_t)p * d_hid + col] = s;
+  }
+  tc_fence_before();
+  __syncthreads();                                 // dW2 columns are drained: dW1 may overwrite them
+
+  if (warp == 0) {
+    mbar_wait(x_full, 0);
+    tc_fence_after();
+    if (elect_one_sync()) {
+      // dW1[d_in, d_hid] = x^T dh  (K = the 128 batch rows)
+      const uint32_t idesc = umma_idesc_bf16(128, d_hid, 1, 1);
+      const uint64_t da0 = umma_desc_mn_sw128(smem_u32(rH), TW_BLK);
+      const uint64_t db0 = umma_desc_mn_sw128(smem_u32(rW2), TW_BLK);
+      for (int kk = 0; kk < TW_BM / 16; ++kk)
+        umma_bf16_ss(tmem_base + d_in, da0 + 128 * kk, db0 + 128 * kk, idesc, kk != 0);
+      umma_commit(mma_d_done);
+    }
+    __syncwarp();
+  }
+
+  // ---- dx -> HBM fp32 (the embedding-row gradient)
+  mbar_wait(mma_c_done, 0);
+  tc_fence_after();
+  {
+    const int ncol = d_in / 2;
+#pragma unroll 1
+    for (int c0 = hf * ncol; c0 < (hf + 1) * ncol; c0 += 32) {
+      uint32_t rr[32];
+      tmem_ld_32x32b_x32(lane_addr + c0, rr);
+      tmem_ld_wait();
+      if (row_ok) {
+        float4* dst = reinterpret_cast<float4*>(P.dx + row * d_in + c0);
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          dst[g] = make_float4(__uint_as_float(rr[4 * g]), __uint_as_float(rr[4 * g + 1]), __uint_as_float(rr[4 * g + 2]), __uint_as_float(rr[4 * g + 3]));
+      }
+    }
+  }
+  // ---- dW1 partial -> HBM (rows = d_in index)
+  mbar_wait(mma_d_done, 0);
+  tc_fence_after();
+  {
+    const int ncol = d_hid / 2;
+    float* out = P.dw1_parts + (int64_t)p * d_in * d_hid + (int64_t)r * d_hid;
+#pragma unroll 1
+    for (int c0 = hf * ncol; c0 < (hf + 1) * ncol; c0 += 32) {
+      uint32_t rr[32];
+      tmem_ld_32x32b_x32(lane_addr + d_in + c0, rr);
+      tmem_ld_wait();
+      float4* dst = reinterpret_cast<float4*>(out + c0);
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        dst[g] = make_float4(__uint_as_float(rr[4 * g]), __uint_as_float(rr[4 * g + 1]), __uint_as_float(rr[4 * g + 2]), __uint_as_float(rr[4 * g + 3]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- host ----------------------------------------------------------------------------
+static bool mlp2_supported(int d_in, int d_hid, int d_out) {
+  if (d_in != 128) return false;                           // M of the dW1 GEMM
+  if (d_hid != 128 && d_hid != 256) return false;          // M tiles of the dW2 GEMM
+  if (d_out != 64 && d_out != 128) return false;
+  const BwdTLayout L = bwdt_layout(d_in, d_hid, d_out);
+  if ((L.nk1 - L.w1lo_blocks) * L.w1blk > L.dy_bytes) return false;
+  return fwd_layout(d_in, d_hid, d_out).total <= 227 * 1024 && L.total <= 227 * 1024;
+}
+
+static int check_tower(const char* fn, const tt_tower_mlp2& s, bool bwd) {
+  TT_REQUIRE(mlp2_supported(s.d_in, s.d_hid, s.d_out), "%s: unsupported tower shape %d-%d-%d (see tt_tower_mlp2_supported)", fn, s.d_in, s.d_hid, s.d_out);
+  TT_REQUIRE(s.batch > 0 && s.batch < (1ll << 31), "%s: bad batch %lld", fn, (long long)s.batch);
+  TT_REQUIRE(s.w1 && s.w2 && aligned16(s.w1) && aligned16(s.w2), "%s: weights null or unaligned", fn);
+  TT_REQUIRE(s.x && s.h && aligned16(s.x) && aligned16(s.h), "%s: x / h buffers null or unaligned", fn);
+  if (!bwd) {
+    TT_REQUIRE(s.b1 && s.b2, "%s: bias null", fn);
+    TT_REQUIRE(s.y && aligned16(s.y), "%s: y null or unaligned", fn);
+    TT_REQUIRE(s.num_feats >= 1 && s.num_feats <= TT_MAX_FEATURES, "%s: num_feats must be in [1, %d]", fn, TT_MAX_FEATURES);
+    for (int i = 0; i < s.num_feats; ++i) {
+      TT_REQUIRE(s.feats[i].table && aligned16(s.feats[i].table) && s.feats[i].values && s.feats[i].vocab > 0, "%s: feature %d is incomplete", fn, i);
+      TT_REQUIRE(s.feats[i].mode == TT_POOL_SUM || s.feats[i].mode == TT_POOL_MEAN, "%s: feature %d bad pooling mode", fn, i);
+    }
+  } else {
+    TT_REQUIRE(s.dy_parts && aligned16(s.dy_parts) && s.dy_splits >= 1, "%s: dy_parts null/unaligned or dy_splits < 1", fn);
+    TT_REQUIRE(s.dx && s.dw1_parts && s.dw2_parts && s.db1_parts && s.db2_parts, "%s: null output buffer", fn);
+    TT_REQUIRE(aligned16(s.dx) && aligned16(s.dw1_parts) && aligned16(s.dw2_parts), "%s: outputs must be 16-byte aligned", fn);
+  }
+  return TT_OK;
+}
+
+}  // namespace tt
+
+using namespace tt;
+
+extern "C" int32_t tt_tower_mlp2_supported(int32_t d_in, int32_t d_hid, int32_t d_out) {
+  return mlp2_supported(d_in, d_hid, d_out) ? 1 : 0;
+}
+
+extern "C" int tt_tower_mlp2_fwd(const tt_tower_mlp2* towers, int32_t n, int32_t* fault, void* stream) {
+  TT_REQUIRE(towers && n >= 1 && n <= TT_MAX_TOWERS, "tt_tower_mlp2_fwd: num_towers must be in [1, %d]", TT_MAX_TOWERS);
+  static thread_local TowerFwdArgs args;     // 64-byte aligned storage for the tensor maps (copied at launch)
+  int64_t max_b = 0;
+  int smem = 0;
+  for (int i = 0; i < n; ++i) {
+    int rc = check_tower("tt_tower_mlp2_fwd", towers[i], false);
+    if (rc) return rc;
+    const tt_tower_mlp2& s = towers[i];
+    TowerDev& d = args.t[i];
+    d.feats.n = s.num_feats;
+    for (int f = 0; f < s.num_feats; ++f) d.feats.f[f] = s.feats[f];
+    d.B = s.batch; d.d_in = s.d_in; d.d_hid = s.d_hid; d.d_out = s.d_out;
+    d.b1 = s.b1; d.b2 = s.b2; d.x = s.x; d.h = s.h; d.y = s.y;
+    rc = make_tmap_bf16_2d(&args.tmW1[i], s.w1, (uint64_t)s.d_hid, (uint64_t)s.d_in, (uint64_t)s.d_hid * 2, 64, (uint32_t)s.d_in);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&args.tmW2[i], s.w2, (uint64_t)s.d_out, (uint64_t)s.d_hid, (uint64_t)s.d_out * 2, 64, (uint32_t)s.d_hid);
+    if (rc) return rc;
+    max_b = std::max<int64_t>(max_b, s.batch);
+    smem = std::max(smem, fwd_layout(s.d_in, s.d_hid, s.d_out).total);
+  }
+  args.fault = fault;
+  cudaStream_t st = (cudaStream_t)stream;
+  TT_CUDA_OK(cudaFuncSetAttribute(tower_mlp2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  dim3 grid((unsigned)ceil_div(max_b, TW_BM), (unsigned)n);
+  TT_PROF("tower_mlp2_fwd_kernel", st);
+  tower_mlp2_fwd_kernel<<<grid, TW_THREADS, smem, st>>>(args);
+  TT_LAUNCH_OK("tower_mlp2_fwd_kernel");
+  return TT_OK;
+}
+
+extern "C" int tt_tower_mlp2_bwd(const tt_tower_mlp2* towers, int32_t n, void* stream) {
+  TT_REQUIRE(towers && n >= 1 && n <= TT_MAX_TOWERS, "tt_tower_mlp2_bwd: num_towers must be in [1, %d]", TT_MAX_TOWERS);
+  static thread_local TowerBwdArgs args;
+  int64_t max_b = 0;
+  int smem = 0;
+  for (int i = 0; i < n; ++i) {
+    int rc = check_tower("tt_tower_mlp2_bwd", towers[i], true);
+    if (rc) return rc;
+    const tt_tower_mlp2& s = towers[i];
+    TowerBwdDev& d = args.t[i];
+    d.B = s.batch; d.d_in = s.d_in; d.d_hid = s.d_hid; d.d_out = s.d_out;
+    d.dy_parts = s.dy_parts; d.dy_splits = s.dy_splits;
+    d.dx = s.dx; d.dw1_parts = s.dw1_parts; d.dw2_parts = s.dw2_parts; d.db1_parts = s.db1_parts; d.db2_parts = s.db2_parts;
+    rc = make_tmap_bf16_2d(&args.tmX[i], s.x, (uint64_t)s.d_in, (uint64_t)s.batch, (uint64_t)s.d_in * 2, 64, TW_BM);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&args.tmH[i], s.h, (uint64_t)s.d_hid, (uint64_t)s.batch, (uint64_t)s.d_hid * 2, 64, TW_BM);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&args.tmW2[i], s.w2, (uint64_t)s.d_out, (uint64_t)s.d_hid, (uint64_t)s.d_out * 2, 64, (uint32_t)s.d_hid);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&args.tmW1[i], s.w1, (uint64_t)s.d_hid, (uint64_t)s.d_in, (uint64_t)s.d_hid * 2, 64, (uint32_t)s.d_in);
+    if (rc) return rc;
+    max_b = std::max<int64_t>(max_b, s.batch);
+    smem = std::max(smem, bwdt_layout(s.d_in, s.d_hid, s.d_out).total);
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  TT_CUDA_OK(cudaFuncSetAttribute(tower_mlp2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  dim3 grid((unsigned)ceil_div(max_b, TW_BM), (unsigned)n);
+  TT_PROF("tower_mlp2_bwd_kernel", st);
+  tower_mlp2_bwd_kernel<<<grid, TW_THREADS, smem, st>>>(args);
+  TT_LAUNCH_OK("tower_mlp2_bwd_kernel");
+  return TT_OK;
+}

@@ -74,6 +74,9 @@ class Embedding(Layer):
     def _feature(self, inputs):
         return (self.embeddings.value, _as_ids(inputs).reshape(-1), None, "sum")
 
+    def _tower_features(self, inputs):
+        return [self], [self._feature(inputs)]
+
     def __call__(self, inputs, training: bool = False) -> Tensor:
         return _tower_input([self], [inputs])
 
@@ -104,6 +107,7 @@ def _tower_input(layers: Sequence[Embedding], inputs: Sequence) -> Tensor:
             raise ValueError(f"features disagree on the batch size ({b} != {batch})")
     dim = layers[0].output_dim
     bf16 = config.precision == "bf16"
+    GradientTape.note_sparse_lookup([(l.embeddings, f[1], f[2], f[3]) for l, f in zip(layers, feats)])
     out_f32, out_bf16 = ops.tower_input_fwd(feats, batch, dim, want_f32=not bf16, want_bf16=bf16)
     out = Tensor(f32=out_f32, bf16=out_bf16, grad_formats=("f32",))
 
@@ -137,6 +141,11 @@ class FeatureSum(Layer):
     @property
     def trainable_variables(self):
         return [l.embeddings for l in self.features.values()]
+
+    def _tower_features(self, inputs: dict):
+        keys = list(self.features)
+        layers = [self.features[k] for k in keys]
+        return layers, [l._feature(inputs[k]) for l, k in zip(layers, keys)]
 
     def __call__(self, inputs: dict, training: bool = False) -> Tensor:
         keys = list(self.features)
@@ -218,7 +227,8 @@ class Dense(Layer):
                 dy_f32 = g.get("f32")
                 dx, dx_f32, dk, P, db = ops.dense_bwd(
                     "bf16", g["bf16"], x.bf16, self.kernel.shadow, relu_mask_x=x.relu_output,
-                    want_dx=need_dx and "bf16" in want, want_dx_f32=need_dx and "f32" in want,
+                    want_dx=need_dx and "bf16" in want,
+                    want_dx_f32=need_dx and ("f32" in want or "parts" in want),
                     want_dbias=dy_f32 is None)
                 if need_dx:
                     x.grad = dict(f32=dx_f32, bf16=dx)
@@ -232,8 +242,69 @@ class Dense(Layer):
         return out
 
 
+class PendingTowers:
+    """Tower outputs that have been requested but not computed yet.  The first access to any of
+    them runs ONE fused launch (ops.tower_mlp2_fwd: gather + pool + Dense(relu) + Dense for every
+    queued tower, query and candidate side together) and records ONE backward node that will run
+    ops.tower_mlp2_bwd for all of them."""
+
+    def __init__(self):
+        self.items = []
+
+    def add(self, seq, emb_layers, feats, batch, out: Tensor):
+        self.items.append((seq, emb_layers, feats, batch, out))
+
+    def flush(self):
+        items, self.items = self.items, []
+        if not items:
+            return
+        GradientTape.note_sparse_lookup([(l.embeddings, f[1], f[2], f[3])
+                                         for _, emb_layers, feats, _, _ in items for l, f in zip(emb_layers, feats)])
+        specs = []
+        for seq, emb_layers, feats, batch, out in items:
+            d1, d2 = seq.layers[1], seq.layers[2]
+            specs.append(dict(features=feats, batch=batch, w1=d1.kernel.shadow, b1=d1.bias.value,
+                              w2=d2.kernel.shadow, b2=d2.bias.value))
+        results = ops.tower_mlp2_fwd(specs)
+        for (seq, emb_layers, feats, batch, out), spec, (x, h, y) in zip(items, specs, results):
+            out._bf16 = y
+            out._pending = None
+            spec["x"], spec["h"] = x, h
+
+        def backward():
+            live = [(it, sp) for it, sp in zip(items, specs) if it[4].grad is not None]
+            if not live:
+                return
+            towers = []
+            for (seq, emb_layers, feats, batch, out), sp in live:
+                g = out.grad
+                parts = g["parts"] if g.get("parts") is not None else g["f32"].reshape(1, *g["f32"].shape)
+                towers.append(dict(sp, dy_parts=parts.contiguous(), dy_splits=parts.shape[0]))
+            outs = ops.tower_mlp2_bwd(towers)
+            for ((seq, emb_layers, feats, batch, out), sp), o in zip(live, outs):
+                P = o["P"]
+                for layer, f in zip(emb_layers, feats):
+                    if layer.embeddings.grad is not None:
+                        raise NotImplementedError("an embedding table used twice in one step is not supported")
+                    layer.embeddings.grad = IndexedSlices(values=f[1], offsets=f[2], mode=f[3], rows=o["dx"])
+                d1, d2 = seq.layers[1], seq.layers[2]
+                d1.kernel.grad = DenseGrad(o["dw1"], P)
+                d1.bias.grad = DenseGrad(o["db1"].reshape(P, 1, -1), P)
+                d2.kernel.grad = DenseGrad(o["dw2"], P)
+                d2.bias.grad = DenseGrad(o["db2"].reshape(P, 1, -1), P)
+
+        GradientTape.record(backward)
+
+
+_pending_towers = PendingTowers()
+
+
 class Sequential(Layer):
-    """tf.keras.Sequential over the layers above."""
+    """tf.keras.Sequential over the layers above.  In bf16 precision a [Embedding | FeatureSum,
+    Dense(relu), Dense] tower of a supported shape (ops.tower_mlp2_supported) runs as the fused
+    tower kernels; anything else runs layer by layer."""
+
+    fuse = True
 
     def __init__(self, layers: Sequence[Layer] = (), name: Optional[str] = None):
         self.layers = list(layers)
@@ -250,7 +321,37 @@ class Sequential(Layer):
     def losses_l2(self):
         return [p for l in self.layers for p in l.losses_l2]
 
+    def _fusable(self) -> bool:
+        if not (self.fuse and config.precision == "bf16" and len(self.layers) == 3):
+            return False
+        e, d1, d2 = self.layers
+        if not isinstance(e, (Embedding, FeatureSum)) or not isinstance(d1, Dense) or not isinstance(d2, Dense):
+            return False
+        if not d1.relu or d2.relu:
+            return False
+        d_in = e.output_dim if isinstance(e, Embedding) else next(iter(e.features.values())).output_dim
+        return ops.tower_mlp2_supported(d_in, d1.units, d2.units)
+
     def __call__(self, inputs, training: bool = False) -> Tensor:
+        if self._fusable():
+            e, d1, d2 = self.layers
+            emb_layers, feats = e._tower_features(inputs)
+            batch = feats[0][1].numel() if feats[0][2] is None else feats[0][2].numel() - 1
+            for f in feats[1:]:
+                b = f[1].numel() if f[2] is None else f[2].numel() - 1
+                if b != batch:
+                    raise ValueError(f"features disagree on the batch size ({b} != {batch})")
+            if batch > 0:
+                d_in = emb_layers[0].output_dim
+                for layer, width in ((d1, d_in), (d2, d1.units)):
+                    if layer.kernel is None:
+                        layer.build(width)
+                    if layer.kernel.shadow is None:
+                        layer.kernel.want_shadows = True
+                        layer.kernel.refresh_shadows()
+                out = Tensor(grad_formats=("parts",), pending=_pending_towers, shape=(batch, d2.units))
+                _pending_towers.add(self, emb_layers, feats, batch, out)
+                return out
         x = inputs
         for l in self.layers:
             x = l(x, training=training)

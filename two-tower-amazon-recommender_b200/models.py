@@ -76,7 +76,9 @@ class Model:
     def train_step(self, inputs) -> Dict[str, object]:
         if self.optimizer is None:
             raise RuntimeError("call model.compile(optimizer=...) before train_step")
+        self.optimizer.begin_step()
         with GradientTape() as tape:
+            tape.on_sparse_lookup = self.optimizer.prepare_sparse
             loss = self.compute_loss(inputs, training=True)
             reg = self._regularization_loss()
             variables = self.trainable_variables

@@ -167,6 +167,116 @@ def dense_adam_update(w, m, v, grad_parts, num_parts, alpha, beta1, beta2, eps, 
     _count(1)
 
 
+def dense_update_multi(kind: str, items, hyper):
+    """One launch for all dense variables.  items: [(w, slot0, slot1 | None, grad_parts, num_parts, l2, shadow | None)];
+    hyper: (lr, eps) for "adagrad", (alpha, beta1, beta2, eps) for "adam"."""
+    lib = _lib.load()
+    for lo in range(0, len(items), _lib.TT_MAX_DENSE_VARS):
+        chunk = items[lo:lo + _lib.TT_MAX_DENSE_VARS]
+        arr = (_lib.tt_dense_var * len(chunk))()
+        for i, (w, s0, s1, parts, num_parts, l2, shadow) in enumerate(chunk):
+            arr[i].w = _ptr(w, torch.float32)
+            arr[i].slot0 = _ptr(s0, torch.float32)
+            arr[i].slot1 = _ptr(s1, torch.float32)
+            arr[i].grad_parts = _ptr(parts, torch.float32)
+            arr[i].n = w.numel()
+            arr[i].num_parts = int(num_parts)
+            arr[i].l2 = float(l2)
+            arr[i].shadow = _ptr(shadow, torch.bfloat16)
+        if kind == "adagrad":
+            check(lib.tt_dense_adagrad_update_multi(arr, len(chunk), hyper[0], hyper[1], _stream()))
+        else:
+            check(lib.tt_dense_adam_update_multi(arr, len(chunk), hyper[0], hyper[1], hyper[2], hyper[3], _stream()))
+        _count(1)
+
+
+def sparse_update_multi(kind: str, items, hyper):
+    """Three launches (insert, accumulate, apply) for all tables.  items: [(table, slot0, slot1 | None, values,
+    offsets | None, mode, grad, SparseWorkspace, first_flag | None)]."""
+    lib = _lib.load()
+    for lo in range(0, len(items), _lib.TT_MAX_SPARSE_VARS):
+        chunk = items[lo:lo + _lib.TT_MAX_SPARSE_VARS]
+        arr = (_lib.tt_sparse_var * len(chunk))()
+        any_nnz = False
+        for i, (table, s0, s1, values, offsets, mode, grad, ws, first_flag) in enumerate(chunk):
+            arr[i].table = _ptr(table, torch.float32)
+            arr[i].slot0 = _ptr(s0, torch.float32)
+            arr[i].slot1 = _ptr(s1, torch.float32)
+            arr[i].vocab, arr[i].d = table.shape
+            arr[i].values = _ptr(values, torch.int64)
+            arr[i].offsets = _ptr(offsets, torch.int64)
+            arr[i].num_rows = grad.shape[0]
+            arr[i].nnz = values.numel()
+            arr[i].grad = _ptr(grad, torch.float32)
+            arr[i].workspace = _ptr(ws.buf)
+            arr[i].workspace_bytes = ws.nbytes
+            arr[i].first_flag = _ptr(first_flag, torch.uint8)
+            arr[i].mode = pool_code(mode)
+            any_nnz = any_nnz or values.numel() > 0
+        if kind == "adagrad":
+            check(lib.tt_sparse_adagrad_update_multi(arr, len(chunk), hyper[0], hyper[1], _stream()))
+        else:
+            check(lib.tt_sparse_lazy_adam_update_multi(arr, len(chunk), hyper[0], hyper[1], hyper[2], hyper[3], _stream()))
+        _count(3 if any_nnz else 0)
+
+
+def _fill_dense_vars(items):
+    arr = (_lib.tt_dense_var * max(len(items), 1))()
+    for i, (w, s0, s1, parts, num_parts, l2, shadow) in enumerate(items):
+        arr[i].w = _ptr(w, torch.float32)
+        arr[i].slot0 = _ptr(s0, torch.float32)
+        arr[i].slot1 = _ptr(s1, torch.float32)
+        arr[i].grad_parts = _ptr(parts, torch.float32)
+        arr[i].n = w.numel()
+        arr[i].num_parts = int(num_parts)
+        arr[i].l2 = float(l2)
+        arr[i].shadow = _ptr(shadow, torch.bfloat16)
+    return arr
+
+
+def _fill_sparse_vars(items):
+    """items: [(table, slot0 | None, slot1 | None, values, offsets | None, mode, grad | None, SparseWorkspace, first_flag | None)]"""
+    arr = (_lib.tt_sparse_var * max(len(items), 1))()
+    for i, (table, s0, s1, values, offsets, mode, grad, ws, first_flag) in enumerate(items):
+        arr[i].table = _ptr(table, torch.float32)
+        arr[i].slot0 = _ptr(s0, torch.float32)
+        arr[i].slot1 = _ptr(s1, torch.float32)
+        arr[i].vocab, arr[i].d = table.shape
+        arr[i].values = _ptr(values, torch.int64)
+        arr[i].offsets = _ptr(offsets, torch.int64)
+        arr[i].nnz = values.numel()
+        arr[i].num_rows = values.numel() if offsets is None else offsets.numel() - 1
+        arr[i].grad = _ptr(grad, torch.float32)
+        arr[i].workspace = _ptr(ws.buf)
+        arr[i].workspace_bytes = ws.nbytes
+        arr[i].first_flag = _ptr(first_flag, torch.uint8)
+        arr[i].mode = pool_code(mode)
+    return arr
+
+
+def sparse_prepare(items):
+    """Hash insert of the ids of every table (one launch): needs no gradients, so it can run on a side
+    stream while the forward pass executes.  items as in _fill_sparse_vars (slots / grad may be None)."""
+    if not items:
+        return
+    check(_lib.load().tt_optimizer_prepare_sparse(_fill_sparse_vars(items), len(items), _stream()))
+    _count(1 if any(it[3].numel() for it in items) else 0)
+
+
+def optimizer_step(kind: str, dense_items, sparse_items, hyper):
+    """ONE launch: every dense variable and every (prepared) table.  kind "adagrad": hyper = (lr, eps);
+    "lazy_adam": hyper = (alpha, beta1, beta2, eps)."""
+    lib = _lib.load()
+    if len(dense_items) > _lib.TT_MAX_DENSE_VARS or len(sparse_items) > _lib.TT_MAX_SPARSE_VARS:
+        raise ValueError("optimizer_step: too many variables for one launch; split the call")
+    d, s = _fill_dense_vars(dense_items), _fill_sparse_vars(sparse_items)
+    if kind == "adagrad":
+        check(lib.tt_adagrad_step(d, len(dense_items), s, len(sparse_items), hyper[0], hyper[1], _stream()))
+    else:
+        check(lib.tt_lazy_adam_step(d, len(dense_items), s, len(sparse_items), hyper[0], hyper[1], hyper[2], hyper[3], _stream()))
+    _count(1)
+
+
 def sum_squares(x, scale, out, accumulate):
     check(_lib.load().tt_sum_squares(_ptr(x, torch.float32), x.numel(), scale, _ptr(out, torch.float32),
                                      1 if accumulate else 0, _stream()))
@@ -245,6 +355,72 @@ def dense_bwd(precision: str, dy, x, kernel, relu_mask_x: bool, want_dx: bool, w
     return dx, dx_f32, dk, P, db
 
 
+# ------------------------------------------------------------------------ K1+K2 fused tower
+def tower_mlp2_supported(d_in: int, d_hid: int, d_out: int) -> bool:
+    return bool(_lib.load().tt_tower_mlp2_supported(int(d_in), int(d_hid), int(d_out)))
+
+
+def _fill_tower(dst, t):
+    feats = t["features"]
+    dst.num_feats = len(feats)
+    for i, (table, values, offsets, mode) in enumerate(feats):
+        dst.feats[i].table = _ptr(table, torch.float32)
+        dst.feats[i].values = _ptr(values, torch.int64)
+        dst.feats[i].offsets = _ptr(offsets, torch.int64)
+        dst.feats[i].vocab = table.shape[0]
+        dst.feats[i].mode = pool_code(mode)
+    dst.d_in, dst.d_hid = t["w1"].shape
+    dst.d_out = t["w2"].shape[1]
+    dst.batch = t["batch"]
+    dst.w1, dst.b1 = _ptr(t["w1"], torch.bfloat16), _ptr(t["b1"], torch.float32)
+    dst.w2, dst.b2 = _ptr(t["w2"], torch.bfloat16), _ptr(t["b2"], torch.float32)
+
+
+def tower_mlp2_fwd(towers, fault_flag: Optional[torch.Tensor] = None):
+    """towers: [dict(features=[(table, values, offsets, mode)], batch, w1 bf16 [in,hid], b1, w2 bf16 [hid,out], b2)].
+    One launch for all towers.  Returns [(x bf16 [B,in], h bf16 [B,hid], y bf16 [B,out])]."""
+    lib = _lib.load()
+    arr = (_lib.tt_tower_mlp2 * len(towers))()
+    outs = []
+    for i, t in enumerate(towers):
+        _fill_tower(arr[i], t)
+        dev, B = t["w1"].device, t["batch"]
+        x = torch.empty((B, arr[i].d_in), dtype=torch.bfloat16, device=dev)
+        h = torch.empty((B, arr[i].d_hid), dtype=torch.bfloat16, device=dev)
+        y = torch.empty((B, arr[i].d_out), dtype=torch.bfloat16, device=dev)
+        arr[i].x, arr[i].h, arr[i].y = _ptr(x), _ptr(h), _ptr(y)
+        outs.append((x, h, y))
+    check(lib.tt_tower_mlp2_fwd(arr, len(towers), _ptr(fault_flag, torch.int32), _stream()))
+    _count(1)
+    return outs
+
+
+def tower_mlp2_bwd(towers):
+    """towers: the forward dicts plus x, h (saved) and dy_parts fp32 [S, B, out], dy_splits.  One launch.
+    Returns [dict(dx f32 [B,in], dw1 [P,in,hid], dw2 [P,hid,out], db1 [P,hid], db2 [P,out], P)]."""
+    lib = _lib.load()
+    arr = (_lib.tt_tower_mlp2 * len(towers))()
+    outs = []
+    for i, t in enumerate(towers):
+        _fill_tower(arr[i], dict(t, features=[]))
+        dev, B = t["w1"].device, t["batch"]
+        d_in, d_hid, d_out = arr[i].d_in, arr[i].d_hid, arr[i].d_out
+        P = (B + 127) // 128
+        o = dict(dx=torch.empty((B, d_in), dtype=torch.float32, device=dev),
+                 dw1=torch.empty((P, d_in, d_hid), dtype=torch.float32, device=dev),
+                 dw2=torch.empty((P, d_hid, d_out), dtype=torch.float32, device=dev),
+                 db1=torch.empty((P, d_hid), dtype=torch.float32, device=dev),
+                 db2=torch.empty((P, d_out), dtype=torch.float32, device=dev), P=P)
+        arr[i].x, arr[i].h = _ptr(t["x"], torch.bfloat16), _ptr(t["h"], torch.bfloat16)
+        arr[i].dy_parts, arr[i].dy_splits = _ptr(t["dy_parts"], torch.float32), int(t["dy_splits"])
+        arr[i].dx, arr[i].dw1_parts, arr[i].dw2_parts = _ptr(o["dx"]), _ptr(o["dw1"]), _ptr(o["dw2"])
+        arr[i].db1_parts, arr[i].db2_parts = _ptr(o["db1"]), _ptr(o["db2"])
+        outs.append(o)
+    check(lib.tt_tower_mlp2_bwd(arr, len(towers), _stream()))
+    _count(1)
+    return outs
+
+
 def cast_f32_to_bf16(x):
     out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     check(_lib.load().tt_cast_f32_to_bf16(_ptr(x, torch.float32), _ptr(out), x.numel(), _stream()))
@@ -256,12 +432,14 @@ def cast_f32_to_bf16(x):
 _ws_cache = {}
 
 
-def _workspace(nbytes: int, device) -> torch.Tensor:
-    """Scratch reused across calls on one device (grown on demand)."""
-    key = (device.type, device.index)
+def _workspace(nbytes: int, device, tag: str = "scratch") -> torch.Tensor:
+    """Scratch reused across calls on one device (grown on demand), one buffer per user (`tag`).  Buffers are
+    zero-filled when allocated: the retrieval forward keeps arrival tickets at the head of its workspace
+    (tt_retrieval_workspace_init contract) and leaves them zero after every launch."""
+    key = (device.type, device.index, tag)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        buf = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
         _ws_cache[key] = buf
     return buf
 
@@ -279,12 +457,12 @@ def retrieval_loss_fwd(precision: str, q, c, inv_temperature: float, label_offse
     pos = torch.empty((nq,), dtype=torch.float32, device=dev)
     loss = torch.empty((1,), dtype=torch.float32, device=dev)
     nbytes = int(lib.tt_retrieval_workspace_bytes(pc, nq, nc, d))
-    ws = _workspace(nbytes, dev)
+    ws = _workspace(nbytes, dev, "retrieval")
     check(lib.tt_retrieval_loss_fwd(pc, _ptr(q, dt), _ptr(c, dt), nq, nc, d, inv_temperature, label_offset,
                                     _ptr(sample_weight, torch.float32), _ptr(cand_log_q, torch.float32),
                                     _ptr(cand_ids, torch.int64), _ptr(lse), _ptr(pos), _ptr(loss), _ptr(ws),
                                     ws.numel(), _stream()))
-    _count(3 if precision == "bf16" else 2)
+    _count(1 if precision == "bf16" else 2)
     return loss, lse, pos
 
 
@@ -303,7 +481,7 @@ def retrieval_loss_bwd(precision: str, q, c, inv_temperature: float, row_lse, la
     mk = lambda shape, on: torch.empty(shape, dtype=torch.bfloat16, device=dev) if on else None
     dq_b, dc_b = mk((nq, d), want_bf16[0]), mk((nc, d), want_bf16[1])
     nbytes = int(lib.tt_retrieval_workspace_bytes(pc, nq, nc, d))
-    ws = _workspace(nbytes, dev)
+    ws = _workspace(nbytes, dev, "retrieval")
     check(lib.tt_retrieval_loss_bwd(pc, _ptr(q, dt), _ptr(c, dt), nq, nc, d, inv_temperature,
                                     label_offset, _ptr(sample_weight, torch.float32),
                                     _ptr(cand_log_q, torch.float32), _ptr(cand_ids, torch.int64),
@@ -311,6 +489,39 @@ def retrieval_loss_bwd(precision: str, q, c, inv_temperature: float, row_lse, la
                                     _ptr(dc_b), _ptr(ws), ws.numel(), _stream()))
     _count(4 if precision == "bf16" else 2)
     return dict(dq=dq, dc=dc, dq_bf16=dq_b, dc_bf16=dc_b)
+
+
+def retrieval_bwd_num_splits(nq: int, nc: int, d: int):
+    sq, sc = C.c_int32(0), C.c_int32(0)
+    check(_lib.load().tt_retrieval_bwd_num_splits(TT_BF16, nq, nc, d, C.byref(sq), C.byref(sc)))
+    return sq.value, sc.value
+
+
+def retrieval_loss_bwd_parts(q, c, inv_temperature: float, row_lse, label_offset: int = 0, sample_weight=None,
+                             cand_log_q=None, cand_ids=None, grad_scale: float = 1.0):
+    """bf16 only.  Returns (dq_parts f32 [sq, nq, d], dc_parts f32 [sc, nc, d]): dq = dq_parts.sum(0) in index order."""
+    nq, d = q.shape
+    nc = c.shape[0]
+    sq, sc = retrieval_bwd_num_splits(nq, nc, d)
+    dq_parts = torch.empty((sq, nq, d), dtype=torch.float32, device=q.device)
+    dc_parts = torch.empty((sc, nc, d), dtype=torch.float32, device=q.device)
+    check(_lib.load().tt_retrieval_loss_bwd_parts(TT_BF16, _ptr(q, torch.bfloat16), _ptr(c, torch.bfloat16), nq, nc, d,
+                                                  inv_temperature, label_offset, _ptr(sample_weight, torch.float32),
+                                                  _ptr(cand_log_q, torch.float32), _ptr(cand_ids, torch.int64),
+                                                  _ptr(row_lse, torch.float32), grad_scale, _ptr(dq_parts), _ptr(dc_parts),
+                                                  _stream()))
+    _count(2)
+    return dq_parts, dc_parts
+
+
+def combine_parts(parts, want_f32: bool = True, want_bf16: bool = False):
+    """[S, rows, d] fp32 -> ordered sum as fp32 and/or bf16 [rows, d]."""
+    S, rows, d = parts.shape
+    out_f = torch.empty((rows, d), dtype=torch.float32, device=parts.device) if want_f32 else None
+    out_b = torch.empty((rows, d), dtype=torch.bfloat16, device=parts.device) if want_bf16 else None
+    check(_lib.load().tt_combine_parts_f32(_ptr(parts, torch.float32), S, rows, d, _ptr(out_f), _ptr(out_b), _stream()))
+    _count(1)
+    return out_f, out_b
 
 
 # ------------------------------------------------------------------------------------ K6

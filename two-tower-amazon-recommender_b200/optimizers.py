@@ -12,20 +12,102 @@ from .core import DenseGrad, IndexedSlices, Variable
 
 
 class Optimizer:
+    """apply_gradients runs the whole step as ONE launch (all dense variables + all tables) after a
+    hash-insert launch that `prepare_sparse` enqueues on a side stream at lookup time (it needs only
+    the ids), so it overlaps the forward pass (tt_optimizer_prepare_sparse / tt_*_step)."""
+
+    kind = "adagrad"
+
     def __init__(self):
         self.iterations = 0
+        self._prepared = {}        # id(variable) -> values tensor whose insert is in flight on the side stream
+        self._prepared_vars = []
+        self._side = None
+        self._side_busy = False
+
+    # ---- overridden by the concrete optimizers
+    def _dense_item(self, g: DenseGrad, v: Variable):
+        raise NotImplementedError
+
+    def _sparse_item(self, v: Variable, values, offsets, mode, rows):
+        raise NotImplementedError
+
+    def _hyper(self):
+        raise NotImplementedError
+
+    def _check_sparse_supported(self) -> None:
+        pass
+
+    # ---- the step
+    def begin_step(self) -> None:
+        """Called by Model.train_step before the forward.  If an earlier step announced lookups and never
+        applied them (compute_loss raised), their hash tables still hold the ids: rebuild those workspaces."""
+        if self._prepared:
+            if self._side_busy:
+                torch.cuda.current_stream().wait_stream(self._side)
+                self._side_busy = False
+            for ws_owner in self._prepared_vars:
+                ws_owner.slots.pop("_sparse_ws", None)
+            self._prepared.clear()
+        self._prepared_vars = []
+
+    def prepare_sparse(self, lookups) -> None:
+        """lookups: [(variable, values, offsets, mode)].  Enqueue the id dedup (hash insert) of these tables
+        on a side stream; apply_gradients joins it."""
+        self._check_sparse_supported()
+        items = []
+        for var, values, offsets, mode in lookups:
+            if id(var) in self._prepared:
+                raise NotImplementedError("an embedding table used twice in one step is not supported")
+            if values.numel() == 0:
+                continue
+            items.append(self._sparse_item(var, values, offsets, mode, None))
+            self._prepared[id(var)] = values
+            self._prepared_vars.append(var)
+        if not items:
+            return
+        cur = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            ops.sparse_prepare(items)
+        self._side_busy = True
 
     def apply_gradients(self, grads_and_vars: Iterable[Tuple[object, Variable]]) -> None:
         self.iterations += 1
+        dense, sparse, late = [], [], []
         for g, v in grads_and_vars:
             if g is None:
                 continue
             if isinstance(g, IndexedSlices):
-                self._apply_sparse(g, v)
+                if g.values.numel() == 0:
+                    continue
+                item = self._sparse_item(v, g.values, g.offsets, g.mode, g.rows)
+                if self._prepared.get(id(v)) is not g.values:
+                    late.append(item)          # not announced at lookup time: dedup now, on this stream
+                sparse.append(item)
             elif isinstance(g, DenseGrad):
-                self._apply_dense(g, v)
+                dense.append(self._dense_item(g, v))
             else:
                 raise TypeError(f"unsupported gradient type {type(g)} for {v.name}")
+        if sparse:
+            self._check_sparse_supported()
+        if self._side_busy:
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._side_busy = False
+        self._prepared.clear()
+        self._prepared_vars = []
+        if late:
+            ops.sparse_prepare(late)
+        hyper = self._hyper()
+        for lo in range(0, max(len(dense), 1), 16):
+            chunk_d = dense[lo:lo + 16]
+            chunk_s = sparse if lo == 0 else []
+            if chunk_d or chunk_s:
+                ops.optimizer_step(self.kind, chunk_d, chunk_s[:8], hyper)
+        for lo in range(8, len(sparse), 8):
+            ops.optimizer_step(self.kind, [], sparse[lo:lo + 8], hyper)
 
     @staticmethod
     def _sparse_ws(var: Variable, nnz: int) -> ops.SparseWorkspace:
@@ -56,14 +138,15 @@ class Adagrad(Optimizer):
             var.slots["accumulator"] = a
         return a
 
-    def _apply_sparse(self, g: IndexedSlices, var: Variable) -> None:
-        ws = self._sparse_ws(var, g.values.numel())
-        ops.sparse_adagrad_update(var.value, self._acc(var), g.values, g.offsets, g.mode, g.rows,
-                                  self.learning_rate, self.epsilon, ws, var.slots.get("_first_flag"))
+    def _dense_item(self, g: DenseGrad, v: Variable):
+        return (v.value, self._acc(v), None, g.parts, g.num_parts, v.l2, v.shadow if v.want_shadows else None)
 
-    def _apply_dense(self, g: DenseGrad, var: Variable) -> None:
-        ops.dense_adagrad_update(var.value, self._acc(var), g.parts, g.num_parts, self.learning_rate,
-                                 self.epsilon, var.l2, var.shadow if var.want_shadows else None)
+    def _sparse_item(self, v: Variable, values, offsets, mode, rows):
+        return (v.value, self._acc(v), None, values, offsets, mode, rows, self._sparse_ws(v, values.numel()),
+                v.slots.get("_first_flag"))
+
+    def _hyper(self):
+        return (self.learning_rate, self.epsilon)
 
 
 class Adam(Optimizer):
@@ -87,20 +170,23 @@ class Adam(Optimizer):
             var.slots["v"] = torch.zeros_like(var.value)
         return var.slots["m"], var.slots["v"]
 
-    def _apply_dense(self, g: DenseGrad, var: Variable) -> None:
-        m, v = self._mv(var)
-        ops.dense_adam_update(var.value, m, v, g.parts, g.num_parts, self._alpha(), self.beta_1, self.beta_2,
-                              self.epsilon, var.l2, var.shadow if var.want_shadows else None)
+    kind = "lazy_adam"      # Adam arithmetic; tables only with lazy = True
 
-    def _apply_sparse(self, g: IndexedSlices, var: Variable) -> None:
+    def _dense_item(self, g: DenseGrad, v: Variable):
+        return (v.value, *self._mv(v), g.parts, g.num_parts, v.l2, v.shadow if v.want_shadows else None)
+
+    def _sparse_item(self, v: Variable, values, offsets, mode, rows):
+        return (v.value, *self._mv(v), values, offsets, mode, rows, self._sparse_ws(v, values.numel()),
+                v.slots.get("_first_flag"))
+
+    def _hyper(self):
+        return (self._alpha(), self.beta_1, self.beta_2, self.epsilon)
+
+    def _check_sparse_supported(self) -> None:
         if not self.lazy:
             raise NotImplementedError(
                 "Keras Adam on an embedding table is a dense whole-table update (SURVEY.md A.6); "
                 "use LazyAdam (touched rows only) or Adagrad for tables")
-        m, v = self._mv(var)
-        ws = self._sparse_ws(var, g.values.numel())
-        ops.sparse_lazy_adam_update(var.value, m, v, g.values, g.offsets, g.mode, g.rows, self._alpha(),
-                                    self.beta_1, self.beta_2, self.epsilon, ws, var.slots.get("_first_flag"))
 
 
 class LazyAdam(Adam):

@@ -84,6 +84,16 @@ class Retrieval:
 
         def backward():
             bf = prec == "bf16"
+            if bf and ("parts" in q.grad_formats or "parts" in c.grad_formats):
+                # the consumer (fused tower backward) folds the split partials itself
+                dq_parts, dc_parts = ops.retrieval_loss_bwd_parts(qm, cm, inv_t, lse, 0, w, logq, ids, 1.0)
+                for t, parts in ((q, dq_parts), (c, dc_parts)):
+                    if "parts" in t.grad_formats:
+                        t.grad = dict(parts=parts)
+                    else:
+                        f, b = ops.combine_parts(parts, True, "bf16" in t.grad_formats)
+                        t.grad = dict(f32=f, bf16=b)
+                return
             r = ops.retrieval_loss_bwd(prec, qm, cm, inv_t, lse, 0, w, logq, ids, 1.0,
                                        want_bf16=(bf and "bf16" in q.grad_formats, bf and "bf16" in c.grad_formats))
             q.grad = dict(f32=r["dq"], bf16=r["dq_bf16"])
