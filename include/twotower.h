@@ -228,6 +228,8 @@ int tt_cast_f32_to_bf16(const float* in, uint16_t* out, int64_t n, void* stream)
  * the software pipeline of CTA (0,0) of the bf16 loss forward / dQ / dC kernels and per-CTA
  * {entry, setup done, exit, smid} globaltimer records (grids up to 256 CTAs); NULL = off. */
 int tt_debug_trace_buffer(long long* device_buf);
+/* Same for the fused tower kernels: 2 * 16 * 256 int64, per-CTA phase stamps (globaltimer ns). */
+int tt_debug_tower_trace(long long* device_buf);
 
 /* ---------------------------------------------------------------------------------------
  * K1+K2 fused  tower forward / backward for the two-layer tower of the BASELINE configs

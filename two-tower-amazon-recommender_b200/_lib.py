@@ -94,6 +94,7 @@ SIGNATURES = {
     "tt_debug_gemm_bf16": (C.c_int, [_p, _i32, _p, _i32, _i64, _i64, _i64, _p, _p]),
     "tt_cast_f32_to_bf16": (C.c_int, [_p, _p, _i64, _p]),
     "tt_debug_trace_buffer": (C.c_int, [_p]),
+    "tt_debug_tower_trace": (C.c_int, [_p]),
     "tt_retrieval_workspace_bytes": (_i64, [_i32, _i64, _i64, _i64]),
     "tt_retrieval_workspace_init": (C.c_int, [_i32, _p, _i64, _i64, _i64, _i64, _p]),
     "tt_retrieval_loss_fwd": (C.c_int, [_i32, _p, _p, _i64, _i64, _i64, _f, _i64, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),

@@ -225,15 +225,15 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
-                      uint32_t box_inner, uint32_t box_outer) {
+static int make_tmap_2d(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, uint64_t inner, uint64_t outer,
+                        uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return set_error(TT_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {row_stride_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = fn(out, dtype, 2, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -241,6 +241,16 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64
                      (unsigned long long)outer, (unsigned long long)inner, (unsigned long long)row_stride_bytes,
                      box_inner, box_outer);
   return TT_OK;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                      uint32_t box_inner, uint32_t box_outer) {
+  return make_tmap_2d(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, inner, outer, row_stride_bytes, box_inner, box_outer);
+}
+
+int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                     uint32_t box_inner, uint32_t box_outer) {
+  return make_tmap_2d(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, inner, outer, row_stride_bytes, box_inner, box_outer);
 }
 
 // D[M,N] = A * B^T-or-B (+ epilogue); splits over K write out_f32[z].

@@ -531,23 +531,37 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       }
     }
     const bool col_weighted = TRANSPOSED && a.w != nullptr;
+    // per-column terms of a streamed tile (dC: -lse2 and weight of the query columns; EXTRAS: logq / ids),
+    // one column per thread of the warpgroup.  They are fetched one tile AHEAD into registers so that the
+    // global-load latency hides behind the previous tile's exponentials instead of heading every tile.
+    float nx_a = 0.f, nx_w = 1.f;
+    long long nx_id = -2;
+    auto fetch_cols = [&](int t) {
+      if ((TRANSPOSED || EXTRAS) && t < T && wg_tid < BN) {
+        const long long yi = (long long)(tile_begin + t) * BN + wg_tid;
+        if (TRANSPOSED) {
+          nx_a = yi < a.nq ? -a.lse[yi] * kLog2e : 0.f;
+          nx_w = (a.w && yi < a.nq) ? a.w[yi] : 1.f;
+          if (EXTRAS) nx_id = (a.cand_ids && yi < a.nq) ? a.cand_ids[a.label_offset + yi] : -2;
+        } else {
+          nx_a = (a.logq && yi < a.nc) ? a.logq[yi] * kLog2e : 0.f;
+          nx_id = (a.cand_ids && yi < a.nc) ? a.cand_ids[yi] : -2;
+        }
+      }
+    };
+    fetch_cols(g);
     for (int t = g; t < T; t += 2) {
       const int b = t & 1;
       const long long y_tile = (long long)(tile_begin + t) * BN;
       if (TRANSPOSED || EXTRAS) {
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");     // everyone is done reading tile t-2's terms
         if (wg_tid < BN) {
-          const long long yi = y_tile + wg_tid;
-          if (TRANSPOSED) {
-            col_a[b * BN + wg_tid] = yi < a.nq ? a.lse[yi] * kLog2e : 0.f;
-            col_w[b * BN + wg_tid] = (a.w && yi < a.nq) ? a.w[yi] : 1.f;
-            if (EXTRAS) col_id[b * BN + wg_tid] = (a.cand_ids && yi < a.nq) ? a.cand_ids[a.label_offset + yi] : -2;
-          } else {
-            col_a[b * BN + wg_tid] = (a.logq && yi < a.nc) ? a.logq[yi] * kLog2e : 0.f;
-            col_id[b * BN + wg_tid] = (a.cand_ids && yi < a.nc) ? a.cand_ids[yi] : -2;
-          }
+          col_a[b * BN + wg_tid] = nx_a;
+          if (TRANSPOSED) col_w[b * BN + wg_tid] = nx_w;
+          if (EXTRAS) col_id[b * BN + wg_tid] = nx_id;
         }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+        fetch_cols(t + 2);
       }
       if (qd == 0 && lane == 0) TT_TRACE(g, t, 0);
       mbar_wait(&s_full[b], (t >> 1) & 1);
@@ -583,10 +597,12 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 l4 = *reinterpret_cast<const float4*>(col_a + b * BN + c0 + j);
-            p[j] = fmaf(__uint_as_float(rr[c0 + j]), a.k2, -l4.x - row_logq2);
-            p[j + 1] = fmaf(__uint_as_float(rr[c0 + j + 1]), a.k2, -l4.y - row_logq2);
-            p[j + 2] = fmaf(__uint_as_float(rr[c0 + j + 2]), a.k2, -l4.z - row_logq2);
-            p[j + 3] = fmaf(__uint_as_float(rr[c0 + j + 3]), a.k2, -l4.w - row_logq2);
+            // col_a holds -lse2 of the query columns
+            p[j] = fmaf(__uint_as_float(rr[c0 + j]), a.k2, l4.x);
+            p[j + 1] = fmaf(__uint_as_float(rr[c0 + j + 1]), a.k2, l4.y);
+            p[j + 2] = fmaf(__uint_as_float(rr[c0 + j + 2]), a.k2, l4.z);
+            p[j + 3] = fmaf(__uint_as_float(rr[c0 + j + 3]), a.k2, l4.w);
+            if (EXTRAS) { p[j] -= row_logq2; p[j + 1] -= row_logq2; p[j + 2] -= row_logq2; p[j + 3] -= row_logq2; }
           }
           if (EXTRAS) {
 #pragma unroll

@@ -27,6 +27,7 @@ namespace tt {
 constexpr int TW_BM = 128;
 constexpr int TW_THREADS = 256;
 constexpr int TW_BLK = TW_BM * 128;          // bytes of one [128 rows][64 bf16] swizzled block
+constexpr int TW_STAGE = TW_BM * 128;        // one [128 rows][32 fp32] swizzled staging tile of the fp32 TMA stores
 
 struct TowerDev {
   FeatureParams feats;
@@ -42,8 +43,11 @@ struct TowerDev {
 struct TowerFwdArgs {
   CUtensorMap tmW1[TT_MAX_TOWERS];   // W1 [d_in, d_hid]: box {64, d_in}
   CUtensorMap tmW2[TT_MAX_TOWERS];   // W2 [d_hid, d_out]: box {64, d_hid}
+  CUtensorMap tmH[TT_MAX_TOWERS];    // h [B, d_hid] (store): box {64, 128}
+  CUtensorMap tmY[TT_MAX_TOWERS];    // y [B, d_out] (store): box {64, 128}
   TowerDev t[TT_MAX_TOWERS];
   int* fault;
+  long long* trace;
 };
 
 struct TowerBwdDev {
@@ -63,8 +67,24 @@ struct TowerBwdArgs {
   CUtensorMap tmH[TT_MAX_TOWERS];    // h [B, d_hid]: box {64, 128}
   CUtensorMap tmW2[TT_MAX_TOWERS];   // W2 [d_hid, d_out] read K-major (N = d_hid rows): box {64, d_hid}
   CUtensorMap tmW1[TT_MAX_TOWERS];   // W1 [d_in, d_hid]  read K-major (N = d_in rows):  box {64, d_in}
+  CUtensorMap tmDX[TT_MAX_TOWERS];   // stores, fp32, box {32 columns, 32 rows}: dx [B, d_in]
+  CUtensorMap tmDW1[TT_MAX_TOWERS];  //   dW1 partials viewed as [P * d_in, d_hid]
+  CUtensorMap tmDW2[TT_MAX_TOWERS];  //   dW2 partials viewed as [P * d_hid, d_out]
   TowerBwdDev t[TT_MAX_TOWERS];
+  long long* trace;
 };
+
+// Phase stamps for tuning (tools/trace_tower.py): 16 globaltimer slots per CTA, fwd CTAs then bwd CTAs.
+static long long* g_tower_trace = nullptr;
+__device__ __forceinline__ long long tw_now() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TW_STAMP(i)                                                                              \
+  do {                                                                                           \
+    if (a.trace && threadIdx.x == 0) a.trace[16 * (blockIdx.y * gridDim.x + blockIdx.x) + (i)] = tw_now(); \
+  } while (0)
 
 __host__ __device__ inline int imax(int a, int b) { return a > b ? a : b; }
 
@@ -102,6 +122,7 @@ tower_mlp2_fwd_kernel(const __grid_constant__ TowerFwdArgs a) {
   if (m0 >= P.B) return;
   const int d_in = P.d_in, d_hid = P.d_hid, d_out = P.d_out;
   const FwdLayout L = fwd_layout(d_in, d_hid, d_out);
+  TW_STAMP(0);
   uint8_t* sX = smem;
   uint8_t* sR1 = smem + L.off_r1;                 // W1 (MN-major chunks [d_in][64]) then h (K-major blocks)
   uint8_t* sW2 = smem + L.off_w2;                 // MN-major chunks [d_hid][64]
@@ -118,6 +139,8 @@ tower_mlp2_fwd_kernel(const __grid_constant__ TowerFwdArgs a) {
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&a.tmW1[tw]);
     tma_prefetch_desc(&a.tmW2[tw]);
+    tma_prefetch_desc(&a.tmH[tw]);
+    tma_prefetch_desc(&a.tmY[tw]);
     mbar_init(w_full, 1); mbar_init(mma1_done, 1); mbar_init(mma2_done, 1);
     fence_barrier_init();
   }
@@ -127,6 +150,7 @@ tower_mlp2_fwd_kernel(const __grid_constant__ TowerFwdArgs a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  TW_STAMP(1);
   if (warp == 0 && elect_one_sync()) {            // weights: L2-resident after the first CTA
     mbar_arrive_expect_tx(w_full, L.w1_bytes + L.w2_bytes);
     for (int j = 0; j < d_hid / 64; ++j) tma_load_2d(sR1 + j * d_in * 128, &a.tmW1[tw], w_full, 64 * j, 0);
@@ -182,10 +206,12 @@ tower_mlp2_fwd_kernel(const __grid_constant__ TowerFwdArgs a) {
   }
   fence_proxy_async();
   __syncthreads();
+  TW_STAMP(2);
 
   // the whole warp waits, one lane issues (no spinning lanes beside a working one)
   if (warp == 0) {
     mbar_wait(w_full, 0);
+    TW_STAMP(3);
     tc_fence_after();
     if (elect_one_sync()) {
       const uint32_t idesc = umma_idesc_bf16(TW_BM, d_hid, 0, 1);
@@ -201,12 +227,12 @@ tower_mlp2_fwd_kernel(const __grid_constant__ TowerFwdArgs a) {
 
   const int q = warp & 3, hf = warp >> 2;
   const int r = q * 32 + lane;
-  const int64_t row = m0 + r;
-  const bool row_ok = row < P.B;
   const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
 
-  // ---- epilogue 1: h = relu(D1 + b1) -> bf16, into shared memory (over W1) and HBM
+  // ---- epilogue 1: h = relu(D1 + b1) -> bf16 into shared memory (over W1); the swizzled tile is both the
+  // A operand of the second GEMM and the source of the TMA store of h to HBM
   mbar_wait(mma1_done, 0);
+  TW_STAMP(4);
   tc_fence_after();
   {
     const int ncol = d_hid / 2;
@@ -222,17 +248,19 @@ tower_mlp2_fwd_kernel(const __grid_constant__ TowerFwdArgs a) {
         for (int j = 0; j < 8; ++j) v[j] = fmaxf(__uint_as_float(rr[g * 8 + j]) + sB1[c0 + g * 8 + j], 0.f);
         const uint4 pk = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
         st_tile_chunk(sR1, r, c0 + g * 8, pk);
-        if (row_ok && P.h) *reinterpret_cast<uint4*>(P.h + row * d_hid + c0 + g * 8) = pk;
       }
     }
   }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
+  TW_STAMP(5);
 
   if (warp == 0) {
     tc_fence_after();
     if (elect_one_sync()) {
+      for (int j = 0; j < d_hid / 64; ++j) tma_store_2d(&a.tmH[tw], sR1 + j * TW_BLK, 64 * j, (int)m0);
+      tma_store_commit();
       const uint32_t idesc = umma_idesc_bf16(TW_BM, d_out, 0, 1);
       const uint64_t db0 = umma_desc_mn_sw128(smem_u32(sW2), d_hid * 128);
       for (int kk = 0; kk < d_hid / 16; ++kk) {
@@ -244,8 +272,9 @@ tower_mlp2_fwd_kernel(const __grid_constant__ TowerFwdArgs a) {
     __syncwarp();
   }
 
-  // ---- epilogue 2: y = D2 + b2 -> bf16
+  // ---- epilogue 2: y = D2 + b2 -> bf16, staged in the (dead) x tile and written by one TMA store
   mbar_wait(mma2_done, 0);
+  TW_STAMP(6);
   tc_fence_after();
   {
     const int ncol = d_out / 2;
@@ -254,20 +283,26 @@ tower_mlp2_fwd_kernel(const __grid_constant__ TowerFwdArgs a) {
       uint32_t rr[32];
       tmem_ld_32x32b_x32(lane_addr + 256 + c0, rr);
       tmem_ld_wait();
-      if (row_ok) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float v[8];
+      for (int g = 0; g < 4; ++g) {
+        float v[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(rr[g * 8 + j]) + sB2[c0 + g * 8 + j];
-          *reinterpret_cast<uint4*>(P.y + row * d_out + c0 + g * 8) =
-              make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-        }
+        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(rr[g * 8 + j]) + sB2[c0 + g * 8 + j];
+        st_tile_chunk(sX, r, c0 + g * 8,
+                      make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
       }
     }
   }
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
+  TW_STAMP(7);
+  if (warp == 0 && elect_one_sync()) {
+    for (int j = 0; j < d_out / 64; ++j) tma_store_2d(&a.tmY[tw], sX + j * TW_BLK, 64 * j, (int)m0);
+    tma_store_commit();
+    tma_store_wait_read<0>();                      // shared memory must outlive the reads of every bulk store
+  }
+  TW_STAMP(8);
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -298,7 +333,8 @@ __host__ __device__ inline BwdTLayout bwdt_layout(int d_in, int d_hid, int d_out
   L.off_w2 = L.off_h + L.h_bytes;
   L.off_w1 = L.off_w2 + L.w2r_bytes;
   L.off_tail = L.off_w1 + L.w1lo_blocks * L.w1blk;
-  L.total = L.off_tail + 128 + (8 * d_out + d_hid) * 4;
+  // tail: barriers (128 B) + eight 4 KB per-warp staging tiles of the TMA stores (the db2 scratch lives there first)
+  L.total = L.off_tail + 1024 + 2 * TW_STAGE;
   return L;
 }
 
@@ -312,6 +348,7 @@ tower_mlp2_bwd_kernel(const __grid_constant__ TowerBwdArgs a) {
   if (m0 >= P.B) return;
   const int d_in = P.d_in, d_hid = P.d_hid, d_out = P.d_out;
   const BwdTLayout L = bwdt_layout(d_in, d_hid, d_out);
+  TW_STAMP(0);
   uint8_t* rDY = smem;
   uint8_t* rH = smem + L.off_h;
   uint8_t* rW2 = smem + L.off_w2;
@@ -323,7 +360,8 @@ tower_mlp2_bwd_kernel(const __grid_constant__ TowerBwdArgs a) {
   uint64_t* mma_c_done = ld_full + 4;
   uint64_t* mma_d_done = ld_full + 5;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ld_full + 6);
-  float* s_db2 = reinterpret_cast<float*>(smem + L.off_tail + 128);   // [8][d_out]
+  uint8_t* stage = smem + L.off_tail + 1024;       // [8 warps][32 rows][32 fp32]
+  float* s_db2 = reinterpret_cast<float*>(stage);  // [8][d_out], dead before the first store is staged
   const int p = blockIdx.x;                        // partial index of this 128-row slice
   const int n_hi = L.nk1 - L.w1lo_blocks;          // W1 k-blocks that move into R_dy later
 
@@ -333,6 +371,7 @@ tower_mlp2_bwd_kernel(const __grid_constant__ TowerBwdArgs a) {
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&a.tmX[tw]); tma_prefetch_desc(&a.tmH[tw]);
     tma_prefetch_desc(&a.tmW2[tw]); tma_prefetch_desc(&a.tmW1[tw]);
+    tma_prefetch_desc(&a.tmDX[tw]); tma_prefetch_desc(&a.tmDW1[tw]); tma_prefetch_desc(&a.tmDW2[tw]);
     for (int i = 0; i < 6; ++i) mbar_init(ld_full + i, 1);
     fence_barrier_init();
   }
@@ -342,6 +381,7 @@ tower_mlp2_bwd_kernel(const __grid_constant__ TowerBwdArgs a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  TW_STAMP(1);
   if (warp == 0 && elect_one_sync()) {
     mbar_arrive_expect_tx(ld_full, L.h_bytes + d_hid * d_out * 2 + L.w1lo_blocks * L.w1blk);
     for (int j = 0; j < d_hid / 64; ++j) tma_load_2d(rH + j * TW_BLK, &a.tmH[tw], ld_full, 64 * j, (int)m0);
@@ -349,29 +389,41 @@ tower_mlp2_bwd_kernel(const __grid_constant__ TowerBwdArgs a) {
     for (int j = 0; j < L.w1lo_blocks; ++j) tma_load_2d(rW1 + j * L.w1blk, &a.tmW1[tw], ld_full, 64 * j, 0);
   }
 
-  // ---- dy = ordered sum of the split partials; db2 from the fp32 sums; bf16 tile into R_dy
+  // ---- dy = ordered sum of the split partials; db2 from the fp32 sums; bf16 tile into R_dy.
+  // 8 rows x 2 splits = 16 independent 128-bit loads in flight per lane (the phase is latency-bound)
   {
     const int nchunks = d_out >> 2;                // float4 chunks per row (<= 32)
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const int col = 4 * lane;
-#pragma unroll 4
-    for (int i = 0; i < TW_BM / 8; ++i) {
-      const int r = warp + 8 * i;
-      const int64_t b = m0 + r;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (b < P.B && lane < nchunks) {
-        v = __ldg(reinterpret_cast<const float4*>(P.dy_parts + b * d_out) + lane);
-        for (int s = 1; s < P.dy_splits; ++s) {
-          const float4 u = __ldg(reinterpret_cast<const float4*>(P.dy_parts + ((int64_t)s * P.B + b) * d_out) + lane);
-          v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
-        }
+    const bool lane_ok = lane < nchunks;
+    const int S = P.dy_splits;
+#pragma unroll 1
+    for (int i0 = 0; i0 < TW_BM / 8; i0 += 8) {
+      float4 v[8], u[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t b = m0 + warp + 8 * (i0 + i);
+        const bool ok = lane_ok && b < P.B;
+        v[i] = ok ? __ldg(reinterpret_cast<const float4*>(P.dy_parts + b * d_out) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        u[i] = (ok && S > 1) ? __ldg(reinterpret_cast<const float4*>(P.dy_parts + (P.B + b) * d_out) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-      if (lane < nchunks)
-        *reinterpret_cast<uint2*>(rDY + (col >> 6) * TW_BLK + sw128_offset(r, (col & 63) >> 3) + (lane & 1) * 8) =
-            make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = warp + 8 * (i0 + i);
+        const int64_t b = m0 + r;
+        v[i].x += u[i].x; v[i].y += u[i].y; v[i].z += u[i].z; v[i].w += u[i].w;
+        if (lane_ok && b < P.B)
+          for (int sp = 2; sp < S; ++sp) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(P.dy_parts + ((int64_t)sp * P.B + b) * d_out) + lane);
+            v[i].x += w.x; v[i].y += w.y; v[i].z += w.z; v[i].w += w.w;
+          }
+        acc.x += v[i].x; acc.y += v[i].y; acc.z += v[i].z; acc.w += v[i].w;
+        if (lane_ok)
+          *reinterpret_cast<uint2*>(rDY + (col >> 6) * TW_BLK + sw128_offset(r, (col & 63) >> 3) + (lane & 1) * 8) =
+              make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+      }
     }
-    if (lane < nchunks) *reinterpret_cast<float4*>(s_db2 + warp * d_out + col) = acc;
+    if (lane_ok) *reinterpret_cast<float4*>(s_db2 + warp * d_out + col) = acc;
   }
   fence_proxy_async();
   __syncthreads();
@@ -382,7 +434,9 @@ tower_mlp2_bwd_kernel(const __grid_constant__ TowerBwdArgs a) {
     P.db2_parts[(int64_t)p * d_out + threadIdx.x] = s;
   }
 
+  TW_STAMP(2);                                     // dy tile built
   mbar_wait(ld_full, 0);                           // every thread: h is also read with generic loads below
+  TW_STAMP(3);
   if (warp == 0) {
     tc_fence_after();
     if (elect_one_sync()) {
@@ -416,12 +470,25 @@ tower_mlp2_bwd_kernel(const __grid_constant__ TowerBwdArgs a) {
 
   const int q = warp & 3, hf = warp >> 2;
   const int r = q * 32 + lane;
-  const int64_t row = m0 + r;
-  const bool row_ok = row < P.B;
   const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+  // fp32 outputs leave through shared memory: every warp stages its [32 rows x 32 columns] piece (row =
+  // TMEM lane, 128B-swizzled, 4 KB) and its first lane issues a TMA store of it: full-line writes by the
+  // copy engine instead of 32 scattered 16-byte stores per warp instruction, and no cross-warp barrier
+  uint8_t* my_stage = stage + warp * 4096;
+  auto store_tile = [&](const uint32_t (&rr)[32], const CUtensorMap* tm, int c_inner, int c_outer) {
+    if (lane == 0) tma_store_wait_read<0>();       // this warp's previous store has read the tile
+    __syncwarp();
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+      *reinterpret_cast<uint4*>(my_stage + sw128_offset(lane, g)) = make_uint4(rr[4 * g], rr[4 * g + 1], rr[4 * g + 2], rr[4 * g + 3]);
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) { tma_store_2d(tm, my_stage, c_inner, c_outer + 32 * q); tma_store_commit(); }
+  };
 
   // ---- epilogue a: dh = dh_pre * (h > 0) -> bf16 tile over the dead W2
   mbar_wait(mma_ab_done, 0);
+  TW_STAMP(4);
   tc_fence_after();
   {
     const int ncol = d_hid / 2;
@@ -449,6 +516,7 @@ tower_mlp2_bwd_kernel(const __grid_constant__ TowerBwdArgs a) {
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
+  TW_STAMP(5);
 
   if (warp == 0) {
     tc_fence_after();
@@ -477,17 +545,13 @@ tower_mlp2_bwd_kernel(const __grid_constant__ TowerBwdArgs a) {
   // ---- dW2 partial -> HBM (rows = d_hid index, TMEM lanes), while dx runs on the tensor pipe
   {
     const int C = (d_hid / 128) * d_out;           // concatenated columns of the dW2 tiles
-    float* out = P.dw2_parts + (int64_t)p * d_hid * d_out;
 #pragma unroll 1
     for (int cc = hf * (C / 2); cc < (hf + 1) * (C / 2); cc += 32) {
       uint32_t rr[32];
       tmem_ld_32x32b_x32(lane_addr + 256 + cc, rr);
       tmem_ld_wait();
       const int m = cc / d_out, n0 = cc % d_out;
-      float4* dst = reinterpret_cast<float4*>(out + (int64_t)(m * 128 + r) * d_out + n0);
-#pragma unroll
-      for (int g = 0; g < 8; ++g)
-        dst[g] = make_float4(__uint_as_float(rr[4 * g]), __uint_as_float(rr[4 * g + 1]), __uint_as_float(rr[4 * g + 2]), __uint_as_float(rr[4 * g + 3]));
+      store_tile(rr, &a.tmDW2[tw], n0, p * d_hid + m * 128);
     }
   }
   // ---- db1 partial = column sums of the bf16 dh tile (thread = column)
@@ -503,6 +567,7 @@ tower_mlp2_bwd_kernel(const __grid_constant__ TowerBwdArgs a) {
   }
   tc_fence_before();
   __syncthreads();                                 // dW2 columns are drained: dW1 may overwrite them
+  TW_STAMP(6);
 
   if (warp == 0) {
     mbar_wait(x_full, 0);
@@ -519,8 +584,9 @@ tower_mlp2_bwd_kernel(const __grid_constant__ TowerBwdArgs a) {
     __syncwarp();
   }
 
-  // ---- dx -> HBM fp32 (the embedding-row gradient)
+  // ---- dx -> HBM fp32 (the embedding-row gradient); rows past the batch are clipped by the tensor map
   mbar_wait(mma_c_done, 0);
+  TW_STAMP(7);
   tc_fence_after();
   {
     const int ncol = d_in / 2;
@@ -529,31 +595,27 @@ tower_mlp2_bwd_kernel(const __grid_constant__ TowerBwdArgs a) {
       uint32_t rr[32];
       tmem_ld_32x32b_x32(lane_addr + c0, rr);
       tmem_ld_wait();
-      if (row_ok) {
-        float4* dst = reinterpret_cast<float4*>(P.dx + row * d_in + c0);
-#pragma unroll
-        for (int g = 0; g < 8; ++g)
-          dst[g] = make_float4(__uint_as_float(rr[4 * g]), __uint_as_float(rr[4 * g + 1]), __uint_as_float(rr[4 * g + 2]), __uint_as_float(rr[4 * g + 3]));
-      }
+      store_tile(rr, &a.tmDX[tw], c0, (int)m0);
     }
   }
   // ---- dW1 partial -> HBM (rows = d_in index)
   mbar_wait(mma_d_done, 0);
+  TW_STAMP(8);
   tc_fence_after();
   {
     const int ncol = d_hid / 2;
-    float* out = P.dw1_parts + (int64_t)p * d_in * d_hid + (int64_t)r * d_hid;
 #pragma unroll 1
     for (int c0 = hf * ncol; c0 < (hf + 1) * ncol; c0 += 32) {
       uint32_t rr[32];
       tmem_ld_32x32b_x32(lane_addr + d_in + c0, rr);
       tmem_ld_wait();
-      float4* dst = reinterpret_cast<float4*>(out + c0);
-#pragma unroll
-      for (int g = 0; g < 8; ++g)
-        dst[g] = make_float4(__uint_as_float(rr[4 * g]), __uint_as_float(rr[4 * g + 1]), __uint_as_float(rr[4 * g + 2]), __uint_as_float(rr[4 * g + 3]));
+      store_tile(rr, &a.tmDW1[tw], c0, p * d_in);
     }
   }
+  TW_STAMP(9);
+  if (lane == 0) tma_store_wait_read<0>();
+  __syncwarp();
+  TW_STAMP(10);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
@@ -594,6 +656,13 @@ static int check_tower(const char* fn, const tt_tower_mlp2& s, bool bwd) {
 
 using namespace tt;
 
+// Debug hook: device buffer of 2 * 16 * 256 int64 receiving per-CTA phase stamps (globaltimer ns) of the fused
+// tower forward (first half) and backward (second half); NULL = off.
+extern "C" int tt_debug_tower_trace(long long* device_buf) {
+  g_tower_trace = device_buf;
+  return TT_OK;
+}
+
 extern "C" int32_t tt_tower_mlp2_supported(int32_t d_in, int32_t d_hid, int32_t d_out) {
   return mlp2_supported(d_in, d_hid, d_out) ? 1 : 0;
 }
@@ -616,10 +685,15 @@ extern "C" int tt_tower_mlp2_fwd(const tt_tower_mlp2* towers, int32_t n, int32_t
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&args.tmW2[i], s.w2, (uint64_t)s.d_out, (uint64_t)s.d_hid, (uint64_t)s.d_out * 2, 64, (uint32_t)s.d_hid);
     if (rc) return rc;
+    rc = make_tmap_bf16_2d(&args.tmH[i], s.h, (uint64_t)s.d_hid, (uint64_t)s.batch, (uint64_t)s.d_hid * 2, 64, TW_BM);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&args.tmY[i], s.y, (uint64_t)s.d_out, (uint64_t)s.batch, (uint64_t)s.d_out * 2, 64, TW_BM);
+    if (rc) return rc;
     max_b = std::max<int64_t>(max_b, s.batch);
     smem = std::max(smem, fwd_layout(s.d_in, s.d_hid, s.d_out).total);
   }
   args.fault = fault;
+  args.trace = g_tower_trace;
   cudaStream_t st = (cudaStream_t)stream;
   TT_CUDA_OK(cudaFuncSetAttribute(tower_mlp2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid((unsigned)ceil_div(max_b, TW_BM), (unsigned)n);
@@ -650,9 +724,17 @@ extern "C" int tt_tower_mlp2_bwd(const tt_tower_mlp2* towers, int32_t n, void* s
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&args.tmW1[i], s.w1, (uint64_t)s.d_hid, (uint64_t)s.d_in, (uint64_t)s.d_hid * 2, 64, (uint32_t)s.d_in);
     if (rc) return rc;
+    const int64_t P = ceil_div(s.batch, TW_BM);
+    rc = make_tmap_f32_2d(&args.tmDX[i], s.dx, (uint64_t)s.d_in, (uint64_t)s.batch, (uint64_t)s.d_in * 4, 32, 32);
+    if (rc) return rc;
+    rc = make_tmap_f32_2d(&args.tmDW1[i], s.dw1_parts, (uint64_t)s.d_hid, (uint64_t)(P * s.d_in), (uint64_t)s.d_hid * 4, 32, 32);
+    if (rc) return rc;
+    rc = make_tmap_f32_2d(&args.tmDW2[i], s.dw2_parts, (uint64_t)s.d_out, (uint64_t)(P * s.d_hid), (uint64_t)s.d_out * 4, 32, 32);
+    if (rc) return rc;
     max_b = std::max<int64_t>(max_b, s.batch);
     smem = std::max(smem, bwdt_layout(s.d_in, s.d_hid, s.d_out).total);
   }
+  args.trace = g_tower_trace ? g_tower_trace + 16 * 256 : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   TT_CUDA_OK(cudaFuncSetAttribute(tower_mlp2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid((unsigned)ceil_div(max_b, TW_BM), (unsigned)n);
