@@ -173,7 +173,7 @@ def run_reference(args):
 def build_model(tt, cfg, world, rank, group):
     if world > 1:
         from two_tower_b200 import parallel
-        return parallel.build_sharded_two_tower(cfg, group, lr=0.001)
+        return parallel.build_sharded_two_tower(cfg, group, lr=0.001, peer=os.environ.get("TT_PEER_GATHER", "1") != "0")
 
     class TwoTower(tt.models.Model):
         def __init__(self):
@@ -214,6 +214,9 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     group = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         group = dist.group.WORLD
 
@@ -247,9 +250,9 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     model.test_step(dev_pool[0])                      # builds the Dense layers
-    # N > 1: the step contains NCCL collectives; it is launched eagerly (graph capture of the
-    # all-to-all path is not validated yet)
-    use_graph = not args.no_graph and world == 1
+    # N > 1: the step contains NCCL collectives with static shapes (capacity-padded all-to-all buckets); they are
+    # captured into the CUDA graph together with the kernels
+    use_graph = not args.no_graph
     if use_graph:
         step = model.make_graphed_train_step(dev_pool[0], warmup=max(3, args.warmup))
     else:
@@ -317,9 +320,17 @@ def run_ours(args):
                          "us_per_step": 1e3 * float(total) / prof_steps}
     barrier()
 
-    if rank != 0:
+    def finish():
+        # graphs that captured NCCL collectives must be gone before the communicator is torn down; a rank that
+        # still hangs in the teardown must not keep the box busy
         if world > 1:
-            dist.destroy_process_group()
+            sys.stdout.flush()
+            torch.cuda.synchronize()
+            dist.barrier()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     peaks = {}
@@ -370,8 +381,7 @@ def run_ours(args):
     if args.serving and world == 1:
         line["serving"] = serving_bench(tt, torch, dev, peaks)
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 def serving_bench(tt, torch, dev, peaks, nq=16384, nc=2_000_000, d=128, k=100):

@@ -60,12 +60,16 @@ int64_t tt_profile_collect(char* host_buf, int64_t buf_len);
  * /root/reference/src/data/preprocessor.py:481-482,485-489.
  * ------------------------------------------------------------------------------------- */
 typedef struct tt_feature {
-  const float* table;     /* [vocab, d] fp32 */
+  const float* table;     /* [vocab, d] fp32; or, when shard_world >= 2, a DEVICE array of shard_world
+                           * base pointers (const float* const*) of the row shards of the table, local
+                           * and peer-mapped (NVLink P2P): row id lives in shard id % shard_world at local
+                           * row id / shard_world -- the lookup of a row-sharded table then needs no
+                           * all-to-all, the gather kernel loads the rows straight from the owners */
   const int64_t* values;  /* ids: [B] when offsets == NULL, else CSR values [nnz] */
   const int64_t* offsets; /* NULL (one id per row) or CSR offsets [B+1] */
-  int64_t vocab;
+  int64_t vocab;          /* GLOBAL number of rows */
   int32_t mode;           /* tt_pool, used when offsets != NULL */
-  int32_t reserved;
+  int32_t shard_world;    /* 0 / 1: one array */
 } tt_feature;
 
 #define TT_MAX_FEATURES 8
@@ -162,7 +166,10 @@ typedef struct tt_sparse_var {
   int64_t workspace_bytes;
   uint8_t* first_flag;      /* nullable */
   int32_t mode;
-  int32_t reserved;
+  int32_t shard;            /* 0: `values` are rows of `table`.  (world << 16) | rank: `values` are GLOBAL ids of a
+                             * table row-sharded over `world` ranks and `table` is this rank's shard: entries
+                             * owned by other ranks (id % world != rank) are skipped, the others update local
+                             * row id / world (tt_optimizer_prepare_sparse / tt_*_step only) */
 } tt_sparse_var;
 int tt_sparse_adagrad_update_multi(const tt_sparse_var* host_vars, int32_t num_vars, float lr, float eps,
                                    void* stream);
@@ -178,6 +185,9 @@ int tt_sparse_lazy_adam_update_multi(const tt_sparse_var* host_vars, int32_t num
  * Dense variables (Adam arithmetic for tt_lazy_adam_step) as tt_dense_*_update_multi.  The prepare call
  * must have completed (stream order / event) on the SAME workspaces before the step. */
 int tt_optimizer_prepare_sparse(const tt_sparse_var* host_vars, int32_t num_vars, void* stream);
+/* vars[i].w (fp32 [n]) = ordered sum of vars[i].grad_parts [num_parts, n], all variables in one launch:
+ * the dense gradients are folded into one flat bucket before the data-parallel all-reduce. */
+int tt_fold_parts_multi(const tt_dense_var* host_vars, int32_t num_vars, void* stream);
 int tt_adagrad_step(const tt_dense_var* host_dense, int32_t num_dense, const tt_sparse_var* host_sparse,
                     int32_t num_sparse, float lr, float eps, void* stream);
 int tt_lazy_adam_step(const tt_dense_var* host_dense, int32_t num_dense, const tt_sparse_var* host_sparse,
@@ -241,7 +251,8 @@ int tt_debug_tower_trace(long long* device_buf);
  * accumulation (TT_BF16 precision of tt_dense_*).  Same arithmetic as tt_tower_input_fwd ->
  * tt_dense_fwd(relu) -> tt_dense_fwd, so the same oracle checks it.
  *
- * forward : x [B,d_in] = pooled tower input (bf16, saved for the backward),
+ * forward : x [B,d_in] = pooled tower input (bf16, saved for the backward; with num_feats == 0 x is
+ *           an INPUT instead -- the rows a row-sharded lookup has already exchanged),
  *           h [B,d_hid] = relu(x w1 + b1) (bf16, saved), y [B,d_out] = h w2 + b2 (bf16).
  * backward: dy = sum of `dy_splits` stacked fp32 partials [dy_splits, B, d_out] (the split
  *           partials tt_retrieval_loss_bwd_parts leaves, or any fp32 gradient with splits = 1),

@@ -21,7 +21,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, port, precision, results):
+def _worker(rank, port, precision, peer, dim, mlp, results):
     sys.path.insert(0, str(ROOT))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import torch.distributed as dist
@@ -33,8 +33,9 @@ def _worker(rank, port, precision, results):
         from two_tower_b200 import parallel, synth
         tt.set_precision(precision)
         tol = 1e-5 if precision == "fp32" else 2e-2
-        cfg = synth.Config("tiny", 77, 256, 64, 3001, 2003, (128, 64), 0.5)
-        model = parallel.build_sharded_two_tower(cfg, dist.group.WORLD, lr=0.05, capacity_factor=None)
+        cfg = synth.Config("tiny", 77, 256, dim, 3001, 2003, mlp, 0.5)
+        model = parallel.build_sharded_two_tower(cfg, dist.group.WORLD, lr=0.05, capacity_factor=None, peer=peer)
+        assert type(model.user_model.layers[0]).__name__ == ("PeerShardedEmbedding" if peer else "ShardedEmbedding")
         batches = [synth.make_batch(cfg, 10 + r) for r in range(WORLD)]
         model.test_step(batches[rank])                                  # builds the Dense layers
         # one global set of weights: full tables from a common seed, Dense weights from rank 0
@@ -81,13 +82,17 @@ def _worker(rank, port, precision, results):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_sharded_two_tower_matches_global_batch_oracle(precision):
+# peer=False: NCCL all-to-all lookups; peer=True: shards in symmetric memory, P2P gather inside the kernels.
+# (128, (256, 128)) in bf16 is the shape the fused tower kernels take.
+@pytest.mark.parametrize("precision,peer,dim,mlp", [("fp32", False, 64, (128, 64)), ("bf16", False, 64, (128, 64)),
+                                                     ("fp32", True, 64, (128, 64)), ("bf16", True, 128, (256, 128)),
+                                                     ("bf16", False, 128, (256, 128))])
+def test_sharded_two_tower_matches_global_batch_oracle(precision, peer, dim, mlp):
     if torch.cuda.device_count() < WORLD:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     mgr = mp.Manager()
     results = mgr.dict()
-    mp.spawn(_worker, args=(_free_port(), precision, results), nprocs=WORLD, join=True)
+    mp.spawn(_worker, args=(_free_port(), precision, peer, dim, mlp, results), nprocs=WORLD, join=True)
     for r in range(WORLD):
         assert results.get(r) == "ok", results.get(r)

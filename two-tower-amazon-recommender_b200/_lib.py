@@ -24,7 +24,7 @@ class TwoTowerError(RuntimeError):
 
 class tt_feature(C.Structure):
     _fields_ = [("table", C.c_void_p), ("values", C.c_void_p), ("offsets", C.c_void_p),
-                ("vocab", C.c_int64), ("mode", C.c_int32), ("reserved", C.c_int32)]
+                ("vocab", C.c_int64), ("mode", C.c_int32), ("shard_world", C.c_int32)]
 
 
 TT_MAX_TOWERS, TT_MAX_DENSE_VARS, TT_MAX_SPARSE_VARS = 4, 16, 8
@@ -50,7 +50,7 @@ class tt_sparse_var(C.Structure):
                 ("vocab", C.c_int64), ("d", C.c_int64), ("values", C.c_void_p), ("offsets", C.c_void_p),
                 ("num_rows", C.c_int64), ("nnz", C.c_int64), ("grad", C.c_void_p), ("workspace", C.c_void_p),
                 ("workspace_bytes", C.c_int64), ("first_flag", C.c_void_p), ("mode", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("shard", C.c_int32)]
 
 
 _p, _i64, _i32, _f = C.c_void_p, C.c_int64, C.c_int32, C.c_float
@@ -78,6 +78,7 @@ SIGNATURES = {
     "tt_sparse_adagrad_update_multi": (C.c_int, [C.POINTER(tt_sparse_var), _i32, _f, _f, _p]),
     "tt_sparse_lazy_adam_update_multi": (C.c_int, [C.POINTER(tt_sparse_var), _i32, _f, _f, _f, _f, _p]),
     "tt_optimizer_prepare_sparse": (C.c_int, [C.POINTER(tt_sparse_var), _i32, _p]),
+    "tt_fold_parts_multi": (C.c_int, [C.POINTER(tt_dense_var), _i32, _p]),
     "tt_adagrad_step": (C.c_int, [C.POINTER(tt_dense_var), _i32, C.POINTER(tt_sparse_var), _i32, _f, _f, _p]),
     "tt_lazy_adam_step": (C.c_int, [C.POINTER(tt_dense_var), _i32, C.POINTER(tt_sparse_var), _i32, _f, _f, _f, _f, _p]),
     "tt_tower_mlp2_supported": (_i32, [_i32, _i32, _i32]),

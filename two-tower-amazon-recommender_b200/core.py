@@ -113,6 +113,8 @@ class IndexedSlices:
     offsets: Optional[torch.Tensor]   # CSR offsets [rows+1] or None (one id per row)
     mode: str                         # "sum" | "mean"
     rows: torch.Tensor                # [num_rows, d] fp32 upstream gradient
+    shard: Optional[tuple] = None     # (world, rank): values are GLOBAL ids of a row-sharded table, the variable
+                                      # is this rank's shard (entries of other owners are skipped)
 
 
 @dataclass

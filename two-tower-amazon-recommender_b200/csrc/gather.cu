@@ -170,7 +170,7 @@ extern "C" int tt_tower_input_fwd(const tt_feature* host_feats, int32_t num_feat
   TT_REQUIRE(out_f32 == nullptr || aligned16(out_f32), "tt_tower_input_fwd: out_f32 must be 16-byte aligned");
   TT_REQUIRE(out_bf16 == nullptr || (reinterpret_cast<uintptr_t>(out_bf16) & 7u) == 0, "tt_tower_input_fwd: out_bf16 must be 8-byte aligned");
   for (int i = 0; i < num_feats; ++i) {
-    TT_REQUIRE(host_feats[i].table != nullptr && aligned16(host_feats[i].table), "tt_tower_input_fwd: feature %d table null or not 16-byte aligned", i);
+    TT_REQUIRE(host_feats[i].table != nullptr && (host_feats[i].shard_world >= 2 || aligned16(host_feats[i].table)), "tt_tower_input_fwd: feature %d table null or not 16-byte aligned", i);
     TT_REQUIRE(host_feats[i].values != nullptr || B == 0, "tt_tower_input_fwd: feature %d has no ids", i);
     TT_REQUIRE(host_feats[i].vocab > 0, "tt_tower_input_fwd: feature %d vocab must be positive", i);
     TT_REQUIRE(host_feats[i].mode == TT_POOL_SUM || host_feats[i].mode == TT_POOL_MEAN, "tt_tower_input_fwd: feature %d bad pooling mode", i);
@@ -180,13 +180,13 @@ extern "C" int tt_tower_input_fwd(const tt_feature* host_feats, int32_t num_feat
 
 extern "C" int tt_embedding_gather_f32(const float* table, const int64_t* ids, float* out, int64_t B,
                                        int64_t d, int64_t vocab, void* stream) {
-  tt_feature f{table, ids, nullptr, vocab, TT_POOL_SUM, 0};
+  tt_feature f{table, ids, nullptr, vocab, TT_POOL_SUM, 0 /* shard_world */};
   return tt_tower_input_fwd(&f, 1, out, nullptr, B, d, nullptr, stream);
 }
 
 extern "C" int tt_embedding_gather_bf16(const float* table, const int64_t* ids, uint16_t* out, int64_t B,
                                         int64_t d, int64_t vocab, void* stream) {
-  tt_feature f{table, ids, nullptr, vocab, TT_POOL_SUM, 0};
+  tt_feature f{table, ids, nullptr, vocab, TT_POOL_SUM, 0 /* shard_world */};
   return tt_tower_input_fwd(&f, 1, nullptr, out, B, d, nullptr, stream);
 }
 

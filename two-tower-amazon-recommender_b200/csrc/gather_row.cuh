@@ -15,6 +15,15 @@ struct FeatureParams {
 __device__ __forceinline__ float4 ldg_row_chunk(const float* table, int64_t id, int64_t d, int chunk) {
   return __ldg(reinterpret_cast<const float4*>(table + id * d) + chunk);
 }
+// row `id` of a feature's table: one array, or row shards addressed through local / peer-mapped base pointers
+__device__ __forceinline__ float4 ldg_feature_row(const tt_feature& ft, int64_t id, int64_t d, int chunk) {
+  if (ft.shard_world >= 2) {
+    const float* const* shards = reinterpret_cast<const float* const*>(ft.table);
+    const int64_t w = ft.shard_world;
+    return ldg_row_chunk(shards[id % w], id / w, d, chunk);
+  }
+  return ldg_row_chunk(ft.table, id, d, chunk);
+}
 
 template <int CH>
 __device__ __forceinline__ void gather_row(const FeatureParams& p, int64_t b, int64_t d, int lane, int nchunks,
@@ -36,7 +45,7 @@ __device__ __forceinline__ void gather_row(const FeatureParams& p, int64_t b, in
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
           int chunk = lane + 32 * c;
-          if (chunk < nchunks) e[c] = ldg_row_chunk(ft.table, id, d, chunk);
+          if (chunk < nchunks) e[c] = ldg_feature_row(ft, id, d, chunk);
         }
       }
     } else {
@@ -57,7 +66,7 @@ __device__ __forceinline__ void gather_row(const FeatureParams& p, int64_t b, in
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
               int chunk = lane + 32 * c;
-              r[u][c] = (ok && chunk < nchunks) ? ldg_row_chunk(ft.table, id, d, chunk)
+              r[u][c] = (ok && chunk < nchunks) ? ldg_feature_row(ft, id, d, chunk)
                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
             }
           }

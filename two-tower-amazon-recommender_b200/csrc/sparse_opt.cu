@@ -247,6 +247,7 @@ struct SparseMultiVar {
   uint8_t* first_flag;
   int64_t num_rows, nnz, vocab, d;
   int mode;
+  int shard;     // 0, or (world << 16) | rank: values are global ids, foreign ones are skipped
 };
 struct SparseMultiArgs { SparseMultiVar v[TT_MAX_SPARSE_VARS]; };
 
@@ -345,6 +346,8 @@ static int run_sparse_multi(const char* name, bool adam, const tt_sparse_var* va
     ws_layout(s.nnz, s.d, s.workspace, &v.ws);
     v.table = s.table; v.s0 = s.slot0; v.s1 = s.slot1; v.values = s.values; v.offsets = s.offsets; v.grad = s.grad;
     v.first_flag = s.first_flag; v.num_rows = s.num_rows; v.nnz = s.nnz; v.vocab = s.vocab; v.d = s.d; v.mode = s.mode;
+    v.shard = 0;
+    TT_REQUIRE(s.shard == 0, "%s: sharded tables go through tt_optimizer_prepare_sparse + tt_*_step", name);
     max_nnz = std::max<int64_t>(max_nnz, s.nnz);
   }
   if (max_nnz == 0) return TT_OK;
@@ -457,7 +460,11 @@ __global__ void __launch_bounds__(256) sparse_prepare_kernel(const __grid_consta
   const SparseMultiVar& V = a.v[blockIdx.y];
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= V.nnz) return;
-  const int64_t id = V.values[j];
+  int64_t id = V.values[j];
+  if (V.shard && id >= 0) {                     // global id of a row-sharded table: keep what this rank owns
+    const int64_t w = V.shard >> 16, me = V.shard & 0xffff;
+    id = (id % w == me) ? id / w : -1;
+  }
   if (id < 0 || id >= V.vocab) { V.ws.hpos[j] = -1; return; }
   const uint64_t mask = (uint64_t)V.ws.cap - 1;
   uint64_t h = mix64((uint64_t)id) & mask;
@@ -615,6 +622,37 @@ optimizer_step_kernel(const __grid_constant__ StepArgs a, float lr_or_alpha, flo
   if (lane == 0) { V.ws.keys[h] = kEmpty; V.ws.first[h] = INT_MAX; V.ws.cnt[h] = 0; V.ws.done[h] = 0; }
 }
 
+// out_i = ordered sum of the split partials of variable i, for all variables in one launch (before the
+// data-parallel all-reduce of the dense gradients).  `w` of the descriptor is the output.
+__global__ void __launch_bounds__(256) fold_parts_multi_kernel(const __grid_constant__ DenseMultiArgs a) {
+  const DenseMultiVar& V = a.v[blockIdx.y];
+  const bool vec = (V.n & 3) == 0;
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * (vec ? 4 : 1);
+  if (i0 >= V.n) return;
+  if (vec) {
+    const float4* pp = reinterpret_cast<const float4*>(V.parts + i0);
+    const int64_t stride4 = V.n >> 2;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    int p = 0;
+    for (; p + 8 <= V.num_parts; p += 8) {
+      float4 t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = __ldg(pp + (int64_t)(p + u) * stride4);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { g.x = __fadd_rn(g.x, t[u].x); g.y = __fadd_rn(g.y, t[u].y); g.z = __fadd_rn(g.z, t[u].z); g.w = __fadd_rn(g.w, t[u].w); }
+    }
+    for (; p < V.num_parts; ++p) {
+      const float4 t = __ldg(pp + (int64_t)p * stride4);
+      g.x = __fadd_rn(g.x, t.x); g.y = __fadd_rn(g.y, t.y); g.z = __fadd_rn(g.z, t.z); g.w = __fadd_rn(g.w, t.w);
+    }
+    *reinterpret_cast<float4*>(V.w + i0) = g;
+  } else {
+    float g = 0.f;
+    for (int p = 0; p < V.num_parts; ++p) g = __fadd_rn(g, V.parts[(int64_t)p * V.n + i0]);
+    V.w[i0] = g;
+  }
+}
+
 static int fill_sparse(const char* name, bool adam, const tt_sparse_var* vars, int n, SparseMultiArgs* args, int64_t* max_nnz) {
   TT_REQUIRE(n == 0 || vars, "%s: null variable array", name);
   TT_REQUIRE(n >= 0 && n <= TT_MAX_SPARSE_VARS, "%s: at most %d tables per call", name, TT_MAX_SPARSE_VARS);
@@ -633,6 +671,8 @@ static int fill_sparse(const char* name, bool adam, const tt_sparse_var* vars, i
     ws_layout(s.nnz, s.d, s.workspace, &v.ws);
     v.table = s.table; v.s0 = s.slot0; v.s1 = s.slot1; v.values = s.values; v.offsets = s.offsets; v.grad = s.grad;
     v.first_flag = s.first_flag; v.num_rows = s.num_rows; v.nnz = s.nnz; v.vocab = s.vocab; v.d = s.d; v.mode = s.mode;
+    v.shard = s.shard;
+    TT_REQUIRE(s.shard == 0 || ((s.shard >> 16) >= 1 && (s.shard & 0xffff) < (s.shard >> 16)), "%s: table %d has a bad shard descriptor", name, i);
     *max_nnz = std::max<int64_t>(*max_nnz, s.nnz);
   }
   (void)adam;
@@ -817,4 +857,22 @@ extern "C" int tt_adagrad_step(const tt_dense_var* host_dense, int32_t num_dense
 extern "C" int tt_lazy_adam_step(const tt_dense_var* host_dense, int32_t num_dense, const tt_sparse_var* host_sparse,
                                  int32_t num_sparse, float alpha, float beta1, float beta2, float eps, void* stream) {
   return run_step("tt_lazy_adam_step", true, host_dense, num_dense, host_sparse, num_sparse, alpha, beta1, beta2, eps, (cudaStream_t)stream);
+}
+
+extern "C" int tt_fold_parts_multi(const tt_dense_var* host_vars, int32_t num_vars, void* stream) {
+  TT_REQUIRE(host_vars && num_vars >= 1 && num_vars <= TT_MAX_DENSE_VARS, "tt_fold_parts_multi: num_vars must be in [1, %d]", TT_MAX_DENSE_VARS);
+  static thread_local DenseMultiArgs args;
+  int64_t max_threads = 0;
+  for (int i = 0; i < num_vars; ++i) {
+    const tt_dense_var& s = host_vars[i];
+    TT_REQUIRE(s.w && s.grad_parts && s.n > 0 && s.num_parts >= 1, "tt_fold_parts_multi: variable %d is incomplete", i);
+    TT_REQUIRE((s.n & 3) != 0 || (aligned16(s.grad_parts) && aligned16(s.w)), "tt_fold_parts_multi: variable %d must be 16-byte aligned", i);
+    DenseMultiVar& v = args.v[i];
+    v.w = s.w; v.parts = s.grad_parts; v.n = s.n; v.num_parts = s.num_parts;
+    max_threads = std::max<int64_t>(max_threads, (s.n & 3) == 0 ? s.n / 4 : s.n);
+  }
+  TT_PROF("fold_parts_multi_kernel", (cudaStream_t)stream);
+  fold_parts_multi_kernel<<<dim3((unsigned)ceil_div(max_threads, 256), (unsigned)num_vars), 256, 0, (cudaStream_t)stream>>>(args);
+  TT_LAUNCH_OK("fold_parts_multi_kernel");
+  return TT_OK;
 }

@@ -45,6 +45,7 @@ struct TowerFwdArgs {
   CUtensorMap tmW2[TT_MAX_TOWERS];   // W2 [d_hid, d_out]: box {64, d_hid}
   CUtensorMap tmH[TT_MAX_TOWERS];    // h [B, d_hid] (store): box {64, 128}
   CUtensorMap tmY[TT_MAX_TOWERS];    // y [B, d_out] (store): box {64, 128}
+  CUtensorMap tmX[TT_MAX_TOWERS];    // x [B, d_in] (load; only when the tower input is given instead of gathered)
   TowerDev t[TT_MAX_TOWERS];
   int* fault;
   long long* trace;
@@ -129,7 +130,8 @@ tower_mlp2_fwd_kernel(const __grid_constant__ TowerFwdArgs a) {
   uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + L.off_tail);
   uint64_t* mma1_done = w_full + 1;
   uint64_t* mma2_done = w_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 3);
+  uint64_t* x_full = w_full + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 4);
   float* sB1 = reinterpret_cast<float*>(smem + L.off_tail + 64);
   float* sB2 = sB1 + d_hid;
 
@@ -141,7 +143,7 @@ tower_mlp2_fwd_kernel(const __grid_constant__ TowerFwdArgs a) {
     tma_prefetch_desc(&a.tmW2[tw]);
     tma_prefetch_desc(&a.tmH[tw]);
     tma_prefetch_desc(&a.tmY[tw]);
-    mbar_init(w_full, 1); mbar_init(mma1_done, 1); mbar_init(mma2_done, 1);
+    mbar_init(w_full, 1); mbar_init(mma1_done, 1); mbar_init(mma2_done, 1); mbar_init(x_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -155,12 +157,18 @@ tower_mlp2_fwd_kernel(const __grid_constant__ TowerFwdArgs a) {
     mbar_arrive_expect_tx(w_full, L.w1_bytes + L.w2_bytes);
     for (int j = 0; j < d_hid / 64; ++j) tma_load_2d(sR1 + j * d_in * 128, &a.tmW1[tw], w_full, 64 * j, 0);
     for (int j = 0; j < d_out / 64; ++j) tma_load_2d(sW2 + j * d_hid * 128, &a.tmW2[tw], w_full, 64 * j, 0);
+    if (P.feats.n == 0) {                         // tower input given (row-sharded lookup already exchanged): TMA it in
+      mbar_arrive_expect_tx(x_full, L.x_bytes);
+      for (int j = 0; j < d_in / 64; ++j) tma_load_2d(sX + j * TW_BLK, &a.tmX[tw], x_full, 64 * j, (int)m0);
+    }
   }
   for (int i = threadIdx.x; i < d_hid; i += TW_THREADS) sB1[i] = P.b1[i];
   for (int i = threadIdx.x; i < d_out; i += TW_THREADS) sB2[i] = P.b2[i];
 
   // ---- gather / pool the 128 rows: lane l owns columns 4l..4l+3 of the row (d_in == 128)
-  {
+  if (P.feats.n == 0) {
+    mbar_wait(x_full, 0);
+  } else {
     const int nchunks = d_in >> 2;
     const int col = 4 * lane;
     auto put_row = [&](int r, int64_t b, const float4& v) {
@@ -188,7 +196,7 @@ tower_mlp2_fwd_kernel(const __grid_constant__ TowerFwdArgs a) {
 #pragma unroll
       for (int i = 0; i < TW_BM / 8; ++i) {
         const int64_t id = __shfl_sync(0xffffffffu, my_id, i);
-        v[i] = (id >= 0 && lane < nchunks) ? ldg_row_chunk(ft.table, id, d_in, lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[i] = (id >= 0 && lane < nchunks) ? ldg_feature_row(ft, id, d_in, lane) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int i = 0; i < TW_BM / 8; ++i) put_row(warp + 8 * i, m0 + warp + 8 * i, v[i]);
@@ -639,9 +647,9 @@ static int check_tower(const char* fn, const tt_tower_mlp2& s, bool bwd) {
   if (!bwd) {
     TT_REQUIRE(s.b1 && s.b2, "%s: bias null", fn);
     TT_REQUIRE(s.y && aligned16(s.y), "%s: y null or unaligned", fn);
-    TT_REQUIRE(s.num_feats >= 1 && s.num_feats <= TT_MAX_FEATURES, "%s: num_feats must be in [1, %d]", fn, TT_MAX_FEATURES);
+    TT_REQUIRE(s.num_feats >= 0 && s.num_feats <= TT_MAX_FEATURES, "%s: num_feats must be in [0, %d] (0: x is an input)", fn, TT_MAX_FEATURES);
     for (int i = 0; i < s.num_feats; ++i) {
-      TT_REQUIRE(s.feats[i].table && aligned16(s.feats[i].table) && s.feats[i].values && s.feats[i].vocab > 0, "%s: feature %d is incomplete", fn, i);
+      TT_REQUIRE(s.feats[i].table && (s.feats[i].shard_world >= 2 || aligned16(s.feats[i].table)) && s.feats[i].values && s.feats[i].vocab > 0, "%s: feature %d is incomplete", fn, i);
       TT_REQUIRE(s.feats[i].mode == TT_POOL_SUM || s.feats[i].mode == TT_POOL_MEAN, "%s: feature %d bad pooling mode", fn, i);
     }
   } else {
@@ -688,6 +696,8 @@ extern "C" int tt_tower_mlp2_fwd(const tt_tower_mlp2* towers, int32_t n, int32_t
     rc = make_tmap_bf16_2d(&args.tmH[i], s.h, (uint64_t)s.d_hid, (uint64_t)s.batch, (uint64_t)s.d_hid * 2, 64, TW_BM);
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&args.tmY[i], s.y, (uint64_t)s.d_out, (uint64_t)s.batch, (uint64_t)s.d_out * 2, 64, TW_BM);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&args.tmX[i], s.x, (uint64_t)s.d_in, (uint64_t)s.batch, (uint64_t)s.d_in * 2, 64, TW_BM);
     if (rc) return rc;
     max_b = std::max<int64_t>(max_b, s.batch);
     smem = std::max(smem, fwd_layout(s.d_in, s.d_hid, s.d_out).total);

@@ -77,6 +77,13 @@ class Embedding(Layer):
     def _tower_features(self, inputs):
         return [self], [self._feature(inputs)]
 
+    # what the optimizer is told at lookup time / receives as the gradient (overridden by row-sharded tables)
+    def _lookup_note(self, feat):
+        return (self.embeddings, feat[1], feat[2], feat[3])
+
+    def _make_grad(self, feat, rows) -> IndexedSlices:
+        return IndexedSlices(values=feat[1], offsets=feat[2], mode=feat[3], rows=rows)
+
     def __call__(self, inputs, training: bool = False) -> Tensor:
         return _tower_input([self], [inputs])
 
@@ -107,7 +114,7 @@ def _tower_input(layers: Sequence[Embedding], inputs: Sequence) -> Tensor:
             raise ValueError(f"features disagree on the batch size ({b} != {batch})")
     dim = layers[0].output_dim
     bf16 = config.precision == "bf16"
-    GradientTape.note_sparse_lookup([(l.embeddings, f[1], f[2], f[3]) for l, f in zip(layers, feats)])
+    GradientTape.note_sparse_lookup([l._lookup_note(f) for l, f in zip(layers, feats)])
     out_f32, out_bf16 = ops.tower_input_fwd(feats, batch, dim, want_f32=not bf16, want_bf16=bf16)
     out = Tensor(f32=out_f32, bf16=out_bf16, grad_formats=("f32",))
 
@@ -118,7 +125,7 @@ def _tower_input(layers: Sequence[Embedding], inputs: Sequence) -> Tensor:
         for layer, f in zip(layers, feats):
             if layer.embeddings.grad is not None:
                 raise NotImplementedError("an embedding table used twice in one step is not supported")
-            layer.embeddings.grad = IndexedSlices(values=f[1], offsets=f[2], mode=f[3], rows=rows)
+            layer.embeddings.grad = layer._make_grad(f, rows)
 
     GradientTape.record(backward)
     return out
@@ -251,42 +258,52 @@ class PendingTowers:
     def __init__(self):
         self.items = []
 
-    def add(self, seq, emb_layers, feats, batch, out: Tensor):
-        self.items.append((seq, emb_layers, feats, batch, out))
+    def add(self, seq, emb_layers, feats, batch, out: Tensor, x_input: Optional[Tensor] = None):
+        """x_input: the tower input as a Tensor (bf16) produced elsewhere -- a row-sharded lookup that has
+        already exchanged its rows -- instead of features to gather; its gradient is handed back as f32."""
+        self.items.append((seq, emb_layers, feats, batch, out, x_input))
 
     def flush(self):
         items, self.items = self.items, []
         if not items:
             return
-        GradientTape.note_sparse_lookup([(l.embeddings, f[1], f[2], f[3])
-                                         for _, emb_layers, feats, _, _ in items for l, f in zip(emb_layers, feats)])
+        lookups = [l._lookup_note(f) for _, emb_layers, feats, _, _, _ in items for l, f in zip(emb_layers, feats)]
+        if lookups:
+            GradientTape.note_sparse_lookup(lookups)
         specs = []
-        for seq, emb_layers, feats, batch, out in items:
+        for seq, emb_layers, feats, batch, out, x_input in items:
             d1, d2 = seq.layers[1], seq.layers[2]
-            specs.append(dict(features=feats, batch=batch, w1=d1.kernel.shadow, b1=d1.bias.value,
-                              w2=d2.kernel.shadow, b2=d2.bias.value))
+            spec = dict(features=feats, batch=batch, w1=d1.kernel.shadow, b1=d1.bias.value,
+                        w2=d2.kernel.shadow, b2=d2.bias.value)
+            if x_input is not None:
+                spec["x_input"] = x_input.bf16
+            specs.append(spec)
         results = ops.tower_mlp2_fwd(specs)
-        for (seq, emb_layers, feats, batch, out), spec, (x, h, y) in zip(items, specs, results):
+        for (seq, emb_layers, feats, batch, out, x_input), spec, (x, h, y) in zip(items, specs, results):
             out._bf16 = y
             out._pending = None
             spec["x"], spec["h"] = x, h
 
         def backward():
             live = [(it, sp) for it, sp in zip(items, specs) if it[4].grad is not None]
+            for _, sp in live:
+                sp.pop("x_input", None)
             if not live:
                 return
             towers = []
-            for (seq, emb_layers, feats, batch, out), sp in live:
+            for (seq, emb_layers, feats, batch, out, x_input), sp in live:
                 g = out.grad
                 parts = g["parts"] if g.get("parts") is not None else g["f32"].reshape(1, *g["f32"].shape)
                 towers.append(dict(sp, dy_parts=parts.contiguous(), dy_splits=parts.shape[0]))
             outs = ops.tower_mlp2_bwd(towers)
-            for ((seq, emb_layers, feats, batch, out), sp), o in zip(live, outs):
+            for ((seq, emb_layers, feats, batch, out, x_input), sp), o in zip(live, outs):
                 P = o["P"]
+                if x_input is not None:
+                    x_input.grad = dict(f32=o["dx"])
                 for layer, f in zip(emb_layers, feats):
                     if layer.embeddings.grad is not None:
                         raise NotImplementedError("an embedding table used twice in one step is not supported")
-                    layer.embeddings.grad = IndexedSlices(values=f[1], offsets=f[2], mode=f[3], rows=o["dx"])
+                    layer.embeddings.grad = layer._make_grad(f, o["dx"])
                 d1, d2 = seq.layers[1], seq.layers[2]
                 d1.kernel.grad = DenseGrad(o["dw1"], P)
                 d1.bias.grad = DenseGrad(o["db1"].reshape(P, 1, -1), P)
@@ -325,14 +342,34 @@ class Sequential(Layer):
         if not (self.fuse and config.precision == "bf16" and len(self.layers) == 3):
             return False
         e, d1, d2 = self.layers
-        if not isinstance(e, (Embedding, FeatureSum)) or not isinstance(d1, Dense) or not isinstance(d2, Dense):
+        sharded = getattr(e, "provides_tower_input", False)      # parallel.ShardedEmbedding
+        gathers = isinstance(e, (Embedding, FeatureSum)) or hasattr(e, "_tower_features")   # incl. PeerShardedEmbedding
+        if not (gathers or sharded) or not isinstance(d1, Dense) or not isinstance(d2, Dense):
             return False
         if not d1.relu or d2.relu:
             return False
-        d_in = e.output_dim if isinstance(e, Embedding) else next(iter(e.features.values())).output_dim
+        d_in = next(iter(e.features.values())).output_dim if isinstance(e, FeatureSum) else e.output_dim
         return ops.tower_mlp2_supported(d_in, d1.units, d2.units)
 
     def __call__(self, inputs, training: bool = False) -> Tensor:
+        if self._fusable() and getattr(self.layers[0], "provides_tower_input", False):
+            e, d1, d2 = self.layers
+            xt = e(inputs, training=training)                     # exchanges the rows; records its own backward
+            batch = xt.shape[0]
+            if batch > 0:
+                for layer, width in ((d1, e.output_dim), (d2, d1.units)):
+                    if layer.kernel is None:
+                        layer.build(width)
+                    if layer.kernel.shadow is None:
+                        layer.kernel.want_shadows = True
+                        layer.kernel.refresh_shadows()
+                out = Tensor(grad_formats=("parts",), pending=_pending_towers, shape=(batch, d2.units))
+                _pending_towers.add(self, [], [], batch, out, x_input=xt)
+                return out
+            x = xt
+            for l in self.layers[1:]:
+                x = l(x, training=training)
+            return x
         if self._fusable():
             e, d1, d2 = self.layers
             emb_layers, feats = e._tower_features(inputs)

@@ -55,6 +55,32 @@ def pool_code(mode: str) -> int:
     raise ValueError(f"combiner must be 'sum' or 'mean', got {mode!r}")
 
 
+class PeerTable:
+    """A table row-sharded over `world` ranks and addressed through peer-mapped base pointers (NVLink P2P):
+    `ptrs` is a device int64 [world] array of the shard base addresses as seen from THIS rank (its own shard
+    and the peers', e.g. from torch.distributed._symmetric_memory), `shard` this rank's [rows, d] slice.
+    Row id lives on rank id % world at local row id // world."""
+
+    def __init__(self, ptrs: torch.Tensor, shard: torch.Tensor, vocab: int, world: int, rank: int):
+        self.ptrs, self.shard, self.vocab, self.world, self.rank = ptrs, shard, int(vocab), int(world), int(rank)
+        self.shape = (self.vocab, shard.shape[1])
+        self.device = shard.device
+
+
+def _fill_feature(dst, table, values, offsets, mode) -> None:
+    if isinstance(table, PeerTable):
+        dst.table = _ptr(table.ptrs, torch.int64)
+        dst.vocab = table.vocab
+        dst.shard_world = table.world
+    else:
+        dst.table = _ptr(table, torch.float32)
+        dst.vocab = table.shape[0]
+        dst.shard_world = 0
+    dst.values = _ptr(values, torch.int64)
+    dst.offsets = _ptr(offsets, torch.int64)
+    dst.mode = pool_code(mode)
+
+
 def device_check() -> None:
     check(_lib.load().tt_device_check())
 
@@ -69,11 +95,7 @@ def tower_input_fwd(features: Sequence[tuple], batch: int, dim: int, want_f32: b
     arr = (_lib.tt_feature * n)()
     dev = features[0][0].device
     for i, (table, values, offsets, mode) in enumerate(features):
-        arr[i].table = _ptr(table, torch.float32)
-        arr[i].values = _ptr(values, torch.int64)
-        arr[i].offsets = _ptr(offsets, torch.int64)
-        arr[i].vocab = table.shape[0]
-        arr[i].mode = pool_code(mode)
+        _fill_feature(arr[i], table, values, offsets, mode)
         if table.shape[1] != dim:
             raise ValueError("all features of a tower must share the embedding dimension")
     out_f32 = torch.empty((batch, dim), dtype=torch.float32, device=dev) if want_f32 else None
@@ -235,9 +257,14 @@ def _fill_dense_vars(items):
 
 
 def _fill_sparse_vars(items):
-    """items: [(table, slot0 | None, slot1 | None, values, offsets | None, mode, grad | None, SparseWorkspace, first_flag | None)]"""
+    """items: [(table, slot0 | None, slot1 | None, values, offsets | None, mode, grad | None, SparseWorkspace,
+    first_flag | None[, (world, rank)])] -- with (world, rank) `values` are GLOBAL ids of a table row-sharded
+    over the ranks and `table` is this rank's shard."""
     arr = (_lib.tt_sparse_var * max(len(items), 1))()
-    for i, (table, s0, s1, values, offsets, mode, grad, ws, first_flag) in enumerate(items):
+    for i, item in enumerate(items):
+        table, s0, s1, values, offsets, mode, grad, ws, first_flag = item[:9]
+        shard = item[9] if len(item) > 9 else None
+        arr[i].shard = 0 if shard is None else (int(shard[0]) << 16) | int(shard[1])
         arr[i].table = _ptr(table, torch.float32)
         arr[i].slot0 = _ptr(s0, torch.float32)
         arr[i].slot1 = _ptr(s1, torch.float32)
@@ -252,6 +279,30 @@ def _fill_sparse_vars(items):
         arr[i].first_flag = _ptr(first_flag, torch.uint8)
         arr[i].mode = pool_code(mode)
     return arr
+
+
+def fold_parts_into_bucket(grads):
+    """grads: [(parts [P, ...] f32, P)].  Returns (bucket f32 [sum n_i], [views]) with view_i = ordered sum of parts_i,
+    all in one launch (the flat bucket is what the data-parallel all-reduce sends)."""
+    lib = _lib.load()
+    sizes = [p[0].numel() for p, _ in grads]
+    padded = [(n + 3) // 4 * 4 for n in sizes]
+    bucket = torch.empty(sum(padded), dtype=torch.float32, device=grads[0][0].device)
+    views, off = [], 0
+    for (p, _), n, m in zip(grads, sizes, padded):
+        views.append(bucket[off:off + n].view(p[0].shape))
+        off += m
+    for lo in range(0, len(grads), _lib.TT_MAX_DENSE_VARS):
+        chunk = list(zip(grads, views))[lo:lo + _lib.TT_MAX_DENSE_VARS]
+        arr = (_lib.tt_dense_var * len(chunk))()
+        for i, ((p, P), v) in enumerate(chunk):
+            arr[i].w = v.data_ptr()
+            arr[i].grad_parts = _ptr(p, torch.float32)
+            arr[i].n = v.numel()
+            arr[i].num_parts = int(P)
+        check(lib.tt_fold_parts_multi(arr, len(chunk), _stream()))
+        _count(1)
+    return bucket, views
 
 
 def sparse_prepare(items):
@@ -364,11 +415,7 @@ def _fill_tower(dst, t):
     feats = t["features"]
     dst.num_feats = len(feats)
     for i, (table, values, offsets, mode) in enumerate(feats):
-        dst.feats[i].table = _ptr(table, torch.float32)
-        dst.feats[i].values = _ptr(values, torch.int64)
-        dst.feats[i].offsets = _ptr(offsets, torch.int64)
-        dst.feats[i].vocab = table.shape[0]
-        dst.feats[i].mode = pool_code(mode)
+        _fill_feature(dst.feats[i], table, values, offsets, mode)
     dst.d_in, dst.d_hid = t["w1"].shape
     dst.d_out = t["w2"].shape[1]
     dst.batch = t["batch"]
@@ -385,10 +432,14 @@ def tower_mlp2_fwd(towers, fault_flag: Optional[torch.Tensor] = None):
     for i, t in enumerate(towers):
         _fill_tower(arr[i], t)
         dev, B = t["w1"].device, t["batch"]
-        x = torch.empty((B, arr[i].d_in), dtype=torch.bfloat16, device=dev)
+        x = t.get("x_input")                      # given tower input (row-sharded lookup): features must be []
+        if x is None:
+            x = torch.empty((B, arr[i].d_in), dtype=torch.bfloat16, device=dev)
+        elif t["features"]:
+            raise ValueError("tower_mlp2_fwd: pass either features or x_input")
         h = torch.empty((B, arr[i].d_hid), dtype=torch.bfloat16, device=dev)
         y = torch.empty((B, arr[i].d_out), dtype=torch.bfloat16, device=dev)
-        arr[i].x, arr[i].h, arr[i].y = _ptr(x), _ptr(h), _ptr(y)
+        arr[i].x, arr[i].h, arr[i].y = _ptr(x, torch.bfloat16), _ptr(h), _ptr(y)
         outs.append((x, h, y))
     check(lib.tt_tower_mlp2_fwd(arr, len(towers), _ptr(fault_flag, torch.int32), _stream()))
     _count(1)

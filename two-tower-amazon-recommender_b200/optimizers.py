@@ -56,12 +56,14 @@ class Optimizer:
         on a side stream; apply_gradients joins it."""
         self._check_sparse_supported()
         items = []
-        for var, values, offsets, mode in lookups:
+        for look in lookups:
+            var, values, offsets, mode = look[:4]
+            shard = look[4] if len(look) > 4 else None
             if id(var) in self._prepared:
                 raise NotImplementedError("an embedding table used twice in one step is not supported")
             if values.numel() == 0:
                 continue
-            items.append(self._sparse_item(var, values, offsets, mode, None))
+            items.append(self._sparse_item(var, values, offsets, mode, None) + (shard,))
             self._prepared[id(var)] = values
             self._prepared_vars.append(var)
         if not items:
@@ -83,7 +85,7 @@ class Optimizer:
             if isinstance(g, IndexedSlices):
                 if g.values.numel() == 0:
                     continue
-                item = self._sparse_item(v, g.values, g.offsets, g.mode, g.rows)
+                item = self._sparse_item(v, g.values, g.offsets, g.mode, g.rows) + (g.shard,)
                 if self._prepared.get(id(v)) is not g.values:
                     late.append(item)          # not announced at lookup time: dedup now, on this stream
                 sparse.append(item)

@@ -98,6 +98,8 @@ def exchange_grads(prim, coll: Collectives, ctx, grad_rows: torch.Tensor, capaci
 class ShardedEmbedding(Layer):
     """tf.keras.layers.Embedding whose [input_dim, d] table is row-sharded over the group."""
 
+    provides_tower_input = True      # Sequential may feed its output to the fused tower kernels
+
     def __init__(self, input_dim: int, output_dim: int, group=None, capacity_factor: Optional[float] = None,
                  name: Optional[str] = None, prim=None, seed: int = 0):
         self.coll = Collectives(group)
@@ -131,6 +133,8 @@ class ShardedEmbedding(Layer):
         bf16 = config.precision == "bf16"
         rows, ctx = exchange_lookup(self.prim, self.coll, self.embeddings.value, ids, cap,
                                     torch.bfloat16 if bf16 else torch.float32, self.overflow)
+        if self.prim is _cuda_ops:
+            GradientTape.note_sparse_lookup([(self.embeddings, ctx[0], None, "sum")])
         out = Tensor(f32=None if bf16 else rows, bf16=rows if bf16 else None, grad_formats=("f32",))
 
         def backward():
@@ -146,6 +150,72 @@ class ShardedEmbedding(Layer):
         if int(self.overflow.item()) != 0:
             raise RuntimeError(f"{self.name}: an owner bucket exceeded capacity_factor={self.capacity_factor}; "
                                "rerun with capacity_factor=None")
+
+
+class PeerShardedEmbedding(Layer):
+    """tf.keras.layers.Embedding whose [input_dim, d] table is row-sharded over the group (owner = id % world)
+    in SYMMETRIC memory: every rank maps its peers' shards (torch.distributed._symmetric_memory, NVLink P2P),
+    so a lookup is a plain gather -- the tower kernel loads each row straight from its owner over NVLink, fused
+    with the pooling and the tower MLP; there is no id partition, no all-to-all and no row permutation.
+    Backward: the (id, gradient row) pairs of all ranks are all-gathered and each owner's optimizer launch
+    keeps the entries it owns (tt_sparse_var.shard).
+
+    Ordering across ranks: a step's remote reads of a shard happen before its owner's optimizer launch of
+    that step only because collectives sit in between on every rank's stream (candidate all-gather, ...),
+    and the owner's update is visible to the next step's remote reads because DataParallelModel.train_step
+    ends with an all-reduce after the optimizer launch."""
+
+    combiner = None
+
+    def __init__(self, input_dim: int, output_dim: int, group=None, name: Optional[str] = None, seed: int = 0):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.coll = Collectives(group)
+        self.input_dim, self.output_dim = int(input_dim), int(output_dim)
+        self.name = name or "peer_sharded_embedding"
+        world, rank = self.coll.world, self.coll.rank
+        rows = -(-self.input_dim // world)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        shard = symm_mem.empty((rows, self.output_dim), dtype=torch.float32, device=dev)
+        g = torch.Generator(device=dev)
+        g.manual_seed(config.seed * 7919 + seed * 8 + rank)
+        shard.uniform_(-0.05, 0.05, generator=g)
+        handle = symm_mem.rendezvous(shard, group if group is not None else dist.group.WORLD)
+        self._handle = handle
+        ptrs = torch.tensor([int(p) for p in handle.buffer_ptrs], dtype=torch.int64, device=dev)
+        self.table = _cuda_ops.PeerTable(ptrs, shard, self.input_dim, world, rank)
+        self.embeddings = Variable(f"{self.name}/embeddings_shard{rank}", shard, "table")
+        self._ids_all = None
+
+    @property
+    def trainable_variables(self):
+        return [self.embeddings]
+
+    def load_full_table(self, table) -> None:
+        t = torch.as_tensor(table, dtype=torch.float32)
+        mine = t[self.coll.rank::self.coll.world]
+        self.embeddings.value[:mine.shape[0]].copy_(mine.to(self.embeddings.value.device))
+        torch.cuda.synchronize()
+        dist.barrier(self.coll.group)
+
+    def _feature(self, inputs):
+        return (self.table, _as_ids(inputs).reshape(-1), None, "sum")
+
+    def _tower_features(self, inputs):
+        return [self], [self._feature(inputs)]
+
+    def _lookup_note(self, feat):
+        self._ids_all = self.coll.all_gather(feat[1])              # global ids of every rank's batch
+        return (self.embeddings, self._ids_all, None, "sum", (self.coll.world, self.coll.rank))
+
+    def _make_grad(self, feat, rows) -> IndexedSlices:
+        ids_all = self._ids_all if self._ids_all is not None else self.coll.all_gather(feat[1])
+        self._ids_all = None
+        return IndexedSlices(values=ids_all, offsets=None, mode="sum", rows=self.coll.all_gather(rows),
+                             shard=(self.coll.world, self.coll.rank))
+
+    def __call__(self, inputs, training: bool = False) -> Tensor:
+        from .layers import _tower_input
+        return _tower_input([self], [inputs])
 
 
 # ------------------------------------------------------------------- global negatives
@@ -167,6 +237,20 @@ def global_retrieval(task, q: Tensor, c: Tensor, inv_t: float, w, logq, ids, pri
 
     def backward():
         bf = prec == "bf16"
+        if bf and prim is _cuda_ops and ("parts" in q.grad_formats or "parts" in c.grad_formats):
+            dq_parts, dc_parts = prim.retrieval_loss_bwd_parts(qm, c_all, inv_t, lse, label_offset, w, logq_all, ids_all, 1.0)
+            if "parts" in q.grad_formats:
+                q.grad = dict(parts=dq_parts)
+            else:
+                f, b = prim.combine_parts(dq_parts, True, "bf16" in q.grad_formats)
+                q.grad = dict(f32=f, bf16=b)
+            dc_full, _ = prim.combine_parts(dc_parts, True, False)
+            dc = coll.reduce_scatter(dc_full)                     # every rank's partial for my candidates
+            if "parts" in c.grad_formats:
+                c.grad = dict(parts=dc.reshape(1, *dc.shape))
+            else:
+                c.grad = dict(f32=dc, bf16=prim.cast_f32_to_bf16(dc) if "bf16" in c.grad_formats else None)
+            return
         r = prim.retrieval_loss_bwd(prec, qm, c_all, inv_t, lse, label_offset, w, logq_all, ids_all, 1.0,
                                     want_bf16=(bf and "bf16" in q.grad_formats, False))
         q.grad = dict(f32=r["dq"], bf16=r["dq_bf16"])
@@ -190,39 +274,46 @@ class DataParallelModel(Model):
     def train_step(self, inputs):
         if self.optimizer is None:
             raise RuntimeError("call model.compile(optimizer=...) before train_step")
+        self.optimizer.begin_step()
         with GradientTape() as tape:
+            tape.on_sparse_lookup = self.optimizer.prepare_sparse
             loss = self.compute_loss(inputs, training=True)
             variables = self.trainable_variables
             grads = tape.gradient(loss, variables)
-        flat = []
-        for i, g in enumerate(grads):
-            if isinstance(g, DenseGrad):
-                summed = _cuda_ops.sum_parts(g.parts, g.num_parts) if g.num_parts > 1 else g.parts[0]
-                flat.append((i, summed))
-        if flat:
-            # one bucket for every dense gradient: a single latency-bound all-reduce per step
-            bucket = torch.cat([t.reshape(-1) for _, t in flat])
+        dense = [(i, g) for i, g in enumerate(grads) if isinstance(g, DenseGrad)]
+        if dense:
+            # every dense gradient folded into ONE flat bucket (one launch) and summed over the ranks by a
+            # single latency-bound all-reduce per step
+            if any(g.num_parts > 1 for _, g in dense):
+                bucket, views = _cuda_ops.fold_parts_into_bucket([(g.parts, g.num_parts) for _, g in dense])
+            else:
+                bucket = torch.cat([g.parts[0].reshape(-1) for _, g in dense])
+                views, off = [], 0
+                for _, g in dense:
+                    n = g.parts[0].numel()
+                    views.append(bucket[off:off + n].view(g.parts[0].shape))
+                    off += n
             self._coll.all_reduce_(bucket)
-            off = 0
-            for i, t in flat:
-                n = t.numel()
-                grads[i] = DenseGrad(bucket[off:off + n].reshape((1,) + tuple(t.shape)), 1)
-                off += n
+            for (i, g), v in zip(dense, views):
+                grads[i] = DenseGrad(v.reshape((1,) + tuple(v.shape)), 1)
         self.optimizer.apply_gradients(zip(grads, variables))
         total = loss.value.clone()
         self._coll.all_reduce_(total)
         return {"loss": total, "local_loss": loss.value, "regularization_loss": torch.zeros_like(total), "total_loss": total}
 
 
-def build_sharded_two_tower(cfg, group, lr: float = 0.001, capacity_factor: Optional[float] = 2.0):
-    """The bench model at N > 1: ID-only two-tower of `cfg`, tables row-sharded, global negatives."""
+def build_sharded_two_tower(cfg, group, lr: float = 0.001, capacity_factor: Optional[float] = 2.0, peer: bool = True):
+    """The bench model at N > 1: ID-only two-tower of `cfg`, tables row-sharded, global negatives.
+    peer=True: shards in symmetric memory, lookups are P2P gathers fused into the tower kernel
+    (PeerShardedEmbedding); peer=False: NCCL all-to-all lookups (ShardedEmbedding)."""
     from . import optimizers, tasks
 
     class ShardedTwoTower(DataParallelModel):
         def __init__(self):
             super().__init__(group)
             def tower(vocab, seed):
-                layers = [ShardedEmbedding(vocab, cfg.dim, group, capacity_factor, seed=seed)]
+                layers = [PeerShardedEmbedding(vocab, cfg.dim, group, seed=seed) if peer else
+                          ShardedEmbedding(vocab, cfg.dim, group, capacity_factor, seed=seed)]
                 for j, u in enumerate(cfg.mlp):
                     layers.append(Dense(u, "relu" if j < len(cfg.mlp) - 1 else None))
                 return Sequential(layers)
