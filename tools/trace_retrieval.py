@@ -41,6 +41,9 @@ for k in range(3):
     ev = tr[k, :16 * T].reshape(4, T, 4)
     t0 = ev[ev > 0].min()
     name, labels = names[k]
+    xs = tr[k, 16 * T:16 * T + 8]
+    print(f"#### {name} CTA(0,0) thread 0 milestones (cycles): entry, setup, loop done, [3], [4], [5], before last sync, exit:",
+          [int(x - t0) if x > 0 else None for x in xs])
     print(f"==== {name}: cycles relative to the first stamp; softmax WG0 | WG1 rows then MMA thread, TMA thread")
     for role, rn in enumerate(["WG0", "WG1", "MMA", "TMA"]):
         print(f"-- {rn}")

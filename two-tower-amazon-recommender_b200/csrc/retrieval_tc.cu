@@ -9,10 +9,12 @@
 //   partial (max, sum) pairs are merged by a finalize kernel into row_lse and the SUM loss.
 //
 // backward (retrieval_bwd_tc_kernel<TRANSPOSED>): the same streaming structure, plus a second
-//   GEMM per tile.  The softmax warps turn S into dS = softmax - eye (bf16) and store it to
-//   shared memory in the 128B-swizzled K-major layout; the MMA thread then accumulates
-//   dX[128, d] += dS[128, BN] * Y-tile into a TMEM accumulator, reading the SAME shared-memory Y
-//   tile as an MN-major B operand (no transposed copy is loaded or kept in HBM).  TRANSPOSED = false keeps
+//   GEMM per tile.  The softmax warps turn S into dS = softmax - eye (bf16) and write it back to
+//   TENSOR MEMORY (tcgen05.st, packed bf16x2: lane = row, one column = two K elements); the second MMA
+//   thread then accumulates dX[128, d] += dS[128, BN] * Y-tile into a TMEM accumulator with the A operand
+//   read from TMEM and the SAME shared-memory Y tile read as an MN-major B operand (no transposed copy is
+//   loaded or kept in HBM).  dS never touches shared memory: the SS form of both GEMMs would need 128 B/clk
+//   of operand reads -- all of the SM's shared-memory bandwidth -- and the freed 64 KB deepen the TMA ring.  TRANSPOSED = false keeps
 //   query rows stationary (dQ); TRANSPOSED = true keeps candidate rows stationary and streams
 //   queries (dC).  S is recomputed in each pass (5 GEMM units for 3 algorithmic ones).
 //
@@ -30,6 +32,13 @@ static long long* g_trace = nullptr;
   do {                                                                                            \
     if (a.trace && blockIdx.x == 0 && blockIdx.y == 0 && (tile) < TRACE_TILES)                    \
       a.trace[((role) * TRACE_TILES + (tile)) * 4 + (ev)] = clock64();                            \
+  } while (0)
+
+// CTA (0,0), thread 0: clock64() at coarse milestones (entry, setup done, loop done, ..., exit) in the 16 spare slots
+#define TT_TRACE_X(i)                                                                             \
+  do {                                                                                            \
+    if (a.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)                        \
+      a.trace[16 * TRACE_TILES + (i)] = clock64();                                                \
   } while (0)
 
 __device__ __forceinline__ long long globaltimer_ns() {
@@ -82,6 +91,44 @@ __device__ __forceinline__ float ex2_poly(float x) {
 template <int J>
 __device__ __forceinline__ float ex2_mix(float x) {      // compile-time choice per unrolled element index
   return (J % RT_POLY_EVERY) == RT_POLY_EVERY - 1 ? ex2_poly(x) : ex2_approx(x);
+}
+// The same two routes on a packed pair of logits (FFMA2 / FADD2 take one issue slot per pair).  Of every four
+// pairs, FWD_POLY_PAIRS / BWD_POLY_PAIRS go to the FMA pipe and the rest to MUFU: the split that minimises the
+// cycles per 128 x 128 tile in tools/ubench/softmax_pk.cu (forward 1/4: 933 vs 1096 scalar; backward 2/4: 845 vs 905).
+// Measured cost model (B200): a packed FFMA2 / FADD2 holds the FMA pipe ~3 clk per warp, MUFU.EX2 8 clk per warp;
+// a polynomial pair = 6 packed ops, so 3 pairs of 8 on the polynomial balance the two pipes in the backward.
+// Groups are 8 pairs wide: pair u of a group takes the polynomial when (POLY_MASK >> u) & 1.
+constexpr unsigned FWD_POLY_MASK = 0x11, BWD_POLY_MASK = 0x49;   // 2 of 8, 3 of 8
+__device__ __forceinline__ int lea23(int n, int base) {
+  int r;
+  asm("{\n\t.reg .b32 sh;\n\tshf.l.wrap.b32 sh, 0, %1, 23;\n\tadd.s32 %0, sh, %2;\n\t}" : "=r"(r) : "r"(n), "r"(base));
+  return r;
+}
+__device__ __forceinline__ uint64_t ex2_poly2(uint64_t x2) {
+  float x0, x1;
+  up2(x2, x0, x1);
+  x2 = pk2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+  const uint64_t t = add2(x2, pk2(12582912.f, 12582912.f));
+  const uint64_t f = sub2(x2, add2(t, pk2(-12582912.f, -12582912.f)));
+  uint64_t p = fma2(f, pk2(0.05500893f, 0.05500893f), pk2(0.24221095f, 0.24221095f));
+  p = fma2(p, f, pk2(0.69328290f, 0.69328290f));
+  p = fma2(p, f, pk2(1.f, 1.f));
+  float p0, p1, t0, t1;
+  up2(p, p0, p1);
+  up2(t, t0, t1);
+  // exponent patch p + (n << 23) as one ALU-pipe LEA each (ptxas otherwise picks IMAD, which lands on the FMA pipe
+  // the polynomial already saturates)
+  return pk2(__int_as_float(lea23(__float_as_int(t0), __float_as_int(p0))),
+             __int_as_float(lea23(__float_as_int(t1), __float_as_int(p1))));
+}
+__device__ __forceinline__ uint64_t ex2_mufu2(uint64_t x2) {
+  float x0, x1;
+  up2(x2, x0, x1);
+  return pk2(ex2_approx(x0), ex2_approx(x1));
+}
+template <int U, unsigned POLY_MASK>
+__device__ __forceinline__ uint64_t ex2_mix2(uint64_t x2) {   // U = pair index inside a group of eight pairs
+  return ((POLY_MASK >> U) & 1u) ? ex2_poly2(x2) : ex2_mufu2(x2);
 }
 
 struct RetrievalTcArgs {
@@ -142,6 +189,7 @@ retrieval_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   long long* col_id = reinterpret_cast<long long*>(tail + 256 + 1024 + 1024);   // [2][BN] needs 2 KB
 
   TT_TRACE_CTA(0);
+  TT_TRACE_X(0);
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * RT_BM;
@@ -163,6 +211,7 @@ retrieval_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   TT_TRACE_CTA(1);
+  TT_TRACE_X(1);
 
   if (warp == RT_TMA_WARP) {
     if (elect_one_sync()) {
@@ -251,16 +300,19 @@ retrieval_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         }
         float cmax = fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])) * a.k2;
         if (cmax > m2) { l *= ex2_approx(m2 - cmax); m2 = cmax; }
-        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-        const float nm = -m2;
+        const uint64_t K2 = pk2(a.k2, a.k2), NM = pk2(-m2, -m2);
+        uint64_t acc0 = pk2(0.f, 0.f), acc1 = acc0;
 #pragma unroll
-        for (int j = 0; j < BN; j += 4) {
-          acc0 += ex2_mix<0>(fmaf(__uint_as_float(rr[j]), a.k2, nm));
-          acc1 += ex2_mix<1>(fmaf(__uint_as_float(rr[j + 1]), a.k2, nm));
-          acc2 += ex2_mix<2>(fmaf(__uint_as_float(rr[j + 2]), a.k2, nm));
-          acc3 += ex2_mix<3>(fmaf(__uint_as_float(rr[j + 3]), a.k2, nm));
+        for (int j = 0; j < BN; j += 16) {
+#define TT_FWD_PAIR(U, ACC) ACC = add2(ACC, ex2_mix2<U, FWD_POLY_MASK>(fma2(pk2u(rr[j + 2 * U], rr[j + 2 * U + 1]), K2, NM)))
+          TT_FWD_PAIR(0, acc0); TT_FWD_PAIR(1, acc1); TT_FWD_PAIR(2, acc0); TT_FWD_PAIR(3, acc1);
+          TT_FWD_PAIR(4, acc0); TT_FWD_PAIR(5, acc1); TT_FWD_PAIR(6, acc0); TT_FWD_PAIR(7, acc1);
+#undef TT_FWD_PAIR
         }
-        l += (acc0 + acc1) + (acc2 + acc3);
+        float s0, s1, s2, s3;
+        up2(acc0, s0, s1);
+        up2(acc1, s2, s3);
+        l += (s0 + s1) + (s2 + s3);
       } else {
 #pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -301,6 +353,7 @@ retrieval_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       if (qd == 0 && lane == 0) TT_TRACE(g, t, 3);
     }
     // merge the two warpgroups' partials, write one (max, sum) per row and split
+    TT_TRACE_X(2);
     if (g == 1) wg_ml[r] = make_float2(m2, l);
     asm volatile("bar.sync 3, 256;" ::: "memory");
     if (g == 0 && qi < a.nq) {
@@ -310,7 +363,9 @@ retrieval_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       if (mn > -INFINITY) ln = l * ex2_approx(m2 - mn) + o.y * ex2_approx(o.x - mn);
       a.partial_ml[(size_t)blockIdx.y * a.nq + qi] = make_float2(mn, ln);
     }
+    TT_TRACE_X(3);
     __threadfence();                               // partial_ml / row_pos visible before the ticket below
+    TT_TRACE_X(4);
   }
   // ---- the LAST CTA of a row block (all candidate splits arrived) folds the splits into row_lse and
   // the block's loss term; the last row block to finish adds the terms up in index order.  The result
@@ -318,6 +373,7 @@ retrieval_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   __shared__ int s_ticket;
   __shared__ float s_red[RT_BM];
   __syncthreads();
+  TT_TRACE_X(5);
   if (threadIdx.x == 0) s_ticket = atomicAdd(&a.counters[blockIdx.x], 1);
   __syncthreads();
   if (s_ticket == (int)gridDim.y - 1) {
@@ -364,9 +420,11 @@ retrieval_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       }
     }
   }
+  TT_TRACE_X(6);
   tc_fence_before();
   __syncthreads();
   TT_TRACE_CTA(2);
+  TT_TRACE_X(7);
   if (warp == RT_MMA_WARP) tmem_dealloc(tmem_base, 2 * BN);
 }
 
@@ -374,8 +432,9 @@ retrieval_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 // backward
 // ---------------------------------------------------------------------------------------
 struct BwdLayout {
-  int x_bytes, y_bytes, ds_bytes, stage_bytes, stages, total;
+  int x_bytes, y_bytes, stage_bytes, stages, total;
 };
+constexpr int RT_MAX_STAGES = 8;
 // tail = barriers (256 B) + per-column lse/weight vectors (2 KB) + per-column ids (2 KB)
 __host__ __device__ inline int bwd_tail_bytes(bool transposed, bool extras) {
   return 256 + ((transposed || extras) ? 2048 : 0) + (extras ? 2048 : 0);
@@ -384,12 +443,11 @@ __host__ __device__ inline BwdLayout bwd_layout(int d, int BN, int tail_bytes) {
   BwdLayout L;
   L.x_bytes = RT_BM * d * 2;
   L.y_bytes = BN * d * 2;
-  L.ds_bytes = RT_BM * BN * 2;
   L.stage_bytes = L.y_bytes;
-  const int budget = 227 * 1024 - tail_bytes - L.x_bytes - 2 * L.ds_bytes;
+  const int budget = 227 * 1024 - tail_bytes - L.x_bytes;
   L.stages = budget / L.stage_bytes;
-  if (L.stages > 4) L.stages = 4;
-  L.total = L.x_bytes + 2 * L.ds_bytes + L.stages * L.stage_bytes + tail_bytes;
+  if (L.stages > RT_MAX_STAGES) L.stages = RT_MAX_STAGES;
+  L.total = L.x_bytes + L.stages * L.stage_bytes + tail_bytes;
   return L;
 }
 
@@ -404,13 +462,12 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   const BwdLayout L = bwd_layout(d, BN, bwd_tail_bytes(TRANSPOSED, EXTRAS));
   const int STAGES = L.stages;
   uint8_t* sX = smem;
-  uint8_t* sDS = sX + L.x_bytes;                      // [2][BN/64][128 x 64] bf16, SW128
-  uint8_t* sY = sDS + 2 * L.ds_bytes;                 // per stage: Y tile [d/64][BN x 64], SW128
+  uint8_t* sY = sX + L.x_bytes;                       // per stage: Y tile [d/64][BN x 64], SW128
   uint8_t* tail = sY + STAGES * L.stage_bytes;
   uint64_t* x_full = reinterpret_cast<uint64_t*>(tail);
   uint64_t* full = x_full + 1;
-  uint64_t* empty = full + 4;
-  uint64_t* s_full = empty + 4;
+  uint64_t* empty = full + RT_MAX_STAGES;
+  uint64_t* s_full = empty + RT_MAX_STAGES;
   uint64_t* s_empty = s_full + 2;
   uint64_t* ds_full = s_empty + 2;
   uint64_t* ds_empty = ds_full + 2;
@@ -421,6 +478,7 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   long long* col_id = reinterpret_cast<long long*>(tail + 256 + 2048);   // [2][BN] cand ids / positive ids (EXTRAS)
 
   TT_TRACE_CTA(0);
+  TT_TRACE_X(0);
   const int nX = TRANSPOSED ? a.nc : a.nq;
   const int nY = TRANSPOSED ? a.nq : a.nc;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -429,12 +487,13 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   const int tile_begin = blockIdx.y * a.tiles_per_split;
   const int total_tiles = (nY + BN - 1) / BN;
   const int T = max(0, min(a.tiles_per_split, total_tiles - tile_begin));
-  const uint32_t ACC_COL = 2 * BN;                    // TMEM: [S0 | S1 | acc(d)]
+  const uint32_t ACC_COL = 2 * BN;                    // TMEM columns: [S0 | S1 | acc (d) | dS0 | dS1 (BN/2 each, bf16x2)]
+  const uint32_t DS_COL = 2 * BN + d;                 // 3 BN + d <= 512 for (BN, d) = (128, <=128) and (64, <=256)
 
   if (warp == RT_TMA_WARP && lane == 0) {
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmY);
     mbar_init(x_full, 1);
-    for (int s = 0; s < 4; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < RT_MAX_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 128);
       mbar_init(&ds_full[b], 128); mbar_init(&ds_empty[b], 1);
@@ -448,6 +507,7 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   TT_TRACE_CTA(1);
+  TT_TRACE_X(1);
 
   if (warp == RT_TMA_WARP) {
     if (elect_one_sync()) {
@@ -495,15 +555,13 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         mbar_wait(&ds_full[b], (t >> 1) & 1);
         TT_TRACE(2, t, 2);
         tc_fence_after();
-        // K = the BN streamed rows: 16 rows (2048 B) per MMA; the d/64 column chunks of the Y tile
-        // are BN*128 bytes apart (LBO)
+        // K = the BN streamed rows: 16 rows (2048 B of the Y tile, 8 TMEM columns of dS) per MMA; the d/64
+        // column chunks of the Y tile are BN*128 bytes apart (LBO)
         const uint64_t db0 = umma_desc_mn_sw128(smem_u32(sY + s * L.stage_bytes), BN * 128);
-        for (int jb = 0; jb < BN / 64; ++jb) {
-          const uint64_t da = umma_desc_k_sw128(smem_u32(sDS + b * L.ds_bytes + jb * RT_BM * 128));
+        const uint32_t ta0 = tmem_base + DS_COL + b * (BN / 2);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_ss(tmem_base + ACC_COL, da + 2 * k, db0 + 128 * (jb * 4 + k), idesc2, (t | jb | k) != 0);
-        }
+        for (int k = 0; k < BN / 16; ++k)
+          umma_bf16_ts(tmem_base + ACC_COL, ta0 + 8 * k, db0 + 128 * k, idesc2, (t | k) != 0);
         umma_commit(&ds_empty[b]);
         umma_commit(&empty[s]);
         TT_TRACE(2, t, 3);
@@ -578,42 +636,61 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       // dC: element (xi, y) is the positive when xi == label_offset + y
       const long long lab_lo = TRANSPOSED ? y_tile + a.label_offset : y_tile - a.label_offset;
       const bool diag = xi >= lab_lo && xi < lab_lo + BN;
-      uint8_t* ds_base = sDS + b * L.ds_bytes;
       uint32_t pk[BN / 2];                           // the row of dS, packed bf16
 #pragma unroll
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float p[32];
-        if (!TRANSPOSED) {
+        if (!EXTRAS) {
+          // packed pairs: one FFMA2 forms two log2-domain arguments, then MUFU or the FMA-pipe polynomial
+          const uint64_t K2 = pk2(a.k2, a.k2), NL = pk2(-row_lse2, -row_lse2);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) p[j] = fmaf(__uint_as_float(rr[c0 + j]), a.k2, -row_lse2);
-          if (EXTRAS) {
+          for (int j = 0; j < 32; j += 16) {
+            uint64_t ad[8] = {NL, NL, NL, NL, NL, NL, NL, NL};
+            if (TRANSPOSED) {                        // col_a holds -lse2 of the query columns
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              p[j] -= col_a[b * BN + c0 + j];
-              if (col_id[b * BN + c0 + j] == row_id && (y_tile + c0 + j) != a.label_offset + xi) p[j] = -INFINITY;
+              for (int u = 0; u < 4; ++u) {
+                const ulonglong2 l2 = *reinterpret_cast<const ulonglong2*>(col_a + b * BN + c0 + j + 4 * u);
+                ad[2 * u] = l2.x; ad[2 * u + 1] = l2.y;
+              }
             }
+#define TT_BWD_PAIR(U) up2(ex2_mix2<U, BWD_POLY_MASK>(fma2(pk2u(rr[c0 + j + 2 * U], rr[c0 + j + 2 * U + 1]), K2, ad[U])), p[j + 2 * U], p[j + 2 * U + 1])
+            TT_BWD_PAIR(0); TT_BWD_PAIR(1); TT_BWD_PAIR(2); TT_BWD_PAIR(3);
+            TT_BWD_PAIR(4); TT_BWD_PAIR(5); TT_BWD_PAIR(6); TT_BWD_PAIR(7);
+#undef TT_BWD_PAIR
           }
         } else {
+          if (!TRANSPOSED) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) p[j] = fmaf(__uint_as_float(rr[c0 + j]), a.k2, -row_lse2);
+            if (EXTRAS) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                p[j] -= col_a[b * BN + c0 + j];
+                if (col_id[b * BN + c0 + j] == row_id && (y_tile + c0 + j) != a.label_offset + xi) p[j] = -INFINITY;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 l4 = *reinterpret_cast<const float4*>(col_a + b * BN + c0 + j);
+              // col_a holds -lse2 of the query columns
+              p[j] = fmaf(__uint_as_float(rr[c0 + j]), a.k2, l4.x);
+              p[j + 1] = fmaf(__uint_as_float(rr[c0 + j + 1]), a.k2, l4.y);
+              p[j + 2] = fmaf(__uint_as_float(rr[c0 + j + 2]), a.k2, l4.z);
+              p[j + 3] = fmaf(__uint_as_float(rr[c0 + j + 3]), a.k2, l4.w);
+              if (EXTRAS) { p[j] -= row_logq2; p[j + 1] -= row_logq2; p[j + 2] -= row_logq2; p[j + 3] -= row_logq2; }
+            }
+            if (EXTRAS) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col_id[b * BN + c0 + j] == row_id && xi != a.label_offset + y_tile + c0 + j) p[j] = -INFINITY;
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 l4 = *reinterpret_cast<const float4*>(col_a + b * BN + c0 + j);
-            // col_a holds -lse2 of the query columns
-            p[j] = fmaf(__uint_as_float(rr[c0 + j]), a.k2, l4.x);
-            p[j + 1] = fmaf(__uint_as_float(rr[c0 + j + 1]), a.k2, l4.y);
-            p[j + 2] = fmaf(__uint_as_float(rr[c0 + j + 2]), a.k2, l4.z);
-            p[j + 3] = fmaf(__uint_as_float(rr[c0 + j + 3]), a.k2, l4.w);
-            if (EXTRAS) { p[j] -= row_logq2; p[j + 1] -= row_logq2; p[j + 2] -= row_logq2; p[j + 3] -= row_logq2; }
+            p[j] = ex2_mix<0>(p[j]); p[j + 1] = ex2_mix<1>(p[j + 1]);
+            p[j + 2] = ex2_mix<2>(p[j + 2]); p[j + 3] = ex2_mix<3>(p[j + 3]);
           }
-          if (EXTRAS) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col_id[b * BN + c0 + j] == row_id && xi != a.label_offset + y_tile + c0 + j) p[j] = -INFINITY;
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          p[j] = ex2_mix<0>(p[j]); p[j + 1] = ex2_mix<1>(p[j + 1]);
-          p[j + 2] = ex2_mix<2>(p[j + 2]); p[j + 3] = ex2_mix<3>(p[j + 3]);
         }
         if (diag) {
           const long long jj = xi - lab_lo - c0;
@@ -630,20 +707,23 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       // all exponentials are done before the dS buffer is needed (MMA2 of tile t-2 has long finished)
       if (qd == 0 && lane == 0) TT_TRACE(g, t, 2);
       mbar_wait(&ds_empty[b], ((t >> 1) & 1) ^ 1);
-      // swizzled store: 16-byte chunk c of row r in sub-tile (c / 8)
+      // the row goes back to tensor memory as the A operand of the dX GEMM
+      tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < BN / 8; ++c)
-        *reinterpret_cast<uint4*>(ds_base + (c >> 3) * (RT_BM * 128) + sw128_offset(r, c & 7)) =
-            make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-      fence_proxy_async();
+      for (int c = 0; c < BN / 64; ++c)
+        tmem_st32(tmem_base + ((uint32_t)(qd * 32) << 16) + DS_COL + b * (BN / 2) + c * 32, pk + c * 32);
+      tmem_st_wait();
+      tc_fence_before();
       mbar_arrive(&ds_full[b]);
       if (qd == 0 && lane == 0) TT_TRACE(g, t, 3);
     }
     // epilogue: accumulator [128 x d] -> fp32 partial; warpgroup g takes column half g
+    TT_TRACE_X(2);
     if (T > 0) {
       mbar_wait(acc_full, 0);
       tc_fence_after();
     }
+    TT_TRACE_X(3);
     float* out = a.partial_out + ((size_t)blockIdx.y * nX + (size_t)xi) * d;
     const int half = d / 2;
 #pragma unroll 1
@@ -665,9 +745,11 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       }
     }
   }
+  TT_TRACE_X(6);
   tc_fence_before();
   __syncthreads();
   TT_TRACE_CTA(2);
+  TT_TRACE_X(7);
   if (warp == RT_MMA_WARP) tmem_dealloc(tmem_base, 512);
 }
 
