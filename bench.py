@@ -173,7 +173,10 @@ def run_reference(args):
 def build_model(tt, cfg, world, rank, group):
     if world > 1:
         from two_tower_b200 import parallel
-        return parallel.build_sharded_two_tower(cfg, group, lr=0.001, peer=os.environ.get("TT_PEER_GATHER", "1") != "0")
+        # TT_EXCHANGE = peer (default: every exchange is a peer-memory kernel), nccl (P2P lookups + NCCL collectives),
+        # a2a (NCCL all-to-all lookups)
+        mode = os.environ.get("TT_EXCHANGE", "peer")
+        return parallel.build_sharded_two_tower(cfg, group, lr=0.001, peer={"peer": "exchange", "nccl": True, "a2a": False}[mode])
 
     class TwoTower(tt.models.Model):
         def __init__(self):

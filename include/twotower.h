@@ -240,6 +240,10 @@ int tt_cast_f32_to_bf16(const float* in, uint16_t* out, int64_t n, void* stream)
 int tt_debug_trace_buffer(long long* device_buf);
 /* Same for the fused tower kernels: 2 * 16 * 256 int64, per-CTA phase stamps (globaltimer ns). */
 int tt_debug_tower_trace(long long* device_buf);
+/* In-stream timeline of one training step: 32 int64 (16 kernel ids), {earliest CTA entry, latest CTA entry/exit} in globaltimer ns
+ * for kernel ids 0 tower fwd, 1 loss fwd, 2 dQ, 3 dC, 4 tower bwd, 5 optimizer step, 6 sparse prepare.  The pointer
+ * is read at run time (works on captured graphs).  Caller presets even slots to INT64_MAX, odd slots to 0. */
+int tt_debug_timeline(long long* device_buf);
 
 /* ---------------------------------------------------------------------------------------
  * K1+K2 fused  tower forward / backward for the two-layer tower of the BASELINE configs
@@ -393,6 +397,40 @@ int tt_partition_ids(const int64_t* ids, int64_t n, int32_t world, int64_t capac
  * (inverse = 1); entries with perm[j] < 0 are skipped. */
 int tt_permute_rows(const void* in, const int64_t* perm, void* out, int64_t n, int64_t row_bytes,
                     int32_t inverse, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * NVLink peer-memory exchange (csrc/peer.cu): the collectives of the row-sharded step as kernels on a
+ * SYMMETRIC workspace -- same layout on every rank, every rank maps all copies.  `bases` / `flag_bases`
+ * are DEVICE arrays [world] of the peer-mapped addresses of the workspace / of its flag block (8 slots x 16
+ * uint64, zeroed once); `step_counter` is a device uint64[16] of this rank: [0, 8) the epoch of each slot
+ * (initialised to 1), [8, 16) zero.  The k-th barrier on a slot signals k into that slot of every rank, waits until
+ * every rank has signalled >= k, and advances the slot's epoch.  They replace, one for one:
+ *   tt_peer_push      all-gather (producer writes its block into every rank's copy; up to 4 segments)
+ *   tt_peer_combine_scatter  reduce-scatter, producer side: row i of the ordered sum of `splits` stacked partials
+ *                     [splits, world * rows_per_rank, d] goes to slot [rank] of the [world, rows_per_rank, d]
+ *                     receive area (dst_offset) of rank i / rows_per_rank; the owner folds the slots
+ *   tt_peer_push_rows gradient row j of table t -> row [rank * b + j] of the [world * b, d] area (dst_offset[t]) of
+ *                     the rank that owns table row ids[t][j] (id % world); rows of other owners stay untouched there
+ *   tt_peer_sum_f32   all-reduce: out[i] = sum_r source_r[offset + r * stride + i], added in rank order on every
+ *                     rank (bit-identical replicas); slot >= 0 runs a barrier first, slot < 0 none
+ *   tt_peer_pull_rows owner-side gather of the gradient rows of a row-sharded table: for every global batch
+ *                     position j (produced by rank j / rows_per_rank) whose id this rank owns (id % world ==
+ *                     rank), out[t][j, :] = that rank's rows at src_offset[t]; other rows of out are untouched
+ * No NCCL inside; torch.distributed only allocates / rendezvouses the workspace.
+ * ------------------------------------------------------------------------------------- */
+int tt_peer_barrier(const void* flag_bases, void* step_counter, int32_t world, int32_t rank, int32_t slot,
+                    void* stream);
+int tt_peer_push(const void* bases, int32_t world, int32_t nseg, const void* const* src,
+                 const int64_t* dst_offset, const int64_t* bytes, void* stream);
+int tt_peer_sum_f32(const void* bases, int64_t offset_bytes, int64_t stride_bytes, int64_t n, float* out,
+                    const void* flag_bases, void* step_counter, int32_t world, int32_t rank, int32_t slot, void* stream);
+int tt_peer_combine_scatter(const void* bases, const float* parts, int32_t splits, int64_t rows, int64_t d,
+                            int64_t rows_per_rank, int64_t dst_offset, int32_t world, int32_t rank, void* stream);
+int tt_peer_push_rows(const void* bases, int32_t ntab, const int64_t* const* ids, const float* const* src,
+                      const int64_t* dst_offset, int64_t b, int64_t d, int32_t world, int32_t rank, void* stream);
+int tt_peer_pull_rows(const void* bases, int32_t ntab, const int64_t* const* ids, const int64_t* src_offset,
+                      float* const* out, int64_t rows_per_rank, int64_t d, const void* flag_bases,
+                      void* step_counter, int32_t world, int32_t rank, int32_t slot, void* stream);
 
 #ifdef __cplusplus
 }

@@ -36,6 +36,7 @@ def _worker(rank, port, precision, peer, dim, mlp, results):
         cfg = synth.Config("tiny", 77, 256, dim, 3001, 2003, mlp, 0.5)
         model = parallel.build_sharded_two_tower(cfg, dist.group.WORLD, lr=0.05, capacity_factor=None, peer=peer)
         assert type(model.user_model.layers[0]).__name__ == ("PeerShardedEmbedding" if peer else "ShardedEmbedding")
+        assert (model.exchange is not None) == (peer == "exchange")
         batches = [synth.make_batch(cfg, 10 + r) for r in range(WORLD)]
         model.test_step(batches[rank])                                  # builds the Dense layers
         # one global set of weights: full tables from a common seed, Dense weights from rank 0
@@ -74,6 +75,32 @@ def _worker(rank, port, precision, peer, dim, mlp, results):
             assert err < 10 * tol, err
             k0 = model.user_model.layers[1].kernel.numpy()
             assert np.abs(k0 - qp["kernels"][0]).max() / np.abs(qp["kernels"][0]).max() < 10 * tol
+        if peer == "exchange":
+            # the peer-memory exchange against the NCCL collectives over several steps (barrier epochs, workspace
+            # reuse): same weights, same batches -> same losses and the same table shard
+            ref_model = parallel.build_sharded_two_tower(cfg, dist.group.WORLD, lr=0.05, capacity_factor=None, peer=True)
+            ref_model.test_step(batches[rank])
+            for m in (model, ref_model):
+                m.user_model.layers[0].load_full_table(U); m.item_model.layers[0].load_full_table(I)
+                for seq in (m.user_model, m.item_model):
+                    seq.layers[0].embeddings.slots.clear()
+            for seq_a, seq_b in ((model.user_model, ref_model.user_model), (model.item_model, ref_model.item_model)):
+                for la, lb in zip(seq_a.layers[1:], seq_b.layers[1:]):
+                    for va, vb in ((la.kernel, lb.kernel), (la.bias, lb.bias)):
+                        vb.value.copy_(va.value); vb.refresh_shadows()
+                        for k, sl in va.slots.items():
+                            if isinstance(sl, torch.Tensor):
+                                vb.slots[k] = sl.clone()
+            for s in range(4):
+                bt = synth.make_batch(cfg, 100 + 10 * s + rank)
+                la, lb = float(model.train_step(bt)["loss"].item()), float(ref_model.train_step(bt)["loss"].item())
+                assert abs(la - lb) <= 1e-4 * abs(lb), (s, la, lb)
+            ta, tb = model.user_model.layers[0].embeddings.numpy(), ref_model.user_model.layers[0].embeddings.numpy()
+            assert np.abs(ta - tb).max() <= 1e-5 * np.abs(tb).max() + 1e-7, np.abs(ta - tb).max()
+            g = model.make_graphed_train_step({k: torch.from_numpy(v).cuda() for k, v in batches[rank].items()}, warmup=2)
+            for s in range(3):                                           # replay: epochs live in device memory
+                out = g({k: torch.from_numpy(v).cuda() for k, v in synth.make_batch(cfg, 200 + 10 * s + rank).items()})
+            assert np.isfinite(float(out["loss"].item()))
         results[rank] = "ok"
     except Exception:
         import traceback
@@ -86,7 +113,7 @@ def _worker(rank, port, precision, peer, dim, mlp, results):
 # (128, (256, 128)) in bf16 is the shape the fused tower kernels take.
 @pytest.mark.parametrize("precision,peer,dim,mlp", [("fp32", False, 64, (128, 64)), ("bf16", False, 64, (128, 64)),
                                                      ("fp32", True, 64, (128, 64)), ("bf16", True, 128, (256, 128)),
-                                                     ("bf16", False, 128, (256, 128))])
+                                                     ("bf16", False, 128, (256, 128)), ("bf16", "exchange", 128, (256, 128))])
 def test_sharded_two_tower_matches_global_batch_oracle(precision, peer, dim, mlp):
     if torch.cuda.device_count() < WORLD:
         pytest.skip("needs 2 GPUs")

@@ -96,6 +96,7 @@ SIGNATURES = {
     "tt_cast_f32_to_bf16": (C.c_int, [_p, _p, _i64, _p]),
     "tt_debug_trace_buffer": (C.c_int, [_p]),
     "tt_debug_tower_trace": (C.c_int, [_p]),
+    "tt_debug_timeline": (C.c_int, [_p]),
     "tt_retrieval_workspace_bytes": (_i64, [_i32, _i64, _i64, _i64]),
     "tt_retrieval_workspace_init": (C.c_int, [_i32, _p, _i64, _i64, _i64, _i64, _p]),
     "tt_retrieval_loss_fwd": (C.c_int, [_i32, _p, _p, _i64, _i64, _i64, _f, _i64, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
@@ -109,6 +110,13 @@ SIGNATURES = {
     "tt_rowwise_dot": (C.c_int, [_i32, _p, _p, _p, _i64, _i64, _p]),
     "tt_partition_ids": (C.c_int, [_p, _i64, _i32, _i64, _p, _p, _p, _p, _p]),
     "tt_permute_rows": (C.c_int, [_p, _p, _p, _i64, _i64, _i32, _p]),
+    "tt_peer_barrier": (C.c_int, [_p, _p, _i32, _i32, _i32, _p]),
+    "tt_peer_push": (C.c_int, [_p, _i32, _i32, C.POINTER(_p), C.POINTER(_i64), C.POINTER(_i64), _p]),
+    "tt_peer_sum_f32": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _i32, _i32, _i32, _p]),
+    "tt_peer_combine_scatter": (C.c_int, [_p, _p, _i32, _i64, _i64, _i64, _i64, _i32, _i32, _p]),
+    "tt_peer_push_rows": (C.c_int, [_p, _i32, C.POINTER(_p), C.POINTER(_p), C.POINTER(_i64), _i64, _i64, _i32, _i32, _p]),
+    "tt_peer_pull_rows": (C.c_int, [_p, _i32, C.POINTER(_p), C.POINTER(_i64), C.POINTER(_p), _i64, _i64, _p, _p,
+                                    _i32, _i32, _i32, _p]),
 }
 
 _lib = None

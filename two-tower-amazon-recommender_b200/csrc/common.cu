@@ -5,6 +5,7 @@
 #include <vector>
 #include <algorithm>
 #include <string.h>
+#include <stdlib.h>
 
 namespace tt {
 
@@ -18,6 +19,27 @@ int set_error(int code, const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return code;
+}
+
+}  // namespace tt
+// Debug hook: device buffer of 32 int64 = {earliest CTA entry, latest CTA entry/exit} (globaltimer ns) per step
+// kernel (ids in common.cuh); fill the even slots with INT64_MAX and the odd ones with 0 before a step.  NULL = off.
+extern "C" int tt_debug_timeline(long long* device_buf) {
+  tt::set_timeline_retrieval(device_buf);
+  tt::set_timeline_tower(device_buf);
+  tt::set_timeline_opt(device_buf);
+  tt::set_timeline_peer(device_buf);
+  return cudaGetLastError() == cudaSuccess ? TT_OK : tt::set_error(TT_ERR_CUDA, "tt_debug_timeline: cudaMemcpyToSymbol failed");
+}
+namespace tt {
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("TT_NO_PDL");
+    on = (e && e[0] && e[0] != '0') ? 0 : 1;
+  }
+  return on == 1;
 }
 
 int num_sms() {

@@ -41,6 +41,47 @@ void prof_begin(const char* name, cudaStream_t st);
 void prof_end();
 #define TT_PROF(name, st) ::tt::prof_begin(name, st)
 
+// Programmatic dependent launch (PDL).  The kernels of one training step form a chain on one stream; launched
+// with programmatic stream serialization, kernel N+1 may be scheduled while kernel N drains: its CTAs run their
+// prologue (barrier init, TMEM allocation, descriptor prefetch) on SMs that kernel N has left and then block in
+// pdl_wait() until kernel N has completed and its writes are visible.  Rules kept by every PDL kernel here:
+// nothing before pdl_wait() touches global memory, and EVERY thread executes pdl_wait() (so the completion of
+// kernel N+1 implies the completion of kernel N for whoever follows).  TT_NO_PDL=1 falls back to plain launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// In-stream timeline (tt_debug_timeline): kernel k records {earliest CTA entry, latest CTA entry or exit} in
+// globaltimer ns at tl[2k], tl[2k+1].  Read through a per-translation-unit __device__ pointer at run time, so it
+// also works inside an already captured CUDA graph.  Kernel ids: 0 tower fwd, 1 loss fwd, 2 dQ, 3 dC,
+// 4 tower bwd, 5 optimizer step, 6 sparse prepare, 7 combine partials, 8 fold dense parts, 9-14 peer.cu.
+#define TT_TL_DEFINE(setter)                                                              \
+  static __device__ long long* g_tl = nullptr;                                            \
+  void setter(long long* p) { cudaMemcpyToSymbol(g_tl, &p, sizeof(p)); }
+__device__ __forceinline__ void tl_mark(long long* tl, int k, bool entry) {
+  if (tl && threadIdx.x == 0) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (entry) atomicMin(&tl[2 * k], t);
+    atomicMax(&tl[2 * k + 1], t);
+  }
+}
+void set_timeline_retrieval(long long* p);
+void set_timeline_tower(long long* p);
+void set_timeline_opt(long long* p);
+void set_timeline_peer(long long* p);
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }

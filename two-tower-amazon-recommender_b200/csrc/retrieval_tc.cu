@@ -55,6 +55,8 @@ __device__ __forceinline__ long long globaltimer_ns() {
     }                                                                                             \
   } while (0)
 
+TT_TL_DEFINE(set_timeline_retrieval)
+
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr int RT_BM = 128;           // stationary rows per CTA
@@ -190,6 +192,8 @@ retrieval_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 
   TT_TRACE_CTA(0);
   TT_TRACE_X(0);
+  long long* const tl = g_tl;
+  tl_mark(tl, 1, true);
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * RT_BM;
@@ -210,6 +214,8 @@ retrieval_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                       // everything above overlapped the tail of the previous kernel in the stream
+  pdl_launch_dependents();
   TT_TRACE_CTA(1);
   TT_TRACE_X(1);
 
@@ -425,6 +431,7 @@ retrieval_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   __syncthreads();
   TT_TRACE_CTA(2);
   TT_TRACE_X(7);
+  tl_mark(tl, 1, false);
   if (warp == RT_MMA_WARP) tmem_dealloc(tmem_base, 2 * BN);
 }
 
@@ -454,7 +461,7 @@ __host__ __device__ inline BwdLayout bwd_layout(int d, int BN, int tail_bytes) {
 template <int BN, bool TRANSPOSED, bool EXTRAS>
 __global__ void __launch_bounds__(RT_THREADS, 1)
 retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
-                        const RetrievalTcArgs a) {
+                        const __grid_constant__ CUtensorMap tmP, const RetrievalTcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;      // no slack: the swizzled tiles need the 1024-byte alignment the declaration asks for
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
@@ -479,6 +486,8 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
 
   TT_TRACE_CTA(0);
   TT_TRACE_X(0);
+  long long* const tl = g_tl;
+  tl_mark(tl, TRANSPOSED ? 3 : 2, true);
   const int nX = TRANSPOSED ? a.nc : a.nq;
   const int nY = TRANSPOSED ? a.nq : a.nc;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -491,7 +500,7 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   const uint32_t DS_COL = 2 * BN + d;                 // 3 BN + d <= 512 for (BN, d) = (128, <=128) and (64, <=256)
 
   if (warp == RT_TMA_WARP && lane == 0) {
-    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmY);
+    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmY); tma_prefetch_desc(&tmP);
     mbar_init(x_full, 1);
     for (int s = 0; s < RT_MAX_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) {
@@ -506,6 +515,8 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                       // everything above overlapped the tail of the previous kernel in the stream
+  pdl_launch_dependents();
   TT_TRACE_CTA(1);
   TT_TRACE_X(1);
 
@@ -724,24 +735,58 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       tc_fence_after();
     }
     TT_TRACE_X(3);
-    float* out = a.partial_out + ((size_t)blockIdx.y * nX + (size_t)xi) * d;
     const int half = d / 2;
+    if (x0 + RT_BM <= nX) {
+      // full row block: every warp stages its [32 rows x 32 columns] pieces (128B-swizzled, 4 KB, two in flight) in
+      // the now idle tile ring and one lane hands them to the copy engine: full-line writes instead of 32 scattered
+      // 16-byte stores per warp instruction (which cost the LSU one cycle per touched line, ~4000 cycles per CTA)
+      uint8_t* my_stage = sY + warp * 8192;
+      int it = 0;
 #pragma unroll 1
-    for (int c0 = g * half; c0 < (g + 1) * half; c0 += 32) {
-      uint32_t rr[32];
-      if (T > 0) {
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(qd * 32) << 16) + ACC_COL + c0, rr);
-        tmem_ld_wait();
-      } else {
+      for (int c0 = g * half; c0 < (g + 1) * half; c0 += 32, ++it) {
+        uint32_t rr[32];
+        if (T > 0) {
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(qd * 32) << 16) + ACC_COL + c0, rr);
+          tmem_ld_wait();
+        } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) rr[j] = 0u;
+          for (int j = 0; j < 32; ++j) rr[j] = 0u;
+        }
+        if (lane == 0) tma_store_wait_read<1>();           // the store issued two pieces ago has read its buffer
+        __syncwarp();
+        uint8_t* st = my_stage + (it & 1) * 4096;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<float4*>(st + sw128_offset(lane, c)) =
+              make_float4(__uint_as_float(rr[4 * c]) * row_scale, __uint_as_float(rr[4 * c + 1]) * row_scale,
+                          __uint_as_float(rr[4 * c + 2]) * row_scale, __uint_as_float(rr[4 * c + 3]) * row_scale);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmP, st, c0, (int)(blockIdx.y * nX + x0 + qd * 32));
+          tma_store_commit();
+        }
       }
-      if (xi < nX) {
+      if (lane == 0) tma_store_wait_all();
+    } else {
+      float* out = a.partial_out + ((size_t)blockIdx.y * nX + (size_t)xi) * d;
+#pragma unroll 1
+      for (int c0 = g * half; c0 < (g + 1) * half; c0 += 32) {
+        uint32_t rr[32];
+        if (T > 0) {
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(qd * 32) << 16) + ACC_COL + c0, rr);
+          tmem_ld_wait();
+        } else {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(out + c0 + j) =
-              make_float4(__uint_as_float(rr[j]) * row_scale, __uint_as_float(rr[j + 1]) * row_scale,
-                          __uint_as_float(rr[j + 2]) * row_scale, __uint_as_float(rr[j + 3]) * row_scale);
+          for (int j = 0; j < 32; ++j) rr[j] = 0u;
+        }
+        if (xi < nX) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(out + c0 + j) =
+                make_float4(__uint_as_float(rr[j]) * row_scale, __uint_as_float(rr[j + 1]) * row_scale,
+                            __uint_as_float(rr[j + 2]) * row_scale, __uint_as_float(rr[j + 3]) * row_scale);
+        }
       }
     }
   }
@@ -750,6 +795,7 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   __syncthreads();
   TT_TRACE_CTA(2);
   TT_TRACE_X(7);
+  tl_mark(tl, TRANSPOSED ? 3 : 2, false);
   if (warp == RT_MMA_WARP) tmem_dealloc(tmem_base, 512);
 }
 
@@ -757,6 +803,7 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
 __global__ void __launch_bounds__(256)
 combine_partials_kernel(const float* __restrict__ partial, int splits, int64_t rows, int d, float* __restrict__ out_f32,
                         uint16_t* __restrict__ out_bf16) {
+  tl_mark(g_tl, 7, true);
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -845,11 +892,11 @@ int tc_retrieval_fwd(const void* q, const void* c, int64_t nq, int64_t nc, int64
   if (logq || cand_ids) {
     TT_CUDA_OK(cudaFuncSetAttribute(retrieval_fwd_tc_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     TT_PROF("retrieval_fwd_tc_kernel", st);
-    retrieval_fwd_tc_kernel<BN, true><<<grid, RT_THREADS, smem, st>>>(tmQ, tmC, a);
+    TT_CUDA_OK(launch_pdl(retrieval_fwd_tc_kernel<BN, true>, grid, dim3(RT_THREADS), (size_t)smem, st, tmQ, tmC, a));
   } else {
     TT_CUDA_OK(cudaFuncSetAttribute(retrieval_fwd_tc_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     TT_PROF("retrieval_fwd_tc_kernel", st);
-    retrieval_fwd_tc_kernel<BN, false><<<grid, RT_THREADS, smem, st>>>(tmQ, tmC, a);
+    TT_CUDA_OK(launch_pdl(retrieval_fwd_tc_kernel<BN, false>, grid, dim3(RT_THREADS), (size_t)smem, st, tmQ, tmC, a));
   }
   TT_LAUNCH_OK("retrieval_fwd_tc_kernel");
   return TT_OK;
@@ -868,6 +915,9 @@ static int launch_bwd(const void* x, const void* y, int64_t nX, int64_t nY, Retr
   rc = make_tmap_bf16_2d(&tmY, y, (uint64_t)d, (uint64_t)nY, (uint64_t)d * 2, 64, BN);
   if (rc) return rc;
   a.partial_out = partial; a.tiles_per_split = tps;
+  CUtensorMap tmP;                                   // partials [splits * nX, d] fp32, 32 x 32 boxes for the epilogue stores
+  rc = make_tmap_f32_2d(&tmP, partial, (uint64_t)d, (uint64_t)splits * (uint64_t)nX, (uint64_t)d * 4, 32, 32);
+  if (rc) return rc;
   a.trace = g_trace ? g_trace + (TRANSPOSED ? 2 : 1) * (4 * 4 * TRACE_TILES + 16) : nullptr;
   a.trace_cta = g_trace ? g_trace + 3 * (4 * 4 * TRACE_TILES + 16) + (TRANSPOSED ? 2 : 1) * 4 * 256 : nullptr;
   const bool extras = a.logq || a.cand_ids;
@@ -877,7 +927,8 @@ static int launch_bwd(const void* x, const void* y, int64_t nX, int64_t nY, Retr
 #define TT_BWD_LAUNCH(EX)                                                                                     \
   {                                                                                                           \
     TT_CUDA_OK(cudaFuncSetAttribute(retrieval_bwd_tc_kernel<BN, TRANSPOSED, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total)); \
-    TT_PROF("retrieval_bwd_tc_kernel", st), retrieval_bwd_tc_kernel<BN, TRANSPOSED, EX><<<grid, RT_THREADS, L.total, st>>>(tmX, tmY, a);        \
+    TT_PROF("retrieval_bwd_tc_kernel", st);                                                                   \
+    TT_CUDA_OK(launch_pdl(retrieval_bwd_tc_kernel<BN, TRANSPOSED, EX>, grid, dim3(RT_THREADS), (size_t)L.total, st, tmX, tmY, tmP, a)); \
   }
   if (extras) TT_BWD_LAUNCH(true) else TT_BWD_LAUNCH(false)
 #undef TT_BWD_LAUNCH

@@ -26,6 +26,7 @@
 namespace tt {
 
 static constexpr unsigned long long kEmpty = 0xFFFFFFFFFFFFFFFFull;
+TT_TL_DEFINE(set_timeline_opt)
 
 struct SparseWs {
   unsigned long long* keys;  // [cap]
@@ -457,6 +458,7 @@ static int run_dense_multi(const char* name, bool adam, const tt_dense_var* vars
 //     cleans the slot ("last block done", per key).  Dense variables: 4 lanes share a float4 of weights
 //     and each folds a quarter of the split-K partials (fixed association: deterministic).
 __global__ void __launch_bounds__(256) sparse_prepare_kernel(const __grid_constant__ SparseMultiArgs a) {
+  tl_mark(g_tl, 6, true);
   const SparseMultiVar& V = a.v[blockIdx.y];
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= V.nnz) return;
@@ -509,6 +511,9 @@ __device__ __forceinline__ void apply_row(const SparseMultiVar& V, int64_t id, i
 template <bool ADAM>
 __global__ void __launch_bounds__(256)
 optimizer_step_kernel(const __grid_constant__ StepArgs a, float lr_or_alpha, float b1, float b2, float eps) {
+  tl_mark(g_tl, 5, true);
+  pdl_wait();                       // launched while the backward tower kernel drains
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int bid = blockIdx.x;
   if (bid < a.dense_blocks[a.n_dense]) {
@@ -625,6 +630,7 @@ optimizer_step_kernel(const __grid_constant__ StepArgs a, float lr_or_alpha, flo
 // out_i = ordered sum of the split partials of variable i, for all variables in one launch (before the
 // data-parallel all-reduce of the dense gradients).  `w` of the descriptor is the output.
 __global__ void __launch_bounds__(256) fold_parts_multi_kernel(const __grid_constant__ DenseMultiArgs a) {
+  tl_mark(g_tl, 8, true);
   const DenseMultiVar& V = a.v[blockIdx.y];
   const bool vec = (V.n & 3) == 0;
   const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * (vec ? 4 : 1);
@@ -725,8 +731,8 @@ static int run_step(const char* name, bool adam, const tt_dense_var* dense, int 
   args.n_dense = nd; args.n_sparse = ns;
   if (blocks == 0) return TT_OK;
   TT_PROF("optimizer_step_kernel", stream);
-  if (adam) optimizer_step_kernel<true><<<blocks, 256, 0, stream>>>(args, lr_or_alpha, b1, b2, eps);
-  else optimizer_step_kernel<false><<<blocks, 256, 0, stream>>>(args, lr_or_alpha, b1, b2, eps);
+  if (adam) TT_CUDA_OK(launch_pdl(optimizer_step_kernel<true>, dim3(blocks), dim3(256), (size_t)0, stream, args, lr_or_alpha, b1, b2, eps));
+  else TT_CUDA_OK(launch_pdl(optimizer_step_kernel<false>, dim3(blocks), dim3(256), (size_t)0, stream, args, lr_or_alpha, b1, b2, eps));
   TT_LAUNCH_OK("optimizer_step_kernel");
   return TT_OK;
 }

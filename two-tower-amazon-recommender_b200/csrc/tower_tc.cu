@@ -77,6 +77,7 @@ struct TowerBwdArgs {
 
 // Phase stamps for tuning (tools/trace_tower.py): 16 globaltimer slots per CTA, fwd CTAs then bwd CTAs.
 static long long* g_tower_trace = nullptr;
+TT_TL_DEFINE(set_timeline_tower)
 __device__ __forceinline__ long long tw_now() {
   long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -124,6 +125,8 @@ tower_mlp2_fwd_kernel(const __grid_constant__ TowerFwdArgs a) {
   const int d_in = P.d_in, d_hid = P.d_hid, d_out = P.d_out;
   const FwdLayout L = fwd_layout(d_in, d_hid, d_out);
   TW_STAMP(0);
+  long long* const tl = g_tl;
+  tl_mark(tl, 0, true);
   uint8_t* sX = smem;
   uint8_t* sR1 = smem + L.off_r1;                 // W1 (MN-major chunks [d_in][64]) then h (K-major blocks)
   uint8_t* sW2 = smem + L.off_w2;                 // MN-major chunks [d_hid][64]
@@ -151,6 +154,8 @@ tower_mlp2_fwd_kernel(const __grid_constant__ TowerFwdArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                       // the prologue above overlapped the tail of the previous kernel in the stream
+  pdl_launch_dependents();
 
   TW_STAMP(1);
   if (warp == 0 && elect_one_sync()) {            // weights: L2-resident after the first CTA
@@ -311,6 +316,7 @@ tower_mlp2_fwd_kernel(const __grid_constant__ TowerFwdArgs a) {
     tma_store_wait_read<0>();                      // shared memory must outlive the reads of every bulk store
   }
   TW_STAMP(8);
+  tl_mark(tl, 0, false);
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -357,6 +363,8 @@ tower_mlp2_bwd_kernel(const __grid_constant__ TowerBwdArgs a) {
   const int d_in = P.d_in, d_hid = P.d_hid, d_out = P.d_out;
   const BwdTLayout L = bwdt_layout(d_in, d_hid, d_out);
   TW_STAMP(0);
+  long long* const tl = g_tl;
+  tl_mark(tl, 4, true);
   uint8_t* rDY = smem;
   uint8_t* rH = smem + L.off_h;
   uint8_t* rW2 = smem + L.off_w2;
@@ -388,6 +396,8 @@ tower_mlp2_bwd_kernel(const __grid_constant__ TowerBwdArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                       // the prologue above overlapped the tail of the previous kernel in the stream
+  pdl_launch_dependents();
 
   TW_STAMP(1);
   if (warp == 0 && elect_one_sync()) {
@@ -626,6 +636,7 @@ tower_mlp2_bwd_kernel(const __grid_constant__ TowerBwdArgs a) {
   TW_STAMP(10);
   tc_fence_before();
   __syncthreads();
+  tl_mark(tl, 4, false);
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -708,7 +719,7 @@ extern "C" int tt_tower_mlp2_fwd(const tt_tower_mlp2* towers, int32_t n, int32_t
   TT_CUDA_OK(cudaFuncSetAttribute(tower_mlp2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid((unsigned)ceil_div(max_b, TW_BM), (unsigned)n);
   TT_PROF("tower_mlp2_fwd_kernel", st);
-  tower_mlp2_fwd_kernel<<<grid, TW_THREADS, smem, st>>>(args);
+  TT_CUDA_OK(launch_pdl(tower_mlp2_fwd_kernel, grid, dim3(TW_THREADS), (size_t)smem, st, args));
   TT_LAUNCH_OK("tower_mlp2_fwd_kernel");
   return TT_OK;
 }
@@ -749,7 +760,7 @@ extern "C" int tt_tower_mlp2_bwd(const tt_tower_mlp2* towers, int32_t n, void* s
   TT_CUDA_OK(cudaFuncSetAttribute(tower_mlp2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid((unsigned)ceil_div(max_b, TW_BM), (unsigned)n);
   TT_PROF("tower_mlp2_bwd_kernel", st);
-  tower_mlp2_bwd_kernel<<<grid, TW_THREADS, smem, st>>>(args);
+  TT_CUDA_OK(launch_pdl(tower_mlp2_bwd_kernel, grid, dim3(TW_THREADS), (size_t)smem, st, args));
   TT_LAUNCH_OK("tower_mlp2_bwd_kernel");
   return TT_OK;
 }

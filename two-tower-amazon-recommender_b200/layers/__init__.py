@@ -114,7 +114,9 @@ def _tower_input(layers: Sequence[Embedding], inputs: Sequence) -> Tensor:
             raise ValueError(f"features disagree on the batch size ({b} != {batch})")
     dim = layers[0].output_dim
     bf16 = config.precision == "bf16"
-    GradientTape.note_sparse_lookup([l._lookup_note(f) for l, f in zip(layers, feats)])
+    notes = [n for n in (l._lookup_note(f) for l, f in zip(layers, feats)) if n is not None]
+    if notes:
+        GradientTape.note_sparse_lookup(notes)
     out_f32, out_bf16 = ops.tower_input_fwd(feats, batch, dim, want_f32=not bf16, want_bf16=bf16)
     out = Tensor(f32=out_f32, bf16=out_bf16, grad_formats=("f32",))
 
@@ -268,6 +270,7 @@ class PendingTowers:
         if not items:
             return
         lookups = [l._lookup_note(f) for _, emb_layers, feats, _, _, _ in items for l, f in zip(emb_layers, feats)]
+        lookups = [n for n in lookups if n is not None]       # None: announced later (peer-memory exchange)
         if lookups:
             GradientTape.note_sparse_lookup(lookups)
         specs = []

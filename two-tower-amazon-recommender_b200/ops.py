@@ -281,13 +281,24 @@ def _fill_sparse_vars(items):
     return arr
 
 
-def fold_parts_into_bucket(grads):
+def bucket_layout(shapes):
+    """Offsets (in floats, each variable padded to a multiple of 4) of the flat dense-gradient bucket."""
+    offs, off = [], 0
+    for shp in shapes:
+        offs.append(off)
+        off += (int(torch.Size(shp).numel()) + 3) // 4 * 4
+    return offs, off
+
+
+def fold_parts_into_bucket(grads, out=None):
     """grads: [(parts [P, ...] f32, P)].  Returns (bucket f32 [sum n_i], [views]) with view_i = ordered sum of parts_i,
-    all in one launch (the flat bucket is what the data-parallel all-reduce sends)."""
+    all in one launch (the flat bucket is what the data-parallel all-reduce sends).  out: caller-owned bucket."""
     lib = _lib.load()
     sizes = [p[0].numel() for p, _ in grads]
     padded = [(n + 3) // 4 * 4 for n in sizes]
-    bucket = torch.empty(sum(padded), dtype=torch.float32, device=grads[0][0].device)
+    bucket = out if out is not None else torch.empty(sum(padded), dtype=torch.float32, device=grads[0][0].device)
+    if bucket.numel() < sum(padded):
+        raise ValueError("fold_parts_into_bucket: destination bucket too small")
     views, off = [], 0
     for (p, _), n, m in zip(grads, sizes, padded):
         views.append(bucket[off:off + n].view(p[0].shape))
@@ -565,10 +576,11 @@ def retrieval_loss_bwd_parts(q, c, inv_temperature: float, row_lse, label_offset
     return dq_parts, dc_parts
 
 
-def combine_parts(parts, want_f32: bool = True, want_bf16: bool = False):
-    """[S, rows, d] fp32 -> ordered sum as fp32 and/or bf16 [rows, d]."""
+def combine_parts(parts, want_f32: bool = True, want_bf16: bool = False, out_f32=None):
+    """[S, rows, d] fp32 -> ordered sum as fp32 and/or bf16 [rows, d] (out_f32: caller-owned fp32 destination)."""
     S, rows, d = parts.shape
-    out_f = torch.empty((rows, d), dtype=torch.float32, device=parts.device) if want_f32 else None
+    out_f = out_f32 if out_f32 is not None else (
+        torch.empty((rows, d), dtype=torch.float32, device=parts.device) if want_f32 else None)
     out_b = torch.empty((rows, d), dtype=torch.bfloat16, device=parts.device) if want_bf16 else None
     check(_lib.load().tt_combine_parts_f32(_ptr(parts, torch.float32), S, rows, d, _ptr(out_f), _ptr(out_b), _stream()))
     _count(1)
@@ -648,3 +660,80 @@ def permute_rows(x, perm, inverse: bool, out_rows: int = 0, zero_fill: bool = Fa
                                       1 if inverse else 0, _stream()))
     _count(1)
     return out
+
+
+# ------------------------------------------------------------------ NVLink peer-memory exchange
+class PeerWorkspace:
+    """Symmetric workspace of the row-sharded step (include/twotower.h, csrc/peer.cu): `local` is this rank's
+    uint8 buffer (first 1 KB = barrier flags), `bases` a device int64 [world] array of every rank's
+    peer-mapped base address, `step` this rank's device step counter."""
+
+    FLAG_BYTES = 1024
+
+    def __init__(self, local: torch.Tensor, bases: torch.Tensor, world: int, rank: int):
+        self.local, self.bases, self.world, self.rank = local, bases, int(world), int(rank)
+        self.step = torch.zeros(16, dtype=torch.int64, device=local.device)    # [0, 8) slot epochs, [8, 16) blocks done
+        self.step[:8] = 1
+        self.bases_self = bases[rank:rank + 1].repeat(world).contiguous()      # every source = my own copy (slab sums)
+        # flag blocks sit at offset 0 of every copy, so the flag base table is the base table itself
+
+    def view(self, offset: int, shape, dtype) -> torch.Tensor:
+        n = int(torch.Size(shape).numel()) * torch.empty((), dtype=dtype).element_size()
+        return self.local[offset:offset + n].view(dtype).view(shape)
+
+
+def peer_barrier(ws: PeerWorkspace, slot: int) -> None:
+    check(_lib.load().tt_peer_barrier(_ptr(ws.bases, torch.int64), _ptr(ws.step, torch.int64), ws.world, ws.rank, slot,
+                                      _stream()))
+    _count(1)
+
+
+def peer_push(ws: PeerWorkspace, segments) -> None:
+    """segments: [(src tensor, dst_offset_bytes)] (<= 4): src -> the same offset of EVERY rank's workspace."""
+    n = len(segments)
+    src = (C.c_void_p * n)(*[_ptr(t) for t, _ in segments])
+    off = (C.c_int64 * n)(*[int(o) for _, o in segments])
+    nb = (C.c_int64 * n)(*[t.numel() * t.element_size() for t, _ in segments])
+    check(_lib.load().tt_peer_push(_ptr(ws.bases, torch.int64), ws.world, n, src, off, nb, _stream()))
+    _count(1)
+
+
+def peer_sum(ws: PeerWorkspace, offset: int, out: torch.Tensor, slot: int = -1, local_stride: int = 0) -> torch.Tensor:
+    """out (fp32, numel % 4 == 0) = sum over r, in rank order, of the fp32 block at `offset` of rank r's workspace, or
+    (local_stride > 0) of the `world` slabs at offset + r * local_stride of MY workspace (filled by the peers)."""
+    src = ws.bases_self if local_stride else ws.bases
+    check(_lib.load().tt_peer_sum_f32(_ptr(src, torch.int64), int(offset), int(local_stride), out.numel(), _ptr(out, torch.float32),
+                                      _ptr(ws.bases, torch.int64), _ptr(ws.step, torch.int64), ws.world, ws.rank, slot,
+                                      _stream()))
+    _count(1)
+    return out
+
+
+def peer_pull_rows(ws: PeerWorkspace, tables, rows_per_rank: int, d: int, slot: int = -1) -> None:
+    """tables: [(ids_all int64 [world*b], src_offset_bytes, out fp32 [world*b, d])] (<= 4)."""
+    n = len(tables)
+    ids = (C.c_void_p * n)(*[_ptr(i, torch.int64) for i, _, _ in tables])
+    off = (C.c_int64 * n)(*[int(o) for _, o, _ in tables])
+    out = (C.c_void_p * n)(*[_ptr(o, torch.float32) for _, _, o in tables])
+    check(_lib.load().tt_peer_pull_rows(_ptr(ws.bases, torch.int64), n, ids, off, out, int(rows_per_rank), int(d),
+                                        _ptr(ws.bases, torch.int64), _ptr(ws.step, torch.int64), ws.world, ws.rank, slot,
+                                        _stream()))
+    _count(1)
+
+
+def peer_combine_scatter(ws: PeerWorkspace, parts: torch.Tensor, rows_per_rank: int, dst_offset: int) -> None:
+    """Ordered sum of parts [S, world * b, d]; row i lands in slot [rank] of the receive area of rank i // b."""
+    S, rows, d = parts.shape
+    check(_lib.load().tt_peer_combine_scatter(_ptr(ws.bases, torch.int64), _ptr(parts, torch.float32), S, rows, d,
+                                              int(rows_per_rank), int(dst_offset), ws.world, ws.rank, _stream()))
+    _count(1)
+
+
+def peer_push_rows(ws: PeerWorkspace, tables, b: int, d: int) -> None:
+    """tables: [(ids int64 [b], rows fp32 [b, d], dst_offset_bytes)] (<= 4): row j -> the owner of table row ids[j]."""
+    n = len(tables)
+    ids = (C.c_void_p * n)(*[_ptr(i, torch.int64) for i, _, _ in tables])
+    src = (C.c_void_p * n)(*[_ptr(r, torch.float32) for _, r, _ in tables])
+    off = (C.c_int64 * n)(*[int(o) for _, _, o in tables])
+    check(_lib.load().tt_peer_push_rows(_ptr(ws.bases, torch.int64), n, ids, src, off, int(b), int(d), ws.world, ws.rank, _stream()))
+    _count(1)

@@ -152,6 +152,141 @@ class ShardedEmbedding(Layer):
                                "rerun with capacity_factor=None")
 
 
+class PeerExchange:
+    """The exchanges of one row-sharded training step as kernels on a symmetric NVLink workspace
+    (csrc/peer.cu, include/twotower.h) instead of NCCL collectives:
+
+        push(candidates, ids) to every rank          -> barrier 0 -> loss forward / dQ / dC on the gathered candidates
+        combine dC, each row to its owner's slot     -> barrier 1 -> the owner's tower backward folds the slots
+                                                                     (was reduce-scatter)
+        push gradient rows to the table-row owners,                  (was all-gather of rows)
+        fold + push the dense bucket and the loss    -> barrier 2 + sum of the slots  (was 2 all-reduces)
+        optimizer step                               -> barrier 3 (closes the step: peers may overwrite my
+                                                                     workspace and read my tables again)
+
+    All traffic is producer-side WRITES over NVLink (posted; SM loads from peer memory are round trips and ran
+    ~4x slower here).  torch.distributed only allocates the workspace (symmetric memory rendezvous)."""
+
+    BUCKET_FLOATS = 1 << 18          # dense-gradient bucket capacity per rank (1 MB): cfg2 needs 132 K floats
+
+    def __init__(self, group=None):
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.ws = None
+        self.tables = []              # PeerShardedEmbedding layers in lookup order of the current step
+        self.step_ids = {}            # table index -> this rank's ids of the current step
+
+    # ---- workspace
+    def ensure(self, b: int, d_out: int) -> None:
+        ntab = len(self.tables)
+        d_emb = max([l.output_dim for l in self.tables], default=d_out)
+        key = (b, d_out, d_emb, ntab)
+        if self.ws is not None:
+            if self.key != key:
+                raise NotImplementedError(f"PeerExchange: the step shape changed {self.key} -> {key}")
+            return
+        import torch.distributed._symmetric_memory as symm_mem
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("PeerExchange: run one eager step before capturing a CUDA graph")
+        W, bg = self.world, self.world * b
+        al = lambda n: (n + 1023) // 1024 * 1024
+        off = _cuda_ops.PeerWorkspace.FLAG_BYTES
+        self.off_c = off; off += al(bg * d_out * 2)                    # candidates of all ranks, bf16
+        self.off_ids = off; off += al(max(ntab, 1) * bg * 8)           # ids of all ranks, per table
+        self.off_dc = off; off += al(bg * d_out * 4)                   # dC of MY candidates: one [b, d] slot per producing rank
+        self.off_rows = off; off += al(max(ntab, 1) * bg * d_emb * 4)  # gradient rows of table rows I own, per table
+        self.off_bucket = off; off += al(W * self.BUCKET_FLOATS * 4)   # dense gradients + loss: one slab per rank
+        dev = torch.device("cuda", torch.cuda.current_device())
+        buf = symm_mem.empty((off,), dtype=torch.uint8, device=dev)
+        buf.zero_()
+        torch.cuda.synchronize()
+        handle = symm_mem.rendezvous(buf, self.group)
+        self._handle = handle
+        bases = torch.tensor([int(p) for p in handle.buffer_ptrs], dtype=torch.int64, device=dev)
+        self.ws = _cuda_ops.PeerWorkspace(buf, bases, W, self.rank)
+        self.key, self.b, self.d_out, self.d_emb = key, b, d_out, d_emb
+        v = self.ws.view
+        self.c_all = v(self.off_c, (bg, d_out), torch.bfloat16)
+        self.ids_all = [v(self.off_ids + t * bg * 8, (bg,), torch.int64) for t in range(ntab)]
+        self.dc_slots = v(self.off_dc, (W, b, d_out), torch.float32)
+        self.rows_all = [v(self.off_rows + t * bg * d_emb * 4, (bg, d_emb), torch.float32) for t in range(ntab)]
+        self.dc_mine = torch.empty((b, d_out), dtype=torch.float32, device=dev)
+        self.bucket_local = torch.empty((self.BUCKET_FLOATS,), dtype=torch.float32, device=dev)
+        self.bucket_sum = torch.empty((self.BUCKET_FLOATS,), dtype=torch.float32, device=dev)
+        self.loss4 = torch.zeros(4, dtype=torch.float32, device=dev)
+        torch.cuda.synchronize()
+        dist.barrier(self.group)
+
+    # ---- step protocol
+    def begin_step(self) -> None:
+        self.step_ids = {}
+        self.step_rows = {}
+
+    def register_ids(self, layer, ids: torch.Tensor) -> int:
+        if layer not in self.tables:
+            if self.ws is not None:
+                raise NotImplementedError("PeerExchange: a new sharded table appeared after the workspace was built")
+            self.tables.append(layer)
+        t = self.tables.index(layer)
+        self.step_ids[t] = ids
+        return t
+
+    def gather_candidates(self, cm: torch.Tensor) -> torch.Tensor:
+        """All ranks' candidate embeddings (and the step's ids): every rank writes its block into every copy."""
+        b, d = cm.shape
+        self.ensure(b, d)
+        bg = self.world * b
+        segs = [(cm, self.off_c + self.rank * b * d * 2)]
+        for t, ids in sorted(self.step_ids.items()):
+            if ids.numel() != b:
+                raise NotImplementedError("PeerExchange: every sharded table must be looked up once per example")
+            segs.append((ids, self.off_ids + (t * bg + self.rank * b) * 8))
+        for lo in range(0, len(segs), 4):
+            _cuda_ops.peer_push(self.ws, segs[lo:lo + 4])
+        _cuda_ops.peer_barrier(self.ws, 0)
+        notes = [(self.tables[t].embeddings, self.ids_all[t], None, "sum", (self.world, self.rank)) for t in sorted(self.step_ids)]
+        if notes:
+            GradientTape.note_sparse_lookup(notes)          # the optimizer's id dedup starts now, on its side stream
+        return self.c_all
+
+    def reduce_scatter_dc(self, dc_parts: torch.Tensor, as_parts: bool) -> torch.Tensor:
+        """dC of my candidates: [world, b, d] stacked per-rank partials (as_parts) or their sum [b, d]."""
+        _cuda_ops.peer_combine_scatter(self.ws, dc_parts, self.b, self.off_dc)
+        if as_parts:
+            _cuda_ops.peer_barrier(self.ws, 1)
+            return self.dc_slots
+        return _cuda_ops.peer_sum(self.ws, self.off_dc, self.dc_mine, slot=1, local_stride=self.b * self.d_out * 4)
+
+    def table_grad(self, layer, rows: torch.Tensor) -> IndexedSlices:
+        t = self.tables.index(layer)
+        self.step_rows[t] = rows
+        return IndexedSlices(values=self.ids_all[t], offsets=None, mode="sum", rows=self.rows_all[t],
+                             shard=(self.world, self.rank))
+
+    def finish_backward(self, dense_grads, loss: torch.Tensor):
+        """dense_grads: [DenseGrad].  Returns ([summed dense gradient views], global loss [1])."""
+        offs, n = _cuda_ops.bucket_layout([g.parts[0].shape for g in dense_grads])
+        if n + 4 > self.BUCKET_FLOATS:
+            raise NotImplementedError("PeerExchange: dense gradients exceed the bucket capacity")
+        bg = self.world * self.b
+        tabs = [(self.step_ids[t], self.step_rows[t], self.off_rows + t * bg * self.d_emb * 4) for t in sorted(self.step_rows)]
+        if tabs:
+            _cuda_ops.peer_push_rows(self.ws, tabs, self.b, self.d_emb)
+        slab = self.off_bucket + self.rank * self.BUCKET_FLOATS * 4
+        self.loss4[:1].copy_(loss.reshape(1))
+        segs = [(self.loss4, slab + n * 4)]
+        if dense_grads:
+            _cuda_ops.fold_parts_into_bucket([(g.parts, g.num_parts) for g in dense_grads], out=self.bucket_local)
+            segs.insert(0, (self.bucket_local[:n], slab))
+        _cuda_ops.peer_push(self.ws, segs)
+        _cuda_ops.peer_sum(self.ws, self.off_bucket, self.bucket_sum[:n + 4], slot=2, local_stride=self.BUCKET_FLOATS * 4)
+        views = [self.bucket_sum[o:o + g.parts[0].numel()].view(g.parts[0].shape) for o, g in zip(offs, dense_grads)]
+        return views, self.bucket_sum[n:n + 1]
+
+    def end_step(self) -> None:
+        _cuda_ops.peer_barrier(self.ws, 3)
+
+
 class PeerShardedEmbedding(Layer):
     """tf.keras.layers.Embedding whose [input_dim, d] table is row-sharded over the group (owner = id % world)
     in SYMMETRIC memory: every rank maps its peers' shards (torch.distributed._symmetric_memory, NVLink P2P),
@@ -185,6 +320,7 @@ class PeerShardedEmbedding(Layer):
         self.table = _cuda_ops.PeerTable(ptrs, shard, self.input_dim, world, rank)
         self.embeddings = Variable(f"{self.name}/embeddings_shard{rank}", shard, "table")
         self._ids_all = None
+        self.exchange = None          # PeerExchange: ids / gradient rows travel through the symmetric workspace
 
     @property
     def trainable_variables(self):
@@ -204,10 +340,15 @@ class PeerShardedEmbedding(Layer):
         return [self], [self._feature(inputs)]
 
     def _lookup_note(self, feat):
+        if self.exchange is not None:
+            self.exchange.register_ids(self, feat[1])              # announced after the id exchange (gather_candidates)
+            return None
         self._ids_all = self.coll.all_gather(feat[1])              # global ids of every rank's batch
         return (self.embeddings, self._ids_all, None, "sum", (self.coll.world, self.coll.rank))
 
     def _make_grad(self, feat, rows) -> IndexedSlices:
+        if self.exchange is not None:
+            return self.exchange.table_grad(self, rows)
         ids_all = self._ids_all if self._ids_all is not None else self.coll.all_gather(feat[1])
         self._ids_all = None
         return IndexedSlices(values=ids_all, offsets=None, mode="sum", rows=self.coll.all_gather(rows),
@@ -229,7 +370,10 @@ def global_retrieval(task, q: Tensor, c: Tensor, inv_t: float, w, logq, ids, pri
     qm = q.f32 if prec == "fp32" else q.bf16
     cm = c.f32 if prec == "fp32" else c.bf16
     nq = qm.shape[0]
-    c_all = coll.all_gather(cm)                                   # [world*b, d]
+    ex = getattr(task, "exchange", None)
+    if ex is not None and not (prec == "bf16" and prim is _cuda_ops):
+        raise NotImplementedError("the peer-memory exchange runs the bf16 kernels only")
+    c_all = ex.gather_candidates(cm) if ex is not None else coll.all_gather(cm)      # [world*b, d]
     label_offset = coll.rank * nq
     logq_all = None if logq is None else coll.all_gather(logq)
     ids_all = None if ids is None else coll.all_gather(ids)
@@ -244,13 +388,18 @@ def global_retrieval(task, q: Tensor, c: Tensor, inv_t: float, w, logq, ids, pri
             else:
                 f, b = prim.combine_parts(dq_parts, True, "bf16" in q.grad_formats)
                 q.grad = dict(f32=f, bf16=b)
-            dc_full, _ = prim.combine_parts(dc_parts, True, False)
-            dc = coll.reduce_scatter(dc_full)                     # every rank's partial for my candidates
+            if ex is not None:
+                dc = ex.reduce_scatter_dc(dc_parts, as_parts="parts" in c.grad_formats)   # [world, b, d] slots if parts
+            else:
+                dc_full, _ = prim.combine_parts(dc_parts, True, False)
+                dc = coll.reduce_scatter(dc_full)                 # every rank's partial for my candidates
             if "parts" in c.grad_formats:
-                c.grad = dict(parts=dc.reshape(1, *dc.shape))
+                c.grad = dict(parts=dc if dc.dim() == 3 else dc.reshape(1, *dc.shape))
             else:
                 c.grad = dict(f32=dc, bf16=prim.cast_f32_to_bf16(dc) if "bf16" in c.grad_formats else None)
             return
+        if ex is not None:
+            raise NotImplementedError("the peer-memory exchange needs the fused tower kernels (split-partial gradients)")
         r = prim.retrieval_loss_bwd(prec, qm, c_all, inv_t, lse, label_offset, w, logq_all, ids_all, 1.0,
                                     want_bf16=(bf and "bf16" in q.grad_formats, False))
         q.grad = dict(f32=r["dq"], bf16=r["dq_bf16"])
@@ -270,17 +419,28 @@ class DataParallelModel(Model):
         super().__init__(name)
         self.process_group = group
         self._coll = Collectives(group)
+        self.exchange = None          # PeerExchange (build_sharded_two_tower(peer="exchange"))
 
     def train_step(self, inputs):
         if self.optimizer is None:
             raise RuntimeError("call model.compile(optimizer=...) before train_step")
         self.optimizer.begin_step()
+        ex = self.exchange
+        if ex is not None:
+            ex.begin_step()
         with GradientTape() as tape:
             tape.on_sparse_lookup = self.optimizer.prepare_sparse
             loss = self.compute_loss(inputs, training=True)
             variables = self.trainable_variables
             grads = tape.gradient(loss, variables)
         dense = [(i, g) for i, g in enumerate(grads) if isinstance(g, DenseGrad)]
+        if ex is not None:
+            views, total = ex.finish_backward([g for _, g in dense], loss.value)
+            for (i, g), v in zip(dense, views):
+                grads[i] = DenseGrad(v.reshape((1,) + tuple(v.shape)), 1)
+            self.optimizer.apply_gradients(zip(grads, variables))
+            ex.end_step()
+            return {"loss": total, "local_loss": loss.value, "regularization_loss": torch.zeros_like(total), "total_loss": total}
         if dense:
             # every dense gradient folded into ONE flat bucket (one launch) and summed over the ranks by a
             # single latency-bound all-reduce per step
@@ -302,10 +462,12 @@ class DataParallelModel(Model):
         return {"loss": total, "local_loss": loss.value, "regularization_loss": torch.zeros_like(total), "total_loss": total}
 
 
-def build_sharded_two_tower(cfg, group, lr: float = 0.001, capacity_factor: Optional[float] = 2.0, peer: bool = True):
+def build_sharded_two_tower(cfg, group, lr: float = 0.001, capacity_factor: Optional[float] = 2.0, peer=True):
     """The bench model at N > 1: ID-only two-tower of `cfg`, tables row-sharded, global negatives.
-    peer=True: shards in symmetric memory, lookups are P2P gathers fused into the tower kernel
-    (PeerShardedEmbedding); peer=False: NCCL all-to-all lookups (ShardedEmbedding)."""
+    peer="exchange": shards in symmetric memory, lookups are P2P gathers fused into the tower kernel AND every
+    exchange of the step (candidates, dC, gradient rows, dense gradients, loss) is a peer-memory kernel
+    (PeerExchange; bf16 only); peer=True: P2P lookups, NCCL collectives for the rest; peer=False: NCCL
+    all-to-all lookups (ShardedEmbedding)."""
     from . import optimizers, tasks
 
     class ShardedTwoTower(DataParallelModel):
@@ -320,6 +482,11 @@ def build_sharded_two_tower(cfg, group, lr: float = 0.001, capacity_factor: Opti
             self.user_model = tower(cfg.v_user, 1)
             self.item_model = tower(cfg.v_item, 2)
             self.task = tasks.Retrieval(temperature=cfg.temperature, process_group=group)
+            if peer == "exchange":
+                self.exchange = PeerExchange(group)
+                self.task.exchange = self.exchange
+                self.user_model.layers[0].exchange = self.exchange
+                self.item_model.layers[0].exchange = self.exchange
 
         def compute_loss(self, features, training=False):
             return self.task(self.user_model(features["user_id_encoded"]), self.item_model(features["item_id_encoded"]))
