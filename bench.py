@@ -33,14 +33,14 @@ METRIC = "train examples/s (fwd+bwd, B=8192, d=128)"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=["cfg1", "cfg2", "cfg3"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--serving", action="store_true", help="also time top-100 brute-force retrieval (queries/s)")
+    ap.add_argument("--no-serving", action="store_true", help="skip the top-100 brute-force retrieval line (queries/s)")
     return ap.parse_args()
 
 
@@ -198,6 +198,16 @@ def build_model(tt, cfg, world, rank, group):
     return model
 
 
+def ncu_traffic(kernel, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture
+    of this command (profiles/traffic.json, written by tools/summarize_ncu.py traffic); None if not captured."""
+    p = ROOT / "profiles" / "traffic.json"
+    if world != 1 or not p.exists():
+        return None
+    rec = json.loads(p.read_text()).get(kernel)
+    return None if rec is None else rec["dram_bytes_per_launch"]
+
+
 def algorithmic_flops(cfg, world):
     """K3+K4 = 3 * 2*b*B_glob*d per GPU; K2 = 3 * 2*b*sum(in*out) per tower."""
     b, d = cfg.batch, cfg.dim
@@ -267,13 +277,16 @@ def run_ours(args):
     # ---- kernel-side timed region: inputs already in HBM, EXACTLY K steps, CUDA events, max over ranks
     launches0 = ops.LAUNCHES
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
-        barrier()
-        e0.record()
-        for i in range(args.steps):
-            out = step(dev_pool[i % n_pool])
-        e1.record()
-        barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.__enter__()                                # sampled from here to the end of the e2e region (all under load)
+    for i in range(max(200, args.warmup) if args.steps >= 20 else args.warmup):   # loaded clocks before the timed region
+        step(dev_pool[i % n_pool])
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        out = step(dev_pool[i % n_pool])
+    e1.record()
+    barrier()
     ms_total = e0.elapsed_time(e1)
     gpu_launches = ops.LAUNCHES - launches0
     if world > 1:
@@ -296,6 +309,7 @@ def run_ours(args):
         loss_host = float(res["loss"].item())         # D2H read of the step's result
     barrier()
     e2e_s = time.perf_counter() - t0
+    clocks.__exit__(None, None, None)
     if world > 1:
         t = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -353,7 +367,7 @@ def run_ours(args):
         us = kernels[dom]["us_per_launch"]
         achieved = flops_per_launch / (us * 1e-6) / 1e12
         roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": achieved / peak_tf, "traffic": None, "us_per_launch": us,
+                    "frac": achieved / peak_tf, "traffic": ncu_traffic(dom, world), "us_per_launch": us,
                     "algorithmic_flops_per_launch": flops_per_launch, "peak_source": peak_src,
                     "executed_flops_per_launch": 2 * flops_per_launch if args.precision == "bf16" else None}
     step_flops = algorithmic_flops(cfg, world)
@@ -363,11 +377,14 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": workload_name(cfg, world), "global_batch": cfg.batch * world,
                    "l2_policy": "inputs larger than L2: tables+Adagrad slots are 1.5 GB of random rows vs 126 MB L2; no flush",
-                   "launch": "cuda graph replay" if use_graph else "eager"},
+                   "launch": "cuda graph replay" if use_graph else "eager",
+                   "exchange": None if world == 1 else os.environ.get("TT_EXCHANGE", "peer") +
+                   " (peer: every exchange is a kernel on the symmetric NVLink workspace, no NCCL in the step)"},
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": "examples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "last_loss": loss_host},
         "gpu_launches": gpu_launches,
+        "logit_pairs_per_s": float(cfg.batch) * cfg.batch * world * world / (ms_step * 1e-3),
         "step_tflops": step_flops / (ms_step * 1e-3) / 1e12 / world,
         "step_frac_of_bf16_peak": step_flops / (ms_step * 1e-3) / 1e12 / world / peaks.get("bf16_tflops_sustained", 1384.0),
         "roofline": roofline,
@@ -381,7 +398,7 @@ def run_ours(args):
                                 "sample": f"{len(times)} full {cfg.name} steps (B={cfg.batch}) of the numpy TFRS-equivalent restatement, host BLAS on all cores"}
     else:
         line["cpu_baseline"] = None
-    if args.serving and world == 1:
+    if not args.no_serving and world == 1:
         line["serving"] = serving_bench(tt, torch, dev, peaks)
     print(json.dumps(line))
     finish()

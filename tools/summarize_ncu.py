@@ -69,5 +69,26 @@ def report(path):
         print()
 
 
+def traffic(path):
+    """profiles/traffic.json: per kernel (name up to '<'), mean dram bytes per launch over the captured launches."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    col = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    acc = collections.defaultdict(list)
+    for r in rows[2:]:
+        name = re.sub(r"^void ", "", r[col["Kernel Name"]]).split("<")[0].split("(")[0].replace("tt::", "")
+        tot = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(r[col[k]].replace(",", "")) * scale[units[col[k]]]
+        acc[name].append((tot, float(r[col["gpu__time_duration.sum"]].replace(",", "")), units[col["gpu__time_duration.sum"]]))
+    res = {k: {"dram_bytes_per_launch": sum(x[0] for x in v) / len(v), "launches": len(v),
+               "ncu_duration": sum(x[1] for x in v) / len(v), "ncu_duration_unit": v[0][2], "source": path.split("/")[-1]}
+           for k, v in acc.items()}
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "report": report, "traffic": traffic}[sys.argv[1]](sys.argv[2])
