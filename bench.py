@@ -404,8 +404,9 @@ def run_ours(args):
     finish()
 
 
-def serving_bench(tt, torch, dev, peaks, nq=16384, nc=2_000_000, d=128, k=100):
-    """Brute-force top-100: a bounded slice of cfg5 (queries x candidates, bf16, fp32 accumulate)."""
+def serving_bench(tt, torch, dev, peaks, nq=16384, nc=10_000_000, d=128, k=100):
+    """Brute-force top-100: a bounded slice of cfg5 -- the full 10 M candidate set (bf16, fp32 accumulate, what one GPU
+    holds when the queries are sharded), 16384 of the 1 M queries."""
     g = torch.Generator(device=dev); g.manual_seed(5678)
     cand = (torch.randn((nc, d), device=dev, generator=g) / d ** 0.5).to(torch.bfloat16)
     q = (torch.randn((nq, d), device=dev, generator=g) / d ** 0.5).to(torch.bfloat16)

@@ -90,4 +90,76 @@ __device__ __forceinline__ void topk_merge_row(const TopkRowState& st, int r, in
   __syncwarp();
 }
 
+// ---- unsorted k-best as 64-bit keys (tcgen05 scoring kernel) ---------------------------------------------
+// key = order-preserving bits of the score << 32 | ~index: a larger key precedes in the tf.math.top_k order
+// (score desc, index asc); 0 marks an empty slot (below every real key).
+__device__ __forceinline__ unsigned long long topk_key(float s, int idx) {
+  const unsigned u = __float_as_uint(s);
+  const unsigned f = u ^ ((unsigned)((int)u >> 31) | 0x80000000u);
+  return ((unsigned long long)f << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)idx);
+}
+__device__ __forceinline__ float topk_key_score(unsigned long long key) {
+  const unsigned f = (unsigned)(key >> 32);
+  return __uint_as_float((f & 0x80000000u) ? (f ^ 0x80000000u) : ~f);
+}
+__device__ __forceinline__ int topk_key_index(unsigned long long key) { return (int)(0xFFFFFFFFu - (unsigned)key); }
+
+// Warp-cooperative: overwrite the row's minimum key (slot *minpos) with `key` (the caller checked key > minimum),
+// find the new minimum.  Returns the new k-th best score (-inf while empty slots remain).  KU * 32 >= k.
+template <int KU>
+__device__ __forceinline__ float topk_replace_min(unsigned long long* rk, int* minpos, int k, unsigned long long key, int lane) {
+  if (lane == 0) rk[*minpos] = key;
+  __syncwarp();
+  unsigned long long lmin = ~0ull;
+  int lpos = 0;
+#pragma unroll
+  for (int u = 0; u < KU; ++u) {
+    const int t = lane + 32 * u;
+    if (t < k) {
+      const unsigned long long kk = rk[t];
+      if (kk < lmin) { lmin = kk; lpos = t; }        // ascending t: the lowest slot wins among equal (empty) keys
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long om = __shfl_xor_sync(0xffffffffu, lmin, o);
+    const int op = __shfl_xor_sync(0xffffffffu, lpos, o);
+    if (om < lmin || (om == lmin && op < lpos)) { lmin = om; lpos = op; }
+  }
+  if (lane == 0) *minpos = lpos;
+  __syncwarp();
+  return lmin == 0ull ? -INFINITY : topk_key_score(lmin);
+}
+
+// Warp bitonic sort, descending, of KU * 32 keys: element e = u * 32 + lane lives in v[u] of lane `lane`.
+template <int KU>
+__device__ __forceinline__ void topk_bitonic_desc(unsigned long long (&v)[KU], int lane) {
+#pragma unroll
+  for (int size = 2; size <= KU * 32; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride >= 32) {
+        const int du = stride / 32;
+#pragma unroll
+        for (int u = 0; u < KU; ++u) {
+          if (u & du) continue;
+          const bool desc = (((u * 32 + lane) & size) == 0);
+          const unsigned long long lo = v[u] < v[u + du] ? v[u] : v[u + du], hi = v[u] < v[u + du] ? v[u + du] : v[u];
+          v[u] = desc ? hi : lo;
+          v[u + du] = desc ? lo : hi;
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < KU; ++u) {
+          const unsigned long long other = __shfl_xor_sync(0xffffffffu, v[u], stride);
+          const bool desc = (((u * 32 + lane) & size) == 0);
+          const bool first = (lane & stride) == 0;               // the lower element of the pair
+          const bool want_max = first == desc;
+          v[u] = want_max ? (v[u] > other ? v[u] : other) : (v[u] < other ? v[u] : other);
+        }
+      }
+    }
+  }
+}
+
 }  // namespace tt

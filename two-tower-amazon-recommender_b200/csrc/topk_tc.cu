@@ -4,13 +4,16 @@
 // A CTA keeps 128 queries resident (shared memory, 128B-swizzled K-major) and streams the
 // candidate range in 128-row tiles through a TMA ring; S = Q C^T goes to TMEM (two buffers so
 // the next tile's MMA overlaps the selection of the current one) and is never written out.
-// Selection warpgroup: thread = one query row.  Per 32-column tcgen05.ld the thread takes the
-// max of its 32 scores and compares it with the row's current k-th best (tau): almost every
-// chunk is rejected with ~1.3 instructions per score.  A hit is handled warp-cooperatively:
-// the row's 32 scores are redistributed over the lanes, the survivors are compacted into a
-// per-warp pending buffer and folded into the row's sorted (score desc, index asc) list kept
-// in shared memory (topk_select.cuh).  Candidate ranges may be split over blockIdx.y for
-// small query batches; partial lists are merged by topk_merge_kernel.
+// Selection warpgroup: thread = one query row.  The whole 128-score row of the tile is pulled into registers with
+// one tcgen05.ld burst and the TMEM buffer is handed back at once (the next tile's MMA overlaps the selection);
+// the thread takes the maximum per 32-score chunk (max3 trees) and compares it with the row's current k-th best
+// (tau): almost every chunk is rejected with ~0.4 instructions per score.  A hit is handled warp-cooperatively:
+// the chunk is redistributed over the lanes through a 128-byte staging line, survivors are taken one by one.
+// The row's k best are kept UNSORTED in shared memory as 64-bit keys (order-preserving score bits << 32 | ~index,
+// so one integer compare is the (score desc, index asc) order of tf.math.top_k): an insertion overwrites the
+// current minimum and a warp arg-min finds the new one -- no shifting, ~45 instructions.  Rows are sorted once,
+// at the end (warp bitonic sort).  Candidate ranges may be split over blockIdx.y for small query batches; partial
+// lists are merged by topk_merge_kernel.
 #include "tc_common.cuh"
 #include "topk_select.cuh"
 #include <limits.h>
@@ -61,12 +64,9 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint64_t* s_full = empty + 4;
   uint64_t* s_empty = s_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + 2);
-  int* row_count = reinterpret_cast<int*>(tail + 256);            // [128]
-  float* row_tau = reinterpret_cast<float*>(tail + 256 + 512);    // [128]
-  float* pend_s = reinterpret_cast<float*>(tail + 256 + 1024);    // [4 warps][32]
-  int* pend_i = reinterpret_cast<int*>(tail + 256 + 1024 + 512);  // [4 warps][32]
-  float* list_s = reinterpret_cast<float*>(tail + 4096);          // [128][k]
-  int* list_i = reinterpret_cast<int*>(tail + 4096 + TK_BM * k * 4);
+  int* row_minpos = reinterpret_cast<int*>(tail + 256);           // [128] slot of the row's current minimum key
+  float* stage_x = reinterpret_cast<float*>(tail + 256 + 512);    // [4 warps][32] one chunk of a hit row
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(tail + 4096);   // [128][k], 0 = empty slot
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -84,7 +84,8 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * TK_BN);
-  if (threadIdx.x >= 64) { row_count[threadIdx.x - 64] = 0; row_tau[threadIdx.x - 64] = -INFINITY; }
+  if (threadIdx.x >= 64) row_minpos[threadIdx.x - 64] = 0;
+  for (int i = threadIdx.x; i < TK_BM * k; i += TK_THREADS) keys[i] = 0ull;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -123,75 +124,94 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
   } else {
     const int qd = warp & 3;
-    const int r = qd * 32 + lane;                  // this thread's query row in the tile
-    const int wslot = warp - 2;                    // pending buffer of this warp
-    float tau = -INFINITY;
-    bool fullk = false;
-    if ((long long)q0 + r >= a.nq) { tau = INFINITY; fullk = true; }    // padding rows never select
+    const int wslot = warp - 2;                    // staging line of this warp
+    float tau = -INFINITY;                         // k-th best score of this thread's row (-inf until k are held)
+    if ((long long)q0 + qd * 32 + lane >= a.nq) tau = INFINITY;          // padding rows never select
     for (int t = 0; t < T; ++t) {
       const int b = t & 1;
       const int c_tile = (tile_begin + t) * TK_BN;
       mbar_wait(&s_full[b], (t >> 1) & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < TK_BN; c0 += 32) {
-        if (c_tile + c0 >= a.nc) break;            // uniform: chunk entirely past the candidates
-        uint32_t rr[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(qd * 32) << 16) + b * TK_BN + c0, rr);
-        tmem_ld_wait();
-        float x[32];
+      uint32_t rr[TK_BN];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(rr[j]);
-        if (c_tile + c0 + 32 > a.nc) {             // uniform: ragged last chunk
+      for (int c = 0; c < TK_BN / 32; ++c) tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + b * TK_BN + c * 32, rr + c * 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_empty[b]);                    // the MMA of tile t + 2 may overwrite the buffer
+      if (c_tile + TK_BN > a.nc) {                 // uniform: ragged last tile
 #pragma unroll
-          for (int j = 0; j < 32; ++j) if (c_tile + c0 + j >= a.nc) x[j] = -INFINITY;
+        for (int j = 0; j < TK_BN; ++j) if (c_tile + j >= a.nc) rr[j] = 0xff800000u;     // -inf
+      }
+      float cm[TK_BN / 32];
+#pragma unroll
+      for (int c = 0; c < TK_BN / 32; ++c) {
+        float m0 = fmax3(__uint_as_float(rr[c * 32]), __uint_as_float(rr[c * 32 + 1]), __uint_as_float(rr[c * 32 + 2]));
+        float m1 = fmax3(__uint_as_float(rr[c * 32 + 3]), __uint_as_float(rr[c * 32 + 4]), __uint_as_float(rr[c * 32 + 5]));
+        float m2 = fmax3(__uint_as_float(rr[c * 32 + 6]), __uint_as_float(rr[c * 32 + 7]), __uint_as_float(rr[c * 32 + 8]));
+        float m3 = fmax3(__uint_as_float(rr[c * 32 + 9]), __uint_as_float(rr[c * 32 + 10]), __uint_as_float(rr[c * 32 + 11]));
+#pragma unroll
+        for (int j = 12; j < 32; j += 10) {        // j = 12, 22: four chains of max3, two scores each
+          m0 = fmax3(m0, __uint_as_float(rr[c * 32 + j]), __uint_as_float(rr[c * 32 + j + 1]));
+          m1 = fmax3(m1, __uint_as_float(rr[c * 32 + j + 2]), __uint_as_float(rr[c * 32 + j + 3]));
+          m2 = fmax3(m2, __uint_as_float(rr[c * 32 + j + 4]), __uint_as_float(rr[c * 32 + j + 5]));
+          m3 = fmax3(m3, __uint_as_float(rr[c * 32 + j + 6]), __uint_as_float(rr[c * 32 + j + 7]));
+          m0 = fmaxf(m0, __uint_as_float(rr[c * 32 + j + 8]));
+          m1 = fmaxf(m1, __uint_as_float(rr[c * 32 + j + 9]));
         }
-        float mx = x[0];
+        cm[c] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      }
+      float mx = cm[0];
 #pragma unroll
-        for (int j = 1; j < 32; ++j) mx = fmaxf(mx, x[j]);
-        const bool hit = !fullk || mx > tau;
-        unsigned hits = __ballot_sync(0xffffffffu, hit);
-        while (hits) {
-          const int src = __ffs(hits) - 1;
-          hits &= hits - 1;
-          // lane j receives score j of lane src's row
-          float mine = 0.f;
+      for (int c = 1; c < TK_BN / 32; ++c) mx = fmaxf(mx, cm[c]);
+      unsigned hits = __ballot_sync(0xffffffffu, mx > tau);
+      while (hits) {
+        const int src = __ffs(hits) - 1;
+        hits &= hits - 1;
+        const int row = qd * 32 + src;
+        unsigned long long* rk = keys + (size_t)row * k;
+        float cur_tau = __shfl_sync(0xffffffffu, tau, src);          // uniform; rises as survivors are inserted
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float v = __shfl_sync(0xffffffffu, x[j], src);
-            if (lane == j) mine = v;
-          }
-          const float src_tau = __shfl_sync(0xffffffffu, tau, src);
-          const int src_full = __shfl_sync(0xffffffffu, (int)fullk, src);
-          const bool pass = (c_tile + c0 + lane < a.nc) && (!src_full || mine > src_tau);
-          const unsigned pm = __ballot_sync(0xffffffffu, pass);
-          if (pass) {
-            const int slot = __popc(pm & ((1u << lane) - 1));
-            pend_s[wslot * 32 + slot] = mine;
-            pend_i[wslot * 32 + slot] = c_tile + c0 + lane;
+        for (int c = 0; c < TK_BN / 32; ++c) {
+          if (!__shfl_sync(0xffffffffu, (int)(cm[c] > tau), src)) continue;          // uniform
+          if (lane == src) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              *reinterpret_cast<uint4*>(stage_x + wslot * 32 + 4 * g) =
+                  make_uint4(rr[c * 32 + 4 * g], rr[c * 32 + 4 * g + 1], rr[c * 32 + 4 * g + 2], rr[c * 32 + 4 * g + 3]);
           }
           __syncwarp();
-          const int row = qd * 32 + src;
-          topk_fold<KU>(list_s + (size_t)row * k, list_i + (size_t)row * k, row_count + row, row_tau + row, k,
-                        pend_s + wslot * 32, pend_i + wslot * 32, __popc(pm), lane);
+          const float mine = stage_x[wslot * 32 + lane];              // score (c * 32 + lane) of row `row`
+          __syncwarp();
+          unsigned pm = __ballot_sync(0xffffffffu, mine > cur_tau);
+          while (pm) {
+            const int j = __ffs(pm) - 1;
+            pm &= pm - 1;
+            const float v = __shfl_sync(0xffffffffu, mine, j);
+            if (!(v > cur_tau)) continue;                              // tau moved up since the ballot
+            cur_tau = topk_replace_min<KU>(rk, row_minpos + row, k, topk_key(v, c_tile + c * 32 + j), lane);
+          }
         }
-        if (hit) { tau = row_tau[r]; fullk = row_count[r] == k; }
+        if (lane == src) tau = cur_tau;
       }
-      tc_fence_before();
-      mbar_arrive(&s_empty[b]);
     }
-    // write this warp's 32 rows
+    // sort and write this warp's 32 rows
     __syncwarp();
     for (int rr2 = 0; rr2 < 32; ++rr2) {
       const int row = qd * 32 + rr2;
       const long long qi = (long long)q0 + row;
       if (qi >= a.nq) break;
-      const int cnt = row_count[row];
+      unsigned long long v[KU];
+#pragma unroll
+      for (int u = 0; u < KU; ++u) v[u] = (lane + 32 * u < k) ? keys[(size_t)row * k + lane + 32 * u] : 0ull;
+      topk_bitonic_desc<KU>(v, lane);
       const size_t o = ((size_t)blockIdx.y * a.nq + qi) * k;
-      for (int t2 = lane; t2 < k; t2 += 32) {
-        if (t2 < cnt) {
-          const int idx = list_i[(size_t)row * k + t2];
-          a.out_s[o + t2] = list_s[(size_t)row * k + t2];
+#pragma unroll
+      for (int u = 0; u < KU; ++u) {
+        const int t2 = lane + 32 * u;
+        if (t2 >= k) continue;
+        if (v[u] != 0ull) {
+          const int idx = topk_key_index(v[u]);
+          a.out_s[o + t2] = topk_key_score(v[u]);
           a.out_i[o + t2] = a.raw_indices ? (long long)idx : (a.identifiers ? a.identifiers[idx] : a.cand_base + idx);
         } else {
           a.out_s[o + t2] = -INFINITY;
