@@ -356,20 +356,23 @@ def run_ours(args):
         peaks = json.loads(pk.read_text())
     peak_tf = peaks.get("bf16_tflops", 1590.0)
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops, burst: kernel timed alone)" if peaks else "fallback 1.59 PFLOP/s"
-    # dominant kernel: the fused loss backward (dQ pass and dC pass are two launches of it per step)
-    dom = "retrieval_bwd_tc_kernel" if args.precision == "bf16" else "retrieval_kernel"
+    # dominant kernel = the retrieval kernel with the largest share of the step.  bf16: the one-pass loss forward + dQ
+    # (2 algorithmic GEMMs, none recomputed) or the dC pass (1 algorithmic GEMM + the S recompute)
+    d_out = (cfg.mlp[-1] if cfg.mlp else cfg.dim)
+    gemm = 2.0 * cfg.batch * (cfg.batch * world) * d_out
+    cands = {"retrieval_fwd_dq_tc_kernel": (2 * gemm, 2 * gemm), "retrieval_bwd_tc_kernel": (gemm, 2 * gemm),
+             "retrieval_fwd_tc_kernel": (gemm, gemm), "retrieval_kernel": (gemm, gemm)}
+    present = [k for k in cands if k in kernels]
     roofline = None
-    if dom in kernels:
-        d_out = (cfg.mlp[-1] if cfg.mlp else cfg.dim)
-        flops_per_launch = 2.0 * cfg.batch * (cfg.batch * world) * d_out       # the dQ (or dC) GEMM; the S recompute is not counted
-        if args.precision != "bf16":
-            flops_per_launch = 3 * 2.0 * cfg.batch * cfg.batch * world * d_out / 3  # fwd / dQ / dC launches, one GEMM each
+    if present:
+        dom = max(present, key=lambda k: kernels[k]["us_per_step"])
+        flops_per_launch, executed = cands[dom]
         us = kernels[dom]["us_per_launch"]
         achieved = flops_per_launch / (us * 1e-6) / 1e12
         roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": achieved / peak_tf, "traffic": ncu_traffic(dom, world), "us_per_launch": us,
                     "algorithmic_flops_per_launch": flops_per_launch, "peak_source": peak_src,
-                    "executed_flops_per_launch": 2 * flops_per_launch if args.precision == "bf16" else None}
+                    "executed_flops_per_launch": executed}
     step_flops = algorithmic_flops(cfg, world)
     line = {
         "metric": METRIC, "value": value, "unit": "examples/s", "n_gpus": world, "steps": args.steps,

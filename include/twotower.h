@@ -335,6 +335,24 @@ int tt_retrieval_loss_bwd(int32_t precision, const void* q, const void* c, int64
  * dq_parts, the dC pass [dc_splits, nc, d] in dc_parts; dq = sum over splits in index order.
  * Buffers are caller-owned, sized with tt_retrieval_bwd_num_splits.  TT_BF16 only.
  * tt_combine_parts_f32 is that ordered sum as a stand-alone kernel (fp32 and/or bf16 output). */
+/* Forward + dQ in one pass (TT_BF16, d = 64 or 128, no log-q correction / accidental-hit mask): the loss forward
+ * with a second GEMM per tile that accumulates sum_j exp(s_ij - m_i) c_j (flash-attention forward shape), so
+ * dq = (w_i / T) (softmax(S) C - c_label) -- d(loss)/dq for an upstream gradient of 1 -- comes out of the same pass
+ * and the backward needs the dC pass only (tt_retrieval_loss_bwd_parts with dq_parts = NULL).  Outputs as
+ * tt_retrieval_loss_fwd plus dq fp32 [nq, d].  The workspace (tt_retrieval_fwd_dq_workspace_bytes; 0 = shape not
+ * supported) must be zero in its first 256 bytes before the first call; the call leaves it so.
+ * finalize_stream (nullable): the fold of the partials into row_lse / loss / dq is forked onto that stream (event
+ * record + wait inside the call; the CALLER joins it back before reading those outputs).  It then overlaps
+ * tt_retrieval_loss_bwd_dc_fused, the dC pass that takes the row maxima / sums straight from this workspace
+ * (dc_parts as in tt_retrieval_loss_bwd_parts) instead of row_lse. */
+int64_t tt_retrieval_fwd_dq_workspace_bytes(int64_t nq, int64_t nc, int64_t d);
+int tt_retrieval_loss_fwd_dq(const void* q, const void* c, int64_t nq, int64_t nc, int64_t d,
+                             float inv_temperature, int64_t label_offset, const float* sample_weight,
+                             float* row_lse, float* row_pos, float* loss, float* dq, void* workspace,
+                             int64_t workspace_bytes, void* stream, void* finalize_stream);
+int tt_retrieval_loss_bwd_dc_fused(const void* q, const void* c, int64_t nq, int64_t nc, int64_t d,
+                                   float inv_temperature, int64_t label_offset, const float* sample_weight,
+                                   const void* fwd_dq_workspace, float grad_scale, float* dc_parts, void* stream);
 int tt_retrieval_bwd_num_splits(int32_t precision, int64_t nq, int64_t nc, int64_t d, int32_t* dq_splits,
                                 int32_t* dc_splits);
 int tt_retrieval_loss_bwd_parts(int32_t precision, const void* q, const void* c, int64_t nq, int64_t nc,

@@ -102,6 +102,18 @@ class TestRetrievalTensorCore:
         assert rel_err(g["dc"].cpu().numpy(), dc_ref) < BF16_RTOL
         assert np.array_equal(g["dq_bf16"].float().cpu().numpy(), oracle.bf16_round(g["dq"].cpu().numpy()))
         assert np.array_equal(g["dc_bf16"].float().cpu().numpy(), oracle.bf16_round(g["dc"].cpu().numpy()))
+        # forward + dQ in one pass (flash-attention forward shape) and the dC-only backward that goes with it
+        if logq is None and ids_d is None and ops.retrieval_fwd_dq_supported(nq, c.shape[0], q.shape[1]):
+            loss2, lse2, pos2, dq2, fws = ops.retrieval_loss_fwd_dq(qb, cb, inv_t, label_offset, w_d, fork=True)
+            dc_f = ops.retrieval_loss_bwd_dc_fused(qb, cb, inv_t, fws, label_offset, w_d, 1.0)   # beside the forked fold
+            ops.join_side_work()
+            assert rel_err(dc_f.sum(0).cpu().numpy(), dc_ref) < BF16_RTOL
+            assert float(loss2.item()) == pytest.approx(r["loss"], rel=2e-4)
+            assert rel_err(lse2.cpu().numpy(), r["lse"]) < 2e-4 and rel_err(pos2.cpu().numpy(), r["pos"]) < 2e-4
+            assert rel_err(dq2.cpu().numpy(), r["dq"]) < BF16_RTOL
+            none, dc_parts = ops.retrieval_loss_bwd_parts(qb, cb, inv_t, lse2, label_offset, w_d, None, None, 1.0, want_dq=False)
+            assert none is None
+            assert rel_err(dc_parts.sum(0).cpu().numpy(), dc_ref) < BF16_RTOL
         return r
 
     @pytest.mark.parametrize("nq,nc,d,off", [(128, 128, 64, 0), (256, 256, 128, 0), (1000, 1000, 128, 0), (8, 8, 64, 0), (77, 203, 64, 100),
@@ -109,6 +121,14 @@ class TestRetrievalTensorCore:
     def test_shapes_splits_and_label_offset(self, ops, nq, nc, d, off):
         _, q, c = self._inputs(nq, nc, d, nq + nc + d)
         self._check(ops, q, c, off, temperature=0.25)
+
+    def test_fused_forward_dq_rescales_when_the_row_maximum_keeps_rising(self, ops):
+        """Candidates ordered by increasing norm: the row maxima grow from tile to tile by far more than the lazy
+        threshold (8 in the log2 domain), so the accumulator rescale of the one-pass forward + dQ kernel runs."""
+        rng, q, c = self._inputs(300, 2304, 128, 11, scale=0.5)
+        c = oracle.bf16_round(c * np.linspace(0.05, 3.0, c.shape[0], dtype=np.float32)[:, None])
+        self._check(ops, q, c, 1000, temperature=0.1)
+        self._check(ops, q, c[::-1].copy(), 0, temperature=0.1)
 
     def test_no_temperature(self, ops):
         _, q, c = self._inputs(512, 512, 128, 3, scale=0.5)

@@ -170,6 +170,8 @@ class GradientTape:
 
     def __exit__(self, *exc):
         GradientTape._stack.pop()
+        from . import ops
+        ops.join_side_work()          # a forward whose backward never ran may have left a forked fold in flight
         return False
 
     @staticmethod

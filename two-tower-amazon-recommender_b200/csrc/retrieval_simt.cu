@@ -26,6 +26,13 @@ int tc_retrieval_bwd_parts(const void* q, const void* c, int64_t nq, int64_t nc,
                            int64_t label_offset, const float* w, const float* logq, const int64_t* cand_ids,
                            const float* row_lse, float grad_scale, float* part_q, float* part_c, cudaStream_t st);
 int tc_combine_parts(const float* parts, int splits, int64_t rows, int64_t d, float* out_f32, uint16_t* out_bf16, cudaStream_t st);
+int64_t tc_retrieval_fwd_dq_workspace_bytes(int64_t nq, int64_t nc, int64_t d);
+int tc_retrieval_fwd_dq(const void* q, const void* c, int64_t nq, int64_t nc, int64_t d, float inv_temp,
+                        int64_t label_offset, const float* w, float* row_lse, float* row_pos, float* loss, float* dq,
+                        void* ws, int64_t ws_bytes, cudaStream_t st, cudaStream_t fin_st);
+int tc_retrieval_bwd_dc_fused(const void* q, const void* c, int64_t nq, int64_t nc, int64_t d, float inv_temp,
+                              int64_t label_offset, const float* w, const void* fwd_ws, float grad_scale, float* part_c,
+                              cudaStream_t st);
 
 struct RetrievalArgs {
   const float* q; const float* c;
@@ -331,6 +338,30 @@ extern "C" int tt_retrieval_loss_bwd_parts(int32_t precision, const void* q, con
   TT_REQUIRE(row_lse, "tt_retrieval_loss_bwd_parts: null row_lse");
   return tc_retrieval_bwd_parts(q, c, nq, nc, d, inv_temperature, label_offset, sample_weight, cand_log_q, cand_ids,
                                 row_lse, grad_scale, dq_parts, dc_parts, (cudaStream_t)stream);
+}
+
+extern "C" int64_t tt_retrieval_fwd_dq_workspace_bytes(int64_t nq, int64_t nc, int64_t d) {
+  if (nq <= 0 || nc <= 0 || d <= 0) return 0;
+  return tc_retrieval_fwd_dq_workspace_bytes(nq, nc, d);
+}
+
+extern "C" int tt_retrieval_loss_fwd_dq(const void* q, const void* c, int64_t nq, int64_t nc, int64_t d,
+                                        float inv_temperature, int64_t label_offset, const float* sample_weight,
+                                        float* row_lse, float* row_pos, float* loss, float* dq, void* workspace,
+                                        int64_t workspace_bytes, void* stream, void* finalize_stream) {
+  int rc = check_retrieval_common("tt_retrieval_loss_fwd_dq", TT_BF16, q, c, nq, nc, d, label_offset);
+  if (rc) return rc;
+  return tc_retrieval_fwd_dq(q, c, nq, nc, d, inv_temperature, label_offset, sample_weight, row_lse, row_pos, loss, dq,
+                             workspace, workspace_bytes, (cudaStream_t)stream, (cudaStream_t)finalize_stream);
+}
+
+extern "C" int tt_retrieval_loss_bwd_dc_fused(const void* q, const void* c, int64_t nq, int64_t nc, int64_t d,
+                                              float inv_temperature, int64_t label_offset, const float* sample_weight,
+                                              const void* fwd_dq_workspace, float grad_scale, float* dc_parts, void* stream) {
+  int rc = check_retrieval_common("tt_retrieval_loss_bwd_dc_fused", TT_BF16, q, c, nq, nc, d, label_offset);
+  if (rc) return rc;
+  return tc_retrieval_bwd_dc_fused(q, c, nq, nc, d, inv_temperature, label_offset, sample_weight, fwd_dq_workspace,
+                                   grad_scale, dc_parts, (cudaStream_t)stream);
 }
 
 extern "C" int tt_combine_parts_f32(const float* parts, int32_t num_parts, int64_t rows, int64_t d, float* out_f32,

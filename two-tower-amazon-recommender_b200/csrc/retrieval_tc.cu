@@ -142,6 +142,8 @@ struct RetrievalTcArgs {
   const float* logq;              // log(clip(p)) per candidate [nc] or null
   const long long* cand_ids;      // [nc] or null (accidental-hit removal)
   const float* lse;               // [nq] natural-log lse (backward)
+  const float2* ml_parts;         // backward after the one-pass forward + dQ: its [ml_nparts][nq] (max2, sum) partials;
+  int ml_nparts;                  //   the dC kernel folds them into the column lse itself (lse may be null then)
   float2* partial_ml;             // forward: [splits][nq] (max2, sum)
   float* row_pos;                 // forward: [nq]
   float* row_lse_out;             // forward: [nq] natural-log lse, written by the last CTA of each row block
@@ -609,7 +611,19 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       if ((TRANSPOSED || EXTRAS) && t < T && wg_tid < BN) {
         const long long yi = (long long)(tile_begin + t) * BN + wg_tid;
         if (TRANSPOSED) {
-          nx_a = yi < a.nq ? -a.lse[yi] * kLog2e : 0.f;
+          if (a.ml_parts) {                            // lse2 of query column yi from the forward's partials
+            float M = -INFINITY, Ls = 0.f;
+            if (yi < a.nq) {
+              for (int s = 0; s < a.ml_nparts; ++s) M = fmaxf(M, a.ml_parts[(size_t)s * a.nq + yi].x);
+              for (int s = 0; s < a.ml_nparts; ++s) {
+                const float2 pm = a.ml_parts[(size_t)s * a.nq + yi];
+                if (pm.x > -INFINITY) Ls += pm.y * exp2f(pm.x - M);
+              }
+            }
+            nx_a = yi < a.nq ? -(M + log2f(Ls)) : 0.f;
+          } else {
+            nx_a = yi < a.nq ? -a.lse[yi] * kLog2e : 0.f;
+          }
           nx_w = (a.w && yi < a.nq) ? a.w[yi] : 1.f;
           if (EXTRAS) nx_id = (a.cand_ids && yi < a.nq) ? a.cand_ids[a.label_offset + yi] : -2;
         } else {
@@ -799,6 +813,373 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   if (warp == RT_MMA_WARP) tmem_dealloc(tmem_base, 512);
 }
 
+
+// ---------------------------------------------------------------------------------------
+// forward + dQ in ONE pass (flash-attention forward shape)
+// ---------------------------------------------------------------------------------------
+// dQ_i = (w_i / T) * (sum_j p_ij c_j - c_label(i)) with p = softmax(S): the forward already forms every
+// exp(s_ij - m_i), so a second MMA per tile accumulates O_i = sum_j exp2(s_ij k2 - m_i) c_j next to the running
+// (m_i, l_i) and the separate dQ pass (one more S recompute, one more exponential per logit) disappears.
+// Same streaming structure as the backward kernel; differences:
+//   * each softmax warpgroup keeps its OWN accumulator O_g and reference maximum (the two warpgroups alternate
+//     tiles of the same rows, so they cannot share a rescaled accumulator).  TMEM: [S0 | S1 | O0 (d) | O1 (d)],
+//     P_b (bf16x2) is written over the first half of S_b, which the S issuer may only overwrite once the O GEMM
+//     of that tile has completed (p_empty).
+//   * online softmax with a LAZY reference maximum: m_i moves (and l_i, O_i are rescaled by the owning thread --
+//     its accumulator is quiescent while it holds S of its next tile) only when the tile maximum exceeds it by
+//     more than 8 in the log2 domain; terms up to 2^8 are harmless in bf16 / fp32.
+// Every (CTA, warpgroup) leaves a partial (m, l, O); retrieval_dq_finalize_kernel folds them into row_lse, the
+// SUM loss and dQ.
+struct FusedLayout { int x_bytes, y_bytes, stages, total; };
+__host__ __device__ inline FusedLayout fused_layout(int d, int BN) {
+  FusedLayout L;
+  L.x_bytes = RT_BM * d * 2;
+  L.y_bytes = BN * d * 2;
+  L.stages = (227 * 1024 - 256 - L.x_bytes) / L.y_bytes;
+  if (L.stages > RT_MAX_STAGES) L.stages = RT_MAX_STAGES;
+  L.total = L.x_bytes + L.stages * L.y_bytes + 256;
+  return L;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(RT_THREADS, 1)
+retrieval_fwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+                           const __grid_constant__ CUtensorMap tmP, const RetrievalTcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
+  const int d = a.d, nkb = d / 64;
+  const FusedLayout L = fused_layout(d, BN);
+  const int STAGES = L.stages;
+  uint8_t* sX = smem;
+  uint8_t* sY = sX + L.x_bytes;
+  uint8_t* tail = sY + STAGES * L.y_bytes;
+  uint64_t* x_full = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* full = x_full + 1;
+  uint64_t* empty = full + RT_MAX_STAGES;
+  uint64_t* s_full = empty + RT_MAX_STAGES;
+  uint64_t* p_full = s_full + 2;
+  uint64_t* p_empty = p_full + 2;
+  uint64_t* acc_full = p_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  long long* const tl = g_tl;
+  tl_mark(tl, 1, true);
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int x0 = blockIdx.x * RT_BM;
+  const int tile_begin = blockIdx.y * a.tiles_per_split;
+  const int total_tiles = (a.nc + BN - 1) / BN;
+  const int T = max(0, min(a.tiles_per_split, total_tiles - tile_begin));
+  const uint32_t O_COL = 2 * BN;                      // TMEM columns: [S0 | S1 | O0 (d) | O1 (d)]; P_b over S_b[0, BN/2)
+
+  if (warp == RT_TMA_WARP && lane == 0) {
+    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmY); tma_prefetch_desc(&tmP);
+    mbar_init(x_full, 1);
+    for (int s = 0; s < RT_MAX_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 128); mbar_init(&p_empty[b], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == RT_MMA_WARP) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == RT_TMA_WARP) {
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(x_full, L.x_bytes);
+      for (int kb = 0; kb < nkb; ++kb) tma_load_2d(sX + kb * RT_BM * 128, &tmX, x_full, kb * 64, x0);
+      for (int t = 0; t < T; ++t) {
+        const int s = t % STAGES;
+        mbar_wait(&empty[s], ((t / STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full[s], L.y_bytes);
+        uint8_t* base = sY + s * L.y_bytes;
+        const int y0 = (tile_begin + t) * BN;
+        for (int kb = 0; kb < nkb; ++kb) tma_load_2d(base + kb * BN * 128, &tmY, &full[s], kb * 64, y0);
+      }
+    }
+  } else if (warp == RT_MMA_WARP) {
+    // S issuer: S(t) = X Y_t^T once the tile has landed and the O GEMM of tile t-2 has consumed P(t-2) (same columns)
+    if (T > 0 && elect_one_sync()) {
+      constexpr uint32_t idesc1 = umma_idesc_bf16(RT_BM, BN);
+      mbar_wait(x_full, 0);
+      for (int t = 0; t < T; ++t) {
+        const int s = t % STAGES, b = t & 1;
+        mbar_wait(&full[s], (t / STAGES) & 1);
+        mbar_wait(&p_empty[b], ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < nkb; ++kb) {
+          const uint64_t da = umma_desc_k_sw128(smem_u32(sX + kb * RT_BM * 128));
+          const uint64_t db = umma_desc_k_sw128(smem_u32(sY + s * L.y_bytes + kb * BN * 128));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + b * BN, da + 2 * k, db + 2 * k, idesc1, (kb | k) != 0);
+        }
+        umma_commit(&s_full[b]);
+      }
+    }
+  } else if (warp == RT_MMA2_WARP) {
+    // O issuer: O_g += P(t) Y_t (A = P from tensor memory, B = the streamed tile read MN-major), g = t & 1
+    if (T > 0 && elect_one_sync()) {
+      const uint32_t idesc2 = umma_idesc_bf16(RT_BM, d, 0, 1);
+      for (int t = 0; t < T; ++t) {
+        const int s = t % STAGES, b = t & 1;
+        mbar_wait(&p_full[b], (t >> 1) & 1);
+        tc_fence_after();
+        const uint64_t db0 = umma_desc_mn_sw128(smem_u32(sY + s * L.y_bytes), BN * 128);
+        const uint32_t ta0 = tmem_base + b * BN;
+#pragma unroll
+        for (int k = 0; k < BN / 16; ++k)
+          umma_bf16_ts(tmem_base + O_COL + b * d, ta0 + 8 * k, db0 + 128 * k, idesc2, ((t >> 1) | k) != 0);
+        umma_commit(&p_empty[b]);
+        umma_commit(&empty[s]);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    const int g = warp >> 2;
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;
+    const long long qi = (long long)x0 + r;
+    const long long label = a.label_offset + qi;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
+    float m2 = -INFINITY, l = 0.f;                   // reference maximum (log2 domain) and row sum of this warpgroup
+    for (int t = g; t < T; t += 2) {
+      const int b = g;
+      const long long c_tile = (long long)(tile_begin + t) * BN;
+      mbar_wait(&s_full[b], (t >> 1) & 1);
+      tc_fence_after();
+      uint32_t rr[BN];
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) tmem_ld32(lane_addr + b * BN + c * 32, rr + c * 32);
+      tmem_ld_wait();
+      if (c_tile + BN > a.nc) {                      // uniform: ragged last tile -> -inf logits
+#pragma unroll
+        for (int j = 0; j < BN; ++j) if (c_tile + j >= a.nc) rr[j] = 0xff800000u;
+      }
+      if (label >= c_tile && label < c_tile + BN) {  // the positive logit of this row lives in this tile
+        const int jj = (int)(label - c_tile);
+        float p = 0.f;
+#pragma unroll
+        for (int j = 0; j < BN; ++j) if (j == jj) p = __uint_as_float(rr[j]);
+        if (qi < a.nq) a.row_pos[qi] = p * a.k2 * kLn2;
+      }
+      float cm[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) cm[u] = fmaxf(__uint_as_float(rr[2 * u]), __uint_as_float(rr[2 * u + 1]));
+#pragma unroll
+      for (int j = 8; j < BN; j += 8) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cm[u] = fmax3(cm[u], __uint_as_float(rr[j + 2 * u]), __uint_as_float(rr[j + 2 * u + 1]));
+      }
+      const float cmax = fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])) * a.k2;
+      // lazy reference maximum
+      float factor = 1.f;
+      bool need = false;
+      if (cmax > m2) {
+        if (m2 == -INFINITY) m2 = cmax;              // first tile of this warpgroup: nothing accumulated yet
+        else if (cmax > m2 + 8.f) { factor = ex2_approx(m2 - cmax); l *= factor; m2 = cmax; need = true; }
+      }
+      const uint64_t K2 = pk2(a.k2, a.k2), NM = pk2(-m2, -m2);
+      uint64_t acc0 = pk2(0.f, 0.f), acc1 = acc0;
+      uint32_t pk[BN / 2];
+#pragma unroll
+      for (int j = 0; j < BN; j += 16) {
+#define TT_FQ_PAIR(U, ACC)                                                                          \
+        {                                                                                           \
+          const uint64_t e2 = ex2_mix2<U, FWD_POLY_MASK>(fma2(pk2u(rr[j + 2 * U], rr[j + 2 * U + 1]), K2, NM)); \
+          ACC = add2(ACC, e2);                                                                      \
+          float e0, e1;                                                                             \
+          up2(e2, e0, e1);                                                                          \
+          pk[(j >> 1) + U] = pack_bf16x2(e0, e1);                                                   \
+        }
+        TT_FQ_PAIR(0, acc0) TT_FQ_PAIR(1, acc1) TT_FQ_PAIR(2, acc0) TT_FQ_PAIR(3, acc1)
+        TT_FQ_PAIR(4, acc0) TT_FQ_PAIR(5, acc1) TT_FQ_PAIR(6, acc0) TT_FQ_PAIR(7, acc1)
+#undef TT_FQ_PAIR
+      }
+      float s0, s1, s2, s3;
+      up2(acc0, s0, s1);
+      up2(acc1, s2, s3);
+      l += (s0 + s1) + (s2 + s3);
+      if (__any_sync(0xffffffffu, need)) {
+        // (after the exponentials: the S row is dead, fewer live registers)  O_g is quiescent here: S(t) was only issued after the O GEMM of this warpgroup's previous tile completed
+#pragma unroll 1
+        for (int c0 = 0; c0 < d; c0 += 32) {
+          uint32_t oo[32];
+          tmem_ld32(lane_addr + O_COL + b * d + c0, oo);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) oo[j] = __float_as_uint(__uint_as_float(oo[j]) * factor);
+          tmem_st32(lane_addr + O_COL + b * d + c0, oo);
+        }
+        tmem_st_wait();
+      }
+      // P(t) over the first half of S_b (this thread has its whole S row in registers)
+#pragma unroll
+      for (int c = 0; c < BN / 64; ++c) tmem_st32(lane_addr + b * BN + c * 32, pk + c * 32);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[b]);
+    }
+    // epilogue: this warpgroup's partial (m, l, O_g) -> slot 2 * split + g
+    const int slot = blockIdx.y * 2 + g;
+    const bool have = T > g;
+    if (T > 0) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+    }
+    if (qi < a.nq) a.partial_ml[(size_t)slot * a.nq + qi] = make_float2(have ? m2 : -INFINITY, have ? l : 0.f);
+    if (x0 + RT_BM <= a.nq) {
+      uint8_t* my_stage = sY + warp * 8192;
+      int it = 0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < d; c0 += 32, ++it) {
+        uint32_t oo[32];
+        if (have) {
+          tmem_ld32(lane_addr + O_COL + g * d + c0, oo);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) oo[j] = 0u;
+        }
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        uint8_t* st = my_stage + (it & 1) * 4096;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(st + sw128_offset(lane, c)) = make_uint4(oo[4 * c], oo[4 * c + 1], oo[4 * c + 2], oo[4 * c + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmP, st, c0, (int)((long long)slot * a.nq + x0 + qd * 32));
+          tma_store_commit();
+        }
+      }
+      if (lane == 0) tma_store_wait_all();
+    } else {
+      float* out = a.partial_out + ((size_t)slot * a.nq + (size_t)qi) * d;
+#pragma unroll 1
+      for (int c0 = 0; c0 < d; c0 += 32) {
+        uint32_t oo[32];
+        if (have) {
+          tmem_ld32(lane_addr + O_COL + g * d + c0, oo);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) oo[j] = 0u;
+        }
+        if (qi < a.nq) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<uint4*>(out + c0 + j) = make_uint4(oo[j], oo[j + 1], oo[j + 2], oo[j + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tl_mark(tl, 1, false);
+  if (warp == RT_MMA_WARP) tmem_dealloc(tmem_base, 512);
+}
+
+// Fold the (m, l, O) partials: row_lse, the SUM loss (fixed summation order) and
+// dQ_i = (w_i / T) (sum_s O_s 2^(m_s - M) / L - c_label(i)).  One warp per row.
+struct DqFinalizeArgs {
+  int nq, d, parts;
+  float inv_temp;
+  long long label_offset;
+  const float2* ml;                // [parts][nq]
+  const float* o_parts;            // [parts][nq][d]
+  const uint16_t* c;               // candidates bf16 [nc][d]
+  const float* w;                  // [nq] or null
+  const float* row_pos;            // [nq]
+  float* row_lse;                  // [nq]
+  float* dq;                       // [nq][d]
+  float* block_loss;               // [gridDim.x]
+  int* ticket;                     // zero before and after
+  float* loss_out;
+};
+__global__ void __launch_bounds__(256) retrieval_dq_finalize_kernel(const DqFinalizeArgs a) {
+  long long* const tl = g_tl;
+  tl_mark(tl, 15, true);
+  pdl_wait();
+  pdl_launch_dependents();
+  __shared__ float s_term[8];
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const long long i = (long long)blockIdx.x * 8 + wi;
+  float term = 0.f;
+  if (i < a.nq) {
+    // every load of the row is issued before the first use (parts <= 8): one L2 round trip instead of one per part
+    constexpr int MAXP = 8;
+    float2 pm[MAXP];
+    float4 o[MAXP];
+    const int c0 = lane * 4;                       // d <= 128: one float4 per lane
+    const bool col = c0 < a.d;
+#pragma unroll
+    for (int s = 0; s < MAXP; ++s) {
+      pm[s] = s < a.parts ? a.ml[(size_t)s * a.nq + i] : make_float2(-INFINITY, 0.f);
+      o[s] = (s < a.parts && col) ? *reinterpret_cast<const float4*>(a.o_parts + ((size_t)s * a.nq + i) * a.d + c0)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const uint2 cb = col ? *reinterpret_cast<const uint2*>(a.c + (size_t)(a.label_offset + i) * a.d + c0) : make_uint2(0u, 0u);
+    const float wgt = a.w ? a.w[i] : 1.f;
+    const float pos = a.row_pos[i];
+    float M = -INFINITY;
+#pragma unroll
+    for (int s = 0; s < MAXP; ++s) M = fmaxf(M, pm[s].x);
+    float f[MAXP], Ls = 0.f;
+#pragma unroll
+    for (int s = 0; s < MAXP; ++s) {
+      f[s] = pm[s].x > -INFINITY ? exp2f(pm[s].x - M) : 0.f;
+      Ls += pm[s].y * f[s];
+    }
+    const float lse = (M + log2f(Ls)) * kLn2;
+    if (lane == 0) a.row_lse[i] = lse;
+    term = wgt * (lse - pos);
+    if (col) {
+      const float scale = wgt * a.inv_temp, invL = 1.f / Ls;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int s = 0; s < MAXP; ++s) {
+        const float fs = f[s] * invL;
+        acc.x = fmaf(o[s].x, fs, acc.x); acc.y = fmaf(o[s].y, fs, acc.y); acc.z = fmaf(o[s].z, fs, acc.z); acc.w = fmaf(o[s].w, fs, acc.w);
+      }
+      acc.x -= __uint_as_float(cb.x << 16); acc.y -= __uint_as_float(cb.x & 0xffff0000u);
+      acc.z -= __uint_as_float(cb.y << 16); acc.w -= __uint_as_float(cb.y & 0xffff0000u);
+      *reinterpret_cast<float4*>(a.dq + (size_t)i * a.d + c0) = make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale);
+    }
+  }
+  __shared__ float s_red[256];
+  __shared__ int s_last;
+  if (lane == 0) s_term[wi] = term;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float bsum = 0.f;
+    for (int k = 0; k < 8; ++k) bsum += s_term[k];
+    a.block_loss[blockIdx.x] = bsum;
+    __threadfence();
+    s_last = atomicAdd(a.ticket, 1) == (int)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last) {
+    // the last block adds the block terms in a fixed order (thread-strided partial sums, then a tree): the loss does
+    // not depend on which block happens to be last
+    __threadfence();
+    float part = 0.f;
+    for (unsigned k = threadIdx.x; k < gridDim.x; k += 256) part += __ldcg(&a.block_loss[k]);
+    s_red[threadIdx.x] = part;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) { a.loss_out[0] = s_red[0]; *a.ticket = 0; }
+  }
+}
+
 // out = sum_s partial[s]; optional bf16 copy.  One warp per row.
 __global__ void __launch_bounds__(256)
 combine_partials_kernel(const float* __restrict__ partial, int splits, int64_t rows, int d, float* __restrict__ out_f32,
@@ -936,6 +1317,101 @@ static int launch_bwd(const void* x, const void* y, int64_t nX, int64_t nY, Retr
   return TT_OK;
 }
 
+// ---- forward + dQ --------------------------------------------------------------------------------------
+static bool fused_supported(int64_t d) { return d % 64 == 0 && d >= 64 && d <= 128; }
+struct FusedPlan { int splits, tps, parts; int64_t off_bl, off_ml, off_o, total, blocks; };
+static FusedPlan fused_plan(int64_t nq, int64_t nc, int64_t d) {
+  FusedPlan p;
+  split_plan(nq, nc, 128, &p.splits, &p.tps);
+  if (p.splits > 4) {                  // at most 8 (m, l, O) partials per row: the fold keeps them all in registers
+    const int64_t y128 = ceil_div(nc, 128), per = ceil_div(y128, 4);
+    p.tps = (int)per;
+    p.splits = (int)ceil_div(y128, per);
+  }
+  p.parts = 2 * p.splits;
+  p.blocks = ceil_div(nq, 8);
+  p.off_bl = 256;
+  p.off_ml = p.off_bl + round_up(p.blocks * 4, 256);
+  p.off_o = p.off_ml + round_up((int64_t)p.parts * nq * 8, 256);
+  p.total = p.off_o + round_up((int64_t)p.parts * nq * d * 4, 256);
+  return p;
+}
+int64_t tc_retrieval_fwd_dq_workspace_bytes(int64_t nq, int64_t nc, int64_t d) {
+  return fused_supported(d) ? fused_plan(nq, nc, d).total : 0;
+}
+
+int tc_retrieval_fwd_dq(const void* q, const void* c, int64_t nq, int64_t nc, int64_t d, float inv_temp,
+                        int64_t label_offset, const float* w, float* row_lse, float* row_pos, float* loss, float* dq,
+                        void* ws, int64_t ws_bytes, cudaStream_t st, cudaStream_t fin_st) {
+  int rc = check_tc_dims("tt_retrieval_loss_fwd_dq", nq, nc, d);
+  if (rc) return rc;
+  TT_REQUIRE(fused_supported(d), "tt_retrieval_loss_fwd_dq: d must be 64 or 128 (got %lld)", (long long)d);
+  TT_REQUIRE(dq && aligned16(dq) && row_lse && row_pos && loss, "tt_retrieval_loss_fwd_dq: null / unaligned output");
+  const FusedPlan plan = fused_plan(nq, nc, d);
+  if (!ws || ws_bytes < plan.total) return set_error(TT_ERR_WORKSPACE, "tt_retrieval_loss_fwd_dq: workspace too small");
+  constexpr int BN = 128;
+  CUtensorMap tmX, tmY, tmP;
+  rc = make_tmap_bf16_2d(&tmX, q, (uint64_t)d, (uint64_t)nq, (uint64_t)d * 2, 64, RT_BM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tmY, c, (uint64_t)d, (uint64_t)nc, (uint64_t)d * 2, 64, BN);
+  if (rc) return rc;
+  float* o_parts = (float*)((char*)ws + plan.off_o);
+  rc = make_tmap_f32_2d(&tmP, o_parts, (uint64_t)d, (uint64_t)plan.parts * (uint64_t)nq, (uint64_t)d * 4, 32, 32);
+  if (rc) return rc;
+  RetrievalTcArgs a{};
+  a.nq = (int)nq; a.nc = (int)nc; a.d = (int)d;
+  a.k2 = inv_temp * kLog2e;
+  a.label_offset = label_offset;
+  a.partial_ml = (float2*)((char*)ws + plan.off_ml); a.row_pos = row_pos; a.partial_out = o_parts;
+  a.tiles_per_split = plan.tps;
+  const FusedLayout L = fused_layout((int)d, BN);
+  TT_REQUIRE(L.stages >= 2, "tt_retrieval_loss_fwd_dq: d=%lld does not fit the shared-memory pipeline", (long long)d);
+  TT_REQUIRE(plan.parts <= 8, "tt_retrieval_loss_fwd_dq: more than 8 partials per row (%d)", plan.parts);
+  dim3 grid((unsigned)ceil_div(nq, RT_BM), (unsigned)plan.splits);
+  TT_CUDA_OK(cudaFuncSetAttribute(retrieval_fwd_dq_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+  TT_PROF("retrieval_fwd_dq_tc_kernel", st);
+  TT_CUDA_OK(launch_pdl(retrieval_fwd_dq_tc_kernel<BN>, grid, dim3(RT_THREADS), (size_t)L.total, st, tmX, tmY, tmP, a));
+  TT_LAUNCH_OK("retrieval_fwd_dq_tc_kernel");
+  DqFinalizeArgs f{};
+  f.nq = (int)nq; f.d = (int)d; f.parts = plan.parts; f.inv_temp = inv_temp; f.label_offset = label_offset;
+  f.ml = a.partial_ml; f.o_parts = o_parts; f.c = (const uint16_t*)c; f.w = w; f.row_pos = row_pos; f.row_lse = row_lse;
+  f.dq = dq; f.block_loss = (float*)((char*)ws + plan.off_bl); f.ticket = (int*)ws; f.loss_out = loss;
+  if (fin_st && fin_st != st) {
+    // fork: the fold runs on its own stream, next to the dC pass (which reads the partial maxima itself)
+    static thread_local cudaEvent_t ev = nullptr;
+    if (!ev) TT_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    TT_CUDA_OK(cudaEventRecord(ev, st));
+    TT_CUDA_OK(cudaStreamWaitEvent(fin_st, ev, 0));
+  } else {
+    fin_st = st;
+  }
+  TT_PROF("retrieval_dq_finalize_kernel", fin_st);
+  TT_CUDA_OK(launch_pdl(retrieval_dq_finalize_kernel, dim3((unsigned)plan.blocks), dim3(256), (size_t)0, fin_st, f));
+  TT_LAUNCH_OK("retrieval_dq_finalize_kernel");
+  return TT_OK;
+}
+
+// dC pass right after the one-pass forward + dQ: column lse from the forward's partials in its workspace
+int tc_retrieval_bwd_dc_fused(const void* q, const void* c, int64_t nq, int64_t nc, int64_t d, float inv_temp,
+                              int64_t label_offset, const float* w, const void* fwd_ws, float grad_scale, float* part_c,
+                              cudaStream_t st) {
+  int rc = check_tc_dims("tt_retrieval_loss_bwd_dc_fused", nq, nc, d);
+  if (rc) return rc;
+  TT_REQUIRE(fused_supported(d) && fwd_ws && part_c && aligned16(part_c), "tt_retrieval_loss_bwd_dc_fused: bad arguments");
+  const FusedPlan fp = fused_plan(nq, nc, d);
+  RetrievalTcArgs a{};
+  a.nq = (int)nq; a.nc = (int)nc; a.d = (int)d;
+  a.k2 = inv_temp * kLog2e; a.out_scale = inv_temp * grad_scale;
+  a.label_offset = label_offset; a.w = w;
+  a.ml_parts = (const float2*)((const char*)fwd_ws + fp.off_ml); a.ml_nparts = fp.parts;
+  const WsPlan plan = ws_plan(nq, nc, d);
+  int sc = 1;
+  rc = launch_bwd<128, true>(c, q, nc, nq, a, part_c, &sc, st);
+  if (rc) return rc;
+  if (sc != plan.sc) return set_error(TT_ERR_INVALID_ARG, "tt_retrieval_loss_bwd_dc_fused: internal split plan mismatch");
+  return TT_OK;
+}
+
 void tc_retrieval_bwd_num_splits(int64_t nq, int64_t nc, int64_t d, int* sq, int* sc) {
   const WsPlan p = ws_plan(nq, nc, d);
   *sq = p.sq; *sc = p.sc;
@@ -947,7 +1423,8 @@ int tc_retrieval_bwd_parts(const void* q, const void* c, int64_t nq, int64_t nc,
                            const float* row_lse, float grad_scale, float* part_q, float* part_c, cudaStream_t st) {
   int rc = check_tc_dims("tt_retrieval_loss_bwd", nq, nc, d);
   if (rc) return rc;
-  TT_REQUIRE(part_q && part_c && aligned16(part_q) && aligned16(part_c), "tt_retrieval_loss_bwd(bf16): partial buffers null or unaligned");
+  TT_REQUIRE(part_c && aligned16(part_c) && (!part_q || aligned16(part_q)), "tt_retrieval_loss_bwd(bf16): partial buffers null or unaligned");
+  const bool want_q = part_q != nullptr;          // null: dQ came out of tt_retrieval_loss_fwd_dq already
   RetrievalTcArgs a{};
   a.nq = (int)nq; a.nc = (int)nc; a.d = (int)d;
   a.k2 = inv_temp * kLog2e; a.out_scale = inv_temp * grad_scale;
@@ -956,15 +1433,16 @@ int tc_retrieval_bwd_parts(const void* q, const void* c, int64_t nq, int64_t nc,
   const WsPlan plan = ws_plan(nq, nc, d);
   int sq = 1, sc = 1;
   if (BN == 128) {
-    rc = launch_bwd<128, false>(q, c, nq, nc, a, part_q, &sq, st);
+    rc = want_q ? launch_bwd<128, false>(q, c, nq, nc, a, part_q, &sq, st) : TT_OK;
     if (rc) return rc;
     rc = launch_bwd<128, true>(c, q, nc, nq, a, part_c, &sc, st);
   } else {
-    rc = launch_bwd<64, false>(q, c, nq, nc, a, part_q, &sq, st);
+    rc = want_q ? launch_bwd<64, false>(q, c, nq, nc, a, part_q, &sq, st) : TT_OK;
     if (rc) return rc;
     rc = launch_bwd<64, true>(c, q, nc, nq, a, part_c, &sc, st);
   }
   if (rc) return rc;
+  if (!want_q) sq = plan.sq;
   if (sq != plan.sq || sc != plan.sc) return set_error(TT_ERR_INVALID_ARG, "tt_retrieval_loss_bwd(bf16): internal split plan mismatch");
   return TT_OK;
 }

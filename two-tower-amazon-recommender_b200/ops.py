@@ -559,20 +559,82 @@ def retrieval_bwd_num_splits(nq: int, nc: int, d: int):
     return sq.value, sc.value
 
 
+def retrieval_fwd_dq_supported(nq: int, nc: int, d: int) -> bool:
+    return int(_lib.load().tt_retrieval_fwd_dq_workspace_bytes(nq, nc, d)) > 0
+
+
+_fin_stream = None
+_fin_pending = False
+
+
+def join_side_work() -> None:
+    """Make the current stream wait for the forked fold of retrieval_loss_fwd_dq(fork=True), if one is in flight."""
+    global _fin_pending
+    if _fin_pending:
+        torch.cuda.current_stream().wait_stream(_fin_stream)
+        _fin_pending = False
+
+
+def retrieval_loss_fwd_dq(q, c, inv_temperature: float, label_offset: int = 0, sample_weight=None, fork: bool = False):
+    """bf16 only: the loss forward and dQ in one pass.  Returns (loss [1], row_lse [nq], row_pos [nq], dq f32 [nq, d],
+    workspace).  fork=True: the fold into lse / loss / dq runs on a side stream -- call join_side_work() before
+    anything reads them (retrieval_loss_bwd_dc_fused does not: it takes the partials from the workspace)."""
+    global _fin_stream, _fin_pending
+    lib = _lib.load()
+    nq, d = q.shape
+    nc = c.shape[0]
+    dev = q.device
+    lse = torch.empty((nq,), dtype=torch.float32, device=dev)
+    pos = torch.empty((nq,), dtype=torch.float32, device=dev)
+    loss = torch.empty((1,), dtype=torch.float32, device=dev)
+    dq = torch.empty((nq, d), dtype=torch.float32, device=dev)
+    nbytes = int(lib.tt_retrieval_fwd_dq_workspace_bytes(nq, nc, d))
+    if nbytes <= 0:
+        raise ValueError(f"retrieval_loss_fwd_dq: shape not supported (d={d})")
+    ws = _workspace(nbytes, dev, "retrieval_fwd_dq")
+    fin = None
+    if fork:
+        join_side_work()
+        if _fin_stream is None:
+            _fin_stream = torch.cuda.Stream()
+        fin = _fin_stream.cuda_stream
+    check(lib.tt_retrieval_loss_fwd_dq(_ptr(q, torch.bfloat16), _ptr(c, torch.bfloat16), nq, nc, d, inv_temperature,
+                                       label_offset, _ptr(sample_weight, torch.float32), _ptr(lse), _ptr(pos), _ptr(loss),
+                                       _ptr(dq), _ptr(ws), ws.numel(), _stream(), fin))
+    _fin_pending = fork
+    _count(2)
+    return loss, lse, pos, dq, ws
+
+
+def retrieval_loss_bwd_dc_fused(q, c, inv_temperature: float, fwd_ws, label_offset: int = 0, sample_weight=None,
+                                grad_scale: float = 1.0):
+    """The dC pass after retrieval_loss_fwd_dq (column lse from its workspace).  Returns dc_parts f32 [sc, nc, d]."""
+    nq, d = q.shape
+    nc = c.shape[0]
+    _sq, sc = retrieval_bwd_num_splits(nq, nc, d)
+    dc_parts = torch.empty((sc, nc, d), dtype=torch.float32, device=q.device)
+    check(_lib.load().tt_retrieval_loss_bwd_dc_fused(_ptr(q, torch.bfloat16), _ptr(c, torch.bfloat16), nq, nc, d,
+                                                     inv_temperature, label_offset, _ptr(sample_weight, torch.float32),
+                                                     _ptr(fwd_ws), grad_scale, _ptr(dc_parts), _stream()))
+    _count(1)
+    return dc_parts
+
+
 def retrieval_loss_bwd_parts(q, c, inv_temperature: float, row_lse, label_offset: int = 0, sample_weight=None,
-                             cand_log_q=None, cand_ids=None, grad_scale: float = 1.0):
-    """bf16 only.  Returns (dq_parts f32 [sq, nq, d], dc_parts f32 [sc, nc, d]): dq = dq_parts.sum(0) in index order."""
+                             cand_log_q=None, cand_ids=None, grad_scale: float = 1.0, want_dq: bool = True):
+    """bf16 only.  Returns (dq_parts f32 [sq, nq, d], dc_parts f32 [sc, nc, d]): dq = dq_parts.sum(0) in index order.
+    want_dq=False: the dC pass only (dq came from retrieval_loss_fwd_dq); dq_parts is None."""
     nq, d = q.shape
     nc = c.shape[0]
     sq, sc = retrieval_bwd_num_splits(nq, nc, d)
-    dq_parts = torch.empty((sq, nq, d), dtype=torch.float32, device=q.device)
+    dq_parts = torch.empty((sq, nq, d), dtype=torch.float32, device=q.device) if want_dq else None
     dc_parts = torch.empty((sc, nc, d), dtype=torch.float32, device=q.device)
     check(_lib.load().tt_retrieval_loss_bwd_parts(TT_BF16, _ptr(q, torch.bfloat16), _ptr(c, torch.bfloat16), nq, nc, d,
                                                   inv_temperature, label_offset, _ptr(sample_weight, torch.float32),
                                                   _ptr(cand_log_q, torch.float32), _ptr(cand_ids, torch.int64),
                                                   _ptr(row_lse, torch.float32), grad_scale, _ptr(dq_parts), _ptr(dc_parts),
                                                   _stream()))
-    _count(2)
+    _count(2 if want_dq else 1)
     return dq_parts, dc_parts
 
 

@@ -377,12 +377,23 @@ def global_retrieval(task, q: Tensor, c: Tensor, inv_t: float, w, logq, ids, pri
     label_offset = coll.rank * nq
     logq_all = None if logq is None else coll.all_gather(logq)
     ids_all = None if ids is None else coll.all_gather(ids)
-    loss, lse, _pos = prim.retrieval_loss_fwd(prec, qm, c_all, inv_t, label_offset, w, logq_all, ids_all)
+    fused = (prec == "bf16" and prim is _cuda_ops and GradientTape.current() is not None and logq_all is None
+             and ids_all is None and ("parts" in q.grad_formats or "parts" in c.grad_formats)
+             and prim.retrieval_fwd_dq_supported(nq, c_all.shape[0], qm.shape[1]))
+    if fused:            # the forward pass also accumulates dQ: the backward is the dC pass only
+        loss, lse, _pos, dq_fused, _fwd_ws = prim.retrieval_loss_fwd_dq(qm, c_all, inv_t, label_offset, w)
+    else:
+        loss, lse, _pos = prim.retrieval_loss_fwd(prec, qm, c_all, inv_t, label_offset, w, logq_all, ids_all)
 
     def backward():
         bf = prec == "bf16"
         if bf and prim is _cuda_ops and ("parts" in q.grad_formats or "parts" in c.grad_formats):
-            dq_parts, dc_parts = prim.retrieval_loss_bwd_parts(qm, c_all, inv_t, lse, label_offset, w, logq_all, ids_all, 1.0)
+            if fused:
+                _none, dc_parts = prim.retrieval_loss_bwd_parts(qm, c_all, inv_t, lse, label_offset, w, None, None, 1.0,
+                                                                want_dq=False)
+                dq_parts = dq_fused.reshape(1, *dq_fused.shape)
+            else:
+                dq_parts, dc_parts = prim.retrieval_loss_bwd_parts(qm, c_all, inv_t, lse, label_offset, w, logq_all, ids_all, 1.0)
             if "parts" in q.grad_formats:
                 q.grad = dict(parts=dq_parts)
             else:

@@ -80,10 +80,31 @@ class Retrieval:
             qm, cm = q.f32, c.f32
         else:
             qm, cm = q.bf16, c.bf16
-        loss, lse, _pos = ops.retrieval_loss_fwd(prec, qm, cm, inv_t, 0, w, logq, ids)
+        # bf16 training step: the forward also accumulates dQ (one exponential and one S GEMM fewer per logit)
+        fused = (prec == "bf16" and GradientTape.current() is not None and logq is None and ids is None
+                 and ops.retrieval_fwd_dq_supported(nq, cm.shape[0], qm.shape[1]))
+        if fused:
+            loss, lse, _pos, dq_fused, _fwd_ws = ops.retrieval_loss_fwd_dq(qm, cm, inv_t, 0, w)
+        else:
+            loss, lse, _pos = ops.retrieval_loss_fwd(prec, qm, cm, inv_t, 0, w, logq, ids)
 
         def backward():
             bf = prec == "bf16"
+            if fused:
+                # (forking the fold next to a dC pass that reads the partials itself -- retrieval_loss_fwd_dq(fork=True)
+                # + retrieval_loss_bwd_dc_fused -- measured SLOWER on B200: 187 vs 164 us per cfg2 step; the fold's
+                # blocks and the per-tile lse recomputation take issue slots from the softmax warps)
+                _none, dc_parts = ops.retrieval_loss_bwd_parts(qm, cm, inv_t, lse, 0, w, None, None, 1.0, want_dq=False)
+                if "parts" in q.grad_formats:
+                    q.grad = dict(parts=dq_fused.reshape(1, *dq_fused.shape))
+                else:
+                    q.grad = dict(f32=dq_fused, bf16=ops.cast_f32_to_bf16(dq_fused) if "bf16" in q.grad_formats else None)
+                if "parts" in c.grad_formats:
+                    c.grad = dict(parts=dc_parts)
+                else:
+                    f, b = ops.combine_parts(dc_parts, True, "bf16" in c.grad_formats)
+                    c.grad = dict(f32=f, bf16=b)
+                return
             if bf and ("parts" in q.grad_formats or "parts" in c.grad_formats):
                 # the consumer (fused tower backward) folds the split partials itself
                 dq_parts, dc_parts = ops.retrieval_loss_bwd_parts(qm, cm, inv_t, lse, 0, w, logq, ids, 1.0)
