@@ -342,9 +342,10 @@ int tt_retrieval_loss_bwd(int32_t precision, const void* q, const void* c, int64
  * tt_retrieval_loss_fwd plus dq fp32 [nq, d].  The workspace (tt_retrieval_fwd_dq_workspace_bytes; 0 = shape not
  * supported) must be zero in its first 256 bytes before the first call; the call leaves it so.
  * finalize_stream (nullable): the fold of the partials into row_lse / loss / dq is forked onto that stream (event
- * record + wait inside the call; the CALLER joins it back before reading those outputs).  It then overlaps
- * tt_retrieval_loss_bwd_dc_fused, the dC pass that takes the row maxima / sums straight from this workspace
- * (dc_parts as in tt_retrieval_loss_bwd_parts) instead of row_lse. */
+ * record + wait inside the call; the CALLER joins it back before reading those outputs or the workspace).
+ * tt_retrieval_loss_bwd_dc_fused: the dC pass for this forward when there are no sample weights (must be NULL).  It
+ * reads -lse per query column (log2 domain, written into the workspace by the fold) with broadcast loads instead of
+ * staging row_lse through shared memory; dc_parts as in tt_retrieval_loss_bwd_parts. */
 int64_t tt_retrieval_fwd_dq_workspace_bytes(int64_t nq, int64_t nc, int64_t d);
 int tt_retrieval_loss_fwd_dq(const void* q, const void* c, int64_t nq, int64_t nc, int64_t d,
                              float inv_temperature, int64_t label_offset, const float* sample_weight,

@@ -105,9 +105,10 @@ class TestRetrievalTensorCore:
         # forward + dQ in one pass (flash-attention forward shape) and the dC-only backward that goes with it
         if logq is None and ids_d is None and ops.retrieval_fwd_dq_supported(nq, c.shape[0], q.shape[1]):
             loss2, lse2, pos2, dq2, fws = ops.retrieval_loss_fwd_dq(qb, cb, inv_t, label_offset, w_d, fork=True)
-            dc_f = ops.retrieval_loss_bwd_dc_fused(qb, cb, inv_t, fws, label_offset, w_d, 1.0)   # beside the forked fold
             ops.join_side_work()
-            assert rel_err(dc_f.sum(0).cpu().numpy(), dc_ref) < BF16_RTOL
+            if w_d is None:                                   # dC pass fed by the fold's -lse2 array (broadcast loads)
+                dc_f = ops.retrieval_loss_bwd_dc_fused(qb, cb, inv_t, fws, label_offset, None, 1.0)
+                assert rel_err(dc_f.sum(0).cpu().numpy(), dc_ref) < BF16_RTOL
             assert float(loss2.item()) == pytest.approx(r["loss"], rel=2e-4)
             assert rel_err(lse2.cpu().numpy(), r["lse"]) < 2e-4 and rel_err(pos2.cpu().numpy(), r["pos"]) < 2e-4
             assert rel_err(dq2.cpu().numpy(), r["dq"]) < BF16_RTOL

@@ -142,8 +142,9 @@ struct RetrievalTcArgs {
   const float* logq;              // log(clip(p)) per candidate [nc] or null
   const long long* cand_ids;      // [nc] or null (accidental-hit removal)
   const float* lse;               // [nq] natural-log lse (backward)
-  const float2* ml_parts;         // backward after the one-pass forward + dQ: its [ml_nparts][nq] (max2, sum) partials;
-  int ml_nparts;                  //   the dC kernel folds them into the column lse itself (lse may be null then)
+  const float* nlse2;             // dC pass, optional: [nq] -lse in the log2 domain (written by the fold kernel).  With it (and
+                                  //   no weights / extras) the per-column terms are read straight from L1 (broadcast loads):
+                                  //   no shared-memory staging, no warpgroup barriers in the tile loop
   float2* partial_ml;             // forward: [splits][nq] (max2, sum)
   float* row_pos;                 // forward: [nq]
   float* row_lse_out;             // forward: [nq] natural-log lse, written by the last CTA of each row block
@@ -460,7 +461,7 @@ __host__ __device__ inline BwdLayout bwd_layout(int d, int BN, int tail_bytes) {
   return L;
 }
 
-template <int BN, bool TRANSPOSED, bool EXTRAS>
+template <int BN, bool TRANSPOSED, bool EXTRAS, bool DIRECT = false>
 __global__ void __launch_bounds__(RT_THREADS, 1)
 retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                         const __grid_constant__ CUtensorMap tmP, const RetrievalTcArgs a) {
@@ -601,29 +602,17 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         if (EXTRAS && a.cand_ids) row_id = a.cand_ids[xi];
       }
     }
-    const bool col_weighted = TRANSPOSED && a.w != nullptr;
+    const bool col_weighted = TRANSPOSED && !DIRECT && a.w != nullptr;
     // per-column terms of a streamed tile (dC: -lse2 and weight of the query columns; EXTRAS: logq / ids),
     // one column per thread of the warpgroup.  They are fetched one tile AHEAD into registers so that the
     // global-load latency hides behind the previous tile's exponentials instead of heading every tile.
     float nx_a = 0.f, nx_w = 1.f;
     long long nx_id = -2;
     auto fetch_cols = [&](int t) {
-      if ((TRANSPOSED || EXTRAS) && t < T && wg_tid < BN) {
+      if ((TRANSPOSED || EXTRAS) && !DIRECT && t < T && wg_tid < BN) {
         const long long yi = (long long)(tile_begin + t) * BN + wg_tid;
         if (TRANSPOSED) {
-          if (a.ml_parts) {                            // lse2 of query column yi from the forward's partials
-            float M = -INFINITY, Ls = 0.f;
-            if (yi < a.nq) {
-              for (int s = 0; s < a.ml_nparts; ++s) M = fmaxf(M, a.ml_parts[(size_t)s * a.nq + yi].x);
-              for (int s = 0; s < a.ml_nparts; ++s) {
-                const float2 pm = a.ml_parts[(size_t)s * a.nq + yi];
-                if (pm.x > -INFINITY) Ls += pm.y * exp2f(pm.x - M);
-              }
-            }
-            nx_a = yi < a.nq ? -(M + log2f(Ls)) : 0.f;
-          } else {
-            nx_a = yi < a.nq ? -a.lse[yi] * kLog2e : 0.f;
-          }
+          nx_a = yi < a.nq ? -a.lse[yi] * kLog2e : 0.f;
           nx_w = (a.w && yi < a.nq) ? a.w[yi] : 1.f;
           if (EXTRAS) nx_id = (a.cand_ids && yi < a.nq) ? a.cand_ids[a.label_offset + yi] : -2;
         } else {
@@ -636,7 +625,7 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     for (int t = g; t < T; t += 2) {
       const int b = t & 1;
       const long long y_tile = (long long)(tile_begin + t) * BN;
-      if (TRANSPOSED || EXTRAS) {
+      if ((TRANSPOSED || EXTRAS) && !DIRECT) {
         asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");     // everyone is done reading tile t-2's terms
         if (wg_tid < BN) {
           col_a[b * BN + wg_tid] = nx_a;
@@ -671,7 +660,13 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
 #pragma unroll
           for (int j = 0; j < 32; j += 16) {
             uint64_t ad[8] = {NL, NL, NL, NL, NL, NL, NL, NL};
-            if (TRANSPOSED) {                        // col_a holds -lse2 of the query columns
+            if (TRANSPOSED && DIRECT) {              // -lse2 of the query columns, broadcast loads (L1-resident 512 B per tile)
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const ulonglong2 l2 = __ldg(reinterpret_cast<const ulonglong2*>(a.nlse2 + y_tile + c0 + j + 4 * u));
+                ad[2 * u] = l2.x; ad[2 * u + 1] = l2.y;
+              }
+            } else if (TRANSPOSED) {                 // col_a holds -lse2 of the query columns
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
                 const ulonglong2 l2 = *reinterpret_cast<const ulonglong2*>(col_a + b * BN + c0 + j + 4 * u);
@@ -1097,6 +1092,7 @@ struct DqFinalizeArgs {
   const float* w;                  // [nq] or null
   const float* row_pos;            // [nq]
   float* row_lse;                  // [nq]
+  float* nlse2;                    // [round_up(nq, 128)] -lse in the log2 domain for the dC pass (pad = 0)
   float* dq;                       // [nq][d]
   float* block_loss;               // [gridDim.x]
   int* ticket;                     // zero before and after
@@ -1136,8 +1132,9 @@ __global__ void __launch_bounds__(256) retrieval_dq_finalize_kernel(const DqFina
       f[s] = pm[s].x > -INFINITY ? exp2f(pm[s].x - M) : 0.f;
       Ls += pm[s].y * f[s];
     }
-    const float lse = (M + log2f(Ls)) * kLn2;
-    if (lane == 0) a.row_lse[i] = lse;
+    const float lse2 = M + log2f(Ls);
+    const float lse = lse2 * kLn2;
+    if (lane == 0) { a.row_lse[i] = lse; a.nlse2[i] = -lse2; }
     term = wgt * (lse - pos);
     if (col) {
       const float scale = wgt * a.inv_temp, invL = 1.f / Ls;
@@ -1151,6 +1148,9 @@ __global__ void __launch_bounds__(256) retrieval_dq_finalize_kernel(const DqFina
       acc.z -= __uint_as_float(cb.y << 16); acc.w -= __uint_as_float(cb.y & 0xffff0000u);
       *reinterpret_cast<float4*>(a.dq + (size_t)i * a.d + c0) = make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale);
     }
+  }
+  if (blockIdx.x == 0) {                           // finite padding for the ragged last tile of the dC pass
+    for (int j = a.nq + threadIdx.x; j < (a.nq + 127) / 128 * 128; j += 256) a.nlse2[j] = 0.f;
   }
   __shared__ float s_red[256];
   __shared__ int s_last;
@@ -1311,7 +1311,11 @@ static int launch_bwd(const void* x, const void* y, int64_t nX, int64_t nY, Retr
     TT_PROF("retrieval_bwd_tc_kernel", st);                                                                   \
     TT_CUDA_OK(launch_pdl(retrieval_bwd_tc_kernel<BN, TRANSPOSED, EX>, grid, dim3(RT_THREADS), (size_t)L.total, st, tmX, tmY, tmP, a)); \
   }
-  if (extras) TT_BWD_LAUNCH(true) else TT_BWD_LAUNCH(false)
+  if (TRANSPOSED && !extras && a.nlse2 && !a.w) {
+    TT_CUDA_OK(cudaFuncSetAttribute(retrieval_bwd_tc_kernel<BN, TRANSPOSED, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    TT_PROF("retrieval_bwd_tc_kernel", st);
+    TT_CUDA_OK(launch_pdl(retrieval_bwd_tc_kernel<BN, TRANSPOSED, false, true>, grid, dim3(RT_THREADS), (size_t)L.total, st, tmX, tmY, tmP, a));
+  } else if (extras) TT_BWD_LAUNCH(true) else TT_BWD_LAUNCH(false)
 #undef TT_BWD_LAUNCH
   TT_LAUNCH_OK("retrieval_bwd_tc_kernel");
   return TT_OK;
@@ -1319,7 +1323,7 @@ static int launch_bwd(const void* x, const void* y, int64_t nX, int64_t nY, Retr
 
 // ---- forward + dQ --------------------------------------------------------------------------------------
 static bool fused_supported(int64_t d) { return d % 64 == 0 && d >= 64 && d <= 128; }
-struct FusedPlan { int splits, tps, parts; int64_t off_bl, off_ml, off_o, total, blocks; };
+struct FusedPlan { int splits, tps, parts; int64_t off_bl, off_nl, off_ml, off_o, total, blocks; };
 static FusedPlan fused_plan(int64_t nq, int64_t nc, int64_t d) {
   FusedPlan p;
   split_plan(nq, nc, 128, &p.splits, &p.tps);
@@ -1331,7 +1335,8 @@ static FusedPlan fused_plan(int64_t nq, int64_t nc, int64_t d) {
   p.parts = 2 * p.splits;
   p.blocks = ceil_div(nq, 8);
   p.off_bl = 256;
-  p.off_ml = p.off_bl + round_up(p.blocks * 4, 256);
+  p.off_nl = p.off_bl + round_up(p.blocks * 4, 256);                  // -lse2 per query, padded to whole 128-row tiles
+  p.off_ml = p.off_nl + round_up(round_up(nq, 128) * 4, 256);
   p.off_o = p.off_ml + round_up((int64_t)p.parts * nq * 8, 256);
   p.total = p.off_o + round_up((int64_t)p.parts * nq * d * 4, 256);
   return p;
@@ -1375,6 +1380,7 @@ int tc_retrieval_fwd_dq(const void* q, const void* c, int64_t nq, int64_t nc, in
   DqFinalizeArgs f{};
   f.nq = (int)nq; f.d = (int)d; f.parts = plan.parts; f.inv_temp = inv_temp; f.label_offset = label_offset;
   f.ml = a.partial_ml; f.o_parts = o_parts; f.c = (const uint16_t*)c; f.w = w; f.row_pos = row_pos; f.row_lse = row_lse;
+  f.nlse2 = (float*)((char*)ws + plan.off_nl);
   f.dq = dq; f.block_loss = (float*)((char*)ws + plan.off_bl); f.ticket = (int*)ws; f.loss_out = loss;
   if (fin_st && fin_st != st) {
     // fork: the fold runs on its own stream, next to the dC pass (which reads the partial maxima itself)
@@ -1391,7 +1397,8 @@ int tc_retrieval_fwd_dq(const void* q, const void* c, int64_t nq, int64_t nc, in
   return TT_OK;
 }
 
-// dC pass right after the one-pass forward + dQ: column lse from the forward's partials in its workspace
+// dC pass right after the one-pass forward + dQ: -lse2 per query column straight from the fold kernel's array in the
+// forward's workspace (broadcast loads, no staging)
 int tc_retrieval_bwd_dc_fused(const void* q, const void* c, int64_t nq, int64_t nc, int64_t d, float inv_temp,
                               int64_t label_offset, const float* w, const void* fwd_ws, float grad_scale, float* part_c,
                               cudaStream_t st) {
@@ -1403,7 +1410,8 @@ int tc_retrieval_bwd_dc_fused(const void* q, const void* c, int64_t nq, int64_t 
   a.nq = (int)nq; a.nc = (int)nc; a.d = (int)d;
   a.k2 = inv_temp * kLog2e; a.out_scale = inv_temp * grad_scale;
   a.label_offset = label_offset; a.w = w;
-  a.ml_parts = (const float2*)((const char*)fwd_ws + fp.off_ml); a.ml_nparts = fp.parts;
+  a.nlse2 = (const float*)((const char*)fwd_ws + fp.off_nl);
+  TT_REQUIRE(!w, "tt_retrieval_loss_bwd_dc_fused: sample weights need tt_retrieval_loss_bwd_parts");
   const WsPlan plan = ws_plan(nq, nc, d);
   int sc = 1;
   rc = launch_bwd<128, true>(c, q, nc, nq, a, part_c, &sc, st);

@@ -91,9 +91,10 @@ class Retrieval:
         def backward():
             bf = prec == "bf16"
             if fused:
-                # (forking the fold next to a dC pass that reads the partials itself -- retrieval_loss_fwd_dq(fork=True)
-                # + retrieval_loss_bwd_dc_fused -- measured SLOWER on B200: 187 vs 164 us per cfg2 step; the fold's
-                # blocks and the per-tile lse recomputation take issue slots from the softmax warps)
+                # Two alternatives were built and measured SLOWER on B200 (cfg2 step, 163 us with this form):
+                # forking the fold onto a side stream next to the dC pass (187 us: its blocks take issue slots from the
+                # softmax warps) and feeding the dC pass -lse2 by broadcast global loads instead of the shared-memory
+                # staging (retrieval_loss_bwd_dc_fused, 173 us).
                 _none, dc_parts = ops.retrieval_loss_bwd_parts(qm, cm, inv_t, lse, 0, w, None, None, 1.0, want_dq=False)
                 if "parts" in q.grad_formats:
                     q.grad = dict(parts=dq_fused.reshape(1, *dq_fused.shape))
