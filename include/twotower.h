@@ -445,6 +445,18 @@ int tt_peer_sum_f32(const void* bases, int64_t offset_bytes, int64_t stride_byte
                     const void* flag_bases, void* step_counter, int32_t world, int32_t rank, int32_t slot, void* stream);
 int tt_peer_combine_scatter(const void* bases, const float* parts, int32_t splits, int64_t rows, int64_t d,
                             int64_t rows_per_rank, int64_t dst_offset, int32_t world, int32_t rank, void* stream);
+/* The reduce-scatter of dC fused into the dC pass (no combine kernel): `peer_maps` is a DEVICE array [world] of
+ * 128-byte tensor maps, 64-byte aligned, built on the host by tt_peer_make_row_maps over every rank's
+ * [world * b, d] fp32 receive area (peer-mapped addresses) and copied to the device once.  The kernel's epilogue
+ * TMA-stores each 128-row block of dC into slot [rank] of the rank that owns those candidates while other CTAs still
+ * compute.  Needs b = nc / world a multiple of 128, d <= 128, no log-q / accidental-hit terms, and an unsplit dC pass
+ * (more 128-row blocks of candidates than half the SMs; else error -> use tt_retrieval_loss_bwd_parts + tt_peer_combine_scatter).  `scratch`: fp32
+ * [nc, d] caller-owned (only used for ragged blocks, i.e. never when the conditions hold). */
+int tt_peer_make_row_maps(const uint64_t* peer_addrs, int32_t world, int64_t rows, int64_t d, void* out_host);
+int tt_peer_retrieval_bwd_dc(const void* q, const void* c, int64_t nq, int64_t nc, int64_t d, float inv_temperature,
+                             int64_t label_offset, const float* sample_weight, const float* row_lse,
+                             float grad_scale, const void* peer_maps, int32_t world, int32_t rank,
+                             float* scratch, void* stream);
 int tt_peer_push_rows(const void* bases, int32_t ntab, const int64_t* const* ids, const float* const* src,
                       const int64_t* dst_offset, int64_t b, int64_t d, int32_t world, int32_t rank, void* stream);
 int tt_peer_pull_rows(const void* bases, int32_t ntab, const int64_t* const* ids, const int64_t* src_offset,

@@ -123,3 +123,60 @@ def test_sharded_two_tower_matches_global_batch_oracle(precision, peer, dim, mlp
     mp.spawn(_worker, args=(_free_port(), precision, peer, dim, mlp, results), nprocs=WORLD, join=True)
     for r in range(WORLD):
         assert results.get(r) == "ok", results.get(r)
+
+
+def _worker_direct(rank, port, results):
+    """The dC pass that scatters its row blocks straight into the owners' slots (TMA stores to peer memory) against the
+    combine + scatter kernel: same arithmetic, so losses and shards must be IDENTICAL.  Needs an unsplit dC pass:
+    world * b >= 128 * #SMs."""
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=WORLD, device_id=torch.device("cuda", rank))
+    try:
+        import two_tower_b200 as tt
+        from two_tower_b200 import parallel, synth
+        tt.set_precision("bf16")
+        sms = torch.cuda.get_device_properties(rank).multi_processor_count
+        b = -(-64 * sms // 128) * 128                                       # 2 * b >= 128 * SMs, multiple of 128
+        cfg = synth.Config("big", 78, b, 128, 40001, 30011, (256, 128), 0.2)
+        out = {}
+        for mode in ("1", "0"):
+            os.environ["TT_DC_DIRECT"] = mode
+            tt.core.config.seed = 1234
+            torch.manual_seed(7)
+            model = parallel.build_sharded_two_tower(cfg, dist.group.WORLD, lr=0.05, peer="exchange")
+            model.test_step(synth.make_batch(cfg, 10 + rank))
+            for ti, seq in enumerate((model.user_model, model.item_model)):
+                for li, l in enumerate(seq.layers[1:]):
+                    for vi, v in enumerate((l.kernel, l.bias)):
+                        g = torch.Generator(device="cuda"); g.manual_seed(100 * ti + 10 * li + vi)
+                        v.value.copy_(torch.randn(v.value.shape, device="cuda", generator=g) * 0.05)
+                        v.refresh_shadows()
+            losses = [float(model.train_step(synth.make_batch(cfg, 100 + 10 * s + rank))["loss"].item()) for s in range(3)]
+            assert (model.exchange.dc_maps is not None) == (mode == "1")
+            out[mode] = (losses, model.item_model.layers[0].embeddings.value.clone(), model.item_model.layers[1].kernel.value.clone())
+        assert out["1"][0] == out["0"][0], (out["1"][0], out["0"][0])
+        assert torch.equal(out["1"][1], out["0"][1]) and torch.equal(out["1"][2], out["0"][2])
+        assert all(np.isfinite(x) for x in out["1"][0])
+        results[rank] = "ok"
+    except Exception:
+        import traceback
+        results[rank] = traceback.format_exc()
+    finally:
+        os.environ.pop("TT_DC_DIRECT", None)
+        dist.destroy_process_group()
+
+
+def test_dc_pass_scattering_into_owner_slots_is_identical_to_combine_scatter():
+    if os.environ.get("TT_TEST_DC_DIRECT") != "1":
+        pytest.skip("experimental path (TT_DC_DIRECT=1), not enabled by default: set TT_TEST_DC_DIRECT=1 to run")
+    if torch.cuda.device_count() < WORLD:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker_direct, args=(_free_port(), results), nprocs=WORLD, join=True)
+    for r in range(WORLD):
+        assert results.get(r) == "ok", results.get(r)

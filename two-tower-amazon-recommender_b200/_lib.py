@@ -117,6 +117,8 @@ SIGNATURES = {
     "tt_peer_push": (C.c_int, [_p, _i32, _i32, C.POINTER(_p), C.POINTER(_i64), C.POINTER(_i64), _p]),
     "tt_peer_sum_f32": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _i32, _i32, _i32, _p]),
     "tt_peer_combine_scatter": (C.c_int, [_p, _p, _i32, _i64, _i64, _i64, _i64, _i32, _i32, _p]),
+    "tt_peer_make_row_maps": (C.c_int, [C.POINTER(C.c_uint64), _i32, _i64, _i64, _p]),
+    "tt_peer_retrieval_bwd_dc": (C.c_int, [_p, _p, _i64, _i64, _i64, _f, _i64, _p, _p, _f, _p, _i32, _i32, _p, _p]),
     "tt_peer_push_rows": (C.c_int, [_p, _i32, C.POINTER(_p), C.POINTER(_p), C.POINTER(_i64), _i64, _i64, _i32, _i32, _p]),
     "tt_peer_pull_rows": (C.c_int, [_p, _i32, C.POINTER(_p), C.POINTER(_i64), C.POINTER(_p), _i64, _i64, _p, _p,
                                     _i32, _i32, _i32, _p]),

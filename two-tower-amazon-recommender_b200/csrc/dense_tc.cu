@@ -253,6 +253,17 @@ int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_
   return make_tmap_2d(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, inner, outer, row_stride_bytes, box_inner, box_outer);
 }
 
+// fp32 map from a raw (possibly peer-mapped) address into a 128-byte host buffer (tt_peer_make_row_maps)
+int make_tmap_f32_2d_raw(void* out128, uint64_t base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                         uint32_t box_inner, uint32_t box_outer) {
+  static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
+  CUtensorMap m;
+  int rc = make_tmap_f32_2d(&m, reinterpret_cast<const void*>(static_cast<uintptr_t>(base)), inner, outer, row_stride_bytes, box_inner, box_outer);
+  if (rc) return rc;
+  memcpy(out128, &m, sizeof(m));
+  return TT_OK;
+}
+
 // D[M,N] = A * B^T-or-B (+ epilogue); splits over K write out_f32[z].
 // a_mn == 0: A is [M, K] row-major; a_mn == 1: A is [K, M] row-major (M contiguous).
 // b_mn == 0: B is [N, K] row-major; b_mn == 1: B is [K, N] row-major (N contiguous).

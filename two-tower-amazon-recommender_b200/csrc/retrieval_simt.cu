@@ -30,6 +30,11 @@ int64_t tc_retrieval_fwd_dq_workspace_bytes(int64_t nq, int64_t nc, int64_t d);
 int tc_retrieval_fwd_dq(const void* q, const void* c, int64_t nq, int64_t nc, int64_t d, float inv_temp,
                         int64_t label_offset, const float* w, float* row_lse, float* row_pos, float* loss, float* dq,
                         void* ws, int64_t ws_bytes, cudaStream_t st, cudaStream_t fin_st);
+int tc_retrieval_bwd_dc_scatter(const void* q, const void* c, int64_t nq, int64_t nc, int64_t d, float inv_temp,
+                                int64_t label_offset, const float* w, const float* row_lse, float grad_scale,
+                                const void* peer_maps, int world, int rank, float* local_part, cudaStream_t st);
+int make_tmap_f32_2d_raw(void* out128, uint64_t base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                         uint32_t box_inner, uint32_t box_outer);
 int tc_retrieval_bwd_dc_fused(const void* q, const void* c, int64_t nq, int64_t nc, int64_t d, float inv_temp,
                               int64_t label_offset, const float* w, const void* fwd_ws, float grad_scale, float* part_c,
                               cudaStream_t st);
@@ -362,6 +367,27 @@ extern "C" int tt_retrieval_loss_bwd_dc_fused(const void* q, const void* c, int6
   if (rc) return rc;
   return tc_retrieval_bwd_dc_fused(q, c, nq, nc, d, inv_temperature, label_offset, sample_weight, fwd_dq_workspace,
                                    grad_scale, dc_parts, (cudaStream_t)stream);
+}
+
+extern "C" int tt_peer_make_row_maps(const uint64_t* peer_addrs, int32_t world, int64_t rows, int64_t d, void* out_host) {
+  TT_REQUIRE(peer_addrs && out_host && world >= 1 && world <= 16 && rows > 0 && d > 0 && d % 32 == 0,
+             "tt_peer_make_row_maps: bad arguments (d must be a multiple of 32)");
+  for (int r = 0; r < world; ++r) {
+    TT_REQUIRE(peer_addrs[r] && (peer_addrs[r] & 15u) == 0, "tt_peer_make_row_maps: address %d null / unaligned", r);
+    int rc = make_tmap_f32_2d_raw((char*)out_host + 128 * r, peer_addrs[r], (uint64_t)d, (uint64_t)rows, (uint64_t)d * 4, 32, 32);
+    if (rc) return rc;
+  }
+  return TT_OK;
+}
+
+extern "C" int tt_peer_retrieval_bwd_dc(const void* q, const void* c, int64_t nq, int64_t nc, int64_t d, float inv_temperature,
+                                        int64_t label_offset, const float* sample_weight, const float* row_lse,
+                                        float grad_scale, const void* peer_maps, int32_t world, int32_t rank,
+                                        float* scratch, void* stream) {
+  int rc = check_retrieval_common("tt_peer_retrieval_bwd_dc", TT_BF16, q, c, nq, nc, d, label_offset);
+  if (rc) return rc;
+  return tc_retrieval_bwd_dc_scatter(q, c, nq, nc, d, inv_temperature, label_offset, sample_weight, row_lse, grad_scale,
+                                     peer_maps, world, rank, scratch, (cudaStream_t)stream);
 }
 
 extern "C" int tt_combine_parts_f32(const float* parts, int32_t num_parts, int64_t rows, int64_t d, float* out_f32,

@@ -142,6 +142,8 @@ struct RetrievalTcArgs {
   const float* logq;              // log(clip(p)) per candidate [nc] or null
   const long long* cand_ids;      // [nc] or null (accidental-hit removal)
   const float* lse;               // [nq] natural-log lse (backward)
+  const CUtensorMap* scatter_maps; // dC pass over NVLink (tt_peer_retrieval_bwd_dc): device array [world] of tensor maps over
+  int scatter_rank, scatter_b;     //   every rank's [world * b, d] fp32 receive area; row block x0 goes to owner x0 / b, slot rank
   const float* nlse2;             // dC pass, optional: [nq] -lse in the log2 domain (written by the fold kernel).  With it (and
                                   //   no weights / extras) the per-column terms are read straight from L1 (broadcast loads):
                                   //   no shared-memory staging, no warpgroup barriers in the tile loop
@@ -772,7 +774,14 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&tmP, st, c0, (int)(blockIdx.y * nX + x0 + qd * 32));
+          if (TRANSPOSED && a.scatter_maps) {
+            // reduce-scatter, producer side: this row block of dC belongs to rank x0 / b -- the copy engine writes it
+            // straight into slot [my rank] of the owner's receive area over NVLink while other CTAs still compute
+            const int owner = x0 / a.scatter_b;
+            tma_store_2d(a.scatter_maps + owner, st, c0, a.scatter_rank * a.scatter_b + (x0 - owner * a.scatter_b) + qd * 32);
+          } else {
+            tma_store_2d(&tmP, st, c0, (int)(blockIdx.y * nX + x0 + qd * 32));
+          }
           tma_store_commit();
         }
       }
@@ -1395,6 +1404,29 @@ int tc_retrieval_fwd_dq(const void* q, const void* c, int64_t nq, int64_t nc, in
   TT_CUDA_OK(launch_pdl(retrieval_dq_finalize_kernel, dim3((unsigned)plan.blocks), dim3(256), (size_t)0, fin_st, f));
   TT_LAUNCH_OK("retrieval_dq_finalize_kernel");
   return TT_OK;
+}
+
+// dC pass whose epilogue scatters every 128-row block of dC to the rank that owns those candidates (slot [rank] of the
+// owner's [world, b, d] fp32 receive area, through the peer tensor maps): the reduce-scatter without a kernel of its own
+int tc_retrieval_bwd_dc_scatter(const void* q, const void* c, int64_t nq, int64_t nc, int64_t d, float inv_temp,
+                                int64_t label_offset, const float* w, const float* row_lse, float grad_scale,
+                                const void* peer_maps, int world, int rank, float* local_part, cudaStream_t st) {
+  int rc = check_tc_dims("tt_peer_retrieval_bwd_dc", nq, nc, d);
+  if (rc) return rc;
+  TT_REQUIRE(peer_maps && (reinterpret_cast<uintptr_t>(peer_maps) & 63u) == 0 && world >= 1 && rank >= 0 && rank < world,
+             "tt_peer_retrieval_bwd_dc: peer maps null / not 64-byte aligned, or bad world / rank");
+  TT_REQUIRE(nc % world == 0 && (nc / world) % RT_BM == 0 && d <= 128, "tt_peer_retrieval_bwd_dc: candidates per rank must be a multiple of 128 (d <= 128)");
+  TT_REQUIRE(row_lse && local_part && aligned16(local_part), "tt_peer_retrieval_bwd_dc: null row_lse / scratch");
+  int splits, tps;
+  split_plan(nc, nq, 128, &splits, &tps);
+  TT_REQUIRE(splits == 1, "tt_peer_retrieval_bwd_dc: needs an unsplit dC pass (got %d splits); use tt_peer_combine_scatter", splits);
+  RetrievalTcArgs a{};
+  a.nq = (int)nq; a.nc = (int)nc; a.d = (int)d;
+  a.k2 = inv_temp * kLog2e; a.out_scale = inv_temp * grad_scale;
+  a.label_offset = label_offset; a.w = w; a.lse = row_lse;
+  a.scatter_maps = (const CUtensorMap*)peer_maps; a.scatter_rank = rank; a.scatter_b = (int)(nc / world);
+  int sc = 1;
+  return launch_bwd<128, true>(c, q, nc, nq, a, local_part, &sc, st);
 }
 
 // dC pass right after the one-pass forward + dQ: -lse2 per query column straight from the fold kernel's array in the

@@ -799,3 +799,29 @@ def peer_push_rows(ws: PeerWorkspace, tables, b: int, d: int) -> None:
     off = (C.c_int64 * n)(*[int(o) for _, _, o in tables])
     check(_lib.load().tt_peer_push_rows(_ptr(ws.bases, torch.int64), n, ids, src, off, int(b), int(d), ws.world, ws.rank, _stream()))
     _count(1)
+
+
+def peer_row_maps(peer_addrs, rows: int, d: int, device) -> torch.Tensor:
+    """Device array [world] of TMA tensor maps over every rank's [rows, d] fp32 area (peer-mapped addresses)."""
+    n = len(peer_addrs)
+    addrs = (C.c_uint64 * n)(*[int(a) for a in peer_addrs])
+    host = torch.zeros(n * 128, dtype=torch.uint8)
+    check(_lib.load().tt_peer_make_row_maps(addrs, n, int(rows), int(d), host.data_ptr()))
+    dev = torch.empty(n * 128 + 64, dtype=torch.uint8, device=device)
+    off = (-dev.data_ptr()) % 64                      # tensor maps must be 64-byte aligned
+    out = dev[off:off + n * 128]
+    out.copy_(host)
+    torch.cuda.synchronize()
+    return out
+
+
+def peer_retrieval_bwd_dc(ws: PeerWorkspace, maps: torch.Tensor, q, c, inv_temperature: float, row_lse, label_offset: int,
+                          sample_weight, scratch: torch.Tensor) -> None:
+    """The dC pass with the reduce-scatter in its epilogue: every 128-row block of dC is TMA-stored into slot [rank] of
+    the receive area of the rank owning those candidates."""
+    nq, d = q.shape
+    nc = c.shape[0]
+    check(_lib.load().tt_peer_retrieval_bwd_dc(_ptr(q, torch.bfloat16), _ptr(c, torch.bfloat16), nq, nc, d, inv_temperature,
+                                               label_offset, _ptr(sample_weight, torch.float32), _ptr(row_lse, torch.float32),
+                                               1.0, _ptr(maps), ws.world, ws.rank, _ptr(scratch, torch.float32), _stream()))
+    _count(1)

@@ -214,6 +214,15 @@ class PeerExchange:
         self.bucket_local = torch.empty((self.BUCKET_FLOATS,), dtype=torch.float32, device=dev)
         self.bucket_sum = torch.empty((self.BUCKET_FLOATS,), dtype=torch.float32, device=dev)
         self.loss4 = torch.zeros(4, dtype=torch.float32, device=dev)
+        # EXPERIMENTAL, off unless TT_DC_DIRECT=1: tensor maps over every rank's dC receive area so that the dC kernel's
+        # epilogue TMA-stores straight into the owners' slots (no combine + scatter kernel).  It ran eagerly at N=2 but a
+        # CUDA-graph replay of the step faulted ("unspecified launch failure"); cause not found in round 1.
+        self.dc_maps = None
+        import os
+        if (os.environ.get("TT_DC_DIRECT", "0") == "1" and b % 128 == 0 and d_out <= 128 and d_out % 32 == 0
+                and 2 * (bg // 128) > torch.cuda.get_device_properties(dev).multi_processor_count):   # unsplit dC pass
+            self.dc_maps = _cuda_ops.peer_row_maps([int(p) + self.off_dc for p in handle.buffer_ptrs], W * b, d_out, dev)
+            self.dc_scratch = torch.empty((16,), dtype=torch.float32, device=dev)
         torch.cuda.synchronize()
         dist.barrier(self.group)
 
@@ -256,6 +265,12 @@ class PeerExchange:
             _cuda_ops.peer_barrier(self.ws, 1)
             return self.dc_slots
         return _cuda_ops.peer_sum(self.ws, self.off_dc, self.dc_mine, slot=1, local_stride=self.b * self.d_out * 4)
+
+    def backward_dc_direct(self, qm, c_all, inv_t, lse, label_offset, w) -> torch.Tensor:
+        """dC pass + reduce-scatter in one kernel: returns the [world, b, d] slots of my candidates (after barrier 1)."""
+        _cuda_ops.peer_retrieval_bwd_dc(self.ws, self.dc_maps, qm, c_all, inv_t, lse, label_offset, w, self.dc_scratch)
+        _cuda_ops.peer_barrier(self.ws, 1)
+        return self.dc_slots
 
     def table_grad(self, layer, rows: torch.Tensor) -> IndexedSlices:
         t = self.tables.index(layer)
@@ -389,9 +404,18 @@ def global_retrieval(task, q: Tensor, c: Tensor, inv_t: float, w, logq, ids, pri
         bf = prec == "bf16"
         if bf and prim is _cuda_ops and ("parts" in q.grad_formats or "parts" in c.grad_formats):
             if fused:
+                dq_parts = dq_fused.reshape(1, *dq_fused.shape)
+                if ex is not None and ex.dc_maps is not None and "parts" in c.grad_formats:
+                    # the dC kernel's epilogue writes every row block straight into its owner's slot over NVLink
+                    c.grad = dict(parts=ex.backward_dc_direct(qm, c_all, inv_t, lse, label_offset, w))
+                    if "parts" in q.grad_formats:
+                        q.grad = dict(parts=dq_parts)
+                    else:
+                        f, b = prim.combine_parts(dq_parts, True, "bf16" in q.grad_formats)
+                        q.grad = dict(f32=f, bf16=b)
+                    return
                 _none, dc_parts = prim.retrieval_loss_bwd_parts(qm, c_all, inv_t, lse, label_offset, w, None, None, 1.0,
                                                                 want_dq=False)
-                dq_parts = dq_fused.reshape(1, *dq_fused.shape)
             else:
                 dq_parts, dc_parts = prim.retrieval_loss_bwd_parts(qm, c_all, inv_t, lse, label_offset, w, logq_all, ids_all, 1.0)
             if "parts" in q.grad_formats:
