@@ -341,8 +341,9 @@ int tt_retrieval_loss_bwd(int32_t precision, const void* q, const void* c, int64
  * and the backward needs the dC pass only (tt_retrieval_loss_bwd_parts with dq_parts = NULL).  Outputs as
  * tt_retrieval_loss_fwd plus dq fp32 [nq, d].  The workspace (tt_retrieval_fwd_dq_workspace_bytes; 0 = shape not
  * supported) must be zero in its first 256 bytes before the first call; the call leaves it so.
- * finalize_stream (nullable): the fold of the partials into row_lse / loss / dq is forked onto that stream (event
- * record + wait inside the call; the CALLER joins it back before reading those outputs or the workspace).
+ * finalize_stream (nullable): the final summation of the scalar loss (one block; nothing on the device waits for it)
+ * is forked onto that stream (event record + wait inside the call; the CALLER joins it back before reading `loss`);
+ * row_lse and dq are produced on `stream`.
  * tt_retrieval_loss_bwd_dc_fused: the dC pass for this forward when there are no sample weights (must be NULL).  It
  * reads -lse per query column (log2 domain, written into the workspace by the fold) with broadcast loads instead of
  * staging row_lse through shared memory; dc_parts as in tt_retrieval_loss_bwd_parts. */

@@ -1104,8 +1104,6 @@ struct DqFinalizeArgs {
   float* nlse2;                    // [round_up(nq, 128)] -lse in the log2 domain for the dC pass (pad = 0)
   float* dq;                       // [nq][d]
   float* block_loss;               // [gridDim.x]
-  int* ticket;                     // zero before and after
-  float* loss_out;
 };
 __global__ void __launch_bounds__(256) retrieval_dq_finalize_kernel(const DqFinalizeArgs a) {
   long long* const tl = g_tl;
@@ -1161,32 +1159,30 @@ __global__ void __launch_bounds__(256) retrieval_dq_finalize_kernel(const DqFina
   if (blockIdx.x == 0) {                           // finite padding for the ragged last tile of the dC pass
     for (int j = a.nq + threadIdx.x; j < (a.nq + 127) / 128 * 128; j += 256) a.nlse2[j] = 0.f;
   }
-  __shared__ float s_red[256];
-  __shared__ int s_last;
   if (lane == 0) s_term[wi] = term;
   __syncthreads();
   if (threadIdx.x == 0) {
     float bsum = 0.f;
     for (int k = 0; k < 8; ++k) bsum += s_term[k];
-    a.block_loss[blockIdx.x] = bsum;
-    __threadfence();
-    s_last = atomicAdd(a.ticket, 1) == (int)gridDim.x - 1;
+    a.block_loss[blockIdx.x] = bsum;               // summed in index order by loss_sum_kernel
   }
+}
+
+// loss = sum of the fold kernel's block terms in a fixed order (thread-strided partial sums, then a tree): bit-reproducible.
+// One block; nothing on the device waits for it, so it may run on a side stream next to the dC pass.
+__global__ void __launch_bounds__(256) loss_sum_kernel(const float* __restrict__ block_loss, int n, float* __restrict__ loss_out) {
+  pdl_wait();
+  pdl_launch_dependents();
+  __shared__ float s_red[256];
+  float part = 0.f;
+  for (int k = threadIdx.x; k < n; k += 256) part += block_loss[k];
+  s_red[threadIdx.x] = part;
   __syncthreads();
-  if (s_last) {
-    // the last block adds the block terms in a fixed order (thread-strided partial sums, then a tree): the loss does
-    // not depend on which block happens to be last
-    __threadfence();
-    float part = 0.f;
-    for (unsigned k = threadIdx.x; k < gridDim.x; k += 256) part += __ldcg(&a.block_loss[k]);
-    s_red[threadIdx.x] = part;
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
     __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-      if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) { a.loss_out[0] = s_red[0]; *a.ticket = 0; }
   }
+  if (threadIdx.x == 0) loss_out[0] = s_red[0];
 }
 
 // out = sum_s partial[s]; optional bf16 copy.  One warp per row.
@@ -1390,9 +1386,12 @@ int tc_retrieval_fwd_dq(const void* q, const void* c, int64_t nq, int64_t nc, in
   f.nq = (int)nq; f.d = (int)d; f.parts = plan.parts; f.inv_temp = inv_temp; f.label_offset = label_offset;
   f.ml = a.partial_ml; f.o_parts = o_parts; f.c = (const uint16_t*)c; f.w = w; f.row_pos = row_pos; f.row_lse = row_lse;
   f.nlse2 = (float*)((char*)ws + plan.off_nl);
-  f.dq = dq; f.block_loss = (float*)((char*)ws + plan.off_bl); f.ticket = (int*)ws; f.loss_out = loss;
+  f.dq = dq; f.block_loss = (float*)((char*)ws + plan.off_bl);
+  TT_PROF("retrieval_dq_finalize_kernel", st);
+  TT_CUDA_OK(launch_pdl(retrieval_dq_finalize_kernel, dim3((unsigned)plan.blocks), dim3(256), (size_t)0, st, f));
+  TT_LAUNCH_OK("retrieval_dq_finalize_kernel");
   if (fin_st && fin_st != st) {
-    // fork: the fold runs on its own stream, next to the dC pass (which reads the partial maxima itself)
+    // fork: nothing on the device waits for the scalar loss, so its (one-block) summation leaves the critical path
     static thread_local cudaEvent_t ev = nullptr;
     if (!ev) TT_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     TT_CUDA_OK(cudaEventRecord(ev, st));
@@ -1400,9 +1399,9 @@ int tc_retrieval_fwd_dq(const void* q, const void* c, int64_t nq, int64_t nc, in
   } else {
     fin_st = st;
   }
-  TT_PROF("retrieval_dq_finalize_kernel", fin_st);
-  TT_CUDA_OK(launch_pdl(retrieval_dq_finalize_kernel, dim3((unsigned)plan.blocks), dim3(256), (size_t)0, fin_st, f));
-  TT_LAUNCH_OK("retrieval_dq_finalize_kernel");
+  TT_PROF("loss_sum_kernel", fin_st);
+  TT_CUDA_OK(launch_pdl(loss_sum_kernel, dim3(1), dim3(256), (size_t)0, fin_st, (const float*)f.block_loss, (int)plan.blocks, loss));
+  TT_LAUNCH_OK("loss_sum_kernel");
   return TT_OK;
 }
 

@@ -577,8 +577,8 @@ def join_side_work() -> None:
 
 def retrieval_loss_fwd_dq(q, c, inv_temperature: float, label_offset: int = 0, sample_weight=None, fork: bool = False):
     """bf16 only: the loss forward and dQ in one pass.  Returns (loss [1], row_lse [nq], row_pos [nq], dq f32 [nq, d],
-    workspace).  fork=True: the fold into lse / loss / dq runs on a side stream -- call join_side_work() before
-    anything reads them (retrieval_loss_bwd_dc_fused does not: it takes the partials from the workspace)."""
+    workspace).  fork=True: the last summation of the scalar loss runs on a side stream (off the critical path of the
+    backward) -- call join_side_work() before anything reads `loss`."""
     global _fin_stream, _fin_pending
     lib = _lib.load()
     nq, d = q.shape
@@ -602,7 +602,7 @@ def retrieval_loss_fwd_dq(q, c, inv_temperature: float, label_offset: int = 0, s
                                        label_offset, _ptr(sample_weight, torch.float32), _ptr(lse), _ptr(pos), _ptr(loss),
                                        _ptr(dq), _ptr(ws), ws.numel(), _stream(), fin))
     _fin_pending = fork
-    _count(2)
+    _count(3)
     return loss, lse, pos, dq, ws
 
 

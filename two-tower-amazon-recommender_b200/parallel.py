@@ -396,7 +396,7 @@ def global_retrieval(task, q: Tensor, c: Tensor, inv_t: float, w, logq, ids, pri
              and ids_all is None and ("parts" in q.grad_formats or "parts" in c.grad_formats)
              and prim.retrieval_fwd_dq_supported(nq, c_all.shape[0], qm.shape[1]))
     if fused:            # the forward pass also accumulates dQ: the backward is the dC pass only
-        loss, lse, _pos, dq_fused, _fwd_ws = prim.retrieval_loss_fwd_dq(qm, c_all, inv_t, label_offset, w)
+        loss, lse, _pos, dq_fused, _fwd_ws = prim.retrieval_loss_fwd_dq(qm, c_all, inv_t, label_offset, w, fork=True)
     else:
         loss, lse, _pos = prim.retrieval_loss_fwd(prec, qm, c_all, inv_t, label_offset, w, logq_all, ids_all)
 
@@ -408,6 +408,7 @@ def global_retrieval(task, q: Tensor, c: Tensor, inv_t: float, w, logq, ids, pri
                 if ex is not None and ex.dc_maps is not None and "parts" in c.grad_formats:
                     # the dC kernel's epilogue writes every row block straight into its owner's slot over NVLink
                     c.grad = dict(parts=ex.backward_dc_direct(qm, c_all, inv_t, lse, label_offset, w))
+                    prim.join_side_work()
                     if "parts" in q.grad_formats:
                         q.grad = dict(parts=dq_parts)
                     else:
@@ -416,6 +417,7 @@ def global_retrieval(task, q: Tensor, c: Tensor, inv_t: float, w, logq, ids, pri
                     return
                 _none, dc_parts = prim.retrieval_loss_bwd_parts(qm, c_all, inv_t, lse, label_offset, w, None, None, 1.0,
                                                                 want_dq=False)
+                prim.join_side_work()                # the forked loss summation joins AFTER the dC launch
             else:
                 dq_parts, dc_parts = prim.retrieval_loss_bwd_parts(qm, c_all, inv_t, lse, label_offset, w, logq_all, ids_all, 1.0)
             if "parts" in q.grad_formats:

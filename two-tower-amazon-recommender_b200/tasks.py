@@ -84,7 +84,7 @@ class Retrieval:
         fused = (prec == "bf16" and GradientTape.current() is not None and logq is None and ids is None
                  and ops.retrieval_fwd_dq_supported(nq, cm.shape[0], qm.shape[1]))
         if fused:
-            loss, lse, _pos, dq_fused, _fwd_ws = ops.retrieval_loss_fwd_dq(qm, cm, inv_t, 0, w)
+            loss, lse, _pos, dq_fused, _fwd_ws = ops.retrieval_loss_fwd_dq(qm, cm, inv_t, 0, w, fork=True)
         else:
             loss, lse, _pos = ops.retrieval_loss_fwd(prec, qm, cm, inv_t, 0, w, logq, ids)
 
@@ -96,6 +96,7 @@ class Retrieval:
                 # softmax warps) and feeding the dC pass -lse2 by broadcast global loads instead of the shared-memory
                 # staging (retrieval_loss_bwd_dc_fused, 173 us).
                 _none, dc_parts = ops.retrieval_loss_bwd_parts(qm, cm, inv_t, lse, 0, w, None, None, 1.0, want_dq=False)
+                ops.join_side_work()                 # the forked loss summation is done before anything downstream
                 if "parts" in q.grad_formats:
                     q.grad = dict(parts=dq_fused.reshape(1, *dq_fused.shape))
                 else:
