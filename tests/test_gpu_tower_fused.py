@@ -341,10 +341,11 @@ class TestFusedTrainStep:
             for wa, wb in zip(la.get_weights(), lb.get_weights()):
                 # same products; the weight-gradient partial sums are grouped differently (fp32 rounding only)
                 assert np.abs(wa - wb).max() <= 2e-3 * max(np.abs(wb).max(), 1e-6)
-        # steady state (sparse workspaces exist): fwd towers 1 + loss 1 + loss bwd 2 + bwd towers 1 + id dedup 1 (side stream) + optimizer 1
+        # steady state (sparse workspaces exist): fwd towers 1 + one-pass loss forward + dQ 3 (kernel, fold, loss sum on a
+        # side stream) + dC pass 1 + bwd towers 1 + id dedup 1 (side stream) + optimizer 1
         before = tt.ops.LAUNCHES
         a.train_step(batch)
-        assert tt.ops.LAUNCHES - before == 7
+        assert tt.ops.LAUNCHES - before == 8
 
     def test_three_steps_track_the_oracle(self, tt):
         vu, vi, d, mlp, B, T, lr = 2000, 1500, 128, (256, 128), 512, 0.5, 0.05
