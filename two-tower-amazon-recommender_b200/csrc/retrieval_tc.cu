@@ -198,7 +198,6 @@ retrieval_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   TT_TRACE_CTA(0);
   TT_TRACE_X(0);
   long long* const tl = g_tl;
-  tl_mark(tl, 1, true);
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * RT_BM;
@@ -221,6 +220,7 @@ retrieval_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                       // everything above overlapped the tail of the previous kernel in the stream
   pdl_launch_dependents();
+  tl_mark(tl, 1, true);             // timeline: the kernel's work starts here (the prologue above may run early under PDL)
   TT_TRACE_CTA(1);
   TT_TRACE_X(1);
 
@@ -492,7 +492,6 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   TT_TRACE_CTA(0);
   TT_TRACE_X(0);
   long long* const tl = g_tl;
-  tl_mark(tl, TRANSPOSED ? 3 : 2, true);
   const int nX = TRANSPOSED ? a.nc : a.nq;
   const int nY = TRANSPOSED ? a.nq : a.nc;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -522,6 +521,7 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                       // everything above overlapped the tail of the previous kernel in the stream
   pdl_launch_dependents();
+  tl_mark(tl, TRANSPOSED ? 3 : 2, true);
   TT_TRACE_CTA(1);
   TT_TRACE_X(1);
 
@@ -868,7 +868,6 @@ retrieval_fwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   long long* const tl = g_tl;
-  tl_mark(tl, 1, true);
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const int x0 = blockIdx.x * RT_BM;
@@ -892,6 +891,7 @@ retrieval_fwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
   pdl_launch_dependents();
+  tl_mark(tl, 1, true);
 
   if (warp == RT_TMA_WARP) {
     if (elect_one_sync()) {
@@ -1107,9 +1107,9 @@ struct DqFinalizeArgs {
 };
 __global__ void __launch_bounds__(256) retrieval_dq_finalize_kernel(const DqFinalizeArgs a) {
   long long* const tl = g_tl;
-  tl_mark(tl, 15, true);
   pdl_wait();
   pdl_launch_dependents();
+  tl_mark(tl, 15, true);
   __shared__ float s_term[8];
   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
   const long long i = (long long)blockIdx.x * 8 + wi;

@@ -511,9 +511,9 @@ __device__ __forceinline__ void apply_row(const SparseMultiVar& V, int64_t id, i
 template <bool ADAM>
 __global__ void __launch_bounds__(256)
 optimizer_step_kernel(const __grid_constant__ StepArgs a, float lr_or_alpha, float b1, float b2, float eps) {
-  tl_mark(g_tl, 5, true);
   pdl_wait();                       // launched while the backward tower kernel drains
   pdl_launch_dependents();
+  tl_mark(g_tl, 5, true);
   const int lane = threadIdx.x & 31;
   const int bid = blockIdx.x;
   if (bid < a.dense_blocks[a.n_dense]) {

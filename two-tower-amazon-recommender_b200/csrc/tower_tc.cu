@@ -126,7 +126,6 @@ tower_mlp2_fwd_kernel(const __grid_constant__ TowerFwdArgs a) {
   const FwdLayout L = fwd_layout(d_in, d_hid, d_out);
   TW_STAMP(0);
   long long* const tl = g_tl;
-  tl_mark(tl, 0, true);
   uint8_t* sX = smem;
   uint8_t* sR1 = smem + L.off_r1;                 // W1 (MN-major chunks [d_in][64]) then h (K-major blocks)
   uint8_t* sW2 = smem + L.off_w2;                 // MN-major chunks [d_hid][64]
@@ -156,6 +155,7 @@ tower_mlp2_fwd_kernel(const __grid_constant__ TowerFwdArgs a) {
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                       // the prologue above overlapped the tail of the previous kernel in the stream
   pdl_launch_dependents();
+  tl_mark(tl, 0, true);
 
   TW_STAMP(1);
   if (warp == 0 && elect_one_sync()) {            // weights: L2-resident after the first CTA
@@ -364,7 +364,6 @@ tower_mlp2_bwd_kernel(const __grid_constant__ TowerBwdArgs a) {
   const BwdTLayout L = bwdt_layout(d_in, d_hid, d_out);
   TW_STAMP(0);
   long long* const tl = g_tl;
-  tl_mark(tl, 4, true);
   uint8_t* rDY = smem;
   uint8_t* rH = smem + L.off_h;
   uint8_t* rW2 = smem + L.off_w2;
@@ -398,6 +397,7 @@ tower_mlp2_bwd_kernel(const __grid_constant__ TowerBwdArgs a) {
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                       // the prologue above overlapped the tail of the previous kernel in the stream
   pdl_launch_dependents();
+  tl_mark(tl, 4, true);
 
   TW_STAMP(1);
   if (warp == 0 && elect_one_sync()) {
