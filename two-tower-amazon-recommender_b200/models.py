@@ -80,6 +80,7 @@ class Model:
         with GradientTape() as tape:
             tape.on_sparse_lookup = self.optimizer.prepare_sparse
             loss = self.compute_loss(inputs, training=True)
+            self.optimizer.join_prepare()
             reg = self._regularization_loss()
             variables = self.trainable_variables
             grads = tape.gradient(loss, variables)

@@ -76,6 +76,14 @@ class Optimizer:
             ops.sparse_prepare(items)
         self._side_busy = True
 
+    def join_prepare(self) -> None:
+        """Make the current stream wait for the side-stream id dedup now.  Model.train_step calls this between the
+        forward and the backward pass: the dedup has long finished there, and the optimizer launch then follows the
+        backward tower kernel directly (a programmatic dependent launch) instead of an event wait."""
+        if self._side_busy:
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._side_busy = False
+
     def apply_gradients(self, grads_and_vars: Iterable[Tuple[object, Variable]]) -> None:
         self.iterations += 1
         dense, sparse, late = [], [], []

@@ -468,6 +468,7 @@ class DataParallelModel(Model):
         with GradientTape() as tape:
             tape.on_sparse_lookup = self.optimizer.prepare_sparse
             loss = self.compute_loss(inputs, training=True)
+            self.optimizer.join_prepare()
             variables = self.trainable_variables
             grads = tape.gradient(loss, variables)
         dense = [(i, g) for i, g in enumerate(grads) if isinstance(g, DenseGrad)]
