@@ -58,3 +58,45 @@ def test_training_from_a_parquet_in_the_reference_schema(tt, tmp_path):
     # a permutation of the rows: every (user, item) pair drawn exists in the frame, no row twice
     key = lambda a: a[:, 0].astype(np.int64) * 100000 + a[:, 1]
     assert np.array_equal(np.sort(key(seen)), np.sort(key(ref)))
+
+
+def test_fit_with_corpus_wide_validation_and_early_stopping(tt, tmp_path):
+    """Recall@k / NDCG@k against the whole item corpus through the brute-force top-k kernel; the
+    learnable toy frame must end far above chance, and patience stops the loop."""
+    from two_tower_b200 import data, evaluation
+    tt.set_precision("bf16")
+    tt.set_seed(4)
+    df = _frame(n=8192, vu=400, vi=300, seed=10)
+    train = data.InteractionBatches(df.iloc[:7168], batch_size=512, seed=2)
+    val = data.InteractionBatches(df.iloc[7168:], batch_size=512, shuffle=False)
+
+    class TwoTower(tt.models.Model):
+        def __init__(s):
+            super().__init__()
+            s.user_model = tt.Sequential([tt.layers.Embedding(400, 128), tt.layers.Dense(256, "relu"), tt.layers.Dense(128)])
+            s.item_model = tt.Sequential([tt.layers.Embedding(300, 128), tt.layers.Dense(256, "relu"), tt.layers.Dense(128)])
+            s.task = tt.tasks.Retrieval(temperature=0.2)
+
+        def compute_loss(s, f, training=False):
+            return s.task(s.user_model(f["user_id_encoded"]), s.item_model(f["item_id_encoded"]))
+
+    model = TwoTower()
+    model.compile(optimizer=tt.optimizers.Adagrad(0.05))
+    model.test_step({k: v.cuda() for k, v in train.example().items()})
+    ev = evaluation.RetrievalEvaluator(model.user_model, model.item_model, num_items=300)
+    before = ev.evaluate(val)
+    assert before["n_queries"] == 1024 and set(f"recall@{k}" for k in evaluation.TOP_K_EVAL) <= set(before)
+    hist = evaluation.fit(model, train, epochs=20, validation_batches=val, evaluator=ev, validation_freq=1)
+    assert len(hist["val"]) == len(hist["loss"]) == 20 and hist["loss"][-1] < hist["loss"][0] and hist["stopped_epoch"] is None
+    best = max(m["recall@10"] for m in hist["val"])
+    # each user has 3 plausible items out of 300 (chance: recall@10 = 0.033); measured ~0.6 after 20 epochs
+    assert best > 5 * before["recall@10"] and best > 0.3, [round(m["recall@10"], 3) for m in hist["val"]]
+    # early stopping on a noisy metric with the loop's own bookkeeping: validation every 2nd epoch, patience 1
+    es = evaluation.EarlyStopping(monitor="recall@1", patience=1)
+    h2 = evaluation.fit(model, train, epochs=30, validation_batches=val, evaluator=ev, validation_freq=2, early_stopping=es)
+    assert h2["val_epoch"] == list(range(1, 2 * len(h2["val"]), 2))
+    assert h2["stopped_epoch"] is not None and h2["stopped_epoch"] == h2["val_epoch"][-1] and h2["stopped_epoch"] - es.best_epoch == 2
+    for m in hist["val"]:
+        ks = evaluation.TOP_K_EVAL
+        assert all(m[f"recall@{a}"] <= m[f"recall@{b}"] + 1e-12 for a, b in zip(ks, ks[1:]))
+        assert all(m[f"ndcg@{k}"] <= m[f"recall@{k}"] + 1e-12 for k in ks)

@@ -65,7 +65,8 @@ def _read_columns(source, wanted: Sequence[str]) -> Dict[str, np.ndarray]:
 
 
 class InteractionBatches:
-    """Epoch iterator over the interactions of one frame.
+    """Epoch iterator over the interactions of one frame.  A yielded batch stays valid until `ring` further batches
+    have been drawn AND the device work the consumer enqueued for it (on the current stream) has finished.
 
         ds = InteractionBatches("data/processed/combined_interactions.parquet", batch_size=8192, seed=0)
         model = TwoTower(ds.num_users, ds.num_items); step = model.make_graphed_train_step(ds.example())
@@ -106,6 +107,9 @@ class InteractionBatches:
         self.epoch = 0
         self._pin = torch.cuda.is_available() if pin is None else bool(pin)
         self._ring = [self._alloc() for _ in range(max(2, int(ring)))]
+        # one CUDA event per staging slot: recorded after the consumer's turn, waited for before the slot is rewritten
+        # (the consumer may copy a pinned batch to the device asynchronously and run many steps ahead of the GPU)
+        self._events = [torch.cuda.Event() for _ in self._ring] if self._pin and torch.cuda.is_available() else None
         self._slot = 0
 
     def _alloc(self):
@@ -135,8 +139,11 @@ class InteractionBatches:
         self.epoch += 1
         for b in range(len(self)):
             rows = perm[b * self.batch_size:(b + 1) * self.batch_size]
-            stage = self._ring[self._slot]
+            slot = self._slot
+            stage = self._ring[slot]
             self._slot = (self._slot + 1) % len(self._ring)
+            if self._events is not None:
+                self._events[slot].synchronize()
             seen = set()
             for k, v in self._columns.items():
                 t = stage[k]
@@ -145,6 +152,8 @@ class InteractionBatches:
                 seen.add(id(t))
                 np.take(v, rows, out=t.numpy()[:len(rows)])
             yield stage if len(rows) == self.batch_size else {k: t[:len(rows)] for k, t in stage.items()}
+            if self._events is not None:
+                self._events[slot].record()          # everything the consumer enqueued for this batch precedes it
 
     def to_device(self, device=None) -> "DeviceInteractionBatches":
         return DeviceInteractionBatches(self, device)
@@ -162,7 +171,7 @@ class DeviceInteractionBatches:
         self._columns = {}
         for k, v in host._columns.items():
             if id(v) not in done:
-                done[id(v)] = torch.from_numpy(v).to(self.device)
+                done[id(v)] = torch.tensor(v, dtype=torch.int64, device=self.device)
             self._columns[k] = done[id(v)]
         self.epoch = 0
 
