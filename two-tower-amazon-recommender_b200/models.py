@@ -4,6 +4,7 @@ from __future__ import annotations
 
 from typing import Dict, Iterable, List, Optional
 
+import numpy as np
 import torch
 
 from . import ops
@@ -100,6 +101,41 @@ class Model:
         out["regularization_loss"] = zero
         out["total_loss"] = loss.value if reg is None else loss.value + reg
         return out
+
+    # ---- raw-tensor checkpoint: tables, Dense kernels / biases, optimizer slots -----------------
+    def save_weights(self, path) -> None:
+        """One .npz: every trainable variable (fp32 master copy) in `trainable_variables` order, its optimizer slots
+        (Adagrad accumulator / Adam m, v) and the optimizer's iteration count.  Layers must be built."""
+        arrays, names = {}, []
+        for i, v in enumerate(self.trainable_variables):
+            names.append(v.name)
+            arrays[f"v{i}"] = v.value.detach().cpu().numpy()
+            for k, s in v.slots.items():
+                if isinstance(s, torch.Tensor) and not k.startswith("_"):
+                    arrays[f"s{i}.{k}"] = s.detach().cpu().numpy()
+        arrays["names"] = np.array(names)
+        arrays["iterations"] = np.array([self.optimizer.iterations if self.optimizer is not None else 0], dtype=np.int64)
+        with open(path, "wb") as f:
+            np.savez(f, **arrays)
+
+    def load_weights(self, path) -> None:
+        """Inverse of save_weights onto a BUILT model of the same architecture (shapes are checked)."""
+        z = np.load(path, allow_pickle=False)
+        variables = self.trainable_variables
+        n = len(z["names"])
+        if n != len(variables):
+            raise ValueError(f"checkpoint holds {n} variables, the model has {len(variables)}")
+        for i, v in enumerate(variables):
+            a = z[f"v{i}"]
+            if tuple(a.shape) != v.shape:
+                raise ValueError(f"variable {i} ({v.name}): checkpoint shape {tuple(a.shape)} != {v.shape}")
+            v.assign(a)
+            prefix = f"s{i}."
+            for key in z.files:
+                if key.startswith(prefix):
+                    v.slots[key[len(prefix):]] = torch.as_tensor(z[key]).to(v.value.device)
+        if self.optimizer is not None:
+            self.optimizer.iterations = int(z["iterations"][0])
 
     def fit(self, dataset: Iterable, epochs: int = 1, verbose: int = 0):
         history = {"loss": [], "total_loss": []}
