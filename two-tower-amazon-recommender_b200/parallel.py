@@ -215,8 +215,9 @@ class PeerExchange:
         self.bucket_sum = torch.empty((self.BUCKET_FLOATS,), dtype=torch.float32, device=dev)
         self.loss4 = torch.zeros(4, dtype=torch.float32, device=dev)
         # EXPERIMENTAL, off unless TT_DC_DIRECT=1: tensor maps over every rank's dC receive area so that the dC kernel's
-        # epilogue TMA-stores straight into the owners' slots (no combine + scatter kernel).  It ran eagerly at N=2 but a
-        # CUDA-graph replay of the step faulted ("unspecified launch failure"); cause not found in round 1.
+        # epilogue TMA-stores straight into the owners' slots (no combine + scatter kernel).  Bit-identical to the combine
+        # path on one GPU (tools/dc_scatter_selftest.py), but at N=2 one rank hung after ~2000 graph-replayed steps;
+        # cause not found in round 1.
         self.dc_maps = None
         import os
         if (os.environ.get("TT_DC_DIRECT", "0") == "1" and b % 128 == 0 and d_out <= 128 and d_out % 32 == 0
