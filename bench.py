@@ -160,7 +160,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "examples/s", "n_gpus": args.gpus,
         "steps": len(times), "warmup": min(args.warmup, 2), "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(cfg, 1)},
+        "config": {"workload": workload_name(cfg, 1), "global_batch": cfg.batch,
+                   "sample": "full cfg2 steps at B=8192 on the host cores (rank 0 only under torchrun); the N-GPU arm's global "
+                             "batch is N x 8192 with in-batch negatives over all of it"},
         "cpu_baseline": {"value": value, "unit": "examples/s", "cores": cores, "kind": "port",
                          "sample": f"{len(times)} full {cfg.name} steps (B={cfg.batch}) of the numpy TFRS-equivalent restatement "
                                    "(oracle/; TensorFlow/TFRS are not installable here), host BLAS on all cores"},

@@ -29,7 +29,7 @@ namespace tt {
 TT_TL_DEFINE(set_timeline_peer)      // ids: 9 push, 10 / 14 barrier (slot 0 / other), 11 / 12 sum (with / without barrier), 13 pull
 
 constexpr int kMaxWorld = 16;
-constexpr long long kPeerSpinLimit = 1ll << 31;   // a lost peer traps instead of hanging the box
+constexpr long long kPeerSpinLimit = 1ll << 26;   // ~15-60 s of polling: a lost peer traps instead of hanging the box
 
 struct PeerBarrierArgs {
   unsigned long long* const* flag_bases;   // device array [world]: every rank's flag block (peer-mapped)
