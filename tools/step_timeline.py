@@ -1,5 +1,6 @@
-"""In-graph timeline of one cfg2 training step (tt_debug_timeline): when each kernel's first CTA starts and its
-last CTA ends inside the replayed CUDA graph, i.e. the real gaps and overlaps the per-kernel event timings hide.
+"""In-graph timeline of one cfg2 training step (tt_debug_timeline): when each kernel's first CTA starts its work (after
+the PDL wait) and its last CTA ends inside the replayed CUDA graph, i.e. the real gaps and overlaps the per-kernel
+event timings hide.  Kernels launched several times per step (peer pushes, barriers 1 and 3) show one merged span.
    python tools/step_timeline.py [--no-graph]"""
 import sys
 from pathlib import Path
@@ -33,8 +34,9 @@ for i in range(10):
 lib = tt._lib.load()
 I64MAX = np.iinfo(np.int64).max
 names = ["tower fwd", "loss fwd", "loss bwd dQ", "loss bwd dC", "tower bwd", "optimizer step", "sparse prepare (side stream)",
-         "combine partials", "fold dense parts", "peer push (candidates, ids)", "peer barrier 0", "peer sum dC (+barrier 1)",
-         "peer sum dense+loss", "peer pull rows (+barrier 2)", "peer barrier 3"]
+         "combine partials (N>1: + scatter to owners)", "fold dense parts", "peer pushes (candidates+ids ... dense bucket)",
+         "peer barrier 0", "peer sum dense+loss (+barrier 2)", "peer sum (no barrier)", "peer push rows", "peer barriers 1 .. 3",
+         "loss fold (block entries)"]
 rows = []
 for rep in range(5):
     buf = torch.tensor([I64MAX, 0] * 16, dtype=torch.int64, device=dev)
@@ -53,13 +55,13 @@ for rep in range(5):
     tt._lib.check(lib.tt_debug_timeline(None))
     rows.append((buf.cpu().numpy().reshape(16, 2), e0.elapsed_time(e1) * 1e3))
 tl, us = rows[-1]
-t0 = min(int(tl[k, 0]) for k in range(15) if tl[k, 1] > 0)
+t0 = min(int(tl[k, 0]) for k in range(16) if tl[k, 1] > 0)
 if rank != 0:
     torch.cuda.synchronize(); dist.barrier(); os._exit(0)
 print(f"step (events around one replay): {us:.1f} us")
 print(f"{'kernel':32s} {'first CTA in':>12s} {'last CTA out':>12s} {'span':>8s}   gap to previous end")
 prev_end = None
-for k in sorted([k for k in range(15) if tl[k, 1] > 0], key=lambda k: tl[k, 0]):
+for k in sorted([k for k in range(16) if tl[k, 1] > 0], key=lambda k: tl[k, 0]):
     if tl[k, 1] == 0:
         continue
     a, b = (int(tl[k, 0]) - t0) / 1e3, (int(tl[k, 1]) - t0) / 1e3
