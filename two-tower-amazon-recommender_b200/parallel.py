@@ -216,7 +216,7 @@ class PeerExchange:
         self.loss4 = torch.zeros(4, dtype=torch.float32, device=dev)
         # EXPERIMENTAL, off unless TT_DC_DIRECT=1: tensor maps over every rank's dC receive area so that the dC kernel's
         # epilogue TMA-stores straight into the owners' slots (no combine + scatter kernel).  Bit-identical to the combine
-        # path on one GPU (tools/dc_scatter_selftest.py), but at N=2 one rank hung after ~2000 graph-replayed steps;
+        # path on one GPU (tests/test_gpu_peer_local.py), but at N=2 one rank hung after ~2000 graph-replayed steps;
         # cause not found in round 1.
         self.dc_maps = None
         import os
