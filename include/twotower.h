@@ -335,6 +335,21 @@ int tt_retrieval_loss_bwd(int32_t precision, const void* q, const void* c, int64
  * dq_parts, the dC pass [dc_splits, nc, d] in dc_parts; dq = sum over splits in index order.
  * Buffers are caller-owned, sized with tt_retrieval_bwd_num_splits.  TT_BF16 only.
  * tt_combine_parts_f32 is that ordered sum as a stand-alone kernel (fp32 and/or bf16 output). */
+/* tfrs.tasks.Retrieval(num_hard_negatives = n) (tfrs layers/loss.py HardNegativeMining): the loss over the positive and
+ * the n highest-scoring negatives of every query row.  `selected` int64 [nq, k_sel]: column 0 = index of the positive
+ * candidate, then the selected negatives (-1 = unused slot) -- built by the caller from tt_topk_bruteforce with
+ * k = n + 1 (tf.math.top_k order).  Evaluates the gathered logits only: scores [nq, k_sel] fp32 (scaled by
+ * inv_temperature; -inf for unused slots), row_lse, row_pos, row_loss [nq] and the SUM loss [1] (fixed summation order).
+ * Backward: dq [nq, d] and dc [nc, d] fp32 (dc is zeroed, then accumulated with fp32 atomics).  q / c: fp32 (TT_F32) or
+ * bf16 (TT_BF16), d <= 256, arithmetic in fp32. */
+int tt_hard_negative_loss_fwd(int32_t precision, const void* q, const void* c, const int64_t* selected, int64_t nq,
+                              int64_t nc, int64_t k_sel, int64_t d, float inv_temperature, const float* sample_weight,
+                              float* scores, float* row_lse, float* row_pos, float* row_loss, float* loss, void* stream);
+int tt_hard_negative_loss_bwd(int32_t precision, const void* q, const void* c, const int64_t* selected, int64_t nq,
+                              int64_t nc, int64_t k_sel, int64_t d, float inv_temperature, float grad_scale,
+                              const float* sample_weight, const float* scores, const float* row_lse, float* dq,
+                              float* dc, void* stream);
+
 /* Forward + dQ in one pass (TT_BF16, d = 64 or 128, no log-q correction / accidental-hit mask): the loss forward
  * with a second GEMM per tile that accumulates sum_j exp(s_ij - m_i) c_j (flash-attention forward shape), so
  * dq = (w_i / T) (softmax(S) C - c_label) -- d(loss)/dq for an upstream gradient of 1 -- comes out of the same pass

@@ -84,6 +84,8 @@ SIGNATURES = {
     "tt_tower_mlp2_supported": (_i32, [_i32, _i32, _i32]),
     "tt_tower_mlp2_fwd": (C.c_int, [C.POINTER(tt_tower_mlp2), _i32, _p, _p]),
     "tt_tower_mlp2_bwd": (C.c_int, [C.POINTER(tt_tower_mlp2), _i32, _p]),
+    "tt_hard_negative_loss_fwd": (C.c_int, [_i32, _p, _p, _p, _i64, _i64, _i64, _i64, _f, _p, _p, _p, _p, _p, _p, _p]),
+    "tt_hard_negative_loss_bwd": (C.c_int, [_i32, _p, _p, _p, _i64, _i64, _i64, _i64, _f, _f, _p, _p, _p, _p, _p, _p]),
     "tt_retrieval_fwd_dq_workspace_bytes": (_i64, [_i64, _i64, _i64]),
     "tt_retrieval_loss_fwd_dq": (C.c_int, [_p, _p, _i64, _i64, _i64, _f, _i64, _p, _p, _p, _p, _p, _p, _i64, _p, _p]),
     "tt_retrieval_loss_bwd_dc_fused": (C.c_int, [_p, _p, _i64, _i64, _i64, _f, _i64, _p, _p, _f, _p, _p]),

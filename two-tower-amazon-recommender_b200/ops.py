@@ -825,3 +825,54 @@ def peer_retrieval_bwd_dc(ws: PeerWorkspace, maps: torch.Tensor, q, c, inv_tempe
                                                label_offset, _ptr(sample_weight, torch.float32), _ptr(row_lse, torch.float32),
                                                1.0, _ptr(maps), ws.world, ws.rank, _ptr(scratch, torch.float32), _stream()))
     _count(1)
+
+
+# ------------------------------------------------------------------ hard-negative mining (tfrs num_hard_negatives)
+def select_hard_negatives(precision: str, q, c, num_hard_negatives: int, label_offset: int = 0) -> torch.Tensor:
+    """[nq, k] int64, k = min(n + 1, nc): column 0 = the positive (label_offset + row), then the n highest-scoring other
+    candidates in tf.math.top_k order (score desc, index asc) -- tfrs HardNegativeMining's top_k(scores + labels * MAX).
+    The scores come from the brute-force top-k kernel; the rest is index bookkeeping."""
+    nq, nc = q.shape[0], c.shape[0]
+    k = min(int(num_hard_negatives) + 1, nc)
+    _scores, ids = topk_bruteforce(precision, q, c, k)
+    label = torch.arange(nq, device=q.device, dtype=torch.int64) + int(label_offset)
+    is_pos = ids == label[:, None]
+    order = torch.argsort(is_pos.to(torch.int8), dim=1, stable=True)          # negatives first, original order kept
+    neg = torch.gather(ids, 1, order)[:, :k - 1]
+    return torch.cat([label[:, None], neg], dim=1).contiguous()
+
+
+def hard_negative_loss_fwd(precision: str, q, c, selected, inv_temperature: float, sample_weight=None):
+    """Returns (loss [1], row_lse [nq], row_pos [nq], scores [nq, k]) on the selected logits."""
+    pc = precision_code(precision)
+    dt = torch.float32 if precision == "fp32" else torch.bfloat16
+    nq, d = q.shape
+    K = selected.shape[1]
+    dev = q.device
+    scores = torch.empty((nq, K), dtype=torch.float32, device=dev)
+    lse = torch.empty((nq,), dtype=torch.float32, device=dev)
+    pos = torch.empty((nq,), dtype=torch.float32, device=dev)
+    row_loss = torch.empty((nq,), dtype=torch.float32, device=dev)
+    loss = torch.empty((1,), dtype=torch.float32, device=dev)
+    check(_lib.load().tt_hard_negative_loss_fwd(pc, _ptr(q, dt), _ptr(c, dt), _ptr(selected, torch.int64), nq, c.shape[0], K, d,
+                                                inv_temperature, _ptr(sample_weight, torch.float32), _ptr(scores), _ptr(lse),
+                                                _ptr(pos), _ptr(row_loss), _ptr(loss), _stream()))
+    _count(2)
+    return loss, lse, pos, scores
+
+
+def hard_negative_loss_bwd(precision: str, q, c, selected, inv_temperature: float, scores, row_lse, sample_weight=None,
+                           grad_scale: float = 1.0):
+    """Returns (dq f32 [nq, d], dc f32 [nc, d])."""
+    pc = precision_code(precision)
+    dt = torch.float32 if precision == "fp32" else torch.bfloat16
+    nq, d = q.shape
+    nc = c.shape[0]
+    dq = torch.empty((nq, d), dtype=torch.float32, device=q.device)
+    dc = torch.empty((nc, d), dtype=torch.float32, device=q.device)
+    check(_lib.load().tt_hard_negative_loss_bwd(pc, _ptr(q, dt), _ptr(c, dt), _ptr(selected, torch.int64), nq, nc, selected.shape[1], d,
+                                                inv_temperature, grad_scale, _ptr(sample_weight, torch.float32),
+                                                _ptr(scores, torch.float32), _ptr(row_lse, torch.float32), _ptr(dq), _ptr(dc),
+                                                _stream()))
+    _count(1)
+    return dq, dc

@@ -35,7 +35,11 @@ class Retrieval:
         if loss is not None:
             raise NotImplementedError("only the default CategoricalCrossentropy(from_logits=True, reduction=SUM) is built")
         if num_hard_negatives is not None:
-            raise NotImplementedError("num_hard_negatives is not on the built path yet (SURVEY.md 8f, row f2)")
+            if int(num_hard_negatives) < 1:
+                raise ValueError("num_hard_negatives must be a positive integer")
+            if process_group is not None:
+                raise NotImplementedError("num_hard_negatives with global-batch negatives (process_group) is not built")
+        self._num_hard_negatives = None if num_hard_negatives is None else int(num_hard_negatives)
         self._factorized_metrics = metrics
         self._batch_metrics = batch_metrics
         self._loss_metrics = loss_metrics
@@ -75,6 +79,31 @@ class Retrieval:
         if self.process_group is not None:
             from . import parallel
             return parallel.global_retrieval(self, q, c, inv_t, w, logq, ids)
+
+        if self._num_hard_negatives is not None:
+            # tfrs HardNegativeMining: the positive + the n highest-scoring negatives of each row.  Selection by the
+            # brute-force top-k kernel (k = n + 1), loss and gradients on the gathered logits (csrc/hard_negatives.cu).
+            if logq is not None or ids is not None:
+                raise NotImplementedError("num_hard_negatives together with candidate_sampling_probability / "
+                                          "remove_accidental_hits is not built (the selection runs on the plain scores)")
+            qm, cm = (q.f32, c.f32) if prec == "fp32" else (q.bf16, c.bf16)
+            sel = ops.select_hard_negatives(prec, qm, cm, self._num_hard_negatives, 0)
+            loss, lse, _pos, scores = ops.hard_negative_loss_fwd(prec, qm, cm, sel, inv_t, w)
+
+            def backward_hard():
+                dq, dc = ops.hard_negative_loss_bwd(prec, qm, cm, sel, inv_t, scores, lse, w, 1.0)
+                for t, g in ((q, dq), (c, dc)):
+                    if "parts" in t.grad_formats:
+                        t.grad = dict(parts=g.reshape(1, *g.shape))
+                    else:
+                        t.grad = dict(f32=g, bf16=ops.cast_f32_to_bf16(g) if (prec == "bf16" and "bf16" in t.grad_formats) else None)
+
+            GradientTape.record(backward_hard)
+            if compute_metrics and self._factorized_metrics is not None:
+                self._factorized_metrics.update_state(q, _first_rows(c, nq),
+                                                      true_candidate_ids=None if candidate_ids is None else candidate_ids,
+                                                      sample_weight=sample_weight)
+            return Scalar(loss)
 
         if prec == "fp32":
             qm, cm = q.f32, c.f32
