@@ -32,3 +32,10 @@ def test_early_stopping_patience(tt):
         es.update(9, {"other": 1.0})
     with pytest.raises(ValueError):
         ev.EarlyStopping(mode="up")
+
+
+def test_dense_bucket_layout(tt):
+    """Offsets of the flat dense-gradient bucket (every variable padded to a multiple of 4 floats: 16-byte vector loads)."""
+    offs, total = tt.ops.bucket_layout([(128, 256), (1, 256), (256, 128), (1, 130), (3,)])
+    assert offs == [0, 32768, 33024, 65792, 65924] and total == 65928
+    assert all(o % 4 == 0 for o in offs) and total % 4 == 0
