@@ -1,3 +1,4 @@
+# Diagnostic script (not collected by pytest): lives under tests/ because it uses the oracle as the checker.
 import sys; sys.path.insert(0, '.')
 import numpy as np, torch
 import oracle, two_tower_b200 as tt
