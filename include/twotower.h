@@ -28,7 +28,8 @@
 extern "C" {
 #endif
 
-#define TT_VERSION 110 /* 0.1.1 */
+#define TT_VERSION 120 /* 0.2.0 */
+#define TT_TOPK_RERANK_MARGIN 16
 
 enum tt_status {
   TT_OK = 0,
@@ -45,13 +46,6 @@ int tt_version(void);
 const char* tt_last_error(void);
 /* 0 when the current CUDA device is compute capability 10.x, TT_ERR_UNSUPPORTED otherwise. */
 int tt_device_check(void);
-
-/* Per-kernel timing for bench.py: while enabled, every kernel the library launches outside a
- * CUDA-graph capture is bracketed by a cudaEvent pair on its own stream.  tt_profile_collect
- * synchronises and writes "kernel_name launches total_ms\n" lines into host_buf; returns the
- * buffer size needed.  tt_profile_enable(0/1) also clears the records. */
-int tt_profile_enable(int32_t on);
-int64_t tt_profile_collect(char* host_buf, int64_t buf_len);
 
 /* ---------------------------------------------------------------------------------------
  * K1  tower input: Embedding gather and multi-hot sum/mean pooling.
@@ -227,23 +221,7 @@ int tt_colsum_f32(const float* x, float* out_parts, int64_t rows, int64_t cols, 
                   void* stream);
 int tt_sum_parts_f32(const float* parts, int32_t num_parts, int64_t n, float* out, void* stream);
 
-/* Test hook: D[M,N] (fp32) = A * B with bf16 operands in either storage order
- * (a_mn = 0: A is [M,K]; 1: A is [K,M].  b_mn = 0: B is [N,K]; 1: B is [K,N]). */
-int tt_debug_gemm_bf16(const void* A, int32_t a_mn, const void* B, int32_t b_mn, int64_t M,
-                       int64_t N, int64_t K, float* out, void* stream);
-
 int tt_cast_f32_to_bf16(const float* in, uint16_t* out, int64_t n, void* stream);
-
-/* Tuning hook: device buffer of 3 * (16 * 64 + 16) + 3 * 4 * 256 int64 that receives clock64() stamps of
- * the software pipeline of CTA (0,0) of the bf16 loss forward / dQ / dC kernels and per-CTA
- * {entry, setup done, exit, smid} globaltimer records (grids up to 256 CTAs); NULL = off. */
-int tt_debug_trace_buffer(long long* device_buf);
-/* Same for the fused tower kernels: 2 * 16 * 256 int64, per-CTA phase stamps (globaltimer ns). */
-int tt_debug_tower_trace(long long* device_buf);
-/* In-stream timeline of one training step: 32 int64 (16 kernel ids), {earliest CTA entry, latest CTA entry/exit} in globaltimer ns
- * for kernel ids 0 tower fwd, 1 loss fwd, 2 dQ, 3 dC, 4 tower bwd, 5 optimizer step, 6 sparse prepare.  The pointer
- * is read at run time (works on captured graphs).  Caller presets even slots to INT64_MAX, odd slots to 0. */
-int tt_debug_timeline(long long* device_buf);
 
 /* ---------------------------------------------------------------------------------------
  * K1+K2 fused  tower forward / backward for the two-layer tower of the BASELINE configs
@@ -389,13 +367,20 @@ int tt_combine_parts_f32(const float* parts, int32_t num_parts, int64_t rows, in
  * out_ids[q, j] = identifiers ? identifiers[idx] : cand_index_base + idx.
  * The candidate range may be split over `num_splits` CTAs columns (workspace holds the
  * partial lists) and merged with the same ordering rule.
+ * Two stages, so that the ids do not depend on the accumulation order of the scoring kernel:
+ * the scoring stage keeps the best k + TT_TOPK_RERANK_MARGIN candidates per query, the second
+ * stage recomputes their scores exactly (fp64 sum of the exact products), rounds once to fp32
+ * (the dtype of the TFRS score tensor) and orders by (score desc, index asc).  out_scores are
+ * those correctly rounded scores.  uncertain_rows (device int32, optional, incremented): number
+ * of query rows for which the margin could not be shown to be wide enough (expected 0).
+ * workspace_bytes >= tt_topk_workspace_bytes(...) is always required.
  * ------------------------------------------------------------------------------------- */
 int32_t tt_topk_num_splits(int32_t precision, int64_t nq, int64_t nc, int64_t d, int32_t k);
 int64_t tt_topk_workspace_bytes(int32_t precision, int64_t nq, int64_t nc, int64_t d, int32_t k);
 int tt_topk_bruteforce(int32_t precision, const void* queries, const void* candidates, int64_t nq,
                        int64_t nc, int64_t d, int32_t k, int64_t cand_index_base,
                        const int64_t* identifiers, float* out_scores, int64_t* out_ids,
-                       void* workspace, int64_t workspace_bytes, void* stream);
+                       int32_t* uncertain_rows, void* workspace, int64_t workspace_bytes, void* stream);
 /* Merge `num_lists` sorted top-k lists per query: scores/ids are [num_lists, nq, k_in]
  * (list-major, as written by per-shard searches after an all-gather); ids are candidate
  * INDICES and the ordering rule is (score desc, index asc).  Writes [nq, k_out] with

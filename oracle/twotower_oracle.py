@@ -312,20 +312,29 @@ def top_k(scores: np.ndarray, k: int):
     return np.take_along_axis(scores, order, axis=1), order
 
 
-def brute_force_topk(queries, candidates, k, identifiers=None, dtype=np.float64, block=4096):
+def brute_force_topk(queries, candidates, k, identifiers=None, dtype=np.float64, block=4096, score_dtype=None):
     """tfrs.layers.factorized_top_k.BruteForce.call == faiss.IndexFlatIP.search on tie-free
     data: scores = q @ cand^T, top_k, ids = gather(identifiers, indices).  Blocked over
     candidates (what IndexFlatIP does with sgemm blocks + heaps), merging with the
-    (score desc, index asc) rule so the result equals the unblocked tf.math.top_k."""
+    (score desc, index asc) rule so the result equals the unblocked tf.math.top_k.
+
+    score_dtype: dtype of the score TENSOR that top_k orders.  TFRS orders an fp32 matmul result whose last
+    bits depend on the BLAS summation order; the implementation-independent statement of that is
+    dtype=float64, score_dtype=float32: the exact dot product (fp64 sum of exact products) rounded ONCE to
+    fp32, ordered by (score desc, index asc).  None: order the `dtype` scores themselves."""
     q = queries.astype(dtype)
     nq = q.shape[0]
     n = candidates.shape[0]
     k = min(k, n)
-    best_s = np.full((nq, 0), 0, dtype=dtype)
+    sd = dtype if score_dtype is None else score_dtype
+    best_s = np.full((nq, 0), 0, dtype=sd)
     best_i = np.zeros((nq, 0), dtype=np.int64)
     for lo in range(0, n, block):
         hi = min(n, lo + block)
-        s = q @ candidates[lo:hi].astype(dtype).T
+        s = (q @ candidates[lo:hi].astype(dtype).T).astype(sd)
+        if hi - lo > 4 * k and best_s.shape[1] == k:
+            best_s, best_i = _merge_block_filtered(best_s, best_i, s, lo, k)
+            continue
         cs = np.concatenate([best_s, s], axis=1)
         ci = np.concatenate([best_i, np.broadcast_to(np.arange(lo, hi), (nq, hi - lo))], axis=1)
         # existing entries have lower indices and come first -> stable sort keeps the rule
@@ -334,6 +343,25 @@ def brute_force_topk(queries, candidates, k, identifiers=None, dtype=np.float64,
         best_i = np.take_along_axis(ci, order, axis=1)
     ids = best_i if identifiers is None else np.asarray(identifiers)[best_i]
     return best_s, ids
+
+
+def _merge_block_filtered(best_s, best_i, s, lo, k):
+    """Same result as the concat + stable argsort above, for wide blocks: only block entries that are >= the
+    row's current k-th best can enter (an equal score with a higher index never displaces a kept entry, but it
+    is harmless to consider it); survivors are merged with the stable rule."""
+    thr = best_s[:, k - 1]
+    rows, cols = np.nonzero(s > thr[:, None])            # row-major: ascending column inside a row
+    if rows.size == 0:
+        return best_s, best_i
+    starts = np.searchsorted(rows, np.arange(s.shape[0] + 1))
+    for r in np.unique(rows):
+        a, b = starts[r], starts[r + 1]
+        cs = np.concatenate([best_s[r], s[r, cols[a:b]]])
+        ci = np.concatenate([best_i[r], cols[a:b] + lo])
+        order = np.argsort(-cs, kind="stable")[:k]
+        best_s[r] = cs[order]
+        best_i[r] = ci[order]
+    return best_s, best_i
 
 
 def streaming_topk(queries, candidate_batches, k, dtype=np.float64):

@@ -291,15 +291,35 @@ class TestTopKTensorCore:
         self._check(ops, q, c, k, identifiers=ident)
         self._check(ops, q, c, k, base=777)
 
-    def test_gaussian_bf16_scores(self, ops):
-        rng = synth.rng_for(17)
-        q = oracle.bf16_round((rng.normal(size=(512, 128)) / np.sqrt(128)).astype(np.float32))
-        c = oracle.bf16_round((rng.normal(size=(50000, 128)) / np.sqrt(128)).astype(np.float32))
-        s, i = ops.topk_bruteforce("bf16", bf(q), bf(c), 100)
-        ref_s, ref_i = oracle.brute_force_topk(q, c, 100)
-        assert rel_err(s.cpu().numpy(), ref_s) < 1e-5
-        # fp32 accumulation order may swap near-ties only
-        assert (i.cpu().numpy() != ref_i).mean() < 1e-3
+    @pytest.mark.parametrize("nq,nc,d,k", [(512, 50000, 128, 100), (300, 20000, 64, 10), (4096, 200000, 128, 100),
+                                           (64, 100000, 256, 64)])
+    def test_gaussian_bf16_bit_exact_ids(self, ops, nq, nc, d, k):
+        """Real-valued data: the ids equal tf.math.top_k on the correctly rounded fp32 score tensor (exact re-rank of
+        the k + 16 pool, csrc/topk_rerank.cu) -- bit-exact, not 'up to near-tie swaps'."""
+        rng = synth.rng_for(17 + nq)
+        q = oracle.bf16_round((rng.normal(size=(nq, d)) / np.sqrt(d)).astype(np.float32))
+        c = oracle.bf16_round((rng.normal(size=(nc, d)) / np.sqrt(d)).astype(np.float32))
+        unc = torch.zeros(1, dtype=torch.int32, device="cuda")
+        s, i = ops.topk_bruteforce("bf16", bf(q), bf(c), k, uncertain=unc)
+        ref_s, ref_i = oracle.brute_force_topk(q, c, k, score_dtype=np.float32, block=16384)
+        assert np.array_equal(i.cpu().numpy(), ref_i)
+        assert np.array_equal(s.cpu().numpy(), ref_s)
+        assert int(unc.item()) == 0
+
+    def test_cfg5_distribution_10m_candidates_bit_exact_ids(self, ops):
+        """BASELINE configs[4] at full candidate count: 10 M x 128 bf16 candidates ~ N(0,1)/sqrt(d), top-100, a
+        256-query subset (the oracle's fp64 scoring of 2.56 G pairs takes ~1 min on the host)."""
+        nq, nc, d, k = 256, 10_000_000, 128, 100
+        g = torch.Generator(device="cuda"); g.manual_seed(5678)
+        cand = (torch.randn((nc, d), device="cuda", generator=g) / d ** 0.5).to(torch.bfloat16)
+        q = (torch.randn((nq, d), device="cuda", generator=g) / d ** 0.5).to(torch.bfloat16)
+        unc = torch.zeros(1, dtype=torch.int32, device="cuda")
+        s, i = ops.topk_bruteforce("bf16", q, cand, k, uncertain=unc)
+        c_host = cand.float().cpu().numpy(); q_host = q.float().cpu().numpy()
+        ref_s, ref_i = oracle.brute_force_topk(q_host, c_host, k, score_dtype=np.float32, block=65536)
+        assert np.array_equal(i.cpu().numpy(), ref_i)
+        assert np.array_equal(s.cpu().numpy(), ref_s)
+        assert int(unc.item()) == 0
 
     def test_brute_force_layer_and_metric(self, tt):
         tt.set_precision("bf16")

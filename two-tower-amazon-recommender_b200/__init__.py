@@ -9,9 +9,9 @@ TensorFlow-Recommenders-shaped Python surface.  See DESIGN.md / INTEGRATION.md.
             return self.task(self.user_model(features["user_id_encoded"]),
                              self.item_model(features["item_id_encoded"]))
 """
-from . import _lib, core, data, evaluation, layers, metrics, models, ops, optimizers, tasks  # noqa: F401
+from . import _lib, core, data, evaluation, layers, metrics, models, ops, optimizers, recipes, tasks  # noqa: F401
 from ._lib import TwoTowerError  # noqa: F401
 from .core import GradientTape, Tensor, Variable, config, set_precision, set_seed  # noqa: F401
 from .layers import Dense, Embedding, EmbeddingBag, FeatureSum, Sequential  # noqa: F401
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"

@@ -43,7 +43,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile every csrc/*.cu (one nvcc per file, in parallel) and link libtwotower.so."""
     nvcc = _nvcc()
     OBJ_DIR.mkdir(exist_ok=True)
-    headers = sorted(CSRC.glob("*.cuh")) + [PKG_DIR.parent / "include" / "twotower.h"]
+    headers = sorted(CSRC.glob("*.cuh")) + sorted((PKG_DIR.parent / "include").glob("*.h"))
     jobs = []
     for src in sources():
         obj = OBJ_DIR / (src.stem + ".o")

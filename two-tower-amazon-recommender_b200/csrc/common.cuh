@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include "../../include/twotower.h"
+#include "../../include/twotower_debug.h"
 
 namespace tt {
 

@@ -1,0 +1,110 @@
+// K6, second stage -- exact re-rank of the brute-force candidate pool.
+//
+// The scoring kernels (topk_tc.cu: tcgen05, fp32 accumulation inside the tensor core; topk_simt.cu: an fp32 FMA
+// chain) order candidates by a score whose last bits depend on the accumulation order, so on real-valued data
+// near-ties may come out in a different order than tf.math.top_k on the reference's score matrix (SURVEY.md A.4,
+// section 7 "hard parts").  The order is therefore fixed on an accumulation-order-INDEPENDENT score: the
+// scoring stage keeps a pool of k + margin candidates per query, this kernel recomputes the pool's scores
+// exactly -- products of bf16 (or fp32) inputs are exact in fp64, the d <= 256 terms are summed in fp64 -- rounds
+// them ONCE to fp32 (the dtype of the TFRS score tensor) and sorts by (score desc, candidate index asc).
+// A query row is counted in `uncertain` when the margin cannot be shown to have been wide enough: the k-th exact
+// score does not clear the pool's lowest stage-one score by 4x the largest stage-one error seen in the pool.
+#include "common.cuh"
+#include <limits.h>
+
+namespace tt {
+
+template <typename T> __device__ __forceinline__ double rr_ld(const T* p, int64_t i);
+template <> __device__ __forceinline__ double rr_ld<float>(const float* p, int64_t i) { return (double)__ldg(p + i); }
+template <> __device__ __forceinline__ double rr_ld<uint16_t>(const uint16_t* p, int64_t i) {
+  return (double)bf16_bits_to_float(__ldg(p + i));
+}
+
+constexpr int RR_WARPS = 8;
+constexpr int RR_MAXJ = 8;      // d <= 256: 8 elements per lane
+
+template <typename T>
+__global__ void __launch_bounds__(RR_WARPS * 32)
+topk_rerank_kernel(const T* __restrict__ Q, const T* __restrict__ C, int64_t nq, int d, const float* __restrict__ pool_s,
+                   const int64_t* __restrict__ pool_i, int kp, int k, int64_t base, const int64_t* __restrict__ identifiers,
+                   float* __restrict__ out_s, int64_t* __restrict__ out_i, int* __restrict__ uncertain, int has_discarded) {
+  extern __shared__ __align__(16) uint8_t rr_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* s32 = reinterpret_cast<float*>(rr_smem) + (size_t)warp * 2 * kp;
+  int* idx = reinterpret_cast<int*>(s32 + kp);
+  const int64_t qi = (int64_t)blockIdx.x * RR_WARPS + warp;
+  if (qi >= nq) return;
+  double qv[RR_MAXJ];
+#pragma unroll
+  for (int j = 0; j < RR_MAXJ; ++j) {
+    const int e = lane + 32 * j;
+    qv[j] = e < d ? rr_ld<T>(Q, qi * d + e) : 0.0;
+  }
+  float delta = 0.f, tmin = INFINITY;
+  for (int t = 0; t < kp; ++t) {
+    const int64_t ci = __ldg(pool_i + qi * kp + t);
+    if (ci == LLONG_MAX) {                      // short pool (fewer candidates than kp): never selected
+      if (lane == 0) { s32[t] = -INFINITY; idx[t] = INT_MAX; }
+      continue;
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < RR_MAXJ; ++j) {
+      const int e = lane + 32 * j;
+      if (e < d) acc = fma(qv[j], rr_ld<T>(C, ci * d + e), acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);     // commutative: same value in every lane
+    const float f = (float)acc;                 // ONE rounding, to nearest even
+    const float approx = __ldg(pool_s + qi * kp + t);
+    delta = fmaxf(delta, fabsf(approx - f));
+    tmin = fminf(tmin, approx);
+    if (lane == 0) { s32[t] = f; idx[t] = (int)ci; }
+  }
+  __syncwarp();
+  float kth = -INFINITY;
+  for (int e = lane; e < kp; e += 32) {
+    const float se = s32[e];
+    const int ie = idx[e];
+    if (ie == INT_MAX) continue;
+    int rank = 0;
+    for (int j = 0; j < kp; ++j) {
+      const float sj = s32[j];
+      const int ij = idx[j];
+      rank += (sj > se || (sj == se && ij < ie)) ? 1 : 0;
+    }
+    if (rank < k) {
+      out_s[qi * k + rank] = se;
+      out_i[qi * k + rank] = identifiers ? __ldg(identifiers + ie) : base + ie;
+      if (rank == k - 1) kth = se;
+    }
+  }
+  if (uncertain != nullptr && has_discarded) {
+    kth = warp_max(kth);
+    if (lane == 0 && delta > 0.f && !(kth > tmin + 4.f * delta)) atomicAdd(uncertain, 1);
+  }
+}
+
+int topk_rerank(int precision, const void* queries, const void* candidates, int64_t nq, int64_t nc, int64_t d,
+                const float* pool_s, const int64_t* pool_i, int kp, int k, int64_t base, const int64_t* identifiers,
+                float* out_s, int64_t* out_i, int32_t* uncertain, cudaStream_t st) {
+  TT_REQUIRE(d <= 32 * RR_MAXJ, "tt_topk_bruteforce: exact re-rank needs d <= %d", 32 * RR_MAXJ);
+  const size_t smem = (size_t)RR_WARPS * 2 * kp * 4;
+  const unsigned blocks = (unsigned)ceil_div(nq, RR_WARPS);
+  const int has_discarded = nc > kp ? 1 : 0;
+  if (precision == TT_F32) {
+    TT_CUDA_OK(cudaFuncSetAttribute(topk_rerank_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TT_PROF("topk_rerank_kernel", st), topk_rerank_kernel<float><<<blocks, RR_WARPS * 32, smem, st>>>(
+        (const float*)queries, (const float*)candidates, nq, (int)d, pool_s, pool_i, kp, k, base, identifiers, out_s, out_i,
+        uncertain, has_discarded);
+  } else {
+    TT_CUDA_OK(cudaFuncSetAttribute(topk_rerank_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TT_PROF("topk_rerank_kernel", st), topk_rerank_kernel<uint16_t><<<blocks, RR_WARPS * 32, smem, st>>>(
+        (const uint16_t*)queries, (const uint16_t*)candidates, nq, (int)d, pool_s, pool_i, kp, k, base, identifiers, out_s, out_i,
+        uncertain, has_discarded);
+  }
+  TT_LAUNCH_OK("topk_rerank_kernel");
+  return TT_OK;
+}
+
+}  // namespace tt

@@ -15,6 +15,7 @@ int tc_topk(const void* queries, const void* candidates, int64_t nq, int64_t nc,
             int64_t cand_index_base, const int64_t* identifiers, float* out_scores, int64_t* out_ids, void* ws,
             int64_t ws_bytes, cudaStream_t st);
 int tc_topk_num_splits(int64_t nq, int64_t nc, int64_t d, int k);
+int tc_topk_max_k(int64_t d);
 
 // Partial (or final) result writer shared with the tensor-core kernel: row r of the state ->
 // out arrays, padding short lists with (-inf, INT64_MAX).
@@ -198,10 +199,24 @@ extern "C" int32_t tt_topk_num_splits(int32_t precision, int64_t nq, int64_t nc,
   return simt_num_splits(nq, nc);
 }
 
-extern "C" int64_t tt_topk_workspace_bytes(int32_t precision, int64_t nq, int64_t nc, int64_t d, int32_t k) {
-  const int s = tt_topk_num_splits(precision, nq, nc, d, k);
+// Pool size of the scoring stage: k + margin candidates per query go to the exact re-rank (topk_rerank.cu).
+static int pool_k(int32_t precision, int64_t d, int k, int64_t nc) {
+  int64_t kp = std::min<int64_t>(k + TT_TOPK_RERANK_MARGIN, 512);
+  if (precision == TT_BF16) kp = std::min<int64_t>(kp, tc_topk_max_k(d));     // the margin shrinks before k is refused
+  if (kp < k) kp = k;
+  return (int)std::min<int64_t>(kp, nc);
+}
+
+static int64_t stage1_bytes(int32_t precision, int64_t nq, int64_t nc, int64_t d, int kp) {
+  const int s = tt_topk_num_splits(precision, nq, nc, d, kp);
   if (s <= 1) return 256;
-  return round_up((int64_t)s * nq * k * 4, 256) + round_up((int64_t)s * nq * k * 8, 256);
+  return round_up((int64_t)s * nq * kp * 4, 256) + round_up((int64_t)s * nq * kp * 8, 256);
+}
+
+extern "C" int64_t tt_topk_workspace_bytes(int32_t precision, int64_t nq, int64_t nc, int64_t d, int32_t k) {
+  const int kp = pool_k(precision, d, k, nc);
+  // [pool scores | pool indices | partial lists of the split scoring stage]
+  return round_up(nq * kp * 4, 256) + round_up(nq * kp * 8, 256) + stage1_bytes(precision, nq, nc, d, kp);
 }
 
 extern "C" int tt_topk_merge(const float* scores, const int64_t* ids, int32_t num_lists, int64_t nq, int32_t k_in,
@@ -217,27 +232,15 @@ extern "C" int tt_topk_merge(const float* scores, const int64_t* ids, int32_t nu
   return TT_OK;
 }
 
-extern "C" int tt_topk_bruteforce(int32_t precision, const void* queries, const void* candidates, int64_t nq,
-                                  int64_t nc, int64_t d, int32_t k, int64_t cand_index_base,
-                                  const int64_t* identifiers, float* out_scores, int64_t* out_ids,
-                                  void* workspace, int64_t workspace_bytes, void* stream) {
-  TT_REQUIRE(precision == TT_F32 || precision == TT_BF16, "tt_topk_bruteforce: unknown precision %d", precision);
-  TT_REQUIRE(queries && candidates && out_scores && out_ids, "tt_topk_bruteforce: null buffer");
-  TT_REQUIRE(nq > 0 && nc > 0 && d > 0 && nc < INT_MAX, "tt_topk_bruteforce: bad sizes");
-  TT_REQUIRE(k >= 1 && k <= nc, "tt_topk_bruteforce: k=%d must be in [1, num_candidates=%lld]", k, (long long)nc);
-  TT_REQUIRE(k <= 512, "tt_topk_bruteforce: k=%d exceeds the supported maximum 512", k);
-  TT_REQUIRE(aligned16(queries) && aligned16(candidates), "tt_topk_bruteforce: inputs must be 16-byte aligned");
-  cudaStream_t st = (cudaStream_t)stream;
-  if (precision == TT_BF16)
-    return tc_topk(queries, candidates, nq, nc, d, k, cand_index_base, identifiers, out_scores, out_ids, workspace,
-                   workspace_bytes, st);
+static int simt_topk(const void* queries, const void* candidates, int64_t nq, int64_t nc, int64_t d, int k,
+                     float* out_scores, int64_t* out_ids, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
   TT_REQUIRE(d % 4 == 0 && d <= 256, "tt_topk_bruteforce: fp32 path needs d %% 4 == 0 and d <= 256");
   const size_t smem = simt_topk_smem((int)d, k);
   if (smem > kMaxSmem) return set_error(TT_ERR_UNSUPPORTED, "tt_topk_bruteforce: d=%lld k=%d needs %zu bytes of shared memory (> %zu)", (long long)d, k, smem, kMaxSmem);
   const int splits = simt_num_splits(nq, nc);
   float* ps = out_scores; int64_t* pi = out_ids;
   if (splits > 1) {
-    const int64_t need = tt_topk_workspace_bytes(precision, nq, nc, d, k);
+    const int64_t need = round_up((int64_t)splits * nq * k * 4, 256) + round_up((int64_t)splits * nq * k * 8, 256);
     if (!workspace || workspace_bytes < need) return set_error(TT_ERR_WORKSPACE, "tt_topk_bruteforce: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
     ps = (float*)workspace;
     pi = (int64_t*)((char*)workspace + round_up((int64_t)splits * nq * k * 4, 256));
@@ -248,7 +251,7 @@ extern "C" int tt_topk_bruteforce(int32_t precision, const void* queries, const 
   {                                                                                                         \
     TT_CUDA_OK(cudaFuncSetAttribute(topk_simt_kernel<KU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     TT_PROF("topk_simt_kernel", st), topk_simt_kernel<KU><<<grid, 256, smem, st>>>((const float*)queries, (const float*)candidates, nq, nc, (int)d, k, \
-                                                  cand_index_base, identifiers, split_len, ps, pi);          \
+                                                  0, nullptr, split_len, ps, pi);                           \
   }
   if (k <= 32) TT_TOPK_LAUNCH(1)
   else if (k <= 64) TT_TOPK_LAUNCH(2)
@@ -257,8 +260,46 @@ extern "C" int tt_topk_bruteforce(int32_t precision, const void* queries, const 
   else TT_TOPK_LAUNCH(16)
 #undef TT_TOPK_LAUNCH
   TT_LAUNCH_OK("topk_simt_kernel");
-  if (splits > 1) return tt_topk_merge(ps, pi, splits, nq, k, k, cand_index_base, identifiers, out_scores, out_ids, stream);
+  if (splits > 1) return tt_topk_merge(ps, pi, splits, nq, k, k, 0, nullptr, out_scores, out_ids, st);
   return TT_OK;
+}
+
+namespace tt {
+int topk_rerank(int precision, const void* queries, const void* candidates, int64_t nq, int64_t nc, int64_t d,
+                const float* pool_s, const int64_t* pool_i, int kp, int k, int64_t base, const int64_t* identifiers,
+                float* out_s, int64_t* out_i, int32_t* uncertain, cudaStream_t st);
+}
+
+// Two stages: (1) scoring fused with a running top-(k + margin) -- tcgen05 (bf16) or CUDA-core (fp32) -- into a pool
+// of raw candidate indices; (2) exact re-rank of the pool (topk_rerank.cu), which fixes the order on the correctly
+// rounded fp32 score and applies identifiers / cand_index_base.
+extern "C" int tt_topk_bruteforce(int32_t precision, const void* queries, const void* candidates, int64_t nq,
+                                  int64_t nc, int64_t d, int32_t k, int64_t cand_index_base,
+                                  const int64_t* identifiers, float* out_scores, int64_t* out_ids,
+                                  int32_t* uncertain_rows, void* workspace, int64_t workspace_bytes, void* stream) {
+  TT_REQUIRE(precision == TT_F32 || precision == TT_BF16, "tt_topk_bruteforce: unknown precision %d", precision);
+  TT_REQUIRE(queries && candidates && out_scores && out_ids, "tt_topk_bruteforce: null buffer");
+  TT_REQUIRE(nq > 0 && nc > 0 && d > 0 && nc < INT_MAX, "tt_topk_bruteforce: bad sizes");
+  TT_REQUIRE(k >= 1 && k <= nc, "tt_topk_bruteforce: k=%d must be in [1, num_candidates=%lld]", k, (long long)nc);
+  TT_REQUIRE(k <= 512, "tt_topk_bruteforce: k=%d exceeds the supported maximum 512", k);
+  TT_REQUIRE(aligned16(queries) && aligned16(candidates), "tt_topk_bruteforce: inputs must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int kp = pool_k(precision, d, k, nc);
+  const int64_t need = tt_topk_workspace_bytes(precision, nq, nc, d, k);
+  if (!workspace || workspace_bytes < need)
+    return set_error(TT_ERR_WORKSPACE, "tt_topk_bruteforce: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
+  float* pool_s = (float*)workspace;
+  int64_t* pool_i = (int64_t*)((char*)workspace + round_up(nq * kp * 4, 256));
+  char* rest = (char*)pool_i + round_up(nq * kp * 8, 256);
+  const int64_t rest_bytes = workspace_bytes - (rest - (char*)workspace);
+  int rc;
+  if (precision == TT_BF16)
+    rc = tc_topk(queries, candidates, nq, nc, d, kp, 0, nullptr, pool_s, pool_i, rest, rest_bytes, st);
+  else
+    rc = simt_topk(queries, candidates, nq, nc, d, kp, pool_s, pool_i, rest, rest_bytes, st);
+  if (rc) return rc;
+  return topk_rerank(precision, queries, candidates, nq, nc, d, pool_s, pool_i, kp, k, cand_index_base, identifiers,
+                     out_scores, out_ids, uncertain_rows, st);
 }
 
 extern "C" int tt_topk_hits(const float* positive, const float* topk_scores, const int64_t* topk_ids,

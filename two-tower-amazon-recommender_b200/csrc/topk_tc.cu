@@ -239,6 +239,15 @@ static int tc_topk_splits(int64_t nq, int64_t nc, int bn, int* tiles_per_split) 
   return (int)ceil_div(y128, per128);
 }
 
+// largest k whose key lists leave room for a 2-stage candidate ring
+int tc_topk_max_k(int64_t d) {
+  if (d % 64 != 0 || d < 64 || d > 256) return 0;
+  const int bn = tk_bn_for(d);
+  int k = 512;
+  while (k > 0 && topk_tc_layout((int)d, k, bn).stages < 2) --k;
+  return k;
+}
+
 int tc_topk_num_splits(int64_t nq, int64_t nc, int64_t d, int k) {
   int tps;
   return tc_topk_splits(nq, nc, tk_bn_for(d), &tps);

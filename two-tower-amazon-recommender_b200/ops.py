@@ -650,7 +650,10 @@ def combine_parts(parts, want_f32: bool = True, want_bf16: bool = False, out_f32
 
 
 # ------------------------------------------------------------------------------------ K6
-def topk_bruteforce(precision: str, queries, candidates, k: int, cand_index_base: int = 0, identifiers=None):
+def topk_bruteforce(precision: str, queries, candidates, k: int, cand_index_base: int = 0, identifiers=None,
+                    uncertain: Optional[torch.Tensor] = None):
+    """Exact top-k: scoring stage (k + margin pool) + exact re-rank.  uncertain: optional device int32 [1] counter of
+    rows whose margin could not be shown wide enough (see include/twotower.h)."""
     lib = _lib.load()
     pc = precision_code(precision)
     dt = torch.float32 if precision == "fp32" else torch.bfloat16
@@ -659,13 +662,15 @@ def topk_bruteforce(precision: str, queries, candidates, k: int, cand_index_base
     dev = queries.device
     scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
     ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    if nq == 0:
+        return scores, ids
     nbytes = int(lib.tt_topk_workspace_bytes(pc, nq, nc, d, k))
     ws = _workspace(nbytes, dev)
     splits = int(lib.tt_topk_num_splits(pc, nq, nc, d, k))
     check(lib.tt_topk_bruteforce(pc, _ptr(queries, dt), _ptr(candidates, dt), nq, nc, d, k, cand_index_base,
-                                 _ptr(identifiers, torch.int64), _ptr(scores), _ptr(ids), _ptr(ws), ws.numel(),
-                                 _stream()))
-    _count(2 if splits > 1 else 1)
+                                 _ptr(identifiers, torch.int64), _ptr(scores), _ptr(ids), _ptr(uncertain, torch.int32),
+                                 _ptr(ws), ws.numel(), _stream()))
+    _count(3 if splits > 1 else 2)
     return scores, ids
 
 

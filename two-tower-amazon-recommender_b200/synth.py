@@ -32,6 +32,8 @@ CONFIGS = {
     # ID + multi-hot category/brand with mean pooling, 10M items, B=16384
     "cfg3": Config("cfg3", 3456, 16384, 128, 10_000_000, 10_000_000, (256, 128), 0.1,
                    bags={"category": (32768, 1, 8), "brand": (1_048_576, 1, 2)}),
+    # row-sharded 100M-row tables across 8 GPUs, B_glob = 65536 (8192 per GPU), global-batch negatives
+    "cfg4": Config("cfg4", 4567, 8192, 128, 100_000_000, 100_000_000, (256, 128), 0.1),
 }
 
 
@@ -56,8 +58,10 @@ def draw_bags(rng: np.random.Generator, n: int, vocab: int, lmin: int, lmax: int
     return values, offsets
 
 
-def make_batch(cfg: Config, step: int = 0, batch: int | None = None) -> Dict[str, object]:
-    """One batch of the config: user_id_encoded / item_id_encoded (+ bag features)."""
+def make_batch(cfg: Config, step: int = 0, batch: int | None = None, pad_bags: bool = False) -> Dict[str, object]:
+    """One batch of the config: user_id_encoded / item_id_encoded (+ bag features as CSR (values, offsets)).
+    pad_bags: `values` padded with -1 to the static capacity batch * Lmax (CUDA-graph replay needs fixed shapes; the
+    kernels read offsets[batch] members and drop negative ids)."""
     rng = rng_for(cfg.seed * 1_000_003 + step)
     b = batch or cfg.batch
     out = {
@@ -65,7 +69,12 @@ def make_batch(cfg: Config, step: int = 0, batch: int | None = None) -> Dict[str
         "item_id_encoded": draw_ids(rng, b, cfg.v_item, cfg.zipf),
     }
     for name, (vocab, lmin, lmax) in cfg.bags.items():
-        out[name] = draw_bags(rng, b, vocab, lmin, lmax)
+        values, offsets = draw_bags(rng, b, vocab, lmin, lmax)
+        if pad_bags:
+            padded = np.full(b * lmax, -1, dtype=np.int64)
+            padded[:values.size] = values
+            values = padded
+        out[name] = (values, offsets)
     return out
 
 
