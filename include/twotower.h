@@ -381,6 +381,17 @@ int tt_topk_bruteforce(int32_t precision, const void* queries, const void* candi
                        int64_t nc, int64_t d, int32_t k, int64_t cand_index_base,
                        const int64_t* identifiers, float* out_scores, int64_t* out_ids,
                        int32_t* uncertain_rows, void* workspace, int64_t workspace_bytes, void* stream);
+/* Candidate-sharded serving (BASELINE configs[4]): every rank scores ALL nq queries against ITS shard
+ * (global index of local candidate 0 = cand_index_base) and the exact partial top-k of query qi is written by the kernel's
+ * epilogue -- posted NVLink stores, no exchange kernel -- into the symmetric workspace of the rank that merges that query,
+ * owner = qi / queries_per_rank: scores [world, queries_per_rank, k] fp32 at peer_bases[owner] + recv_scores_offset,
+ * global candidate indices [world, queries_per_rank, k] int64 at + recv_ids_offset, list slot [rank].  After a
+ * tt_peer_barrier the owner runs tt_topk_merge over its `world` lists.  peer_bases: device int64 [world]. */
+int tt_topk_bruteforce_peer(int32_t precision, const void* queries, const void* candidates, int64_t nq,
+                            int64_t nc, int64_t d, int32_t k, int64_t cand_index_base,
+                            const int64_t* peer_bases, int32_t world, int32_t rank, int64_t queries_per_rank,
+                            int64_t recv_scores_offset, int64_t recv_ids_offset, int32_t* uncertain_rows,
+                            void* workspace, int64_t workspace_bytes, void* stream);
 /* Merge `num_lists` sorted top-k lists per query: scores/ids are [num_lists, nq, k_in]
  * (list-major, as written by per-shard searches after an all-gather); ids are candidate
  * INDICES and the ordering rule is (score desc, index asc).  Writes [nq, k_out] with

@@ -118,3 +118,34 @@ def test_dc_pass_scattering_through_tensor_maps_matches_the_combine_path(tt):
     torch.cuda.synchronize()
     for o in range(world):
         assert torch.equal(recv[o][rank * b:(rank + 1) * b], dc_parts[0][o * b:(o + 1) * b])
+
+
+def test_topk_partials_written_into_owner_receive_areas_and_merged(tt):
+    """Candidate-sharded serving on one GPU: each emulated rank scores ALL queries against its shard; the re-rank epilogue
+    writes the partial list of query qi into list slot [rank] of the receive area of rank qi // qpr; every owner then
+    merges its W lists.  Result == the single-device search == the oracle (ids bit-exact, incl. cross-shard ties)."""
+    import oracle
+    from two_tower_b200 import synth
+    ops = tt.ops
+    d, k, qpr, per = 128, 100, 96, 6000 + 64
+    nq = W * qpr
+    rng = synth.rng_for(808)
+    cand = oracle.bf16_round((rng.normal(size=(W * per, d)) / np.sqrt(d)).astype(np.float32))
+    cand[per + 5] = cand[5]                                   # an exact duplicate in the other shard
+    q = oracle.bf16_round((rng.normal(size=(nq, d)) / np.sqrt(d)).astype(np.float32))
+    off_s = 1024
+    off_i = off_s + W * qpr * k * 4
+    bufs, wss = _workspaces(tt, off_i + W * qpr * k * 8)
+    qd = torch.as_tensor(q).cuda().to(torch.bfloat16)
+    unc = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for r in range(W):
+        shard = torch.as_tensor(cand[r * per:(r + 1) * per]).cuda().to(torch.bfloat16)
+        ops.topk_bruteforce_peer("bf16", qd, shard, k, r * per, wss[r], qpr, off_s, off_i, uncertain=unc)
+    ref_s, ref_i = oracle.brute_force_topk(q, cand, k, score_dtype=np.float32, block=4096)
+    for o in range(W):
+        s, i = ops.topk_merge(wss[o].view(off_s, (W, qpr, k), torch.float32), wss[o].view(off_i, (W, qpr, k), torch.int64), k)
+        assert np.array_equal(i.cpu().numpy(), ref_i[o * qpr:(o + 1) * qpr])
+        assert np.array_equal(s.cpu().numpy(), ref_s[o * qpr:(o + 1) * qpr])
+    assert int(unc.item()) == 0
+    s1, i1 = ops.topk_bruteforce("bf16", qd, torch.as_tensor(cand).cuda().to(torch.bfloat16), k)
+    assert np.array_equal(i1.cpu().numpy(), ref_i)

@@ -81,6 +81,21 @@ class CpuPrims:
         return dict(dq=torch.from_numpy(r["dq"]), dc=torch.from_numpy(dc), dq_bf16=None, dc_bf16=None)
 
 
+    @staticmethod
+    def topk_bruteforce(prec, q, c, k, cand_index_base=0, identifiers=None, uncertain=None):
+        import oracle
+        s, i = oracle.brute_force_topk(q.numpy(), c.numpy(), k, score_dtype=np.float32)
+        return torch.from_numpy(s), torch.from_numpy(i + cand_index_base)
+
+    @staticmethod
+    def topk_merge(scores, ids, k_out, index_base=0, identifiers=None):
+        import oracle
+        L = scores.shape[0]
+        s, i = oracle.topk_merge([scores[l].numpy() for l in range(L)], [ids[l].numpy() for l in range(L)], k_out)
+        i = i + index_base if identifiers is None else identifiers.numpy()[i]
+        return torch.from_numpy(s), torch.from_numpy(i)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -163,5 +178,49 @@ def test_sharded_lookup_gradients_and_global_negatives_world2():
     results = mgr.dict()
     port = _free_port()
     mp.spawn(_worker, args=(port, results), nprocs=WORLD, join=True)
+    for r in range(WORLD):
+        assert results.get(r) == "ok", results.get(r)
+
+
+def _serving_worker(rank, port, results):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    try:
+        import oracle
+        import two_tower_b200 as tt
+        from two_tower_b200 import synth
+        rng = synth.rng_for(91)
+        d, k, nq = 16, 10, 6 * WORLD
+        sizes = [300, 211]                                   # ragged shards
+        cand = synth.exact_matrix(rng, sum(sizes), d, 2)     # dyadic: real ties, also ACROSS shards
+        q = synth.exact_matrix(rng, nq, d, 2)
+        ident = rng.permutation(sum(sizes)).astype(np.int64) + 1000
+        lo = sum(sizes[:rank])
+        ref_s, ref_i = oracle.brute_force_topk(q, cand, k, score_dtype=np.float32)
+        for use_ident in (False, True):
+            index = tt.serving.ShardedBruteForce(k=k, group=dist.group.WORLD, precision="fp32", prim=CpuPrims)
+            assert index.exchange == "collective"
+            index.index(torch.from_numpy(cand[lo:lo + sizes[rank]]),
+                        identifiers=torch.from_numpy(ident[lo:lo + sizes[rank]]) if use_ident else None)
+            s, i = index(torch.from_numpy(q))
+            a, b = rank * (nq // WORLD), (rank + 1) * (nq // WORLD)
+            want = ident[ref_i[a:b]] if use_ident else ref_i[a:b]
+            assert np.array_equal(i.numpy(), want)
+            assert np.array_equal(s.numpy(), ref_s[a:b])
+        with pytest.raises(ValueError, match="multiple of the group size"):
+            index(torch.from_numpy(q[:nq - 1]))
+        results[rank] = "ok"
+    except Exception:
+        import traceback
+        results[rank] = traceback.format_exc()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_candidate_sharded_topk_routing_world2():
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_serving_worker, args=(_free_port(), results), nprocs=WORLD, join=True)
     for r in range(WORLD):
         assert results.get(r) == "ok", results.get(r)

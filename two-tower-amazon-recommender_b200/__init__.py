@@ -10,6 +10,7 @@ TensorFlow-Recommenders-shaped Python surface.  See DESIGN.md / INTEGRATION.md.
                              self.item_model(features["item_id_encoded"]))
 """
 from . import _lib, core, data, evaluation, layers, metrics, models, ops, optimizers, recipes, tasks  # noqa: F401
+from . import serving  # noqa: F401,E402
 from ._lib import TwoTowerError  # noqa: F401
 from .core import GradientTape, Tensor, Variable, config, set_precision, set_seed  # noqa: F401
 from .layers import Dense, Embedding, EmbeddingBag, FeatureSum, Sequential  # noqa: F401

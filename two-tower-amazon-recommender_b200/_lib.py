@@ -110,6 +110,7 @@ SIGNATURES = {
     "tt_topk_num_splits": (_i32, [_i32, _i64, _i64, _i64, _i32]),
     "tt_topk_workspace_bytes": (_i64, [_i32, _i64, _i64, _i64, _i32]),
     "tt_topk_bruteforce": (C.c_int, [_i32, _p, _p, _i64, _i64, _i64, _i32, _i64, _p, _p, _p, _p, _p, _i64, _p]),
+    "tt_topk_bruteforce_peer": (C.c_int, [_i32, _p, _p, _i64, _i64, _i64, _i32, _i64, _p, _i32, _i32, _i64, _i64, _i64, _p, _p, _i64, _p]),
     "tt_topk_merge": (C.c_int, [_p, _p, _i32, _i64, _i32, _i32, _i64, _p, _p, _p, _p]),
     "tt_topk_hits": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, C.POINTER(_i32), _i32, _p, _p, _p]),
     "tt_rowwise_dot": (C.c_int, [_i32, _p, _p, _p, _i64, _i64, _p]),

@@ -509,11 +509,7 @@ __device__ __forceinline__ void apply_row(const SparseMultiVar& V, int64_t id, i
 }
 
 template <bool ADAM>
-__global__ void __launch_bounds__(256)
-optimizer_step_kernel(const __grid_constant__ StepArgs a, float lr_or_alpha, float b1, float b2, float eps) {
-  pdl_wait();                       // launched while the backward tower kernel drains
-  pdl_launch_dependents();
-  tl_mark(g_tl, 5, true);
+__device__ __forceinline__ void optimizer_step_body(const StepArgs& a, float lr_or_alpha, float b1, float b2, float eps) {
   const int lane = threadIdx.x & 31;
   const int bid = blockIdx.x;
   if (bid < a.dense_blocks[a.n_dense]) {
@@ -625,6 +621,20 @@ optimizer_step_kernel(const __grid_constant__ StepArgs a, float lr_or_alpha, flo
     apply_row<ADAM>(V, id, c, g, lr_or_alpha, b1, b2, eps);
   }
   if (lane == 0) { V.ws.keys[h] = kEmpty; V.ws.first[h] = INT_MAX; V.ws.cnt[h] = 0; V.ws.done[h] = 0; }
+}
+
+template <bool ADAM>
+__global__ void __launch_bounds__(256)
+optimizer_step_kernel(const __grid_constant__ StepArgs a, float lr_or_alpha, float b1, float b2, float eps) {
+  pdl_wait();                       // launched while the backward tower kernel drains
+  pdl_launch_dependents();
+  long long* const tl = g_tl;
+  tl_mark(tl, 5, true);
+  optimizer_step_body<ADAM>(a, lr_or_alpha, b1, b2, eps);
+  if (tl) {                         // timeline only: the span runs to the EXIT of the last block
+    __syncthreads();
+    tl_mark(tl, 5, false);
+  }
 }
 
 // out_i = ordered sum of the split partials of variable i, for all variables in one launch (before the

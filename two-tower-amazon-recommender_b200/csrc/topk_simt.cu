@@ -265,20 +265,26 @@ static int simt_topk(const void* queries, const void* candidates, int64_t nq, in
 }
 
 namespace tt {
+struct TopkPeerOut {
+  unsigned char* const* bases;
+  long long off_s, off_i;
+  int queries_per_rank, rank;
+};
 int topk_rerank(int precision, const void* queries, const void* candidates, int64_t nq, int64_t nc, int64_t d,
                 const float* pool_s, const int64_t* pool_i, int kp, int k, int64_t base, const int64_t* identifiers,
-                float* out_s, int64_t* out_i, int32_t* uncertain, cudaStream_t st);
+                float* out_s, int64_t* out_i, int32_t* uncertain, const TopkPeerOut* peer_out, cudaStream_t st);
 }
 
 // Two stages: (1) scoring fused with a running top-(k + margin) -- tcgen05 (bf16) or CUDA-core (fp32) -- into a pool
 // of raw candidate indices; (2) exact re-rank of the pool (topk_rerank.cu), which fixes the order on the correctly
 // rounded fp32 score and applies identifiers / cand_index_base.
-extern "C" int tt_topk_bruteforce(int32_t precision, const void* queries, const void* candidates, int64_t nq,
-                                  int64_t nc, int64_t d, int32_t k, int64_t cand_index_base,
-                                  const int64_t* identifiers, float* out_scores, int64_t* out_ids,
-                                  int32_t* uncertain_rows, void* workspace, int64_t workspace_bytes, void* stream) {
+static int topk_bruteforce_impl(int32_t precision, const void* queries, const void* candidates, int64_t nq,
+                                int64_t nc, int64_t d, int32_t k, int64_t cand_index_base,
+                                const int64_t* identifiers, float* out_scores, int64_t* out_ids,
+                                int32_t* uncertain_rows, const TopkPeerOut* peer, void* workspace, int64_t workspace_bytes,
+                                void* stream) {
   TT_REQUIRE(precision == TT_F32 || precision == TT_BF16, "tt_topk_bruteforce: unknown precision %d", precision);
-  TT_REQUIRE(queries && candidates && out_scores && out_ids, "tt_topk_bruteforce: null buffer");
+  TT_REQUIRE(queries && candidates && (peer || (out_scores && out_ids)), "tt_topk_bruteforce: null buffer");
   TT_REQUIRE(nq > 0 && nc > 0 && d > 0 && nc < INT_MAX, "tt_topk_bruteforce: bad sizes");
   TT_REQUIRE(k >= 1 && k <= nc, "tt_topk_bruteforce: k=%d must be in [1, num_candidates=%lld]", k, (long long)nc);
   TT_REQUIRE(k <= 512, "tt_topk_bruteforce: k=%d exceeds the supported maximum 512", k);
@@ -299,7 +305,34 @@ extern "C" int tt_topk_bruteforce(int32_t precision, const void* queries, const 
     rc = simt_topk(queries, candidates, nq, nc, d, kp, pool_s, pool_i, rest, rest_bytes, st);
   if (rc) return rc;
   return topk_rerank(precision, queries, candidates, nq, nc, d, pool_s, pool_i, kp, k, cand_index_base, identifiers,
-                     out_scores, out_ids, uncertain_rows, st);
+                     out_scores, out_ids, uncertain_rows, peer, st);
+}
+
+// Two stages: (1) scoring fused with a running top-(k + margin) -- tcgen05 (bf16) or CUDA-core (fp32) -- into a pool
+// of raw candidate indices; (2) exact re-rank of the pool (topk_rerank.cu), which fixes the order on the correctly
+// rounded fp32 score and applies identifiers / cand_index_base.
+extern "C" int tt_topk_bruteforce(int32_t precision, const void* queries, const void* candidates, int64_t nq,
+                                  int64_t nc, int64_t d, int32_t k, int64_t cand_index_base,
+                                  const int64_t* identifiers, float* out_scores, int64_t* out_ids,
+                                  int32_t* uncertain_rows, void* workspace, int64_t workspace_bytes, void* stream) {
+  return topk_bruteforce_impl(precision, queries, candidates, nq, nc, d, k, cand_index_base, identifiers, out_scores,
+                              out_ids, uncertain_rows, nullptr, workspace, workspace_bytes, stream);
+}
+
+// Candidate-sharded serving: this rank's shard is scored for ALL nq queries; the exact partial list of query qi is
+// written by the re-rank epilogue into list slot [rank] of the receive area of rank qi / queries_per_rank.
+extern "C" int tt_topk_bruteforce_peer(int32_t precision, const void* queries, const void* candidates, int64_t nq,
+                                       int64_t nc, int64_t d, int32_t k, int64_t cand_index_base,
+                                       const int64_t* peer_bases, int32_t world, int32_t rank, int64_t queries_per_rank,
+                                       int64_t recv_scores_offset, int64_t recv_ids_offset, int32_t* uncertain_rows,
+                                       void* workspace, int64_t workspace_bytes, void* stream) {
+  TT_REQUIRE(peer_bases && world >= 1 && world <= 16 && rank >= 0 && rank < world, "tt_topk_bruteforce_peer: bad world / rank");
+  TT_REQUIRE(queries_per_rank >= 1 && queries_per_rank * world >= nq, "tt_topk_bruteforce_peer: queries_per_rank * world < nq");
+  TT_REQUIRE((recv_scores_offset & 15) == 0 && (recv_ids_offset & 15) == 0, "tt_topk_bruteforce_peer: offsets must be 16-byte aligned");
+  TopkPeerOut peer{reinterpret_cast<unsigned char* const*>(peer_bases), recv_scores_offset, recv_ids_offset,
+                   (int)queries_per_rank, rank};
+  return topk_bruteforce_impl(precision, queries, candidates, nq, nc, d, k, cand_index_base, nullptr, nullptr, nullptr,
+                              uncertain_rows, &peer, workspace, workspace_bytes, stream);
 }
 
 extern "C" int tt_topk_hits(const float* positive, const float* topk_scores, const int64_t* topk_ids,

@@ -674,6 +674,27 @@ def topk_bruteforce(precision: str, queries, candidates, k: int, cand_index_base
     return scores, ids
 
 
+def topk_bruteforce_peer(precision: str, queries, candidates, k: int, cand_index_base: int, ws: "PeerWorkspace",
+                         queries_per_rank: int, recv_scores_offset: int, recv_ids_offset: int,
+                         uncertain: Optional[torch.Tensor] = None) -> None:
+    """Candidate-sharded serving: score ALL queries against this rank's shard; the exact partial list of query qi lands in
+    list slot [rank] of the receive area ([world, queries_per_rank, k] scores / global indices at the given offsets of
+    the symmetric workspace) of rank qi // queries_per_rank.  Follow with peer_barrier + topk_merge."""
+    lib = _lib.load()
+    pc = precision_code(precision)
+    dt = torch.float32 if precision == "fp32" else torch.bfloat16
+    nq, d = queries.shape
+    nc = candidates.shape[0]
+    nbytes = int(lib.tt_topk_workspace_bytes(pc, nq, nc, d, k))
+    scratch = _workspace(nbytes, queries.device)
+    splits = int(lib.tt_topk_num_splits(pc, nq, nc, d, k))
+    check(lib.tt_topk_bruteforce_peer(pc, _ptr(queries, dt), _ptr(candidates, dt), nq, nc, d, k, int(cand_index_base),
+                                      _ptr(ws.bases, torch.int64), ws.world, ws.rank, int(queries_per_rank),
+                                      int(recv_scores_offset), int(recv_ids_offset), _ptr(uncertain, torch.int32),
+                                      _ptr(scratch), scratch.numel(), _stream()))
+    _count(3 if splits > 1 else 2)
+
+
 def topk_merge(scores, ids, k_out: int, index_base: int = 0, identifiers=None):
     """scores/ids (candidate indices): [L, nq, k_in] -> ([nq, k_out], [nq, k_out])."""
     L, nq, k_in = scores.shape
