@@ -184,8 +184,13 @@ int tt_optimizer_prepare_sparse(const tt_sparse_var* host_vars, int32_t num_vars
 int tt_fold_parts_multi(const tt_dense_var* host_vars, int32_t num_vars, void* stream);
 int tt_adagrad_step(const tt_dense_var* host_dense, int32_t num_dense, const tt_sparse_var* host_sparse,
                     int32_t num_sparse, float lr, float eps, void* stream);
+/* alpha_device (nullable): device fp32 scalar that overrides `alpha` -- the bias-corrected step size of the current
+ * iteration written by tt_adam_bias_correction, so that a captured CUDA graph applies a fresh alpha on every replay. */
 int tt_lazy_adam_step(const tt_dense_var* host_dense, int32_t num_dense, const tt_sparse_var* host_sparse,
-                      int32_t num_sparse, float alpha, float beta1, float beta2, float eps, void* stream);
+                      int32_t num_sparse, float alpha, const float* alpha_device, float beta1, float beta2, float eps,
+                      void* stream);
+/* Keras Adam step size: t = ++(*step_device); *alpha_device = lr * sqrt(1 - beta2^t) / (1 - beta1^t). */
+int tt_adam_bias_correction(int64_t* step_device, float lr, float beta1, float beta2, float* alpha_device, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * K2  tower MLP: tf.keras.layers.Dense forward / backward (layer sizes

@@ -57,3 +57,62 @@ def test_restored_model_continues_identically(tt, tmp_path, opt_name):
         other.user_model = tt.Sequential([tt.layers.Embedding(901, 128), tt.layers.Dense(256, "relu"), tt.layers.Dense(128)])
         other.test_step({"user_id_encoded": batches[0]["user_id_encoded"], "item_id_encoded": batches[0]["item_id_encoded"]})
         other.load_weights(path)
+
+
+def test_graphed_lazy_adam_matches_eager_and_counts_iterations(tt):
+    """Adam's bias-corrected step size changes every iteration: a captured graph must not freeze it.  The step count and
+    alpha_t live on the device (tt_adam_bias_correction in the graph), optimizer.iterations follows the replays."""
+    tt.set_precision("bf16")
+    rng = synth.rng_for(91)
+    mkb = lambda: {"user_id_encoded": torch.as_tensor(synth.draw_ids(rng, 384, 900)).cuda(),
+                   "item_id_encoded": torch.as_tensor(synth.draw_ids(rng, 384, 700)).cuda()}
+    b0 = mkb()
+    a, b = _model(tt, tt.optimizers.LazyAdam(0.01)), _model(tt, tt.optimizers.LazyAdam(0.01))
+    a.test_step(b0); b.test_step(b0)
+    for va, vb in zip(a.trainable_variables, b.trainable_variables):
+        vb.assign(va.numpy())
+    graphed = b.make_graphed_train_step(b0, warmup=2)
+    assert b.optimizer.iterations == 2
+    for _ in range(2):
+        a.train_step(b0)                                # mirror the two warm-up steps
+    for s in range(6):
+        bt = mkb()
+        la, lb = float(a.train_step(bt)["loss"].item()), float(graphed(bt)["loss"].item())
+        assert lb == pytest.approx(la, rel=2e-4), s
+    assert a.optimizer.iterations == b.optimizer.iterations == 8
+    assert int(b.optimizer._dev_state[0].item()) == 8
+    # alpha_8 on the device == the host formula at t = 8 (it would be alpha_3 if frozen at capture)
+    assert float(b.optimizer._dev_state[1].item()) == pytest.approx(b.optimizer._alpha(), rel=1e-6)
+    for va, vb in zip(a.trainable_variables, b.trainable_variables):
+        assert torch.allclose(va.value, vb.value, rtol=2e-3, atol=2e-5), va.name
+
+
+def test_checkpoint_restore_is_seen_by_a_captured_graph(tt, tmp_path):
+    """load_weights copies IN PLACE (values, bf16 shadows, optimizer slots): a graph captured before the restore
+    trains the restored state, not stale buffers."""
+    tt.set_precision("bf16")
+    rng = synth.rng_for(92)
+    mkb = lambda: {"user_id_encoded": torch.as_tensor(synth.draw_ids(rng, 384, 900)).cuda(),
+                   "item_id_encoded": torch.as_tensor(synth.draw_ids(rng, 384, 700)).cuda()}
+    b0, b1 = mkb(), mkb()
+    m = _model(tt, tt.optimizers.Adagrad(0.05))
+    m.test_step(b0)
+    m.train_step(b0)
+    path = tmp_path / "c.npz"
+    m.save_weights(path)
+    ptrs = [(v.value.data_ptr(), None if v.shadow is None else v.shadow.data_ptr(), v.slots["accumulator"].data_ptr())
+            for v in m.trainable_variables]
+    graphed = m.make_graphed_train_step(b0, warmup=2)
+    for _ in range(3):
+        graphed(b1)                                     # move away from the checkpoint
+    m.load_weights(path)
+    assert ptrs == [(v.value.data_ptr(), None if v.shadow is None else v.shadow.data_ptr(), v.slots["accumulator"].data_ptr())
+                    for v in m.trainable_variables]
+    ref = _model(tt, tt.optimizers.Adagrad(0.05))
+    ref.test_step(b0)
+    ref.load_weights(path)
+    l_graph = float(graphed(b1)["loss"].item())
+    l_ref = float(ref.train_step(b1)["loss"].item())
+    assert l_graph == pytest.approx(l_ref, rel=1e-6)
+    for va, vb in zip(m.trainable_variables, ref.trainable_variables):
+        assert torch.allclose(va.value, vb.value, rtol=1e-4, atol=1e-6), va.name

@@ -80,7 +80,8 @@ SIGNATURES = {
     "tt_optimizer_prepare_sparse": (C.c_int, [C.POINTER(tt_sparse_var), _i32, _p]),
     "tt_fold_parts_multi": (C.c_int, [C.POINTER(tt_dense_var), _i32, _p]),
     "tt_adagrad_step": (C.c_int, [C.POINTER(tt_dense_var), _i32, C.POINTER(tt_sparse_var), _i32, _f, _f, _p]),
-    "tt_lazy_adam_step": (C.c_int, [C.POINTER(tt_dense_var), _i32, C.POINTER(tt_sparse_var), _i32, _f, _f, _f, _f, _p]),
+    "tt_lazy_adam_step": (C.c_int, [C.POINTER(tt_dense_var), _i32, C.POINTER(tt_sparse_var), _i32, _f, _p, _f, _f, _f, _p]),
+    "tt_adam_bias_correction": (C.c_int, [_p, _f, _f, _f, _p, _p]),
     "tt_tower_mlp2_supported": (_i32, [_i32, _i32, _i32]),
     "tt_tower_mlp2_fwd": (C.c_int, [C.POINTER(tt_tower_mlp2), _i32, _p, _p]),
     "tt_tower_mlp2_bwd": (C.c_int, [C.POINTER(tt_tower_mlp2), _i32, _p]),

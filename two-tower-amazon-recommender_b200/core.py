@@ -150,9 +150,20 @@ class Variable:
         self.refresh_shadows()
 
     def refresh_shadows(self) -> None:
+        """bf16 copy of the value, rewritten IN PLACE once it exists: captured CUDA graphs and the optimizer kernel hold
+        its address."""
         from . import ops
         if self.want_shadows:
-            self.shadow = ops.cast_f32_to_bf16(self.value)
+            self.shadow = ops.cast_f32_to_bf16(self.value, out=self.shadow)
+
+    def assign_slot(self, key: str, array) -> None:
+        """Set an optimizer slot, in place when it already exists with the same shape (same reason)."""
+        t = torch.as_tensor(np.asarray(array)) if not isinstance(array, torch.Tensor) else array
+        cur = self.slots.get(key)
+        if isinstance(cur, torch.Tensor) and tuple(cur.shape) == tuple(t.shape):
+            cur.copy_(t.to(device=cur.device, dtype=cur.dtype))
+        else:
+            self.slots[key] = t.to(self.value.device).clone()
 
 
 class GradientTape:

@@ -625,11 +625,13 @@ __device__ __forceinline__ void optimizer_step_body(const StepArgs& a, float lr_
 
 template <bool ADAM>
 __global__ void __launch_bounds__(256)
-optimizer_step_kernel(const __grid_constant__ StepArgs a, float lr_or_alpha, float b1, float b2, float eps) {
+optimizer_step_kernel(const __grid_constant__ StepArgs a, float lr_or_alpha, const float* __restrict__ alpha_dev,
+                      float b1, float b2, float eps) {
   pdl_wait();                       // launched while the backward tower kernel drains
   pdl_launch_dependents();
   long long* const tl = g_tl;
   tl_mark(tl, 5, true);
+  if (alpha_dev != nullptr) lr_or_alpha = __ldg(alpha_dev);      // Adam: bias-corrected step size of THIS iteration (graph-replayable)
   optimizer_step_body<ADAM>(a, lr_or_alpha, b1, b2, eps);
   if (tl) {                         // timeline only: the span runs to the EXIT of the last block
     __syncthreads();
@@ -708,7 +710,7 @@ static int run_prepare(const tt_sparse_var* vars, int n, cudaStream_t stream) {
 }
 
 static int run_step(const char* name, bool adam, const tt_dense_var* dense, int nd, const tt_sparse_var* sparse, int ns,
-                    float lr_or_alpha, float b1, float b2, float eps, cudaStream_t stream) {
+                    float lr_or_alpha, const float* alpha_dev, float b1, float b2, float eps, cudaStream_t stream) {
   TT_REQUIRE(nd >= 0 && nd <= TT_MAX_DENSE_VARS && (nd == 0 || dense), "%s: at most %d dense variables per call", name, TT_MAX_DENSE_VARS);
   static thread_local StepArgs args;
   int64_t max_nnz;
@@ -741,10 +743,20 @@ static int run_step(const char* name, bool adam, const tt_dense_var* dense, int 
   args.n_dense = nd; args.n_sparse = ns;
   if (blocks == 0) return TT_OK;
   TT_PROF("optimizer_step_kernel", stream);
-  if (adam) TT_CUDA_OK(launch_pdl(optimizer_step_kernel<true>, dim3(blocks), dim3(256), (size_t)0, stream, args, lr_or_alpha, b1, b2, eps));
-  else TT_CUDA_OK(launch_pdl(optimizer_step_kernel<false>, dim3(blocks), dim3(256), (size_t)0, stream, args, lr_or_alpha, b1, b2, eps));
+  if (adam) TT_CUDA_OK(launch_pdl(optimizer_step_kernel<true>, dim3(blocks), dim3(256), (size_t)0, stream, args, lr_or_alpha, alpha_dev, b1, b2, eps));
+  else TT_CUDA_OK(launch_pdl(optimizer_step_kernel<false>, dim3(blocks), dim3(256), (size_t)0, stream, args, lr_or_alpha, alpha_dev, b1, b2, eps));
   TT_LAUNCH_OK("optimizer_step_kernel");
   return TT_OK;
+}
+
+// Keras Adam: alpha_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t) with t = ++iterations.  The counter lives in device memory
+// so that a captured CUDA graph advances it on every replay (a host-computed alpha would be frozen at capture time).
+__global__ void adam_bias_correction_kernel(long long* step, float lr, float b1, float b2, float* alpha) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const long long t = *step + 1;
+    *step = t;
+    *alpha = (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t)));
+  }
 }
 
 __global__ void __launch_bounds__(1024)
@@ -867,12 +879,21 @@ extern "C" int tt_optimizer_prepare_sparse(const tt_sparse_var* host_vars, int32
 
 extern "C" int tt_adagrad_step(const tt_dense_var* host_dense, int32_t num_dense, const tt_sparse_var* host_sparse,
                                int32_t num_sparse, float lr, float eps, void* stream) {
-  return run_step("tt_adagrad_step", false, host_dense, num_dense, host_sparse, num_sparse, lr, 0.f, 0.f, eps, (cudaStream_t)stream);
+  return run_step("tt_adagrad_step", false, host_dense, num_dense, host_sparse, num_sparse, lr, nullptr, 0.f, 0.f, eps, (cudaStream_t)stream);
 }
 
 extern "C" int tt_lazy_adam_step(const tt_dense_var* host_dense, int32_t num_dense, const tt_sparse_var* host_sparse,
-                                 int32_t num_sparse, float alpha, float beta1, float beta2, float eps, void* stream) {
-  return run_step("tt_lazy_adam_step", true, host_dense, num_dense, host_sparse, num_sparse, alpha, beta1, beta2, eps, (cudaStream_t)stream);
+                                 int32_t num_sparse, float alpha, const float* alpha_device, float beta1, float beta2, float eps,
+                                 void* stream) {
+  return run_step("tt_lazy_adam_step", true, host_dense, num_dense, host_sparse, num_sparse, alpha, alpha_device, beta1, beta2, eps, (cudaStream_t)stream);
+}
+
+extern "C" int tt_adam_bias_correction(int64_t* step_device, float lr, float beta1, float beta2, float* alpha_device, void* stream) {
+  TT_REQUIRE(step_device && alpha_device, "tt_adam_bias_correction: null buffer");
+  TT_PROF("adam_bias_correction_kernel", (cudaStream_t)stream);
+  adam_bias_correction_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((long long*)step_device, lr, beta1, beta2, alpha_device);
+  TT_LAUNCH_OK("adam_bias_correction_kernel");
+  return TT_OK;
 }
 
 extern "C" int tt_fold_parts_multi(const tt_dense_var* host_vars, int32_t num_vars, void* stream) {

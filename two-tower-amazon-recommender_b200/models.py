@@ -129,13 +129,13 @@ class Model:
             a = z[f"v{i}"]
             if tuple(a.shape) != v.shape:
                 raise ValueError(f"variable {i} ({v.name}): checkpoint shape {tuple(a.shape)} != {v.shape}")
-            v.assign(a)
+            v.assign(a)                       # in place: value and bf16 shadow keep their addresses (captured graphs)
             prefix = f"s{i}."
             for key in z.files:
                 if key.startswith(prefix):
-                    v.slots[key[len(prefix):]] = torch.as_tensor(z[key]).to(v.value.device)
+                    v.assign_slot(key[len(prefix):], z[key])
         if self.optimizer is not None:
-            self.optimizer.iterations = int(z["iterations"][0])
+            self.optimizer.set_iterations(int(z["iterations"][0]))
 
     def fit(self, dataset: Iterable, epochs: int = 1, verbose: int = 0):
         history = {"loss": [], "total_loss": []}
@@ -181,10 +181,11 @@ class GraphedStep:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         before = ops.LAUNCHES
+        iterations = model.optimizer.iterations
         with torch.cuda.graph(self.graph):
             self.static_out = model.train_step(self.static_in)
         self.launches_per_replay = ops.LAUNCHES - before
-        self.iterations0 = model.optimizer.iterations
+        model.optimizer.iterations = iterations       # the capture executed nothing: no step was taken
 
     def __call__(self, inputs=None):
         if inputs is not None:
@@ -192,6 +193,7 @@ class GraphedStep:
                 _copy_inputs(self.static_in, inputs)
         self.graph.replay()
         ops._count(self.launches_per_replay)
+        self.model.optimizer.iterations += 1          # host mirror of the step count (Adam's device counter advanced in-graph)
         return self.static_out
 
 
@@ -201,7 +203,9 @@ class _PackedInputs:
     def __init__(self, example):
         leaves = []
         _leaves(example, leaves)
-        dev = leaves[0].device
+        dev = next((t.device for t in leaves if t.is_cuda), None)
+        if dev is None:                               # host example (e.g. data.InteractionBatches.example()): static inputs live on the GPU
+            dev = torch.device("cuda", torch.cuda.current_device())
         offs, off = [], 0
         for t in leaves:
             offs.append(off)
@@ -217,7 +221,7 @@ class _PackedInputs:
         self._next = 0
         self._n_leaves = len(leaves)
         for v, t in zip(dviews, leaves):
-            v.copy_(t)
+            v.copy_(t.to(dev))
         it = iter(dviews)
         self.device_views = _rebuild(example, it)
 

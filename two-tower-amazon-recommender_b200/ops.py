@@ -325,9 +325,15 @@ def sparse_prepare(items):
     _count(1 if any(it[3].numel() for it in items) else 0)
 
 
+def adam_bias_correction(step_dev: torch.Tensor, alpha_dev: torch.Tensor, lr: float, beta1: float, beta2: float) -> None:
+    """t = ++step_dev[0]; alpha_dev[0] = lr * sqrt(1 - beta2^t) / (1 - beta1^t), on the device (graph-replayable)."""
+    check(_lib.load().tt_adam_bias_correction(_ptr(step_dev, torch.int64), lr, beta1, beta2, _ptr(alpha_dev, torch.float32), _stream()))
+    _count(1)
+
+
 def optimizer_step(kind: str, dense_items, sparse_items, hyper):
     """ONE launch: every dense variable and every (prepared) table.  kind "adagrad": hyper = (lr, eps);
-    "lazy_adam": hyper = (alpha, beta1, beta2, eps)."""
+    "lazy_adam": hyper = (alpha float | device fp32 [1] tensor, beta1, beta2, eps)."""
     lib = _lib.load()
     if len(dense_items) > _lib.TT_MAX_DENSE_VARS or len(sparse_items) > _lib.TT_MAX_SPARSE_VARS:
         raise ValueError("optimizer_step: too many variables for one launch; split the call")
@@ -335,7 +341,9 @@ def optimizer_step(kind: str, dense_items, sparse_items, hyper):
     if kind == "adagrad":
         check(lib.tt_adagrad_step(d, len(dense_items), s, len(sparse_items), hyper[0], hyper[1], _stream()))
     else:
-        check(lib.tt_lazy_adam_step(d, len(dense_items), s, len(sparse_items), hyper[0], hyper[1], hyper[2], hyper[3], _stream()))
+        a = hyper[0]
+        a_host, a_dev = (0.0, _ptr(a, torch.float32)) if isinstance(a, torch.Tensor) else (float(a), None)
+        check(lib.tt_lazy_adam_step(d, len(dense_items), s, len(sparse_items), a_host, a_dev, hyper[1], hyper[2], hyper[3], _stream()))
     _count(1)
 
 
@@ -483,8 +491,12 @@ def tower_mlp2_bwd(towers):
     return outs
 
 
-def cast_f32_to_bf16(x):
-    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+def cast_f32_to_bf16(x, out=None):
+    """out: existing bf16 tensor of the same shape to cast INTO (keeps its address: CUDA graphs, shadows)."""
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    elif out.shape != x.shape or out.dtype != torch.bfloat16:
+        raise ValueError("cast_f32_to_bf16: `out` must be a bf16 tensor of the input's shape")
     check(_lib.load().tt_cast_f32_to_bf16(_ptr(x, torch.float32), _ptr(out), x.numel(), _stream()))
     _count(1)
     return out
@@ -492,16 +504,21 @@ def cast_f32_to_bf16(x):
 
 # --------------------------------------------------------------------------------- K3/K4
 _ws_cache = {}
+_ws_retired = []      # outgrown scratch buffers: kept alive, because a captured CUDA graph may still launch kernels on them
 
 
 def _workspace(nbytes: int, device, tag: str = "scratch") -> torch.Tensor:
-    """Scratch reused across calls on one device (grown on demand), one buffer per user (`tag`).  Buffers are
-    zero-filled when allocated: the retrieval forward keeps arrival tickets at the head of its workspace
-    (tt_retrieval_workspace_init contract) and leaves them zero after every launch."""
+    """Scratch reused across calls on one device (grown on demand, geometrically), one buffer per user (`tag`).
+    Buffers are zero-filled when allocated: the retrieval forward keeps arrival tickets at the head of its workspace
+    (tt_retrieval_workspace_init contract) and leaves them zero after every launch.  A buffer that has to grow is
+    RETIRED, not freed: a CUDA graph captured earlier keeps replaying on the old one (each buffer is self-contained)."""
     key = (device.type, device.index, tag)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        if buf is not None:
+            _ws_retired.append(buf)
+        grown = 0 if buf is None else 2 * buf.numel()
+        buf = torch.zeros(max(nbytes, grown, 1 << 20), dtype=torch.uint8, device=device)
         _ws_cache[key] = buf
     return buf
 

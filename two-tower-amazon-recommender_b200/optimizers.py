@@ -19,7 +19,7 @@ class Optimizer:
     kind = "adagrad"
 
     def __init__(self):
-        self.iterations = 0
+        self.iterations = 0        # host mirror of the step count (a GraphedStep adds 1 per replay)
         self._prepared = {}        # id(variable) -> values tensor whose insert is in flight on the side stream
         self._prepared_vars = []
         self._side = None
@@ -129,6 +129,10 @@ class Optimizer:
         return ws
 
 
+    def set_iterations(self, t: int) -> None:
+        self.iterations = int(t)
+
+
 class Adagrad(Optimizer):
     """tf.keras.optimizers.Adagrad(learning_rate=0.001, initial_accumulator_value=0.1,
     epsilon=1e-7): acc += g^2; w -= lr * g / sqrt(acc + eps)  (learning_rate default from
@@ -174,6 +178,32 @@ class Adam(Optimizer):
         t = self.iterations
         return self.learning_rate * math.sqrt(1.0 - self.beta_2 ** t) / (1.0 - self.beta_1 ** t)
 
+    # The step count and the bias-corrected step size live on the DEVICE: tt_adam_bias_correction advances the
+    # counter and writes alpha_t at the head of every step, inside the captured graph as well, so that a replayed
+    # step uses the alpha of ITS iteration (a host scalar would freeze alpha at capture time).
+    def _device_state(self, device):
+        st = getattr(self, "_dev_state", None)
+        if st is None or st[0].device != device:
+            st = (torch.tensor([self.iterations], dtype=torch.int64, device=device),
+                  torch.zeros(1, dtype=torch.float32, device=device))
+            self._dev_state = st
+        return st
+
+    def set_iterations(self, t: int) -> None:
+        """Restore the step count (checkpoint load): host mirror and device counter, in place."""
+        self.iterations = int(t)
+        st = getattr(self, "_dev_state", None)
+        if st is not None:
+            st[0].fill_(int(t))
+
+    def apply_gradients(self, grads_and_vars) -> None:
+        gv = list(grads_and_vars)
+        dev = next((v.value.device for _g, v in gv), None)
+        if dev is not None:
+            step_dev, alpha_dev = self._device_state(dev)
+            ops.adam_bias_correction(step_dev, alpha_dev, self.learning_rate, self.beta_1, self.beta_2)
+        super().apply_gradients(gv)
+
     def _mv(self, var: Variable):
         if "m" not in var.slots:
             var.slots["m"] = torch.zeros_like(var.value)
@@ -190,7 +220,8 @@ class Adam(Optimizer):
                 v.slots.get("_first_flag"))
 
     def _hyper(self):
-        return (self._alpha(), self.beta_1, self.beta_2, self.epsilon)
+        st = getattr(self, "_dev_state", None)
+        return (st[1] if st is not None else self._alpha(), self.beta_1, self.beta_2, self.epsilon)
 
     def _check_sparse_supported(self) -> None:
         if not self.lazy:

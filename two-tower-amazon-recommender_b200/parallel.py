@@ -459,6 +459,16 @@ class DataParallelModel(Model):
         self._coll = Collectives(group)
         self.exchange = None          # PeerExchange (build_sharded_two_tower(peer="exchange"))
 
+    # every rank holds different table shards: one checkpoint file per rank
+    def _rank_path(self, path) -> str:
+        return f"{path}.rank{self._coll.rank}of{self._coll.world}.npz"
+
+    def save_weights(self, path) -> None:
+        super().save_weights(self._rank_path(path))
+
+    def load_weights(self, path) -> None:
+        super().load_weights(self._rank_path(path))
+
     def train_step(self, inputs):
         if self.optimizer is None:
             raise RuntimeError("call model.compile(optimizer=...) before train_step")
