@@ -163,6 +163,22 @@ class TestRetrievalTensorCore:
         assert float(g["dq"].abs().max().item()) < 1e-3 and float(g["dc"].abs().max().item()) < 1e-3
 
 
+    def test_one_workspace_across_shapes(self, ops):
+        """A caller re-uses one workspace for every shape: the partials a small shape leaves behind must never be read as
+        arrival tickets by a larger one (round 2: the ticket area has one size for all shapes)."""
+        B, d = 8192, 128
+        q = torch.full((B, d), 0.0625, device="cuda", dtype=torch.bfloat16); c = q.clone()
+        loss0, lse0, _ = ops.retrieval_loss_fwd("bf16", q, c, 10.0)            # sizes the cached workspace for the big shape
+        rng = synth.rng_for(5)
+        for nq, nc in ((128, 256), (200, 1000), (1024, 1024)):
+            qs = bf((rng.normal(size=(nq, d)) * 0.1).astype(np.float32)); cs = bf((rng.normal(size=(nc, d)) * 0.1).astype(np.float32))
+            _l, lse, _p = ops.retrieval_loss_fwd("bf16", qs, cs, 10.0)
+            ops.retrieval_loss_bwd("bf16", qs, cs, 10.0, lse)                     # dQ / dC partials live in the same workspace
+        loss1, lse1, _ = ops.retrieval_loss_fwd("bf16", q, c, 10.0)
+        assert float(loss1.item()) == float(loss0.item()) == pytest.approx(B * np.log(B), rel=1e-4)
+        assert torch.equal(lse0, lse1)
+
+
 class TestTrainStepBf16:
     def _model(self, tt, vu, vi, d, mlp, T, lr):
         tt.set_precision("bf16")

@@ -1228,7 +1228,10 @@ static WsPlan ws_plan(int64_t nq, int64_t nc, int64_t d) {
   split_plan(nq, nc, 128, &p.sq, &tps);
   split_plan(nc, nq, 128, &p.sc, &tps);
   const int64_t xb = ceil_div(nq, RT_BM);
-  p.sync_bytes = round_up((xb + 1) * 4, 256);
+  // The ticket area has ONE size for every shape up to 4095 row blocks (524 K queries): a caller re-uses one workspace
+  // across shapes, and a data region of one shape must never alias the tickets of another (stale partials would be
+  // read as arrival counts).
+  p.sync_bytes = std::max<int64_t>(round_up((xb + 1) * 4, 256), 16384);
   p.off_bl = p.sync_bytes;
   p.off_ml = p.off_bl + round_up(xb * 4, 256);
   p.off_q = p.off_ml + round_up((int64_t)p.sf * nq * 8, 256);

@@ -68,10 +68,14 @@ class PeerTable:
 
 
 def _fill_feature(dst, table, values, offsets, mode) -> None:
-    if isinstance(table, PeerTable):
+    if isinstance(table, PeerTable) and table.world >= 2:
         dst.table = _ptr(table.ptrs, torch.int64)
         dst.vocab = table.vocab
         dst.shard_world = table.world
+    elif isinstance(table, PeerTable):            # a one-rank group: the shard IS the table
+        dst.table = _ptr(table.shard, torch.float32)
+        dst.vocab = table.vocab
+        dst.shard_world = 0
     else:
         dst.table = _ptr(table, torch.float32)
         dst.vocab = table.shape[0]
