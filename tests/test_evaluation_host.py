@@ -39,3 +39,21 @@ def test_dense_bucket_layout(tt):
     offs, total = tt.ops.bucket_layout([(128, 256), (1, 256), (256, 128), (1, 130), (3,)])
     assert offs == [0, 32768, 33024, 65792, 65924] and total == 65928
     assert all(o % 4 == 0 for o in offs) and total % 4 == 0
+
+
+def test_model_spec_defaults_are_the_reference_config(tmp_path):
+    """cli.load_model_spec: the `model:` block of the reference's configs/data_config.yaml:54-71 (defaults when no file
+    is given) and overrides from a file."""
+    from two_tower_b200 import cli
+    s = cli.load_model_spec(None)
+    assert (s.embedding_dim, s.user_tower_dims, s.item_tower_dims) == (128, (512, 256, 128), (512, 256, 128))
+    assert (s.batch_size, s.learning_rate, s.epochs, s.patience, s.validation_freq) == (1024, 0.001, 50, 5, 1)
+    assert s.temperature == 0.1 and s.top_k_eval == (1, 5, 10, 20, 50, 100) and s.l2 == 1e-6
+    p = tmp_path / "c.yaml"
+    p.write_text("model:\n  embedding_dim: 64\n  training:\n    batch_size: 256\n  retrieval:\n    temperature: 0.5\n")
+    s = cli.load_model_spec(str(p))
+    assert (s.embedding_dim, s.batch_size, s.temperature, s.epochs) == (64, 256, 0.5, 50)
+    p.write_text("model:\n  retrieval:\n    candidate_sampling: uniform\n")
+    import pytest
+    with pytest.raises(NotImplementedError):
+        cli.load_model_spec(str(p))

@@ -824,14 +824,25 @@ retrieval_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
 // dQ_i = (w_i / T) * (sum_j p_ij c_j - c_label(i)) with p = softmax(S): the forward already forms every
 // exp(s_ij - m_i), so a second MMA per tile accumulates O_i = sum_j exp2(s_ij k2 - m_i) c_j next to the running
 // (m_i, l_i) and the separate dQ pass (one more S recompute, one more exponential per logit) disappears.
-// Same streaming structure as the backward kernel; differences:
-//   * each softmax warpgroup keeps its OWN accumulator O_g and reference maximum (the two warpgroups alternate
-//     tiles of the same rows, so they cannot share a rescaled accumulator).  TMEM: [S0 | S1 | O0 (d) | O1 (d)],
-//     P_b (bf16x2) is written over the first half of S_b, which the S issuer may only overwrite once the O GEMM
-//     of that tile has completed (p_empty).
-//   * online softmax with a LAZY reference maximum: m_i moves (and l_i, O_i are rescaled by the owning thread --
-//     its accumulator is quiescent while it holds S of its next tile) only when the tile maximum exceeds it by
-//     more than 8 in the log2 domain; terms up to 2^8 are harmless in bf16 / fp32.
+//
+// Round 2: the pipeline is THROUGHPUT-bound, not latency-bound.  Round 1 wrote P(t) over S(t) in tensor memory, so
+// S(t+2) could not be issued before the O GEMM of tile t had retired: every buffer ran the serial chain
+// S GEMM -> softmax -> O GEMM -> S GEMM ... and the pipeline trace (tools/trace_fwd_dq.py, profiles/r02_*) showed both
+// warpgroups idle 55 % of the time waiting for S (2130 cycles per 128 x 128 tile against 1024 of MMA).  Now
+//   * a streamed 128-candidate tile is scored as two 64-candidate SUB-TILES (N = 64 MMAs run at the same rate per
+//     column); warpgroup g takes sub-tile g of every tile;
+//   * S(t) (128 columns) is released as soon as both warpgroups have pulled their halves into registers (s_free),
+//     P has its own two 32-column buffers, so the S issuer never waits for an O GEMM and an O GEMM has a whole
+//     softmax turn to retire before its P buffer is needed again;
+//   * the stationary query tile lives in tensor memory and the S GEMM reads it from there (TS form): per 128
+//     candidates the SS form read 64 KB of A + 32 KB of B from shared memory, next to 32 KB of B for the O GEMM and
+//     32 KB of TMA writes -- more than the 128 B/clk the 1024 tensor cycles of a tile leave room for.
+// TMEM: [S (128) | P0 | P1 (32 each) | Q (d/2) | O0 (d) | O1 (d)] = 256 + 2 d <= 512 columns.
+//   * each softmax warpgroup keeps its OWN accumulator O_g and reference maximum (the warpgroups take different
+//     candidates of the same rows, so they cannot share a rescaled accumulator);
+//   * online softmax with a LAZY reference maximum: m_i moves (and l_i, O_i are rescaled by the owning thread, after
+//     its previous O GEMM has retired) only when the sub-tile maximum exceeds it by more than 8 in the log2 domain;
+//     terms up to 2^8 are harmless in bf16 / fp32.
 // Every (CTA, warpgroup) leaves a partial (m, l, O); retrieval_dq_finalize_kernel folds them into row_lse, the
 // SUM loss and dQ.
 struct FusedLayout { int x_bytes, y_bytes, stages, total; };
@@ -845,10 +856,16 @@ __host__ __device__ inline FusedLayout fused_layout(int d, int BN) {
   return L;
 }
 
+constexpr int FQ_SUB = 64;                 // candidates per sub-tile (one softmax warpgroup turn)
+constexpr uint32_t FQ_P_COL = 2 * FQ_SUB;                // 128: S occupies [0, 128), warpgroup g reads columns [64 g, 64 g + 64)
+constexpr uint32_t FQ_Q_COL = FQ_P_COL + 2 * (FQ_SUB / 2);   // 192: the stationary query tile as packed bf16x2, d / 2 <= 64 columns
+constexpr uint32_t FQ_O_COL = 256;
+
 template <int BN>
 __global__ void __launch_bounds__(RT_THREADS, 1)
 retrieval_fwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                            const __grid_constant__ CUtensorMap tmP, const RetrievalTcArgs a) {
+  static_assert(BN == 2 * FQ_SUB, "a streamed tile is two sub-tiles");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
@@ -861,11 +878,13 @@ retrieval_fwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
   uint64_t* x_full = reinterpret_cast<uint64_t*>(tail);
   uint64_t* full = x_full + 1;
   uint64_t* empty = full + RT_MAX_STAGES;
-  uint64_t* s_full = empty + RT_MAX_STAGES;
-  uint64_t* p_full = s_full + 2;
-  uint64_t* p_empty = p_full + 2;
+  uint64_t* s_full = empty + RT_MAX_STAGES;        // S(t) (128 columns) in tensor memory
+  uint64_t* s_free = s_full + 1;                   // both warpgroups have pulled their halves into registers
+  uint64_t* p_full = s_free + 1;                   // [2] P_g stored
+  uint64_t* p_empty = p_full + 2;                  // [2] the O GEMM that read P_g has retired
   uint64_t* acc_full = p_empty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* q_ready = acc_full + 1;                // the query tile sits in tensor memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_ready + 1);
 
   long long* const tl = g_tl;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -874,14 +893,16 @@ retrieval_fwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
   const int tile_begin = blockIdx.y * a.tiles_per_split;
   const int total_tiles = (a.nc + BN - 1) / BN;
   const int T = max(0, min(a.tiles_per_split, total_tiles - tile_begin));
-  const uint32_t O_COL = 2 * BN;                      // TMEM columns: [S0 | S1 | O0 (d) | O1 (d)]; P_b over S_b[0, BN/2)
+  const int U = 2 * T;                                // sub-tiles
 
   if (warp == RT_TMA_WARP && lane == 0) {
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmY); tma_prefetch_desc(&tmP);
     mbar_init(x_full, 1);
     for (int s = 0; s < RT_MAX_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 128); mbar_init(&p_empty[b], 1); }
+    mbar_init(s_full, 1); mbar_init(s_free, 256);
+    for (int b = 0; b < 2; ++b) { mbar_init(&p_full[b], 128); mbar_init(&p_empty[b], 1); }
     mbar_init(acc_full, 1);
+    mbar_init(q_ready, 128);
     fence_barrier_init();
   }
   if (warp == RT_MMA_WARP) tmem_alloc(tmem_slot, 512);
@@ -907,39 +928,50 @@ retrieval_fwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
       }
     }
   } else if (warp == RT_MMA_WARP) {
-    // S issuer: S(t) = X Y_t^T once the tile has landed and the O GEMM of tile t-2 has consumed P(t-2) (same columns)
+    // S issuer: S(t) = X Y_t^T (128 x 128, one buffer) once the tile has landed and both warpgroups have pulled their
+    // halves of S(t-1) into registers -- early in their softmax turn, so S(t) is ready when they come back.
+    // A = the query tile in TENSOR MEMORY (TS form): the SS form would read 4 KB of A from shared memory per K = 16
+    // step, and with the O GEMM's B reads and the TMA writes the stream is shared-memory-bandwidth bound (128 B/clk).
     if (T > 0 && elect_one_sync()) {
       constexpr uint32_t idesc1 = umma_idesc_bf16(RT_BM, BN);
-      mbar_wait(x_full, 0);
+      mbar_wait(q_ready, 0);
+      tc_fence_after();
       for (int t = 0; t < T; ++t) {
-        const int s = t % STAGES, b = t & 1;
+        const int s = t % STAGES;
+        TT_TRACE(2, t, 0);
         mbar_wait(&full[s], (t / STAGES) & 1);
-        mbar_wait(&p_empty[b], ((t >> 1) & 1) ^ 1);
+        TT_TRACE(2, t, 1);
+        mbar_wait(s_free, (t & 1) ^ 1);
+        TT_TRACE(2, t, 2);
         tc_fence_after();
         for (int kb = 0; kb < nkb; ++kb) {
-          const uint64_t da = umma_desc_k_sw128(smem_u32(sX + kb * RT_BM * 128));
           const uint64_t db = umma_desc_k_sw128(smem_u32(sY + s * L.y_bytes + kb * BN * 128));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + b * BN, da + 2 * k, db + 2 * k, idesc1, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ts(tmem_base, tmem_base + FQ_Q_COL + 8 * (4 * kb + k), db + 2 * k, idesc1, (kb | k) != 0);
         }
-        umma_commit(&s_full[b]);
+        umma_commit(s_full);
+        TT_TRACE(2, t, 3);
       }
     }
   } else if (warp == RT_MMA2_WARP) {
-    // O issuer: O_g += P(t) Y_t (A = P from tensor memory, B = the streamed tile read MN-major), g = t & 1
-    if (T > 0 && elect_one_sync()) {
+    // O issuer: O_g += P_g(u) Y_u (A = P from tensor memory, B = rows [64 h, 64 h + 64) of the streamed tile, MN-major)
+    if (U > 0 && elect_one_sync()) {
       const uint32_t idesc2 = umma_idesc_bf16(RT_BM, d, 0, 1);
-      for (int t = 0; t < T; ++t) {
-        const int s = t % STAGES, b = t & 1;
-        mbar_wait(&p_full[b], (t >> 1) & 1);
+      for (int u = 0; u < U; ++u) {
+        const int t = u >> 1, h = u & 1, s = t % STAGES, n = u >> 1;
+        TT_TRACE(3, u, 0);
+        mbar_wait(&p_full[h], n & 1);
+        TT_TRACE(3, u, 1);
         tc_fence_after();
         const uint64_t db0 = umma_desc_mn_sw128(smem_u32(sY + s * L.y_bytes), BN * 128);
-        const uint32_t ta0 = tmem_base + b * BN;
+        const uint32_t ta0 = tmem_base + FQ_P_COL + h * (FQ_SUB / 2);
 #pragma unroll
-        for (int k = 0; k < BN / 16; ++k)
-          umma_bf16_ts(tmem_base + O_COL + b * d, ta0 + 8 * k, db0 + 128 * k, idesc2, ((t >> 1) | k) != 0);
-        umma_commit(&p_empty[b]);
-        umma_commit(&empty[s]);
+        for (int k = 0; k < FQ_SUB / 16; ++k)
+          umma_bf16_ts(tmem_base + FQ_O_COL + h * d, ta0 + 8 * k, db0 + 128 * (h * (FQ_SUB / 16) + k), idesc2, (n | k) != 0);
+        umma_commit(&p_empty[h]);
+        if (h == 1) umma_commit(&empty[s]);          // both halves of the tile consumed (commits cover all earlier MMAs)
+        TT_TRACE(3, u, 2);
       }
       umma_commit(acc_full);
     }
@@ -950,55 +982,77 @@ retrieval_fwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
     const long long qi = (long long)x0 + r;
     const long long label = a.label_offset + qi;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
-    float m2 = -INFINITY, l = 0.f;                   // reference maximum (log2 domain) and row sum of this warpgroup
-    for (int t = g; t < T; t += 2) {
-      const int b = g;
-      const long long c_tile = (long long)(tile_begin + t) * BN;
-      mbar_wait(&s_full[b], (t >> 1) & 1);
-      tc_fence_after();
-      uint32_t rr[BN];
+    if (g == 0) {
+      // the stationary query tile: shared memory (TMA, zero-filled past nq) -> registers -> tensor memory, row r by
+      // thread r as packed bf16x2 (one 32-bit column = two consecutive K elements, what the TS-form MMA reads)
+      mbar_wait(x_full, 0);
+      for (int kb = 0; kb < nkb; ++kb) {
+        uint32_t qq[32];
 #pragma unroll
-      for (int c = 0; c < BN / 32; ++c) tmem_ld32(lane_addr + b * BN + c * 32, rr + c * 32);
-      tmem_ld_wait();
-      if (c_tile + BN > a.nc) {                      // uniform: ragged last tile -> -inf logits
-#pragma unroll
-        for (int j = 0; j < BN; ++j) if (c_tile + j >= a.nc) rr[j] = 0xff800000u;
+        for (int c = 0; c < 8; ++c) {
+          const uint4 v = *reinterpret_cast<const uint4*>(sX + kb * RT_BM * 128 + sw128_offset(r, c));
+          qq[4 * c] = v.x; qq[4 * c + 1] = v.y; qq[4 * c + 2] = v.z; qq[4 * c + 3] = v.w;
+        }
+        tmem_st32(lane_addr + FQ_Q_COL + kb * 32, qq);
       }
-      if (label >= c_tile && label < c_tile + BN) {  // the positive logit of this row lives in this tile
-        const int jj = (int)(label - c_tile);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(q_ready);
+    }
+    float m2 = -INFINITY, l = 0.f;                   // reference maximum (log2 domain) and row sum of this warpgroup
+    for (int u = g; u < U; u += 2) {
+      const int t = u >> 1, n = u >> 1;
+      const long long c_sub = (long long)(tile_begin + t) * BN + g * FQ_SUB;
+      if (threadIdx.x == g * 128) TT_TRACE(g, u, 0);
+      mbar_wait(s_full, t & 1);
+      if (threadIdx.x == g * 128) TT_TRACE(g, u, 1);
+      tc_fence_after();
+      uint32_t rr[FQ_SUB];
+#pragma unroll
+      for (int c = 0; c < FQ_SUB / 32; ++c) tmem_ld32(lane_addr + g * FQ_SUB + c * 32, rr + c * 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_free);                           // 256 arrivals: the S issuer may overwrite S with tile t + 1
+      if (c_sub + FQ_SUB > a.nc) {                   // uniform: ragged tail -> -inf logits
+#pragma unroll
+        for (int j = 0; j < FQ_SUB; ++j) if (c_sub + j >= a.nc) rr[j] = 0xff800000u;
+      }
+      if (label >= c_sub && label < c_sub + FQ_SUB) {   // the positive logit of this row lives in this sub-tile
+        const int jj = (int)(label - c_sub);
         float p = 0.f;
 #pragma unroll
-        for (int j = 0; j < BN; ++j) if (j == jj) p = __uint_as_float(rr[j]);
+        for (int j = 0; j < FQ_SUB; ++j) if (j == jj) p = __uint_as_float(rr[j]);
         if (qi < a.nq) a.row_pos[qi] = p * a.k2 * kLn2;
       }
       float cm[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) cm[u] = fmaxf(__uint_as_float(rr[2 * u]), __uint_as_float(rr[2 * u + 1]));
+      for (int v = 0; v < 4; ++v) cm[v] = fmaxf(__uint_as_float(rr[2 * v]), __uint_as_float(rr[2 * v + 1]));
 #pragma unroll
-      for (int j = 8; j < BN; j += 8) {
+      for (int j = 8; j < FQ_SUB; j += 8) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) cm[u] = fmax3(cm[u], __uint_as_float(rr[j + 2 * u]), __uint_as_float(rr[j + 2 * u + 1]));
+        for (int v = 0; v < 4; ++v) cm[v] = fmax3(cm[v], __uint_as_float(rr[j + 2 * v]), __uint_as_float(rr[j + 2 * v + 1]));
       }
       const float cmax = fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])) * a.k2;
       // lazy reference maximum
       float factor = 1.f;
       bool need = false;
       if (cmax > m2) {
-        if (m2 == -INFINITY) m2 = cmax;              // first tile of this warpgroup: nothing accumulated yet
+        if (m2 == -INFINITY) m2 = cmax;              // first finite sub-tile of this warpgroup: nothing accumulated yet
         else if (cmax > m2 + 8.f) { factor = ex2_approx(m2 - cmax); l *= factor; m2 = cmax; need = true; }
       }
-      const uint64_t K2 = pk2(a.k2, a.k2), NM = pk2(-m2, -m2);
+      const float mref = (m2 == -INFINITY) ? 0.f : m2;     // a row that has only seen masked columns: exp2(-inf) = 0
+      const uint64_t K2 = pk2(a.k2, a.k2), NM = pk2(-mref, -mref);
       uint64_t acc0 = pk2(0.f, 0.f), acc1 = acc0;
-      uint32_t pk[BN / 2];
+      uint32_t pk[FQ_SUB / 2];
 #pragma unroll
-      for (int j = 0; j < BN; j += 16) {
-#define TT_FQ_PAIR(U, ACC)                                                                          \
+      for (int j = 0; j < FQ_SUB; j += 16) {
+#define TT_FQ_PAIR(V, ACC)                                                                          \
         {                                                                                           \
-          const uint64_t e2 = ex2_mix2<U, FWD_POLY_MASK>(fma2(pk2u(rr[j + 2 * U], rr[j + 2 * U + 1]), K2, NM)); \
+          const uint64_t e2 = ex2_mix2<V, FWD_POLY_MASK>(fma2(pk2u(rr[j + 2 * V], rr[j + 2 * V + 1]), K2, NM)); \
           ACC = add2(ACC, e2);                                                                      \
           float e0, e1;                                                                             \
           up2(e2, e0, e1);                                                                          \
-          pk[(j >> 1) + U] = pack_bf16x2(e0, e1);                                                   \
+          pk[(j >> 1) + V] = pack_bf16x2(e0, e1);                                                   \
         }
         TT_FQ_PAIR(0, acc0) TT_FQ_PAIR(1, acc1) TT_FQ_PAIR(2, acc0) TT_FQ_PAIR(3, acc1)
         TT_FQ_PAIR(4, acc0) TT_FQ_PAIR(5, acc1) TT_FQ_PAIR(6, acc0) TT_FQ_PAIR(7, acc1)
@@ -1008,29 +1062,32 @@ retrieval_fwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
       up2(acc0, s0, s1);
       up2(acc1, s2, s3);
       l += (s0 + s1) + (s2 + s3);
+      if (threadIdx.x == g * 128) TT_TRACE(g, u, 2);
+      // P_g is free (and O_g quiescent) once the O GEMM of this warpgroup's previous sub-tile has retired -- a whole
+      // softmax turn ago in steady state, so this wait does not stall
+      mbar_wait(&p_empty[g], (n & 1) ^ 1);
+      tc_fence_after();
       if (__any_sync(0xffffffffu, need)) {
-        // (after the exponentials: the S row is dead, fewer live registers)  O_g is quiescent here: S(t) was only issued after the O GEMM of this warpgroup's previous tile completed
 #pragma unroll 1
         for (int c0 = 0; c0 < d; c0 += 32) {
           uint32_t oo[32];
-          tmem_ld32(lane_addr + O_COL + b * d + c0, oo);
+          tmem_ld32(lane_addr + FQ_O_COL + g * d + c0, oo);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) oo[j] = __float_as_uint(__uint_as_float(oo[j]) * factor);
-          tmem_st32(lane_addr + O_COL + b * d + c0, oo);
+          tmem_st32(lane_addr + FQ_O_COL + g * d + c0, oo);
         }
         tmem_st_wait();
       }
-      // P(t) over the first half of S_b (this thread has its whole S row in registers)
-#pragma unroll
-      for (int c = 0; c < BN / 64; ++c) tmem_st32(lane_addr + b * BN + c * 32, pk + c * 32);
+      tmem_st32(lane_addr + FQ_P_COL + g * (FQ_SUB / 2), pk);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&p_full[b]);
+      mbar_arrive(&p_full[g]);
+      if (threadIdx.x == g * 128) TT_TRACE(g, u, 3);
     }
     // epilogue: this warpgroup's partial (m, l, O_g) -> slot 2 * split + g
     const int slot = blockIdx.y * 2 + g;
-    const bool have = T > g;
+    const bool have = T > 0;
     if (T > 0) {
       mbar_wait(acc_full, 0);
       tc_fence_after();
@@ -1043,7 +1100,7 @@ retrieval_fwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
       for (int c0 = 0; c0 < d; c0 += 32, ++it) {
         uint32_t oo[32];
         if (have) {
-          tmem_ld32(lane_addr + O_COL + g * d + c0, oo);
+          tmem_ld32(lane_addr + FQ_O_COL + g * d + c0, oo);
           tmem_ld_wait();
         } else {
 #pragma unroll
@@ -1069,7 +1126,7 @@ retrieval_fwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
       for (int c0 = 0; c0 < d; c0 += 32) {
         uint32_t oo[32];
         if (have) {
-          tmem_ld32(lane_addr + O_COL + g * d + c0, oo);
+          tmem_ld32(lane_addr + FQ_O_COL + g * d + c0, oo);
           tmem_ld_wait();
         } else {
 #pragma unroll
@@ -1377,6 +1434,7 @@ int tc_retrieval_fwd_dq(const void* q, const void* c, int64_t nq, int64_t nc, in
   a.label_offset = label_offset;
   a.partial_ml = (float2*)((char*)ws + plan.off_ml); a.row_pos = row_pos; a.partial_out = o_parts;
   a.tiles_per_split = plan.tps;
+  a.trace = g_trace ? g_trace + 1 * (4 * 4 * TRACE_TILES + 16) : nullptr;       // the dQ pass's slot of the trace buffer
   const FusedLayout L = fused_layout((int)d, BN);
   TT_REQUIRE(L.stages >= 2, "tt_retrieval_loss_fwd_dq: d=%lld does not fit the shared-memory pipeline", (long long)d);
   TT_REQUIRE(plan.parts <= 8, "tt_retrieval_loss_fwd_dq: more than 8 partials per row (%d)", plan.parts);
