@@ -886,6 +886,7 @@ retrieval_fwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
   uint64_t* q_ready = acc_full + 1;                // the query tile sits in tensor memory
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_ready + 1);
 
+  TT_TRACE_CTA(0);
   long long* const tl = g_tl;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -913,6 +914,7 @@ retrieval_fwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
   pdl_wait();
   pdl_launch_dependents();
   tl_mark(tl, 1, true);
+  TT_TRACE_CTA(1);
 
   if (warp == RT_TMA_WARP) {
     if (elect_one_sync()) {
@@ -1142,6 +1144,7 @@ retrieval_fwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
   }
   tc_fence_before();
   __syncthreads();
+  TT_TRACE_CTA(2);
   tl_mark(tl, 1, false);
   if (warp == RT_MMA_WARP) tmem_dealloc(tmem_base, 512);
 }
@@ -1435,6 +1438,7 @@ int tc_retrieval_fwd_dq(const void* q, const void* c, int64_t nq, int64_t nc, in
   a.partial_ml = (float2*)((char*)ws + plan.off_ml); a.row_pos = row_pos; a.partial_out = o_parts;
   a.tiles_per_split = plan.tps;
   a.trace = g_trace ? g_trace + 1 * (4 * 4 * TRACE_TILES + 16) : nullptr;       // the dQ pass's slot of the trace buffer
+  a.trace_cta = g_trace ? g_trace + 3 * (4 * 4 * TRACE_TILES + 16) + 1 * 4 * 256 : nullptr;
   const FusedLayout L = fused_layout((int)d, BN);
   TT_REQUIRE(L.stages >= 2, "tt_retrieval_loss_fwd_dq: d=%lld does not fit the shared-memory pipeline", (long long)d);
   TT_REQUIRE(plan.parts <= 8, "tt_retrieval_loss_fwd_dq: more than 8 partials per row (%d)", plan.parts);

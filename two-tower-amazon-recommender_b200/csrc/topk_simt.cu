@@ -86,7 +86,8 @@ topk_simt_kernel(const float* __restrict__ Q, const float* __restrict__ C, int64
   }
 }
 
-// L-way merge of sorted lists, one warp per query; lane l walks list l (L <= 32).
+// L-way merge of sorted lists, one warp per query; lane l walks lists l, l + 32, ... (L <= 32 * MERGE_LPL).
+constexpr int MERGE_LPL = 8;
 __global__ void __launch_bounds__(256)
 topk_merge_kernel(const float* __restrict__ scores, const int64_t* __restrict__ ids, int L, int64_t nq, int k_in,
                   int k_out, int64_t base, const int64_t* __restrict__ identifiers, float* __restrict__ out_s,
@@ -94,13 +95,27 @@ topk_merge_kernel(const float* __restrict__ scores, const int64_t* __restrict__ 
   const int lane = threadIdx.x & 31;
   const int64_t qi = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (qi >= nq) return;
-  int head = 0;
-  const float* ls = scores + ((size_t)lane * nq + qi) * k_in;
-  const int64_t* li = ids + ((size_t)lane * nq + qi) * k_in;
-  float hs = -INFINITY; int64_t hi = LLONG_MAX;
-  if (lane < L && k_in > 0) { hs = ls[0]; hi = li[0]; }
+  int head[MERGE_LPL];
+  float hs[MERGE_LPL];
+  int64_t hi[MERGE_LPL];
+#pragma unroll
+  for (int u = 0; u < MERGE_LPL; ++u) {
+    const int list = lane + 32 * u;
+    head[u] = 0;
+    hs[u] = -INFINITY; hi[u] = LLONG_MAX;
+    if (list < L && k_in > 0) {
+      hs[u] = scores[((size_t)list * nq + qi) * k_in];
+      hi[u] = ids[((size_t)list * nq + qi) * k_in];
+    }
+  }
   for (int t = 0; t < k_out; ++t) {
-    float bs = hs; int64_t bi = hi; int bl = lane;
+    // this lane's best head (ties: lower index, then lower list), then the warp's
+    float bs = hs[0]; int64_t bi = hi[0]; int bl = lane;
+#pragma unroll
+    for (int u = 1; u < MERGE_LPL; ++u) {
+      const bool take = hs[u] > bs || (hs[u] == bs && hi[u] < bi);
+      if (take) { bs = hs[u]; bi = hi[u]; bl = lane + 32 * u; }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const float s2 = __shfl_xor_sync(0xffffffffu, bs, o);
@@ -113,9 +128,17 @@ topk_merge_kernel(const float* __restrict__ scores, const int64_t* __restrict__ 
       out_s[qi * k_out + t] = bs;
       out_i[qi * k_out + t] = (bi == LLONG_MAX) ? bi : (identifiers ? __ldg(identifiers + bi) : base + bi);
     }
-    if (lane == bl) {
-      ++head;
-      if (head < k_in) { hs = ls[head]; hi = li[head]; } else { hs = -INFINITY; hi = LLONG_MAX; }
+    if ((bl & 31) == lane) {
+#pragma unroll
+      for (int u = 0; u < MERGE_LPL; ++u) {
+        if (bl == lane + 32 * u) {
+          ++head[u];
+          if (head[u] < k_in) {
+            hs[u] = scores[((size_t)bl * nq + qi) * k_in + head[u]];
+            hi[u] = ids[((size_t)bl * nq + qi) * k_in + head[u]];
+          } else { hs[u] = -INFINITY; hi[u] = LLONG_MAX; }
+        }
+      }
     }
   }
 }
@@ -223,7 +246,7 @@ extern "C" int tt_topk_merge(const float* scores, const int64_t* ids, int32_t nu
                              int32_t k_out, int64_t index_base, const int64_t* identifiers, float* out_scores,
                              int64_t* out_ids, void* stream) {
   TT_REQUIRE(scores && ids && out_scores && out_ids, "tt_topk_merge: null buffer");
-  TT_REQUIRE(num_lists >= 1 && num_lists <= 32, "tt_topk_merge: num_lists must be in [1, 32], got %d", num_lists);
+  TT_REQUIRE(num_lists >= 1 && num_lists <= 32 * MERGE_LPL, "tt_topk_merge: num_lists must be in [1, %d], got %d", 32 * MERGE_LPL, num_lists);
   TT_REQUIRE(nq >= 0 && k_in >= 1 && k_out >= 1 && k_out <= num_lists * k_in, "tt_topk_merge: bad k (k_in=%d k_out=%d lists=%d)", k_in, k_out, num_lists);
   if (nq == 0) return TT_OK;
   TT_PROF("topk_merge_kernel", (cudaStream_t)stream);

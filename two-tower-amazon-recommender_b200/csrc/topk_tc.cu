@@ -230,10 +230,12 @@ static int tk_bn_for(int64_t d) { return d <= 128 ? 128 : 64; }
 // splits are planned in 128-candidate granules (independent of the tile width)
 static int tc_topk_splits(int64_t nq, int64_t nc, int bn, int* tiles_per_split) {
   const int64_t q_tiles = ceil_div(nq, TK_BM), y128 = ceil_div(nc, 128);
+  // Few query tiles (online / small-batch serving): the scan is HBM-bound, so EVERY SM must stream a slice of the
+  // candidate matrix -- up to one split per SM (the merge kernel walks up to 256 lists per query).
   int64_t s = std::max<int64_t>(1, num_sms() / q_tiles);
   const int64_t max_by_len = std::max<int64_t>(1, y128 / 32);     // >= 4096 candidates per split
   if (s > max_by_len) s = max_by_len;
-  if (s > 32) s = 32;
+  if (s > 256) s = 256;
   const int64_t per128 = ceil_div(y128, s);
   *tiles_per_split = (int)(per128 * (128 / bn));
   return (int)ceil_div(y128, per128);
