@@ -31,3 +31,16 @@ print(f"nq={nq} nc={nc} k={k}: {ms:.2f} ms  {nq / (ms * 1e-3):.0f} queries/s  {t
 ref = (q[:256].float() @ cand.float().T)
 rs, ri = torch.topk(ref, k, dim=1)
 print("max |score diff| on 256 queries:", float((rs - s[:256]).abs().max()), " id agreement:", float((ri == i[:256]).float().mean()))
+# per-kernel times of one call (event pairs around every launch)
+import ctypes
+lib = tt._lib.load()
+lib.tt_profile_enable(1)
+for _ in range(3):
+    index(q)
+buf = ctypes.create_string_buffer(1 << 14)
+lib.tt_profile_collect(buf, len(buf))
+lib.tt_profile_enable(0)
+for ln in buf.value.decode().splitlines():
+    name, cnt, total = ln.split()
+    print(f"   {name:28s} {1e3 * float(total) / int(cnt):10.1f} us per launch")
+print("   splits:", lib.tt_topk_num_splits(1, nq, nc, d, k))
