@@ -379,8 +379,14 @@ int tt_combine_parts_f32(const float* parts, int32_t num_parts, int64_t rows, in
  * those correctly rounded scores.  uncertain_rows (device int32, optional, incremented): number
  * of query rows for which the margin could not be shown to be wide enough (expected 0).
  * workspace_bytes >= tt_topk_workspace_bytes(...) is always required.
+ * bf16 scoring stage, d <= 128 and enough candidates for a sample (csrc/topk_scan.cu): a strided ~1/32 sample of the
+ * candidate tiles gives every query row a score threshold that at least k + margin candidates are guaranteed to
+ * reach; the scan then only compares against it and the few thousand survivors per row are sorted by one CTA.  A row
+ * whose survivor buffer overflows raises a device flag and the list-keeping kernel redoes the batch (same result).
+ * tt_topk_num_launches: kernels one tt_topk_bruteforce call enqueues for this shape.
  * ------------------------------------------------------------------------------------- */
 int32_t tt_topk_num_splits(int32_t precision, int64_t nq, int64_t nc, int64_t d, int32_t k);
+int32_t tt_topk_num_launches(int32_t precision, int64_t nq, int64_t nc, int64_t d, int32_t k);
 int64_t tt_topk_workspace_bytes(int32_t precision, int64_t nq, int64_t nc, int64_t d, int32_t k);
 int tt_topk_bruteforce(int32_t precision, const void* queries, const void* candidates, int64_t nq,
                        int64_t nc, int64_t d, int32_t k, int64_t cand_index_base,

@@ -33,6 +33,11 @@ int tt_debug_tower_trace(long long* device_buf);
  * is read at run time (works on captured graphs).  Caller presets even slots to INT64_MAX, odd slots to 0. */
 int tt_debug_timeline(long long* device_buf);
 
+/* Test hook for the bf16 top-k: 1 = threshold scan where the shape allows it (default; also TT_TOPK_SCAN unset),
+ * 0 = always the list-keeping kernel, 2 = threshold scan with 64-entry survivor buffers, so every row overflows and
+ * the device-side fallback to the list-keeping kernel runs.  Returns the previous mode. */
+int tt_debug_topk_scan_mode(int32_t mode);
+
 #ifdef __cplusplus
 }
 #endif

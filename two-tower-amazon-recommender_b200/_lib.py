@@ -103,12 +103,14 @@ SIGNATURES = {
     "tt_debug_trace_buffer": (C.c_int, [_p]),
     "tt_debug_tower_trace": (C.c_int, [_p]),
     "tt_debug_timeline": (C.c_int, [_p]),
+    "tt_debug_topk_scan_mode": (C.c_int, [_i32]),
     "tt_retrieval_workspace_bytes": (_i64, [_i32, _i64, _i64, _i64]),
     "tt_retrieval_workspace_init": (C.c_int, [_i32, _p, _i64, _i64, _i64, _i64, _p]),
     "tt_retrieval_loss_fwd": (C.c_int, [_i32, _p, _p, _i64, _i64, _i64, _f, _i64, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "tt_retrieval_loss_bwd": (C.c_int, [_i32, _p, _p, _i64, _i64, _i64, _f, _i64, _p, _p, _p, _p, _f,
                                          _p, _p, _p, _p, _p, _i64, _p]),
     "tt_topk_num_splits": (_i32, [_i32, _i64, _i64, _i64, _i32]),
+    "tt_topk_num_launches": (_i32, [_i32, _i64, _i64, _i64, _i32]),
     "tt_topk_workspace_bytes": (_i64, [_i32, _i64, _i64, _i64, _i32]),
     "tt_topk_bruteforce": (C.c_int, [_i32, _p, _p, _i64, _i64, _i64, _i32, _i64, _p, _p, _p, _p, _p, _i64, _p]),
     "tt_topk_bruteforce_peer": (C.c_int, [_i32, _p, _p, _i64, _i64, _i64, _i32, _i64, _p, _i32, _i32, _i64, _i64, _i64, _p, _p, _i64, _p]),

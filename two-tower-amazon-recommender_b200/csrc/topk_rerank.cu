@@ -37,8 +37,9 @@ template <typename T> __device__ __forceinline__ T rr_raw(const T* p, int64_t i)
 __device__ __forceinline__ double rr_cvt(float v) { return (double)v; }
 __device__ __forceinline__ double rr_cvt(uint16_t v) { return (double)bf16_bits_to_float(v); }
 
-// NJ = elements per lane (d <= 32 * NJ).  Pool entries are handled four at a time so that the row loads of four
-// candidates are in flight together (the pool is a random gather of 2*d-byte rows).
+// NJ = elements per lane (d <= 32 * NJ).  One CTA per query: its RR_WARPS warps share the pool, each warp takes four
+// entries at a time so that the row loads of four candidates are in flight together (the pool is a random gather
+// of 2*d-byte rows); a small query batch still spreads over nq CTAs.
 template <typename T, int NJ>
 __global__ void __launch_bounds__(RR_WARPS * 32)
 topk_rerank_kernel(const T* __restrict__ Q, const T* __restrict__ C, int64_t nq, int d, const float* __restrict__ pool_s,
@@ -46,19 +47,20 @@ topk_rerank_kernel(const T* __restrict__ Q, const T* __restrict__ C, int64_t nq,
                    float* __restrict__ out_s, int64_t* __restrict__ out_i, int* __restrict__ uncertain, int has_discarded,
                    const TopkPeerOut peer) {
   extern __shared__ __align__(16) uint8_t rr_smem[];
+  __shared__ float red_delta[RR_WARPS], red_tmin[RR_WARPS], red_kth;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* s32 = reinterpret_cast<float*>(rr_smem) + (size_t)warp * 2 * kp;
+  float* s32 = reinterpret_cast<float*>(rr_smem);
   int* idx = reinterpret_cast<int*>(s32 + kp);
-  const int64_t qi = (int64_t)blockIdx.x * RR_WARPS + warp;
-  if (qi >= nq) return;
+  const int64_t qi = blockIdx.x;
   double qv[NJ];
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
     const int e = lane + 32 * j;
     qv[j] = e < d ? rr_ld<T>(Q, qi * d + e) : 0.0;
   }
+  if (threadIdx.x == 0) red_kth = -INFINITY;
   float delta = 0.f, tmin = INFINITY;
-  for (int t0 = 0; t0 < kp; t0 += 4) {
+  for (int t0 = 4 * warp; t0 < kp; t0 += 4 * RR_WARPS) {
     int64_t ci[4];
     float approx[4];
 #pragma unroll
@@ -94,7 +96,8 @@ topk_rerank_kernel(const T* __restrict__ Q, const T* __restrict__ C, int64_t nq,
       if (lane == 0) { s32[t0 + u] = f; idx[t0 + u] = (int)ci[u]; }
     }
   }
-  __syncwarp();
+  if (lane == 0) { red_delta[warp] = delta; red_tmin[warp] = tmin; }
+  __syncthreads();
   float* dst_s = out_s + qi * k;
   int64_t* dst_i = out_i + qi * k;
   if (peer.bases != nullptr) {
@@ -103,8 +106,7 @@ topk_rerank_kernel(const T* __restrict__ Q, const T* __restrict__ C, int64_t nq,
     dst_s = reinterpret_cast<float*>(peer.bases[owner] + peer.off_s) + slot_row * k;
     dst_i = reinterpret_cast<int64_t*>(peer.bases[owner] + peer.off_i) + slot_row * k;
   }
-  float kth = -INFINITY;
-  for (int e = lane; e < kp; e += 32) {
+  for (int e = threadIdx.x; e < kp; e += RR_WARPS * 32) {
     const float se = s32[e];
     const int ie = idx[e];
     if (ie == INT_MAX) continue;
@@ -117,12 +119,16 @@ topk_rerank_kernel(const T* __restrict__ Q, const T* __restrict__ C, int64_t nq,
     if (rank < k) {
       dst_s[rank] = se;
       dst_i[rank] = identifiers ? __ldg(identifiers + ie) : base + ie;
-      if (rank == k - 1) kth = se;
+      if (rank == k - 1) red_kth = se;
     }
   }
   if (uncertain != nullptr && has_discarded) {
-    kth = warp_max(kth);
-    if (lane == 0 && delta > 0.f && !(kth > tmin + 4.f * delta)) atomicAdd(uncertain, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float dl = 0.f, tm = INFINITY;
+      for (int w = 0; w < RR_WARPS; ++w) { dl = fmaxf(dl, red_delta[w]); tm = fminf(tm, red_tmin[w]); }
+      if (dl > 0.f && !(red_kth > tm + 4.f * dl)) atomicAdd(uncertain, 1);
+    }
   }
 }
 
@@ -132,8 +138,8 @@ int topk_rerank(int precision, const void* queries, const void* candidates, int6
   TopkPeerOut peer{};
   if (peer_out) peer = *peer_out;
   TT_REQUIRE(d <= 32 * RR_MAXJ, "tt_topk_bruteforce: exact re-rank needs d <= %d", 32 * RR_MAXJ);
-  const size_t smem = (size_t)RR_WARPS * 2 * kp * 4;
-  const unsigned blocks = (unsigned)ceil_div(nq, RR_WARPS);
+  const size_t smem = (size_t)2 * kp * 4;
+  const unsigned blocks = (unsigned)nq;
   const int has_discarded = nc > kp ? 1 : 0;
 #define TT_RR_LAUNCH(T, NJ)                                                                                              \
   {                                                                                                                      \

@@ -1,0 +1,423 @@
+// K6 (bf16 precision) -- threshold scan: brute-force scoring on tcgen05 where the running top-k of topk_tc.cu is
+// replaced by a per-row score THRESHOLD known before the scan starts (tfrs BruteForce / faiss.IndexFlatIP
+// replacement; BASELINE configs[4]).
+//
+// A running top-k pays k (1 + ln(n / k)) list insertions per query row and candidate split -- with one split per SM
+// (small query batches, HBM-bound) that is ~1 % of ALL scores, each a warp-cooperative update: 12 ms for a scan that
+// moves 2.56 GB.  Here nothing is kept per split:
+//   1. sample    (topk_scan_kernel<.., true>): score an evenly strided ~1/32 of the candidate tiles and write the row
+//                maximum of every 32-candidate group;
+//   2. threshold (topk_tau_kernel): tau[row] = the K-th largest of the row's G group maxima.  The K maxima above it
+//                are K distinct candidates, so AT LEAST K candidates score >= tau -- a guarantee, not an estimate --
+//                and about K * (n / 32) / G of all n do;
+//   3. scan      (topk_scan_kernel<.., false>): every SM streams its slice of the candidate matrix once (TMA ring ->
+//                tcgen05 -> TMEM); the selection threads (thread = query row, the 128 scores of a tile in registers)
+//                compare 16-score maxima with tau -- 0.5 instructions per score, no shared state -- and park the few
+//                survivors as 64-bit keys in a thread-private shared-memory queue that is flushed to the row's global
+//                buffer in blocks (one atomicAdd per >= 17 survivors);
+//   4. select    (topk_pool_select_kernel): one CTA per row sorts the row's ~4 K survivors (bitonic, shared memory)
+//                and writes the best K in (score desc, index asc) order -- the pool the exact re-rank consumes.
+// The scores of step 1 and step 3 are the same MMA chain on the same operands (bit-identical), so step 4 finds at
+// least K survivors unless a row overflows its buffer (adversarial data); then a device-side flag makes the
+// list-keeping kernel of topk_tc.cu run instead (launched behind the flag, it exits at once otherwise).
+// Two query tiles (256 rows) per CTA share every candidate tile they stream: half the L2 -> shared-memory traffic
+// per flop of the one-tile form.
+#include "tc_common.cuh"
+#include "topk_select.cuh"
+#include "topk_scan.cuh"
+#include <limits.h>
+#include <algorithm>
+#include <stdlib.h>
+
+namespace tt {
+
+constexpr int SC_BM = 128, SC_BN = 128;
+constexpr int SC_QCAP = 32;            // thread-private survivor queue (entries); flushed when fewer than 16 slots are left
+constexpr int SC_MAX_STAGES = 5;
+
+struct ScanArgs {
+  int nq, nc, d;
+  int total_tiles;          // ceil(nc / 128)
+  int tiles_per_split;      // scan: contiguous tiles per blockIdx.y; sample: sample tiles per blockIdx.y
+  int n_samp;               // sample: number of sampled tiles (tile of sample i = i * total_tiles / n_samp)
+  int nq_pad, cap, stages;
+  const float* tau;         // scan: [nq_pad]
+  int* cnt;                 // scan: [nq_pad] survivors per row (may exceed cap: overflow)
+  unsigned long long* buf;  // scan: [nq][cap]
+  float* samp;              // sample: [4 * n_samp][nq_pad]
+};
+
+struct ScanLayout { int q_bytes, y_bytes, pq_bytes, stages, total; };
+__host__ __device__ inline ScanLayout scan_layout(int d, int nqt, bool sample) {
+  ScanLayout L;
+  L.q_bytes = nqt * SC_BM * d * 2;
+  L.y_bytes = SC_BN * d * 2;
+  L.pq_bytes = sample ? 0 : nqt * SC_BM * SC_QCAP * 8;
+  const int fixed = L.q_bytes + L.pq_bytes + 1024;
+  L.stages = (227 * 1024 - fixed) / L.y_bytes;
+  if (L.stages > SC_MAX_STAGES) L.stages = SC_MAX_STAGES;
+  L.total = fixed + L.stages * L.y_bytes;
+  return L;
+}
+
+// survivors of one row: shared-memory queue (entry i at pq[i * 128]) -> the row's global buffer
+__device__ __noinline__ void scan_flush(const unsigned long long* pq, int n, int* cnt, unsigned long long* buf, int cap) {
+  const int pos = atomicAdd(cnt, n);
+  for (int i = 0; i < n; ++i)
+    if (pos + i < cap) buf[pos + i] = pq[i * SC_BM];
+}
+
+template <int NQT, bool SAMPLE>
+__global__ void __launch_bounds__(64 + NQT * 128, 1)
+topk_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmC, const ScanArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  const int d = a.d, nkb = d / 64;
+  const ScanLayout L = scan_layout(d, NQT, SAMPLE);
+  const int STAGES = a.stages;
+  uint8_t* sQ = smem;
+  uint8_t* sY = sQ + L.q_bytes;
+  unsigned long long* pq_all = reinterpret_cast<unsigned long long*>(sY + STAGES * L.y_bytes);
+  uint8_t* tail = reinterpret_cast<uint8_t*>(pq_all) + L.pq_bytes;
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* full = q_full + 1;                    // [SC_MAX_STAGES]
+  uint64_t* empty = full + SC_MAX_STAGES;         // [SC_MAX_STAGES]
+  uint64_t* s_full = empty + SC_MAX_STAGES;       // [2 buffers][NQT]
+  uint64_t* s_empty = s_full + 2 * NQT;           // [2 buffers][NQT]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + 2 * NQT);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (NQT * SC_BM);
+  const int begin = blockIdx.y * a.tiles_per_split;
+  const int limit = SAMPLE ? a.n_samp : a.total_tiles;
+  const int T = max(0, min(a.tiles_per_split, limit - begin));
+  auto tile_of = [&](int t) -> int {
+    return SAMPLE ? (int)(((long long)(begin + t) * a.total_tiles) / a.n_samp) : begin + t;
+  };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmC);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < SC_MAX_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2 * NQT; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * NQT * SC_BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(q_full, L.q_bytes);
+      for (int j = 0; j < NQT; ++j)
+        for (int kb = 0; kb < nkb; ++kb)
+          tma_load_2d(sQ + (j * nkb + kb) * SC_BM * 128, &tmQ, q_full, kb * 64, q0 + j * SC_BM);
+      for (int t = 0; t < T; ++t) {
+        const int s = t % STAGES;
+        mbar_wait(&empty[s], ((t / STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full[s], L.y_bytes);
+        const int y0 = tile_of(t) * SC_BN;
+        for (int kb = 0; kb < nkb; ++kb) tma_load_2d(sY + s * L.y_bytes + kb * SC_BN * 128, &tmC, &full[s], kb * 64, y0);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(SC_BM, SC_BN);
+      mbar_wait(q_full, 0);
+      for (int t = 0; t < T; ++t) {
+        const int s = t % STAGES, b = t & 1;
+        mbar_wait(&full[s], (t / STAGES) & 1);
+#pragma unroll
+        for (int j = 0; j < NQT; ++j) {
+          mbar_wait(&s_empty[b * NQT + j], ((t >> 1) & 1) ^ 1);
+          tc_fence_after();
+          for (int kb = 0; kb < nkb; ++kb) {
+            const uint64_t da = umma_desc_k_sw128(smem_u32(sQ + (j * nkb + kb) * SC_BM * 128));
+            const uint64_t db = umma_desc_k_sw128(smem_u32(sY + s * L.y_bytes + kb * SC_BN * 128));
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_bf16_ss(tmem_base + (b * NQT + j) * SC_BN, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0);
+          }
+          umma_commit(&s_full[b * NQT + j]);
+        }
+        umma_commit(&empty[s]);
+      }
+    }
+  } else {
+    const int j = (warp - 2) >> 2;                 // query tile of this warpgroup
+    const int qd = warp & 3;                       // TMEM lane quadrant this warp may read
+    const int row = qd * 32 + lane;
+    const long long qi = (long long)q0 + j * SC_BM + row;
+    float tau = INFINITY;                          // padding rows never select
+    unsigned long long* pq = nullptr;
+    int pcount = 0;
+    if constexpr (!SAMPLE) {
+      if (qi < a.nq) tau = a.tau[qi];
+      pq = pq_all + (size_t)j * SC_BM * SC_QCAP + row;
+    }
+    for (int t = 0; t < T; ++t) {
+      const int b = t & 1;
+      const int c_tile = tile_of(t) * SC_BN;
+      mbar_wait(&s_full[b * NQT + j], (t >> 1) & 1);
+      tc_fence_after();
+      uint32_t rr[SC_BN];
+#pragma unroll
+      for (int c = 0; c < SC_BN / 32; ++c)
+        tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (b * NQT + j) * SC_BN + c * 32, rr + c * 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_empty[b * NQT + j]);          // the MMA of tile t + 2 may overwrite the buffer
+      if (c_tile + SC_BN > a.nc) {                 // uniform: ragged last tile
+#pragma unroll
+        for (int i = 0; i < SC_BN; ++i) if (c_tile + i >= a.nc) rr[i] = 0xff800000u;     // -inf
+      }
+      float sm[SC_BN / 16];                        // maxima of 16 scores
+#pragma unroll
+      for (int c = 0; c < SC_BN / 16; ++c) {
+        const uint32_t* x = rr + c * 16;
+        float m0 = fmax3(__uint_as_float(x[0]), __uint_as_float(x[1]), __uint_as_float(x[2]));
+        float m1 = fmax3(__uint_as_float(x[3]), __uint_as_float(x[4]), __uint_as_float(x[5]));
+        m0 = fmax3(m0, __uint_as_float(x[6]), __uint_as_float(x[7]));
+        m1 = fmax3(m1, __uint_as_float(x[8]), __uint_as_float(x[9]));
+        m0 = fmax3(m0, __uint_as_float(x[10]), __uint_as_float(x[11]));
+        m1 = fmax3(m1, __uint_as_float(x[12]), __uint_as_float(x[13]));
+        m0 = fmax3(m0, __uint_as_float(x[14]), __uint_as_float(x[15]));
+        sm[c] = fmaxf(m0, m1);
+      }
+      if constexpr (SAMPLE) {
+        if (qi < a.nq) {
+          const size_t g0 = (size_t)(begin + t) * 4;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) a.samp[(g0 + c) * a.nq_pad + qi] = fmaxf(sm[2 * c], sm[2 * c + 1]);
+        }
+      } else {
+        float mx = sm[0];
+#pragma unroll
+        for (int c = 1; c < SC_BN / 16; ++c) mx = fmaxf(mx, sm[c]);
+        if (mx > tau) {
+#pragma unroll
+          for (int c = 0; c < SC_BN / 16; ++c) {
+            if (sm[c] > tau) {
+              if (pcount > SC_QCAP - 16) {
+                scan_flush(pq, pcount, a.cnt + qi, a.buf + (size_t)qi * a.cap, a.cap);
+                pcount = 0;
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float v = __uint_as_float(rr[c * 16 + i]);
+                if (v > tau) {
+                  pq[pcount * SC_BM] = topk_key(v, c_tile + c * 16 + i);
+                  ++pcount;
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    if constexpr (!SAMPLE) {
+      if (pcount > 0) scan_flush(pq, pcount, a.cnt + qi, a.buf + (size_t)qi * a.cap, a.cap);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * NQT * SC_BN);
+}
+
+// ---- block-wide bitonic sort (descending) of P = 2^m keys in shared memory -----------------------------------
+template <typename K>
+__device__ __forceinline__ void block_bitonic_desc(K* s, int P) {
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < (P >> 1); i += blockDim.x) {
+        const int lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
+        const int hi = lo | stride;
+        const bool desc = (lo & size) == 0;
+        const K x = s[lo], y = s[hi];
+        if ((x < y) == desc) { s[lo] = y; s[hi] = x; }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned score_key32(float s) {
+  const unsigned u = __float_as_uint(s);
+  return u ^ ((unsigned)((int)u >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float key32_score(unsigned f) {
+  return __uint_as_float((f & 0x80000000u) ? (f ^ 0x80000000u) : ~f);
+}
+
+// tau[row] = the largest float strictly below the K-th largest of the row's G group maxima (so `score > tau` means
+// `score >= that maximum`); -inf when fewer than K groups hold a finite score.  Also clears the row's survivor count.
+__global__ void __launch_bounds__(1024)
+topk_tau_kernel(const float* __restrict__ samp, int G, int nq_pad, int K, int P, float* __restrict__ tau,
+                int* __restrict__ cnt, int* __restrict__ flag) {
+  extern __shared__ __align__(16) uint8_t tau_smem[];
+  unsigned* s = reinterpret_cast<unsigned*>(tau_smem);
+  const int row = blockIdx.x;
+  for (int g = threadIdx.x; g < P; g += blockDim.x) s[g] = g < G ? score_key32(samp[(size_t)g * nq_pad + row]) : 0u;
+  __syncthreads();
+  block_bitonic_desc(s, P);
+  if (threadIdx.x == 0) {
+    const float kth = K <= G ? key32_score(s[K - 1]) : -INFINITY;
+    float t;
+    if (!(kth > -INFINITY)) t = -INFINITY;                            // also NaN
+    else if (kth == 0.f) t = __uint_as_float(0x80000001u);            // below both zeros
+    else t = key32_score(score_key32(kth) - 1u);
+    tau[row] = t;
+    cnt[row] = 0;
+    if (row == 0) *flag = 0;
+  }
+}
+
+// One CTA per query row: the row's survivors -> the best kp as (score desc, index asc), raw candidate indices.
+// A row with more than cap survivors (or fewer than kp) raises the flag: the list-keeping path redoes the batch.
+__global__ void __launch_bounds__(1024)
+topk_pool_select_kernel(const unsigned long long* __restrict__ buf, const int* __restrict__ cnt, int cap, int kp,
+                        int need, float* __restrict__ pool_s, int64_t* __restrict__ pool_i, int* __restrict__ flag) {
+  extern __shared__ __align__(16) uint8_t sel_smem[];
+  unsigned long long* s = reinterpret_cast<unsigned long long*>(sel_smem);
+  const int row = blockIdx.x;
+  const int n_raw = cnt[row];
+  if (n_raw > cap || n_raw < need) {
+    if (threadIdx.x == 0) atomicExch(flag, 1);
+    return;
+  }
+  int P = 64;
+  while (P < n_raw || P < kp) P <<= 1;
+  const unsigned long long* src = buf + (size_t)row * cap;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) s[i] = i < n_raw ? src[i] : 0ull;
+  __syncthreads();
+  block_bitonic_desc(s, P);
+  for (int t = threadIdx.x; t < kp; t += blockDim.x) {
+    const unsigned long long v = s[t];
+    pool_s[(size_t)row * kp + t] = v ? topk_key_score(v) : -INFINITY;
+    pool_i[(size_t)row * kp + t] = v ? (int64_t)topk_key_index(v) : LLONG_MAX;
+  }
+}
+
+// ---- host ----------------------------------------------------------------------------------------------------
+constexpr int SC_CAP = 16384;          // survivors per row the select kernel can sort (128 KB of shared memory)
+constexpr int SC_EXPECT = 3712;        // planned survivors per row (cap / 4.4)
+
+static int splits_for(int64_t q_groups, int64_t units, int64_t min_units) {
+  const int64_t waves = std::min<int64_t>(16, std::max<int64_t>(1, q_groups / 4));
+  int64_t s = ceil_div((int64_t)num_sms() * waves, q_groups);
+  s = std::min<int64_t>(s, std::max<int64_t>(1, units / min_units));
+  return (int)std::max<int64_t>(1, s);
+}
+
+// TT_TOPK_SCAN=0 / tt_debug_topk_scan_mode(0): always the list-keeping kernel; mode 2: survivor buffers of 64 entries,
+// so every row overflows and the device-side fallback runs (tests)
+static int g_scan_mode = -1;
+static int scan_mode() {
+  if (g_scan_mode < 0) {
+    const char* e = getenv("TT_TOPK_SCAN");
+    g_scan_mode = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_scan_mode;
+}
+
+ScanPlan tc_topk_scan_plan(int64_t nq, int64_t nc, int64_t d, int kp) {
+  ScanPlan p{};
+  if (scan_mode() == 0) return p;
+  if (d % 64 != 0 || d < 64 || d > 128 || nc >= INT_MAX - 256 || nq >= (1 << 30)) return p;
+  const int64_t total_tiles = ceil_div(nc, SC_BN);
+  const int64_t groups_all = total_tiles * 4;
+  // G group maxima -> about kp * groups_all / G survivors per row; at least 4 kp groups so that the K-th largest is
+  // an interior order statistic
+  int64_t G = std::max<int64_t>(4 * (int64_t)kp, ceil_div((int64_t)kp * groups_all, SC_EXPECT));
+  int64_t n_samp = ceil_div(G, 4);
+  if (n_samp * 2 > total_tiles || 4 * n_samp > 32768) return p;       // the sample would be most of the scan / beyond the sort
+  p.use = true;
+  p.nqt = nq > SC_BM ? 2 : 1;
+  p.q_groups = (int)ceil_div(nq, p.nqt * SC_BM);
+  p.nq_pad = (int)round_up(nq, 256);
+  p.total_tiles = (int)total_tiles;
+  p.n_samp = (int)n_samp;
+  p.G = (int)(4 * n_samp);
+  p.P = 64;
+  while (p.P < p.G) p.P <<= 1;
+  p.cap = scan_mode() == 2 ? 64 : SC_CAP;
+  p.kp = kp;
+  const int ss = splits_for(p.q_groups, n_samp, 8);
+  p.samp_tps = (int)ceil_div(n_samp, ss);
+  p.samp_splits = (int)ceil_div(n_samp, p.samp_tps);
+  const int cs = splits_for(p.q_groups, total_tiles, 32);
+  p.scan_tps = (int)ceil_div(total_tiles, cs);
+  p.scan_splits = (int)ceil_div(total_tiles, p.scan_tps);
+  int64_t off = 0;
+  p.off_samp = off; off += round_up((int64_t)p.G * p.nq_pad * 4, 256);
+  p.off_tau = off;  off += round_up((int64_t)p.nq_pad * 4, 256);
+  p.off_cnt = off;  off += round_up((int64_t)p.nq_pad * 4, 256);
+  p.off_flag = off; off += 256;
+  p.off_buf = off;  off += round_up(nq * (int64_t)p.cap * 8, 256);
+  p.bytes = off;
+  return p;
+}
+
+template <int NQT, bool SAMPLE>
+static int launch_scan(const CUtensorMap& tmQ, const CUtensorMap& tmC, ScanArgs a, dim3 grid, cudaStream_t st) {
+  const ScanLayout L = scan_layout(a.d, NQT, SAMPLE);
+  if (L.stages < 2) return set_error(TT_ERR_UNSUPPORTED, "tt_topk_bruteforce(bf16): d=%d does not fit the scan pipeline", a.d);
+  a.stages = L.stages;
+  TT_CUDA_OK(cudaFuncSetAttribute(topk_scan_kernel<NQT, SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+  TT_PROF(SAMPLE ? "topk_scan_kernel(sample)" : "topk_scan_kernel", st);
+  topk_scan_kernel<NQT, SAMPLE><<<grid, 64 + NQT * 128, L.total, st>>>(tmQ, tmC, a);
+  TT_LAUNCH_OK("topk_scan_kernel");
+  return TT_OK;
+}
+
+// Steps 1-4 into pool_s / pool_i ([nq, kp], raw candidate indices).  *flag (device, inside ws) is 1 afterwards iff the
+// caller's list-keeping path has to redo the batch.
+int tc_topk_scan(const ScanPlan& p, const void* queries, const void* candidates, int64_t nq, int64_t nc, int64_t d,
+                 float* pool_s, int64_t* pool_i, void* ws, int** flag_out, cudaStream_t st) {
+  char* base = (char*)ws;
+  float* samp = (float*)(base + p.off_samp);
+  float* tau = (float*)(base + p.off_tau);
+  int* cnt = (int*)(base + p.off_cnt);
+  int* flag = (int*)(base + p.off_flag);
+  unsigned long long* buf = (unsigned long long*)(base + p.off_buf);
+  *flag_out = flag;
+  CUtensorMap tmQ, tmC;
+  int rc = make_tmap_bf16_2d(&tmQ, queries, (uint64_t)d, (uint64_t)nq, (uint64_t)d * 2, 64, SC_BM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tmC, candidates, (uint64_t)d, (uint64_t)nc, (uint64_t)d * 2, 64, SC_BN);
+  if (rc) return rc;
+  ScanArgs a{};
+  a.nq = (int)nq; a.nc = (int)nc; a.d = (int)d;
+  a.total_tiles = p.total_tiles; a.n_samp = p.n_samp; a.nq_pad = p.nq_pad; a.cap = p.cap;
+  a.tau = tau; a.cnt = cnt; a.buf = buf; a.samp = samp;
+  a.tiles_per_split = p.samp_tps;
+  const dim3 gs((unsigned)p.q_groups, (unsigned)p.samp_splits);
+  rc = p.nqt == 2 ? launch_scan<2, true>(tmQ, tmC, a, gs, st) : launch_scan<1, true>(tmQ, tmC, a, gs, st);
+  if (rc) return rc;
+  TT_CUDA_OK(cudaFuncSetAttribute(topk_tau_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.P * 4));
+  TT_PROF("topk_tau_kernel", st);
+  topk_tau_kernel<<<(unsigned)nq, p.P >= 2048 ? 1024 : 256, p.P * 4, st>>>(samp, p.G, p.nq_pad, p.kp, p.P, tau, cnt, flag);
+  TT_LAUNCH_OK("topk_tau_kernel");
+  a.tiles_per_split = p.scan_tps;
+  const dim3 gc((unsigned)p.q_groups, (unsigned)p.scan_splits);
+  rc = p.nqt == 2 ? launch_scan<2, false>(tmQ, tmC, a, gc, st) : launch_scan<1, false>(tmQ, tmC, a, gc, st);
+  if (rc) return rc;
+  TT_CUDA_OK(cudaFuncSetAttribute(topk_pool_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.cap * 8));
+  TT_PROF("topk_pool_select_kernel", st);
+  topk_pool_select_kernel<<<(unsigned)nq, 1024, p.cap * 8, st>>>(buf, cnt, p.cap, p.kp, (int)std::min<int64_t>(p.kp, nc),
+                                                                 pool_s, pool_i, flag);
+  TT_LAUNCH_OK("topk_pool_select_kernel");
+  return TT_OK;
+}
+
+}  // namespace tt
+
+extern "C" int tt_debug_topk_scan_mode(int32_t mode) {
+  const int prev = tt::scan_mode();
+  if (mode >= 0 && mode <= 2) tt::g_scan_mode = mode;
+  return prev;
+}

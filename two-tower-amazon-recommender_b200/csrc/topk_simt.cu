@@ -16,6 +16,8 @@ int tc_topk(const void* queries, const void* candidates, int64_t nq, int64_t nc,
             int64_t ws_bytes, cudaStream_t st);
 int tc_topk_num_splits(int64_t nq, int64_t nc, int64_t d, int k);
 int tc_topk_max_k(int64_t d);
+int64_t tc_topk_stage_bytes(int64_t nq, int64_t nc, int64_t d, int kp);
+bool tc_topk_uses_scan(int64_t nq, int64_t nc, int64_t d, int kp);
 
 // Partial (or final) result writer shared with the tensor-core kernel: row r of the state ->
 // out arrays, padding short lists with (-inf, INT64_MAX).
@@ -91,7 +93,8 @@ constexpr int MERGE_LPL = 8;
 __global__ void __launch_bounds__(256)
 topk_merge_kernel(const float* __restrict__ scores, const int64_t* __restrict__ ids, int L, int64_t nq, int k_in,
                   int k_out, int64_t base, const int64_t* __restrict__ identifiers, float* __restrict__ out_s,
-                  int64_t* __restrict__ out_i) {
+                  int64_t* __restrict__ out_i, const int* __restrict__ run_if) {
+  if (run_if != nullptr && *run_if == 0) return;
   const int lane = threadIdx.x & 31;
   const int64_t qi = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (qi >= nq) return;
@@ -203,6 +206,18 @@ static size_t simt_topk_smem(int d, int k) { return (size_t)2 * d * TLD * 4 + to
 
 }  // namespace tt
 
+namespace tt {
+int topk_merge_launch(const float* scores, const int64_t* ids, int num_lists, int64_t nq, int k_in, int k_out,
+                      int64_t index_base, const int64_t* identifiers, float* out_scores, int64_t* out_ids,
+                      const int* run_if, cudaStream_t st) {
+  TT_PROF("topk_merge_kernel", st);
+  topk_merge_kernel<<<(unsigned)ceil_div(nq, 8), 256, 0, st>>>(scores, ids, num_lists, nq, k_in, k_out, index_base,
+                                                               identifiers, out_scores, out_ids, run_if);
+  TT_LAUNCH_OK("topk_merge_kernel");
+  return TT_OK;
+}
+}  // namespace tt
+
 using namespace tt;
 
 static const size_t kMaxSmem = 227 * 1024;
@@ -231,9 +246,17 @@ static int pool_k(int32_t precision, int64_t d, int k, int64_t nc) {
 }
 
 static int64_t stage1_bytes(int32_t precision, int64_t nq, int64_t nc, int64_t d, int kp) {
+  if (precision == TT_BF16) return tc_topk_stage_bytes(nq, nc, d, kp);
   const int s = tt_topk_num_splits(precision, nq, nc, d, kp);
   if (s <= 1) return 256;
   return round_up((int64_t)s * nq * kp * 4, 256) + round_up((int64_t)s * nq * kp * 8, 256);
+}
+
+extern "C" int32_t tt_topk_num_launches(int32_t precision, int64_t nq, int64_t nc, int64_t d, int32_t k) {
+  const int kp = pool_k(precision, d, k, nc);
+  int n = (tt_topk_num_splits(precision, nq, nc, d, kp) > 1 ? 2 : 1) + 1;      // scoring (+ merge) + re-rank
+  if (precision == TT_BF16 && tc_topk_uses_scan(nq, nc, d, kp)) n += 4;        // sample, threshold, scan, select
+  return n;
 }
 
 extern "C" int64_t tt_topk_workspace_bytes(int32_t precision, int64_t nq, int64_t nc, int64_t d, int32_t k) {
@@ -249,10 +272,8 @@ extern "C" int tt_topk_merge(const float* scores, const int64_t* ids, int32_t nu
   TT_REQUIRE(num_lists >= 1 && num_lists <= 32 * MERGE_LPL, "tt_topk_merge: num_lists must be in [1, %d], got %d", 32 * MERGE_LPL, num_lists);
   TT_REQUIRE(nq >= 0 && k_in >= 1 && k_out >= 1 && k_out <= num_lists * k_in, "tt_topk_merge: bad k (k_in=%d k_out=%d lists=%d)", k_in, k_out, num_lists);
   if (nq == 0) return TT_OK;
-  TT_PROF("topk_merge_kernel", (cudaStream_t)stream);
-  topk_merge_kernel<<<(unsigned)ceil_div(nq, 8), 256, 0, (cudaStream_t)stream>>>(scores, ids, num_lists, nq, k_in, k_out, index_base, identifiers, out_scores, out_ids);
-  TT_LAUNCH_OK("topk_merge_kernel");
-  return TT_OK;
+  return topk_merge_launch(scores, ids, num_lists, nq, k_in, k_out, index_base, identifiers, out_scores, out_ids, nullptr,
+                           (cudaStream_t)stream);
 }
 
 static int simt_topk(const void* queries, const void* candidates, int64_t nq, int64_t nc, int64_t d, int k,

@@ -16,6 +16,7 @@
 // lists are merged by topk_merge_kernel.
 #include "tc_common.cuh"
 #include "topk_select.cuh"
+#include "topk_scan.cuh"
 #include <limits.h>
 
 namespace tt {
@@ -30,6 +31,7 @@ struct TopkTcArgs {
   int tiles_per_split;
   int stages;
   int raw_indices;          // partial lists (splits > 1): write raw candidate indices
+  const int* run_if;        // optional device flag: the kernel exits at once when it is 0 (fallback of the threshold scan)
   float* out_s;
   long long* out_i;
 };
@@ -51,6 +53,7 @@ template <int KU, int TK_BN>
 __global__ void __launch_bounds__(TK_THREADS, 1)
 topk_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmC, const TopkTcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  if (a.run_if != nullptr && *a.run_if == 0) return;
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   const int d = a.d, nkb = d / 64, k = a.k;
   const TopkTcLayout L = topk_tc_layout(d, k, TK_BN);
@@ -241,6 +244,8 @@ static int tc_topk_splits(int64_t nq, int64_t nc, int bn, int* tiles_per_split) 
   return (int)ceil_div(y128, per128);
 }
 
+bool tc_topk_uses_scan(int64_t nq, int64_t nc, int64_t d, int kp) { return tc_topk_scan_plan(nq, nc, d, kp).use; }
+
 // largest k whose key lists leave room for a 2-stage candidate ring
 int tc_topk_max_k(int64_t d) {
   if (d % 64 != 0 || d < 64 || d > 256) return 0;
@@ -255,8 +260,18 @@ int tc_topk_num_splits(int64_t nq, int64_t nc, int64_t d, int k) {
   return tc_topk_splits(nq, nc, tk_bn_for(d), &tps);
 }
 
-extern "C" int tt_topk_merge(const float*, const int64_t*, int32_t, int64_t, int32_t, int32_t, int64_t, const int64_t*,
-                             float*, int64_t*, void*);
+int topk_merge_launch(const float* scores, const int64_t* ids, int num_lists, int64_t nq, int k_in, int k_out,
+                      int64_t index_base, const int64_t* identifiers, float* out_scores, int64_t* out_ids,
+                      const int* run_if, cudaStream_t st);
+
+// workspace of the bf16 scoring stage behind the pool: [partial lists of the list-keeping kernel | threshold scan]
+int64_t tc_topk_stage_bytes(int64_t nq, int64_t nc, int64_t d, int kp) {
+  int tps;
+  const int splits = tc_topk_splits(nq, nc, tk_bn_for(d), &tps);
+  int64_t lists = 256;
+  if (splits > 1) lists = round_up((int64_t)splits * nq * kp * 4, 256) + round_up((int64_t)splits * nq * kp * 8, 256);
+  return lists + tc_topk_scan_plan(nq, nc, d, kp).bytes;
+}
 
 int tc_topk(const void* queries, const void* candidates, int64_t nq, int64_t nc, int64_t d, int k,
             int64_t cand_index_base, const int64_t* identifiers, float* out_scores, int64_t* out_ids, void* ws,
@@ -269,11 +284,19 @@ int tc_topk(const void* queries, const void* candidates, int64_t nq, int64_t nc,
   int tps;
   const int splits = tc_topk_splits(nq, nc, bn, &tps);
   float* ps = out_scores; int64_t* pi = out_ids;
+  const int64_t lists = splits > 1 ? round_up((int64_t)splits * nq * k * 4, 256) + round_up((int64_t)splits * nq * k * 8, 256) : 256;
+  const ScanPlan sp = tc_topk_scan_plan(nq, nc, d, k);
+  if (!ws || ws_bytes < lists + sp.bytes)
+    return set_error(TT_ERR_WORKSPACE, "tt_topk_bruteforce(bf16): workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)(lists + sp.bytes));
   if (splits > 1) {
-    const int64_t need = round_up((int64_t)splits * nq * k * 4, 256) + round_up((int64_t)splits * nq * k * 8, 256);
-    if (!ws || ws_bytes < need) return set_error(TT_ERR_WORKSPACE, "tt_topk_bruteforce(bf16): workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)need);
     ps = (float*)ws;
     pi = (int64_t*)((char*)ws + round_up((int64_t)splits * nq * k * 4, 256));
+  }
+  // threshold scan first (topk_scan.cu); the list-keeping kernel below then runs only if a row overflowed
+  int* run_if = nullptr;
+  if (sp.use) {
+    const int rc0 = tc_topk_scan(sp, queries, candidates, nq, nc, d, out_scores, out_ids, (char*)ws + lists, &run_if, st);
+    if (rc0) return rc0;
   }
   CUtensorMap tmQ, tmC;
   int rc = make_tmap_bf16_2d(&tmQ, queries, (uint64_t)d, (uint64_t)nq, (uint64_t)d * 2, 64, TK_BM);
@@ -284,6 +307,7 @@ int tc_topk(const void* queries, const void* candidates, int64_t nq, int64_t nc,
   a.nq = (int)nq; a.nc = (int)nc; a.d = (int)d; a.k = k;
   a.cand_base = cand_index_base; a.identifiers = (const long long*)identifiers;
   a.tiles_per_split = tps; a.stages = L.stages; a.raw_indices = splits > 1;
+  a.run_if = run_if;
   a.out_s = ps; a.out_i = (long long*)pi;
   dim3 grid((unsigned)ceil_div(nq, TK_BM), (unsigned)splits);
 #define TT_TK2(KU, BNV)                                                                                            \
@@ -300,7 +324,7 @@ int tc_topk(const void* queries, const void* candidates, int64_t nq, int64_t nc,
 #undef TT_TK
 #undef TT_TK2
   TT_LAUNCH_OK("topk_tc_kernel");
-  if (splits > 1) return tt_topk_merge(ps, pi, splits, nq, k, k, cand_index_base, identifiers, out_scores, out_ids, st);
+  if (splits > 1) return topk_merge_launch(ps, pi, splits, nq, k, k, cand_index_base, identifiers, out_scores, out_ids, run_if, st);
   return TT_OK;
 }
 

@@ -687,11 +687,11 @@ def topk_bruteforce(precision: str, queries, candidates, k: int, cand_index_base
         return scores, ids
     nbytes = int(lib.tt_topk_workspace_bytes(pc, nq, nc, d, k))
     ws = _workspace(nbytes, dev)
-    splits = int(lib.tt_topk_num_splits(pc, nq, nc, d, k))
+    launches = int(lib.tt_topk_num_launches(pc, nq, nc, d, k))
     check(lib.tt_topk_bruteforce(pc, _ptr(queries, dt), _ptr(candidates, dt), nq, nc, d, k, cand_index_base,
                                  _ptr(identifiers, torch.int64), _ptr(scores), _ptr(ids), _ptr(uncertain, torch.int32),
                                  _ptr(ws), ws.numel(), _stream()))
-    _count(3 if splits > 1 else 2)
+    _count(launches)
     return scores, ids
 
 
@@ -708,12 +708,12 @@ def topk_bruteforce_peer(precision: str, queries, candidates, k: int, cand_index
     nc = candidates.shape[0]
     nbytes = int(lib.tt_topk_workspace_bytes(pc, nq, nc, d, k))
     scratch = _workspace(nbytes, queries.device)
-    splits = int(lib.tt_topk_num_splits(pc, nq, nc, d, k))
+    launches = int(lib.tt_topk_num_launches(pc, nq, nc, d, k))
     check(lib.tt_topk_bruteforce_peer(pc, _ptr(queries, dt), _ptr(candidates, dt), nq, nc, d, k, int(cand_index_base),
                                       _ptr(ws.bases, torch.int64), ws.world, ws.rank, int(queries_per_rank),
                                       int(recv_scores_offset), int(recv_ids_offset), _ptr(uncertain, torch.int32),
                                       _ptr(scratch), scratch.numel(), _stream()))
-    _count(3 if splits > 1 else 2)
+    _count(launches)
 
 
 def topk_merge(scores, ids, k_out: int, index_base: int = 0, identifiers=None):
