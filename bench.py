@@ -647,13 +647,41 @@ def serving_bench(tt, torch, dist, dev, peaks, world, rank, group, nq=16384, nc=
             ms = float(t.item())
         return ms
 
+    def kernel_times(fn, reps=3):
+        """us per launch of every kernel of one call (CUDA event pair around each launch, stream kept busy)"""
+        import ctypes
+        lib = tt._lib.load()
+        lib.tt_profile_enable(1)
+        for _ in range(reps):
+            torch.cuda._sleep(2_000_000)
+            fn()
+        buf = ctypes.create_string_buffer(1 << 14)
+        lib.tt_profile_collect(buf, len(buf))
+        lib.tt_profile_enable(0)
+        res = {}
+        for ln in buf.value.decode().splitlines():
+            name, cnt, total = ln.split()
+            res[name] = {"launches_per_call": int(cnt) / reps, "us_per_call": round(1e3 * float(total) / reps, 1)}
+        return res
+
     ms = timed(lambda: index(q), 3)
     tf = 2.0 * nq * (per * world) * d / (ms * 1e-3) / 1e12 / world
     out = {"metric": "top-100 queries/s", "value": nq / (ms * 1e-3), "unit": "queries/s", "queries": nq, "candidates": per * world,
            "n_gpus": world, "sharding": None if world == 1 else f"candidates sharded over {world} GPUs ({per} each), partial top-100 lists "
            "written into the merging rank's receive area by the kernel epilogue (NVLink peer stores), one flag barrier, merge",
            "ms": ms, "tflops_per_gpu": tf, "frac_of_bf16_peak": tf / peaks.get("bf16_tflops", 1590.0),
-           "exact": "ids = tf.math.top_k on the correctly rounded fp32 scores (k + 16 pool, fp64 re-rank)"}
+           "exact": "ids = tf.math.top_k on the correctly rounded fp32 scores (k + 16 pool, fp64 re-rank)",
+           "algorithm": "threshold scan (csrc/topk_scan.cu): strided 1/32 sample -> per-row threshold that k + 16 candidates are "
+                        "guaranteed to reach -> streaming tcgen05 pass keeping only survivors (two phases with a refined "
+                        "threshold when more than one query tile is resident) -> per-row radix select -> exact re-rank"}
+    kt = kernel_times(lambda: index(q))
+    out["kernels_us_per_call"] = kt
+    scan_us = kt.get("topk_scan_kernel", {}).get("us_per_call")
+    if scan_us:
+        scan_tf = 2.0 * nq * per * d / (scan_us * 1e-6) / 1e12
+        out["roofline"] = {"bound": "tensor", "kernel": "topk_scan_kernel (both phases)", "achieved": scan_tf, "peak": peaks.get("bf16_tflops", 1590.0),
+                           "unit": "TFLOP/s", "frac": scan_tf / peaks.get("bf16_tflops", 1590.0), "us_per_call": scan_us,
+                           "algorithmic_flops_per_call": 2.0 * nq * per * d}
 
     # end to end with HOST buffers: pinned queries -> H2D -> top-k -> D2H of scores + ids, every call
     q_host = q.cpu().pin_memory()
@@ -690,8 +718,16 @@ def serving_bench(tt, torch, dist, dev, peaks, world, rank, group, nq=16384, nc=
             qq = q[:qs_].contiguous()
             ms_s = timed(lambda: index(qq), 5)
             gbs = (per * d * 2 + qs_ * d * 2 + qs_ * k * 12) / (ms_s * 1e-3) / 1e9
-            small.append({"queries": qs_, "ms": ms_s, "queries_per_s": qs_ / (ms_s * 1e-3), "bound": "hbm", "achieved": gbs, "peak": hbm,
-                          "unit": "GB/s", "frac": gbs / hbm})
+            rec = {"queries": qs_, "ms": ms_s, "queries_per_s": qs_ / (ms_s * 1e-3), "bound": "hbm", "achieved": gbs, "peak": hbm,
+                   "unit": "GB/s", "frac": gbs / hbm}
+            kts = kernel_times(lambda: index(qq), 5)
+            us = kts.get("topk_scan_kernel", {}).get("us_per_call")
+            if us:
+                kg = (per * d * 2 + qs_ * d * 2) / (us * 1e-6) / 1e9
+                rec["scan_kernel"] = {"us_per_call": us, "achieved": kg, "unit": "GB/s", "frac": kg / hbm,
+                                      "algorithmic_bytes_per_call": per * d * 2 + qs_ * d * 2}
+            rec["kernels_us_per_call"] = kts
+            small.append(rec)
         out["small_batch"] = small
     if cpu_baseline and rank == 0:
         out["cpu_baseline"] = serving_cpu_baseline(torch, cand, q, k, world)

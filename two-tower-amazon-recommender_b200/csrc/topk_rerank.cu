@@ -30,7 +30,7 @@ struct TopkPeerOut {
   int queries_per_rank, rank;
 };
 
-constexpr int RR_WARPS = 8;
+constexpr int RR_WARPS = 16;     // at most; small query batches use all 16 (latency), large ones 8 warps per CTA
 constexpr int RR_MAXJ = 8;      // d <= 256: 8 elements per lane
 
 template <typename T> __device__ __forceinline__ T rr_raw(const T* p, int64_t i) { return __ldg(p + i); }
@@ -60,7 +60,8 @@ topk_rerank_kernel(const T* __restrict__ Q, const T* __restrict__ C, int64_t nq,
   }
   if (threadIdx.x == 0) red_kth = -INFINITY;
   float delta = 0.f, tmin = INFINITY;
-  for (int t0 = 4 * warp; t0 < kp; t0 += 4 * RR_WARPS) {
+  const int nwarps = blockDim.x >> 5;
+  for (int t0 = 4 * warp; t0 < kp; t0 += 4 * nwarps) {
     int64_t ci[4];
     float approx[4];
 #pragma unroll
@@ -106,7 +107,7 @@ topk_rerank_kernel(const T* __restrict__ Q, const T* __restrict__ C, int64_t nq,
     dst_s = reinterpret_cast<float*>(peer.bases[owner] + peer.off_s) + slot_row * k;
     dst_i = reinterpret_cast<int64_t*>(peer.bases[owner] + peer.off_i) + slot_row * k;
   }
-  for (int e = threadIdx.x; e < kp; e += RR_WARPS * 32) {
+  for (int e = threadIdx.x; e < kp; e += blockDim.x) {
     const float se = s32[e];
     const int ie = idx[e];
     if (ie == INT_MAX) continue;
@@ -126,7 +127,7 @@ topk_rerank_kernel(const T* __restrict__ Q, const T* __restrict__ C, int64_t nq,
     __syncthreads();
     if (threadIdx.x == 0) {
       float dl = 0.f, tm = INFINITY;
-      for (int w = 0; w < RR_WARPS; ++w) { dl = fmaxf(dl, red_delta[w]); tm = fminf(tm, red_tmin[w]); }
+      for (int w = 0; w < nwarps; ++w) { dl = fmaxf(dl, red_delta[w]); tm = fminf(tm, red_tmin[w]); }
       if (dl > 0.f && !(red_kth > tm + 4.f * dl)) atomicAdd(uncertain, 1);
     }
   }
@@ -144,7 +145,7 @@ int topk_rerank(int precision, const void* queries, const void* candidates, int6
 #define TT_RR_LAUNCH(T, NJ)                                                                                              \
   {                                                                                                                      \
     TT_CUDA_OK(cudaFuncSetAttribute(topk_rerank_kernel<T, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    TT_PROF("topk_rerank_kernel", st), topk_rerank_kernel<T, NJ><<<blocks, RR_WARPS * 32, smem, st>>>(                    \
+    TT_PROF("topk_rerank_kernel", st), topk_rerank_kernel<T, NJ><<<blocks, nq >= 2048 ? 256 : RR_WARPS * 32, smem, st>>>(                    \
         (const T*)queries, (const T*)candidates, nq, (int)d, pool_s, pool_i, kp, k, base, identifiers, out_s, out_i,      \
         uncertain, has_discarded, peer);                                                                                 \
   }

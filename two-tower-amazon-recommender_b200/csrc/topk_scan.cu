@@ -32,7 +32,9 @@
 namespace tt {
 
 constexpr int SC_BM = 128, SC_BN = 128;
-constexpr int SC_QCAP = 32;            // thread-private survivor queue (entries); flushed when fewer than 16 slots are left
+// Thread-private FIFO of flagged 16-score groups in shared memory: entry = 16 scores + the index of the first one.
+// Layout [slot][4 x 16 B][thread] (consecutive threads 16 B apart: conflict-free STS.128) + [slot][thread] indices.
+__host__ __device__ constexpr int sc_depth(int nqt) { return nqt == 1 ? 4 : 3; }
 constexpr int SC_MAX_STAGES = 5;
 
 struct ScanArgs {
@@ -40,11 +42,12 @@ struct ScanArgs {
   int total_tiles;          // ceil(nc / 128)
   int tiles_per_split;      // scan: contiguous tiles per blockIdx.y; sample: sample tiles per blockIdx.y
   int n_samp;               // sample: number of sampled tiles (tile of sample i = i * total_tiles / n_samp)
+  int phase;                // scan: 0 = every tile; 1 = the tiles = 0 mod 8; 2 = the other tiles (after the threshold was refined)
   int nq_pad, cap, stages;
   const float* tau;         // scan: [nq_pad]
   int* cnt;                 // scan: [nq_pad] survivors per row (may exceed cap: overflow)
   unsigned long long* buf;  // scan: [nq][cap]
-  float* samp;              // sample: [4 * n_samp][nq_pad]
+  float* samp;              // sample: [nq][4 * n_samp]
 };
 
 struct ScanLayout { int q_bytes, y_bytes, pq_bytes, stages, total; };
@@ -52,7 +55,7 @@ __host__ __device__ inline ScanLayout scan_layout(int d, int nqt, bool sample) {
   ScanLayout L;
   L.q_bytes = nqt * SC_BM * d * 2;
   L.y_bytes = SC_BN * d * 2;
-  L.pq_bytes = sample ? 0 : nqt * SC_BM * SC_QCAP * 8;
+  L.pq_bytes = sample ? 0 : nqt * SC_BM * sc_depth(nqt) * (64 + 4);
   const int fixed = L.q_bytes + L.pq_bytes + 1024;
   L.stages = (227 * 1024 - fixed) / L.y_bytes;
   if (L.stages > SC_MAX_STAGES) L.stages = SC_MAX_STAGES;
@@ -60,11 +63,31 @@ __host__ __device__ inline ScanLayout scan_layout(int d, int nqt, bool sample) {
   return L;
 }
 
-// survivors of one row: shared-memory queue (entry i at pq[i * 128]) -> the row's global buffer
-__device__ __noinline__ void scan_flush(const unsigned long long* pq, int n, int* cnt, unsigned long long* buf, int cap) {
-  const int pos = atomicAdd(cnt, n);
-  for (int i = 0; i < n; ++i)
-    if (pos + i < cap) buf[pos + i] = pq[i * SC_BM];
+// Drain one thread's FIFO: count the scores above tau, reserve that many slots of the row's global buffer with ONE
+// atomicAdd, write the survivors as 64-bit keys.  Rolled loops: this runs once per ~20 tiles, lanes in parallel.
+__device__ __noinline__ void scan_drain(const uint4* fifo, const int* loc, int n, float tau, int* cnt,
+                                        unsigned long long* buf, int cap) {
+  int m = 0;
+#pragma unroll 1
+  for (int e = 0; e < 4 * n; ++e) {
+    const uint4 v = fifo[e * SC_BM];
+    m += (__uint_as_float(v.x) > tau) + (__uint_as_float(v.y) > tau) + (__uint_as_float(v.z) > tau) + (__uint_as_float(v.w) > tau);
+  }
+  if (m == 0) return;
+  int pos = atomicAdd(cnt, m);
+#pragma unroll 1
+  for (int e = 0; e < 4 * n; ++e) {
+    const uint4 v = fifo[e * SC_BM];
+    const int i0 = loc[(e >> 2) * SC_BM] + 4 * (e & 3);
+    const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (__uint_as_float(x[u]) > tau) {
+        if (pos < cap) buf[pos] = topk_key(__uint_as_float(x[u]), i0 + u);
+        ++pos;
+      }
+    }
+  }
 }
 
 template <int NQT, bool SAMPLE>
@@ -90,10 +113,16 @@ topk_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * (NQT * SC_BM);
   const int begin = blockIdx.y * a.tiles_per_split;
-  const int limit = SAMPLE ? a.n_samp : a.total_tiles;
+  const int n_first = (a.total_tiles + 7) >> 3;                     // tiles = 0 mod 8
+  const int limit = SAMPLE ? a.n_samp : (a.phase == 0 ? a.total_tiles : (a.phase == 1 ? n_first : a.total_tiles - n_first));
   const int T = max(0, min(a.tiles_per_split, limit - begin));
   auto tile_of = [&](int t) -> int {
-    return SAMPLE ? (int)(((long long)(begin + t) * a.total_tiles) / a.n_samp) : begin + t;
+    const int i = begin + t;
+    if (SAMPLE) return (int)(((long long)i * a.total_tiles) / a.n_samp);
+    if (a.phase == 0) return i;
+    if (a.phase == 1) return i << 3;
+    const int q7 = i / 7;
+    return (q7 << 3) + (i - 7 * q7) + 1;
   };
 
   if (warp == 0 && lane == 0) {
@@ -153,11 +182,14 @@ topk_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int row = qd * 32 + lane;
     const long long qi = (long long)q0 + j * SC_BM + row;
     float tau = INFINITY;                          // padding rows never select
-    unsigned long long* pq = nullptr;
-    int pcount = 0;
+    constexpr int DEPTH = sc_depth(NQT);
+    uint4* fifo = nullptr;                         // this thread's FIFO of flagged 16-score groups
+    int* loc = nullptr;
+    int nfifo = 0;
     if constexpr (!SAMPLE) {
       if (qi < a.nq) tau = a.tau[qi];
-      pq = pq_all + (size_t)j * SC_BM * SC_QCAP + row;
+      fifo = reinterpret_cast<uint4*>(pq_all) + (size_t)j * DEPTH * 4 * SC_BM + row;
+      loc = reinterpret_cast<int*>(reinterpret_cast<uint4*>(pq_all) + (size_t)NQT * DEPTH * 4 * SC_BM) + (size_t)j * DEPTH * SC_BM + row;
     }
     for (int t = 0; t < T; ++t) {
       const int b = t & 1;
@@ -189,38 +221,40 @@ topk_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         sm[c] = fmaxf(m0, m1);
       }
       if constexpr (SAMPLE) {
-        if (qi < a.nq) {
-          const size_t g0 = (size_t)(begin + t) * 4;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) a.samp[(g0 + c) * a.nq_pad + qi] = fmaxf(sm[2 * c], sm[2 * c + 1]);
-        }
+        if (qi < a.nq)                               // 16 bytes per row and sampled tile: the threshold kernel reads rows
+          *reinterpret_cast<float4*>(a.samp + (size_t)qi * (4 * a.n_samp) + (size_t)(begin + t) * 4) =
+              make_float4(fmaxf(sm[0], sm[1]), fmaxf(sm[2], sm[3]), fmaxf(sm[4], sm[5]), fmaxf(sm[6], sm[7]));
       } else {
         float mx = sm[0];
 #pragma unroll
         for (int c = 1; c < SC_BN / 16; ++c) mx = fmaxf(mx, sm[c]);
-        if (mx > tau) {
+        // Flagged groups (a few % of the row-tiles hold one) are only PARKED here -- predicated stores, every lane at
+        // once -- and examined later by scan_drain.  Examining them in place costs either 40 KB of unrolled code (the
+        // kernel then stalls on instruction fetch) or a serial dependent loop per hit row with one warp per scheduler.
+        if (__any_sync(0xffffffffu, mx > tau)) {
 #pragma unroll
           for (int c = 0; c < SC_BN / 16; ++c) {
             if (sm[c] > tau) {
-              if (pcount > SC_QCAP - 16) {
-                scan_flush(pq, pcount, a.cnt + qi, a.buf + (size_t)qi * a.cap, a.cap);
-                pcount = 0;
+              if (nfifo == DEPTH) {               // one row with a burst: drained alone
+                scan_drain(fifo, loc, nfifo, tau, a.cnt + qi, a.buf + (size_t)qi * a.cap, a.cap);
+                nfifo = 0;
               }
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float v = __uint_as_float(rr[c * 16 + i]);
-                if (v > tau) {
-                  pq[pcount * SC_BM] = topk_key(v, c_tile + c * 16 + i);
-                  ++pcount;
-                }
-              }
+              for (int g = 0; g < 4; ++g)
+                fifo[(nfifo * 4 + g) * SC_BM] = make_uint4(rr[c * 16 + 4 * g], rr[c * 16 + 4 * g + 1], rr[c * 16 + 4 * g + 2], rr[c * 16 + 4 * g + 3]);
+              loc[nfifo * SC_BM] = c_tile + c * 16;
+              ++nfifo;
             }
+          }
+          if (__any_sync(0xffffffffu, nfifo == DEPTH)) {      // the whole warp drains together
+            if (nfifo > 0) scan_drain(fifo, loc, nfifo, tau, a.cnt + qi, a.buf + (size_t)qi * a.cap, a.cap);
+            nfifo = 0;
           }
         }
       }
     }
     if constexpr (!SAMPLE) {
-      if (pcount > 0) scan_flush(pq, pcount, a.cnt + qi, a.buf + (size_t)qi * a.cap, a.cap);
+      if (nfifo > 0) scan_drain(fifo, loc, nfifo, tau, a.cnt + qi, a.buf + (size_t)qi * a.cap, a.cap);
     }
   }
   tc_fence_before();
@@ -245,6 +279,52 @@ __device__ __forceinline__ void block_bitonic_desc(K* s, int P) {
   }
 }
 
+// ---- block-wide radix select: the k-th largest (k >= 1) of the keys the block holds in registers ----------------
+// Key 0 is padding (below every real key; k never exceeds the number of real keys).  Eight bits per pass from the
+// top; equal digits inside a warp are combined before the shared-memory atomic (scores of one row share their high
+// bits, so the plain form would serialise 32 ways).  hist: shared unsigned[257], bc: shared int[2].
+template <typename K, int NPT>
+__device__ __forceinline__ K block_kth_largest(const K (&key)[NPT], int n_valid, int k, unsigned* hist, int* bc) {
+  const int lane = threadIdx.x & 31;
+  K prefix = 0, mask = 0;
+  for (int shift = (int)sizeof(K) * 8 - 8; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 257; i += blockDim.x) hist[i] = 0u;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NPT; ++i) {
+      if (i * (int)blockDim.x >= n_valid) break;           // uniform: the rest is padding
+      const unsigned dg = (key[i] & mask) == prefix ? (unsigned)((key[i] >> shift) & 255) : 256u;
+      const unsigned peers = __match_any_sync(0xffffffffu, dg);
+      if (lane == __ffs(peers) - 1) atomicAdd(&hist[dg], (unsigned)__popc(peers));
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {                       // lane l owns bins 255 - 8 l ... 248 - 8 l, highest first
+      unsigned c[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { c[j] = hist[255 - 8 * lane - j]; sum += c[j]; }
+      unsigned incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      unsigned run = incl - sum;
+      if (run < (unsigned)k && (unsigned)k <= incl) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (run < (unsigned)k && (unsigned)k <= run + c[j]) { bc[0] = 255 - 8 * lane - j; bc[1] = k - (int)run; }
+          run += c[j];
+        }
+      }
+    }
+    __syncthreads();
+    prefix |= (K)(unsigned)bc[0] << shift;
+    mask |= (K)255 << shift;
+    k = bc[1];
+  }
+  return prefix;
+}
+
 __device__ __forceinline__ unsigned score_key32(float s) {
   const unsigned u = __float_as_uint(s);
   return u ^ ((unsigned)((int)u >> 31) | 0x80000000u);
@@ -253,57 +333,100 @@ __device__ __forceinline__ float key32_score(unsigned f) {
   return __uint_as_float((f & 0x80000000u) ? (f ^ 0x80000000u) : ~f);
 }
 
+constexpr int SC_SEL_THREADS = 1024;
+constexpr int SC_TAU_NPT = 32;         // G <= 32768 group maxima per row
+constexpr int SC_SEL_NPT = 16;         // cap <= 16384 survivors per row
+
 // tau[row] = the largest float strictly below the K-th largest of the row's G group maxima (so `score > tau` means
 // `score >= that maximum`); -inf when fewer than K groups hold a finite score.  Also clears the row's survivor count.
-__global__ void __launch_bounds__(1024)
-topk_tau_kernel(const float* __restrict__ samp, int G, int nq_pad, int K, int P, float* __restrict__ tau,
-                int* __restrict__ cnt, int* __restrict__ flag) {
-  extern __shared__ __align__(16) uint8_t tau_smem[];
-  unsigned* s = reinterpret_cast<unsigned*>(tau_smem);
+__device__ __forceinline__ float just_below(float kth) {
+  if (!(kth > -INFINITY)) return -INFINITY;                            // also NaN
+  if (kth == 0.f) return __uint_as_float(0x80000001u);                 // below both zeros
+  return key32_score(score_key32(kth) - 1u);
+}
+
+__global__ void __launch_bounds__(SC_SEL_THREADS)
+topk_tau_kernel(const float* __restrict__ samp, int G, int K, float* __restrict__ tau, int* __restrict__ cnt,
+                int* __restrict__ flag) {
+  __shared__ unsigned hist[257];
+  __shared__ int bc[2];
   const int row = blockIdx.x;
-  for (int g = threadIdx.x; g < P; g += blockDim.x) s[g] = g < G ? score_key32(samp[(size_t)g * nq_pad + row]) : 0u;
-  __syncthreads();
-  block_bitonic_desc(s, P);
+  unsigned key[SC_TAU_NPT];
+#pragma unroll
+  for (int i = 0; i < SC_TAU_NPT; ++i) {
+    const int g = threadIdx.x + i * SC_SEL_THREADS;
+    key[i] = g < G ? score_key32(samp[(size_t)row * G + g]) : 0u;
+  }
+  const unsigned kk = block_kth_largest<unsigned, SC_TAU_NPT>(key, G, K, hist, bc);
   if (threadIdx.x == 0) {
-    const float kth = K <= G ? key32_score(s[K - 1]) : -INFINITY;
-    float t;
-    if (!(kth > -INFINITY)) t = -INFINITY;                            // also NaN
-    else if (kth == 0.f) t = __uint_as_float(0x80000001u);            // below both zeros
-    else t = key32_score(score_key32(kth) - 1u);
-    tau[row] = t;
+    tau[row] = just_below(key32_score(kk));
     cnt[row] = 0;
     if (row == 0) *flag = 0;
   }
 }
 
-// One CTA per query row: the row's survivors -> the best kp as (score desc, index asc), raw candidate indices.
+// Between the two scan phases: the K-th largest of the survivors the first eighth of the tiles produced is a
+// (much) tighter threshold that K candidates are still guaranteed to reach.  Rows that overflowed keep theirs.
+__global__ void __launch_bounds__(SC_SEL_THREADS)
+topk_tau_refine_kernel(const unsigned long long* __restrict__ buf, const int* __restrict__ cnt, int cap, int K,
+                       float* __restrict__ tau) {
+  __shared__ unsigned hist[257];
+  __shared__ int bc[2];
+  const int row = blockIdx.x;
+  const int n = cnt[row];
+  if (n > cap || n < K) return;
+  const unsigned long long* src = buf + (size_t)row * cap;
+  unsigned key[SC_SEL_NPT];                       // the score half of the 64-bit keys orders them well enough here
+#pragma unroll
+  for (int i = 0; i < SC_SEL_NPT; ++i) {
+    const int e = threadIdx.x + i * SC_SEL_THREADS;
+    key[i] = e < n ? (unsigned)(src[e] >> 32) : 0u;
+  }
+  const unsigned kk = block_kth_largest<unsigned, SC_SEL_NPT>(key, n, K, hist, bc);
+  if (threadIdx.x == 0) tau[row] = fmaxf(tau[row], just_below(key32_score(kk)));
+}
+
+// One CTA per query row: the row's survivors -> the best kp as (score desc, index asc), raw candidate indices:
+// radix select of the kp-th largest key, compaction of the keys at or above it, sort of those kp.
 // A row with more than cap survivors (or fewer than kp) raises the flag: the list-keeping path redoes the batch.
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(SC_SEL_THREADS)
 topk_pool_select_kernel(const unsigned long long* __restrict__ buf, const int* __restrict__ cnt, int cap, int kp,
-                        int need, float* __restrict__ pool_s, int64_t* __restrict__ pool_i, int* __restrict__ flag) {
+                        int P, float* __restrict__ pool_s, int64_t* __restrict__ pool_i, int* __restrict__ flag) {
   extern __shared__ __align__(16) uint8_t sel_smem[];
-  unsigned long long* s = reinterpret_cast<unsigned long long*>(sel_smem);
+  __shared__ unsigned hist[257];
+  __shared__ int bc[2];
+  __shared__ int n_out;
+  unsigned long long* list = reinterpret_cast<unsigned long long*>(sel_smem);      // [P], P = 2^m >= kp
   const int row = blockIdx.x;
   const int n_raw = cnt[row];
-  if (n_raw > cap || n_raw < need) {
+  if (n_raw > cap || n_raw < kp) {
     if (threadIdx.x == 0) atomicExch(flag, 1);
     return;
   }
-  int P = 64;
-  while (P < n_raw || P < kp) P <<= 1;
   const unsigned long long* src = buf + (size_t)row * cap;
-  for (int i = threadIdx.x; i < P; i += blockDim.x) s[i] = i < n_raw ? src[i] : 0ull;
+  unsigned long long key[SC_SEL_NPT];
+#pragma unroll
+  for (int i = 0; i < SC_SEL_NPT; ++i) {
+    const int e = threadIdx.x + i * SC_SEL_THREADS;
+    key[i] = e < n_raw ? src[e] : 0ull;
+  }
+  if (threadIdx.x == 0) n_out = 0;
+  for (int i = threadIdx.x; i < P; i += SC_SEL_THREADS) list[i] = 0ull;
+  const unsigned long long kth = block_kth_largest<unsigned long long, SC_SEL_NPT>(key, n_raw, kp, hist, bc);
+#pragma unroll
+  for (int i = 0; i < SC_SEL_NPT; ++i)
+    if (key[i] >= kth && key[i] != 0ull) list[atomicAdd(&n_out, 1)] = key[i];      // keys are distinct: exactly kp of them
   __syncthreads();
-  block_bitonic_desc(s, P);
-  for (int t = threadIdx.x; t < kp; t += blockDim.x) {
-    const unsigned long long v = s[t];
+  block_bitonic_desc(list, P);
+  for (int t = threadIdx.x; t < kp; t += SC_SEL_THREADS) {
+    const unsigned long long v = list[t];
     pool_s[(size_t)row * kp + t] = v ? topk_key_score(v) : -INFINITY;
     pool_i[(size_t)row * kp + t] = v ? (int64_t)topk_key_index(v) : LLONG_MAX;
   }
 }
 
 // ---- host ----------------------------------------------------------------------------------------------------
-constexpr int SC_CAP = 16384;          // survivors per row the select kernel can sort (128 KB of shared memory)
+constexpr int SC_CAP = 16384;          // survivors per row the select kernel holds in registers (16 keys per thread)
 constexpr int SC_EXPECT = 3712;        // planned survivors per row (cap / 4.4)
 
 static int splits_for(int64_t q_groups, int64_t units, int64_t min_units) {
@@ -349,11 +472,19 @@ ScanPlan tc_topk_scan_plan(int64_t nq, int64_t nc, int64_t d, int kp) {
   const int ss = splits_for(p.q_groups, n_samp, 8);
   p.samp_tps = (int)ceil_div(n_samp, ss);
   p.samp_splits = (int)ceil_div(n_samp, p.samp_tps);
-  const int cs = splits_for(p.q_groups, total_tiles, 32);
-  p.scan_tps = (int)ceil_div(total_tiles, cs);
-  p.scan_splits = (int)ceil_div(total_tiles, p.scan_tps);
+  // more than one query tile: the scan is bound by the tensor pipe and the selection warps, not by HBM, and every
+  // survivor costs issue slots -- scan an eighth of the tiles, tighten the threshold on what they produced, scan the rest
+  p.two_phase = p.nqt == 2 && total_tiles >= 64;
+  const int64_t n_first = ceil_div(total_tiles, 8);
+  const int64_t n_main = p.two_phase ? total_tiles - n_first : total_tiles;
+  const int cs = splits_for(p.q_groups, n_main, 32);
+  p.scan_tps = (int)ceil_div(n_main, cs);
+  p.scan_splits = (int)ceil_div(n_main, p.scan_tps);
+  const int fs = splits_for(p.q_groups, n_first, 16);
+  p.first_tps = (int)ceil_div(n_first, fs);
+  p.first_splits = (int)ceil_div(n_first, p.first_tps);
   int64_t off = 0;
-  p.off_samp = off; off += round_up((int64_t)p.G * p.nq_pad * 4, 256);
+  p.off_samp = off; off += round_up((int64_t)p.G * nq * 4, 256);
   p.off_tau = off;  off += round_up((int64_t)p.nq_pad * 4, 256);
   p.off_cnt = off;  off += round_up((int64_t)p.nq_pad * 4, 256);
   p.off_flag = off; off += 256;
@@ -398,18 +529,29 @@ int tc_topk_scan(const ScanPlan& p, const void* queries, const void* candidates,
   const dim3 gs((unsigned)p.q_groups, (unsigned)p.samp_splits);
   rc = p.nqt == 2 ? launch_scan<2, true>(tmQ, tmC, a, gs, st) : launch_scan<1, true>(tmQ, tmC, a, gs, st);
   if (rc) return rc;
-  TT_CUDA_OK(cudaFuncSetAttribute(topk_tau_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.P * 4));
   TT_PROF("topk_tau_kernel", st);
-  topk_tau_kernel<<<(unsigned)nq, p.P >= 2048 ? 1024 : 256, p.P * 4, st>>>(samp, p.G, p.nq_pad, p.kp, p.P, tau, cnt, flag);
+  topk_tau_kernel<<<(unsigned)nq, SC_SEL_THREADS, 0, st>>>(samp, p.G, p.kp, tau, cnt, flag);
   TT_LAUNCH_OK("topk_tau_kernel");
-  a.tiles_per_split = p.scan_tps;
-  const dim3 gc((unsigned)p.q_groups, (unsigned)p.scan_splits);
-  rc = p.nqt == 2 ? launch_scan<2, false>(tmQ, tmC, a, gc, st) : launch_scan<1, false>(tmQ, tmC, a, gc, st);
-  if (rc) return rc;
-  TT_CUDA_OK(cudaFuncSetAttribute(topk_pool_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.cap * 8));
+  if (!p.two_phase) {
+    a.phase = 0; a.tiles_per_split = p.scan_tps;
+    const dim3 gc((unsigned)p.q_groups, (unsigned)p.scan_splits);
+    rc = p.nqt == 2 ? launch_scan<2, false>(tmQ, tmC, a, gc, st) : launch_scan<1, false>(tmQ, tmC, a, gc, st);
+    if (rc) return rc;
+  } else {
+    a.phase = 1; a.tiles_per_split = p.first_tps;
+    rc = launch_scan<2, false>(tmQ, tmC, a, dim3((unsigned)p.q_groups, (unsigned)p.first_splits), st);
+    if (rc) return rc;
+    TT_PROF("topk_tau_refine_kernel", st);
+    topk_tau_refine_kernel<<<(unsigned)nq, SC_SEL_THREADS, 0, st>>>(buf, cnt, p.cap, p.kp, tau);
+    TT_LAUNCH_OK("topk_tau_refine_kernel");
+    a.phase = 2; a.tiles_per_split = p.scan_tps;
+    rc = launch_scan<2, false>(tmQ, tmC, a, dim3((unsigned)p.q_groups, (unsigned)p.scan_splits), st);
+    if (rc) return rc;
+  }
+  int P = 32;
+  while (P < p.kp) P <<= 1;
   TT_PROF("topk_pool_select_kernel", st);
-  topk_pool_select_kernel<<<(unsigned)nq, 1024, p.cap * 8, st>>>(buf, cnt, p.cap, p.kp, (int)std::min<int64_t>(p.kp, nc),
-                                                                 pool_s, pool_i, flag);
+  topk_pool_select_kernel<<<(unsigned)nq, SC_SEL_THREADS, P * 8, st>>>(buf, cnt, p.cap, p.kp, P, pool_s, pool_i, flag);
   TT_LAUNCH_OK("topk_pool_select_kernel");
   return TT_OK;
 }

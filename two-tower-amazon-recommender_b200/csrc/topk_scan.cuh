@@ -12,6 +12,8 @@ struct ScanPlan {
   int n_samp, G, P;         // sampled tiles, group maxima per row (4 per tile), sort width of the threshold kernel
   int cap, kp;              // survivors per row the buffers hold; pool width
   int samp_splits, samp_tps, scan_splits, scan_tps;
+  bool two_phase;           // scan 1/8 of the tiles, refine the threshold on their survivors, scan the rest
+  int first_splits, first_tps;
   int64_t off_samp, off_tau, off_cnt, off_flag, off_buf, bytes;
 };
 

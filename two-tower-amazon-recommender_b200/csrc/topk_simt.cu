@@ -17,7 +17,7 @@ int tc_topk(const void* queries, const void* candidates, int64_t nq, int64_t nc,
 int tc_topk_num_splits(int64_t nq, int64_t nc, int64_t d, int k);
 int tc_topk_max_k(int64_t d);
 int64_t tc_topk_stage_bytes(int64_t nq, int64_t nc, int64_t d, int kp);
-bool tc_topk_uses_scan(int64_t nq, int64_t nc, int64_t d, int kp);
+int tc_topk_scan_launches(int64_t nq, int64_t nc, int64_t d, int kp);
 
 // Partial (or final) result writer shared with the tensor-core kernel: row r of the state ->
 // out arrays, padding short lists with (-inf, INT64_MAX).
@@ -255,7 +255,7 @@ static int64_t stage1_bytes(int32_t precision, int64_t nq, int64_t nc, int64_t d
 extern "C" int32_t tt_topk_num_launches(int32_t precision, int64_t nq, int64_t nc, int64_t d, int32_t k) {
   const int kp = pool_k(precision, d, k, nc);
   int n = (tt_topk_num_splits(precision, nq, nc, d, kp) > 1 ? 2 : 1) + 1;      // scoring (+ merge) + re-rank
-  if (precision == TT_BF16 && tc_topk_uses_scan(nq, nc, d, kp)) n += 4;        // sample, threshold, scan, select
+  if (precision == TT_BF16) n += tc_topk_scan_launches(nq, nc, d, kp);         // sample, threshold, scan (x2 + refine), select
   return n;
 }
 

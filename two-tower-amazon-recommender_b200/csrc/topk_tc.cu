@@ -244,7 +244,10 @@ static int tc_topk_splits(int64_t nq, int64_t nc, int bn, int* tiles_per_split) 
   return (int)ceil_div(y128, per128);
 }
 
-bool tc_topk_uses_scan(int64_t nq, int64_t nc, int64_t d, int kp) { return tc_topk_scan_plan(nq, nc, d, kp).use; }
+int tc_topk_scan_launches(int64_t nq, int64_t nc, int64_t d, int kp) {
+  const ScanPlan p = tc_topk_scan_plan(nq, nc, d, kp);
+  return !p.use ? 0 : (p.two_phase ? 6 : 4);
+}
 
 // largest k whose key lists leave room for a 2-stage candidate ring
 int tc_topk_max_k(int64_t d) {
