@@ -166,35 +166,74 @@ class Model:
 
 
 class GraphedStep:
-    def __init__(self, model: Model, example_inputs, warmup: int):
+    """CUDA-graph replay of `model.train_step` with DOUBLE-BUFFERED static inputs: the step is captured `buffers` times,
+    each capture reading its own packed input buffer, and successive calls alternate between them.  The copy of step
+    i + 1's inputs (one H2D copy from a pinned staging ring for host batches, one D2D copy for `pack`ed device batches)
+    is issued on a copy stream and overlaps the replay of step i; the replay only waits for its own inputs."""
+
+    def __init__(self, model: Model, example_inputs, warmup: int, buffers: int = 2):
         self.model = model
-        # static inputs are views of ONE device buffer with a pinned host mirror: a step fed from host memory costs one
-        # H2D copy (the tensors of a batch are small: 64 KB of ids each at cfg2), not one per tensor
-        self._packed = _PackedInputs(example_inputs)
-        self.static_in = self._packed.device_views
         side = torch.cuda.Stream()
+        self._slots = []
+        first = _PackedInputs(example_inputs)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup)):
-                model.train_step(self.static_in)
+                model.train_step(first.device_views)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        before = ops.LAUNCHES
         iterations = model.optimizer.iterations
-        with torch.cuda.graph(self.graph):
-            self.static_out = model.train_step(self.static_in)
-        self.launches_per_replay = ops.LAUNCHES - before
-        model.optimizer.iterations = iterations       # the capture executed nothing: no step was taken
+        for b in range(max(1, buffers)):
+            packed = first if b == 0 else _PackedInputs(example_inputs)
+            graph = torch.cuda.CUDAGraph()
+            before = ops.LAUNCHES
+            with torch.cuda.graph(graph):
+                out = model.train_step(packed.device_views)
+            self.launches_per_replay = ops.LAUNCHES - before
+            self._slots.append(_Slot(packed, graph, out))
+        model.optimizer.iterations = iterations       # the captures executed nothing: no step was taken
+        self._copy_stream = torch.cuda.Stream()
+        self._next = 0
+        # single-buffer compatibility names (slot 0)
+        self.static_in, self.static_out, self.graph = first.device_views, self._slots[0].out, self._slots[0].graph
+
+    def pack(self, inputs) -> "PackedBatch":
+        """A device-resident batch laid out like the static inputs: `step(packed)` then costs one D2D copy."""
+        return self._slots[0].packed.pack(inputs)
 
     def __call__(self, inputs=None):
+        slot = self._slots[self._next]
+        self._next = (self._next + 1) % len(self._slots)
+        main = torch.cuda.current_stream()
         if inputs is not None:
-            if not self._packed.load_from_host(inputs):
-                _copy_inputs(self.static_in, inputs)
-        self.graph.replay()
+            cs = self._copy_stream
+            cs.wait_event(slot.consumed)              # the replay that last read this slot's inputs has finished
+            with torch.cuda.stream(cs):
+                if isinstance(inputs, PackedBatch):
+                    slot.packed.flat_dev.copy_(inputs.flat, non_blocking=True)
+                elif not slot.packed.load_from_host(inputs):
+                    _copy_inputs(slot.packed.device_views, inputs)
+                slot.ready.record(cs)
+            main.wait_event(slot.ready)
+        slot.graph.replay()
+        slot.consumed.record(main)
         ops._count(self.launches_per_replay)
         self.model.optimizer.iterations += 1          # host mirror of the step count (Adam's device counter advanced in-graph)
-        return self.static_out
+        return slot.out
+
+
+class _Slot:
+    def __init__(self, packed, graph, out):
+        self.packed, self.graph, self.out = packed, graph, out
+        self.ready, self.consumed = torch.cuda.Event(), torch.cuda.Event()
+        self.consumed.record()
+
+
+class PackedBatch:
+    """Device-resident batch in the flat layout of a GraphedStep's static inputs (GraphedStep.pack)."""
+
+    def __init__(self, flat):
+        self.flat = flat
 
 
 class _PackedInputs:
@@ -220,10 +259,23 @@ class _PackedInputs:
             self._ring.append((fh, [mk(fh, t, o) for t, o in zip(leaves, offs)], torch.cuda.Event()))
         self._next = 0
         self._n_leaves = len(leaves)
+        self._offs, self._nbytes = offs, [t.numel() * t.element_size() for t in leaves]
         for v, t in zip(dviews, leaves):
             v.copy_(t.to(dev))
         it = iter(dviews)
         self.device_views = _rebuild(example, it)
+
+    def pack(self, inputs) -> "PackedBatch":
+        leaves = []
+        _leaves(inputs, leaves)
+        if len(leaves) != self._n_leaves:
+            raise ValueError("pack: the batch does not have the structure of the example inputs")
+        flat = torch.zeros_like(self.flat_dev)
+        for t, o, n in zip(leaves, self._offs, self._nbytes):
+            if t.numel() * t.element_size() != n:
+                raise ValueError("pack: tensor sizes differ from the example inputs (static shapes)")
+            flat[o:o + n].copy_(t.to(flat.device).contiguous().view(-1).view(torch.uint8))
+        return PackedBatch(flat)
 
     def load_from_host(self, inputs) -> bool:
         """If every tensor of `inputs` lives in host memory: stage them and issue ONE H2D copy.  Else False."""
