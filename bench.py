@@ -595,13 +595,20 @@ def gather_roofline(tt, torch, dev, peaks):
         pool.append((feats, nnz))
     for feats, _ in pool:
         ops.tower_input_fwd(feats, cfg.batch, cfg.dim, want_f32=False, want_bf16=True)
+    # the launches of one pass over the pool replayed as a CUDA graph: the interval then holds kernels, not the
+    # host's per-launch cost (ctypes + output allocation: ~20 us, twice the kernel)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        outs = [ops.tower_input_fwd(feats, cfg.batch, cfg.dim, want_f32=False, want_bf16=True) for feats, _ in pool]
+    graph.replay()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 25
     torch.cuda.synchronize(); e0.record()
     for r in range(reps):
-        for feats, _ in pool:
-            ops.tower_input_fwd(feats, cfg.batch, cfg.dim, want_f32=False, want_bf16=True)
+        graph.replay()
     e1.record(); torch.cuda.synchronize()
+    del outs
     us = 1e3 * e0.elapsed_time(e1) / (reps * len(pool))
     nnz = sum(n for _, n in pool) / len(pool)
     algo = nnz * (cfg.dim * 4 + 8) + cfg.batch * cfg.dim * 2 + 2 * (cfg.batch + 1) * 8

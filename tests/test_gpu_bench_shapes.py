@@ -186,6 +186,9 @@ class TestUpdatedTableTolerance:
 
     def _run(self, tt, precision):
         tt.set_precision(precision)
+        # layer initialisers are seeded by (config.seed, process-wide layer counter): pin both (order independence)
+        tt.set_seed(0)
+        tt.layers._layer_counter[0] = 0
         cfg = synth.Config("smoke", 2024, 256, 64, 512, 384, (128, 64), 0.1, zipf=1.2)
         model = recipes.build_two_tower(cfg, lr=0.1)
         batch = synth.make_batch(cfg, 7)

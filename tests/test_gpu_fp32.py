@@ -131,6 +131,27 @@ class TestSparseOptimizer:
         vals, offs = synth.draw_bags(rng, 500, 200, 0, 6)
         self._run(ops, 200, 32, vals, rng.normal(size=(500, 32)).astype(np.float32), offs, mode)
 
+    def test_one_workspace_serves_batches_of_different_sizes(self, ops):
+        """Ragged bags change nnz from step to step while the caller keeps ONE workspace (sized for the largest batch).
+        The workspace layout must not move with nnz: its accumulation rows are only zero where tt_sparse_workspace_init
+        (and the self-cleaning launches) left them.  The allocator hands out DIRTY memory here on purpose."""
+        rng = synth.rng_for(77)
+        V, d, lr = 60, 32, 0.1
+        table = oracle.keras_uniform(rng, (V, d)); acc = np.full((V, d), 0.1, np.float32)
+        t_d, a_d = dev(table), dev(acc)
+        nbytes = ops.SparseWorkspace(700, d, t_d.device).nbytes
+        junk = torch.full((4 * nbytes,), 0x7F, dtype=torch.uint8, device="cuda")      # NaN-ish garbage in the freed blocks
+        del junk
+        ws = ops.SparseWorkspace(700, d, t_d.device)
+        t_ref, a_ref = table.astype(np.float64), acc.astype(np.float64)
+        for rows_n, lo, hi in ((160, 0, 8), (96, 0, 4), (200, 1, 3), (33, 0, 9), (96, 0, 4)):    # nnz ~ 640, 190, 400, 150, 190
+            vals, offs = synth.draw_bags(rng, rows_n, V, lo, hi)
+            g = rng.normal(size=(rows_n, d)).astype(np.float32)
+            ops.sparse_adagrad_update(t_d, a_d, dev(vals), dev(offs), "mean", dev(g), lr, 1e-7, ws)
+            e_ids, e_rows = oracle.embedding_bag_backward(vals, offs, g, "mean")
+            t_ref, a_ref, _ = oracle.adagrad_sparse(t_ref, a_ref, e_ids, e_rows.astype(np.float64), lr, 1e-7)
+            assert rel_err(t_d.cpu().numpy(), t_ref) < RTOL and rel_err(a_d.cpu().numpy(), a_ref) < RTOL
+
     def test_golden_adagrad(self, ops, golden_dir):
         g = np.load(golden_dir / "cfg1.npz")
         cfg = synth.CONFIGS["cfg1"]; rng = synth.rng_for(cfg.seed)

@@ -65,6 +65,28 @@ static int64_t ws_layout(int64_t nnz, int64_t d, void* base, SparseWs* ws) {
   return off;
 }
 
+// The layout of a caller-owned workspace is a function of its SIZE, not of the batch at hand: a workspace made for
+// nnz entries is reused for every batch with at most that many (ragged bags change nnz from step to step), and every
+// array boundary -- in particular the accumulation rows, which must be zero between launches -- has to stay where
+// tt_sparse_workspace_init put it.  capacity = the largest entry count whose layout fits the buffer.
+static int64_t ws_capacity(int64_t workspace_bytes, int64_t d) {
+  if (ws_layout(0, d, nullptr, nullptr) > workspace_bytes) return -1;
+  int64_t lo = 0, hi = 1;
+  while (hi < ((int64_t)1 << 31) && ws_layout(hi, d, nullptr, nullptr) <= workspace_bytes) { lo = hi; hi <<= 1; }
+  while (hi - lo > 1) {
+    const int64_t mid = lo + (hi - lo) / 2;
+    if (ws_layout(mid, d, nullptr, nullptr) <= workspace_bytes) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+// carve `workspace` for a batch of nnz entries; false if it is too small
+static bool ws_carve(int64_t nnz, int64_t d, void* workspace, int64_t workspace_bytes, SparseWs* ws) {
+  const int64_t cap = ws_capacity(workspace_bytes, d);
+  if (cap < nnz) return false;
+  ws_layout(cap, d, workspace, ws);
+  return true;
+}
+
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
   return x;
@@ -192,12 +214,11 @@ static int run_sparse(const char* name, Rule rule, float* table, int64_t vocab, 
   TT_REQUIRE(nnz >= 0 && nnz < INT_MAX && num_rows >= 0, "%s: bad sizes", name);
   TT_REQUIRE(offsets != nullptr || nnz == num_rows, "%s: without offsets nnz must equal num_rows", name);
   TT_REQUIRE(mode == TT_POOL_SUM || mode == TT_POOL_MEAN, "%s: bad pooling mode", name);
-  if (workspace_bytes < ws_layout(nnz, d, nullptr, nullptr))
+  SparseWs ws;
+  if (!ws_carve(nnz, d, workspace, workspace_bytes, &ws))
     return set_error(TT_ERR_WORKSPACE, "%s: workspace too small (%lld < %lld)", name,
                      (long long)workspace_bytes, (long long)ws_layout(nnz, d, nullptr, nullptr));
   if (nnz == 0) return TT_OK;
-  SparseWs ws;
-  ws_layout(nnz, d, workspace, &ws);
   TT_PROF("sparse_insert_kernel", stream);
   sparse_insert_kernel<<<(unsigned)ceil_div(nnz, 256), 256, 0, stream>>>(ws, values, offsets, num_rows, nnz, vocab);
   TT_LAUNCH_OK("sparse_insert_kernel");
@@ -341,10 +362,9 @@ static int run_sparse_multi(const char* name, bool adam, const tt_sparse_var* va
     TT_REQUIRE(s.nnz >= 0 && s.nnz < INT_MAX && s.num_rows >= 0, "%s: bad sizes", name);
     TT_REQUIRE(s.offsets != nullptr || s.nnz == s.num_rows, "%s: without offsets nnz must equal num_rows", name);
     TT_REQUIRE(s.mode == TT_POOL_SUM || s.mode == TT_POOL_MEAN, "%s: bad pooling mode", name);
-    if (s.workspace_bytes < ws_layout(s.nnz, s.d, nullptr, nullptr))
-      return set_error(TT_ERR_WORKSPACE, "%s: workspace of variable %d too small", name, i);
     SparseMultiVar& v = args.v[i];
-    ws_layout(s.nnz, s.d, s.workspace, &v.ws);
+    if (!ws_carve(s.nnz, s.d, s.workspace, s.workspace_bytes, &v.ws))
+      return set_error(TT_ERR_WORKSPACE, "%s: workspace of variable %d too small", name, i);
     v.table = s.table; v.s0 = s.slot0; v.s1 = s.slot1; v.values = s.values; v.offsets = s.offsets; v.grad = s.grad;
     v.first_flag = s.first_flag; v.num_rows = s.num_rows; v.nnz = s.nnz; v.vocab = s.vocab; v.d = s.d; v.mode = s.mode;
     v.shard = 0;
@@ -683,10 +703,9 @@ static int fill_sparse(const char* name, bool adam, const tt_sparse_var* vars, i
     TT_REQUIRE(s.nnz >= 0 && s.nnz < INT_MAX && s.num_rows >= 0, "%s: bad sizes", name);
     TT_REQUIRE(s.offsets != nullptr || s.nnz == s.num_rows, "%s: without offsets nnz must equal num_rows", name);
     TT_REQUIRE(s.mode == TT_POOL_SUM || s.mode == TT_POOL_MEAN, "%s: bad pooling mode", name);
-    if (s.workspace_bytes < ws_layout(s.nnz, s.d, nullptr, nullptr))
-      return set_error(TT_ERR_WORKSPACE, "%s: workspace of table %d too small", name, i);
     SparseMultiVar& v = args->v[i];
-    ws_layout(s.nnz, s.d, s.workspace, &v.ws);
+    if (!ws_carve(s.nnz, s.d, s.workspace, s.workspace_bytes, &v.ws))
+      return set_error(TT_ERR_WORKSPACE, "%s: workspace of table %d too small", name, i);
     v.table = s.table; v.s0 = s.slot0; v.s1 = s.slot1; v.values = s.values; v.offsets = s.offsets; v.grad = s.grad;
     v.first_flag = s.first_flag; v.num_rows = s.num_rows; v.nnz = s.nnz; v.vocab = s.vocab; v.d = s.d; v.mode = s.mode;
     v.shard = s.shard;
@@ -794,12 +813,12 @@ extern "C" int tt_sparse_workspace_init(void* workspace, int64_t workspace_bytes
                                         int64_t d, void* stream) {
   TT_REQUIRE(workspace && aligned16(workspace), "tt_sparse_workspace_init: workspace null or unaligned");
   TT_REQUIRE(nnz >= 0 && d > 0, "tt_sparse_workspace_init: bad sizes");
-  if (workspace_bytes < ws_layout(nnz, d, nullptr, nullptr))
-    return set_error(TT_ERR_WORKSPACE, "tt_sparse_workspace_init: workspace too small");
   SparseWs ws;
-  ws_layout(nnz, d, workspace, &ws);
+  if (!ws_carve(nnz, d, workspace, workspace_bytes, &ws))
+    return set_error(TT_ERR_WORKSPACE, "tt_sparse_workspace_init: workspace too small");
+  // the whole capacity of the buffer is initialised: later batches may hold any entry count up to it
   TT_PROF("sparse_ws_init_kernel", (cudaStream_t)stream);
-  sparse_ws_init_kernel<<<num_sms() * 4, 256, 0, (cudaStream_t)stream>>>(ws, nnz, d);
+  sparse_ws_init_kernel<<<num_sms() * 4, 256, 0, (cudaStream_t)stream>>>(ws, ws_capacity(workspace_bytes, d), d);
   TT_LAUNCH_OK("sparse_ws_init_kernel");
   return TT_OK;
 }

@@ -212,6 +212,10 @@ class GraphedStep:
                 if isinstance(inputs, PackedBatch):
                     slot.packed.flat_dev.copy_(inputs.flat, non_blocking=True)
                 elif not slot.packed.load_from_host(inputs):
+                    # device tensors of unknown provenance: whatever produced them was enqueued on the caller's stream,
+                    # so this copy has to run behind it (no overlap with the previous replay; host batches and
+                    # pack()ed batches do overlap)
+                    cs.wait_stream(main)
                     _copy_inputs(slot.packed.device_views, inputs)
                 slot.ready.record(cs)
             main.wait_event(slot.ready)
@@ -275,6 +279,7 @@ class _PackedInputs:
             if t.numel() * t.element_size() != n:
                 raise ValueError("pack: tensor sizes differ from the example inputs (static shapes)")
             flat[o:o + n].copy_(t.to(flat.device).contiguous().view(-1).view(torch.uint8))
+        torch.cuda.current_stream().synchronize()     # complete before any copy stream may read it
         return PackedBatch(flat)
 
     def load_from_host(self, inputs) -> bool:
