@@ -1,5 +1,5 @@
 """Stand-alone K1 timing at the cfg3 item-tower shape (bench.gather_roofline): python tools/time_gather.py
-TT_GATHER=<bits> selects A/B variants of the launch (bit 0: flattened row list, bit 1: one CTA per 8 rows, uncapped)."""
+The 8 launches of one pass over the batch pool are replayed as a CUDA graph (kernel time, not host launch cost)."""
 import json
 import sys
 from pathlib import Path
