@@ -37,6 +37,11 @@ int tt_debug_timeline(long long* device_buf);
  * 0 = always the list-keeping kernel, 2 = threshold scan with 64-entry survivor buffers, so every row overflows and
  * the device-side fallback to the list-keeping kernel runs.  Returns the previous mode. */
 int tt_debug_topk_scan_mode(int32_t mode);
+/* Tuning hook: device buffer of 3 * 48 * 4 int64 receiving clock64() stamps of CTA (0,0) of the second-phase scan kernel
+ * (roles 0 / 1: first thread of the selection warpgroup of query tile 0 / 1 -- wait begins, accumulator ready, accumulator
+ * read and released, tile done; role 2: the MMA thread -- wait begins, candidate tile landed, first accumulator buffer
+ * free, both units issued); NULL = off.  tools/trace_topk_scan.py */
+int tt_debug_topk_scan_trace(long long* device_buf);
 
 #ifdef __cplusplus
 }

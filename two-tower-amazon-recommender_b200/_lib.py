@@ -104,6 +104,7 @@ SIGNATURES = {
     "tt_debug_tower_trace": (C.c_int, [_p]),
     "tt_debug_timeline": (C.c_int, [_p]),
     "tt_debug_topk_scan_mode": (C.c_int, [_i32]),
+    "tt_debug_topk_scan_trace": (C.c_int, [_p]),
     "tt_retrieval_workspace_bytes": (_i64, [_i32, _i64, _i64, _i64]),
     "tt_retrieval_workspace_init": (C.c_int, [_i32, _p, _i64, _i64, _i64, _i64, _p]),
     "tt_retrieval_loss_fwd": (C.c_int, [_i32, _p, _p, _i64, _i64, _i64, _f, _i64, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),

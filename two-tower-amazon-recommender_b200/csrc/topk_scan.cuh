@@ -11,6 +11,7 @@ struct ScanPlan {
   int total_tiles;          // 128-candidate tiles
   int n_samp, G, P;         // sampled tiles, group maxima per row (4 per tile), sort width of the threshold kernel
   int cap, kp;              // survivors per row the buffers hold; pool width
+  int n_slots, seg_cap;     // the row's buffer = one segment per candidate split of either phase
   int samp_splits, samp_tps, scan_splits, scan_tps;
   bool two_phase;           // scan 1/8 of the tiles, refine the threshold on their survivors, scan the rest
   int first_splits, first_tps;
