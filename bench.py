@@ -512,7 +512,13 @@ def run_ours(args):
                                       "committed ncu --set full capture of this command",
                     "us_per_launch": us,
                     "algorithmic_flops_per_launch": flops_per_launch, "peak_source": peak_src,
-                    "executed_flops_per_launch": executed}
+                    "executed_flops_per_launch": executed,
+                    "timing": "CUDA-event pair around every launch of an eager pass (carries ~3 us of event overhead per launch)"}
+        span = (in_graph or {}).get(dom) or (in_graph or {}).get(dom + "(dC)")
+        if span:                                     # the same kernel inside the replayed graph: first CTA in -> last CTA out
+            roofline["us_in_graph"] = span
+            roofline["achieved_in_graph"] = flops_per_launch / (span * 1e-6) / 1e12
+            roofline["frac_in_graph"] = roofline["achieved_in_graph"] / peak_tf
     step_flops = algorithmic_flops(cfg, world)
     line = {
         "metric": METRIC, "value": value, "unit": "examples/s", "n_gpus": world, "steps": args.steps,

@@ -46,9 +46,11 @@ def test_restored_model_continues_identically(tt, tmp_path, opt_name):
         for k, s in va.slots.items():
             if isinstance(s, torch.Tensor) and not k.startswith("_"):
                 assert torch.equal(s, vb.slots[k]), (va.name, k)
-    for bt in batches[2:]:
+    for i, bt in enumerate(batches[2:]):
         la, lb = float(a.train_step(bt)["loss"].item()), float(b_model.train_step(bt)["loss"].item())
-        assert la == pytest.approx(lb, rel=1e-6)
+        # first step: bit-identical weights in, the same loss out.  Later steps see weights whose duplicate-id gradient sums
+        # were accumulated with fp32 atomics in a different order (last bits differ run to run)
+        assert la == pytest.approx(lb, rel=1e-6 if i == 0 else 1e-4)
     # the two runs continue together (duplicate ids are summed with fp32 atomics: the order, hence the last bits, may differ)
     for va, vb in zip(a.trainable_variables, b_model.trainable_variables):
         assert torch.allclose(va.value, vb.value, rtol=1e-4, atol=1e-6), va.name
