@@ -697,7 +697,10 @@ def serving_bench(tt, torch, dist, dev, peaks, world, rank, group, nq=16384, nc=
         scan_tf = 2.0 * nq * per * d / (scan_us * 1e-6) / 1e12
         out["roofline"] = {"bound": "tensor", "kernel": "topk_scan_kernel (both phases)", "achieved": scan_tf, "peak": peaks.get("bf16_tflops", 1590.0),
                            "unit": "TFLOP/s", "frac": scan_tf / peaks.get("bf16_tflops", 1590.0), "us_per_call": scan_us,
-                           "algorithmic_flops_per_call": 2.0 * nq * per * d}
+                           "algorithmic_flops_per_call": 2.0 * nq * per * d,
+                           "traffic": (2 * ncu_traffic("topk_scan_kernel(256 resident queries, both phases, 16384 x 10M)", world)
+                                       if world == 1 and nq == 16384 and per == 10_000_000 and
+                                       ncu_traffic("topk_scan_kernel(256 resident queries, both phases, 16384 x 10M)", world) else None)}
 
     # end to end with HOST buffers: pinned queries -> H2D -> top-k -> D2H of scores + ids, every call
     q_host = q.cpu().pin_memory()
@@ -741,7 +744,8 @@ def serving_bench(tt, torch, dist, dev, peaks, world, rank, group, nq=16384, nc=
             if us:
                 kg = (per * d * 2 + qs_ * d * 2) / (us * 1e-6) / 1e9
                 rec["scan_kernel"] = {"us_per_call": us, "achieved": kg, "unit": "GB/s", "frac": kg / hbm,
-                                      "algorithmic_bytes_per_call": per * d * 2 + qs_ * d * 2}
+                                      "algorithmic_bytes_per_call": per * d * 2 + qs_ * d * 2,
+                                      "traffic": ncu_traffic("topk_scan_kernel(64 queries x 10M)", 1) if qs_ == 64 and per == 10_000_000 else None}
             rec["kernels_us_per_call"] = kts
             small.append(rec)
         out["small_batch"] = small
