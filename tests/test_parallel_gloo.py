@@ -1,4 +1,4 @@
-"""world_size-2 gloo tests (CPU) of the sharded path's routing logic: all-to-all lookups of a
+"""world_size-2 and -4 gloo tests (CPU) of the sharded path's routing logic: all-to-all lookups of a
 row-sharded table, gradient return to the owners, global-batch negatives.  The local compute
 (`prim`) is a numpy/oracle stand-in defined HERE (test infrastructure); the product's default
 prim is the CUDA library."""
@@ -14,7 +14,6 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 ROOT = Path(__file__).resolve().parent.parent
-WORLD = 2
 
 
 class CpuPrims:
@@ -102,7 +101,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, port, results):
+def _worker(rank, WORLD, port, results):
     sys.path.insert(0, str(ROOT))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=WORLD)
@@ -173,16 +172,17 @@ def _worker(rank, port, results):
         dist.destroy_process_group()
 
 
-def test_sharded_lookup_gradients_and_global_negatives_world2():
+@pytest.mark.parametrize("WORLD", [2, 4])
+def test_sharded_lookup_gradients_and_global_negatives(WORLD):
     mgr = mp.Manager()
     results = mgr.dict()
     port = _free_port()
-    mp.spawn(_worker, args=(port, results), nprocs=WORLD, join=True)
+    mp.spawn(_worker, args=(WORLD, port, results), nprocs=WORLD, join=True)
     for r in range(WORLD):
         assert results.get(r) == "ok", results.get(r)
 
 
-def _serving_worker(rank, port, results):
+def _serving_worker(rank, WORLD, port, results):
     sys.path.insert(0, str(ROOT))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=WORLD)
@@ -192,7 +192,7 @@ def _serving_worker(rank, port, results):
         from two_tower_b200 import synth
         rng = synth.rng_for(91)
         d, k, nq = 16, 10, 6 * WORLD
-        sizes = [300, 211]                                   # ragged shards
+        sizes = [300, 211, 157, 243][:WORLD]                 # ragged shards
         cand = synth.exact_matrix(rng, sum(sizes), d, 2)     # dyadic: real ties, also ACROSS shards
         q = synth.exact_matrix(rng, nq, d, 2)
         ident = rng.permutation(sum(sizes)).astype(np.int64) + 1000
@@ -218,9 +218,10 @@ def _serving_worker(rank, port, results):
         dist.destroy_process_group()
 
 
-def test_candidate_sharded_topk_routing_world2():
+@pytest.mark.parametrize("WORLD", [2, 4])
+def test_candidate_sharded_topk_routing(WORLD):
     mgr = mp.Manager()
     results = mgr.dict()
-    mp.spawn(_serving_worker, args=(_free_port(), results), nprocs=WORLD, join=True)
+    mp.spawn(_serving_worker, args=(WORLD, _free_port(), results), nprocs=WORLD, join=True)
     for r in range(WORLD):
         assert results.get(r) == "ok", results.get(r)
