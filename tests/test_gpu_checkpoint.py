@@ -51,9 +51,12 @@ def test_restored_model_continues_identically(tt, tmp_path, opt_name):
         # first step: bit-identical weights in, the same loss out.  Later steps see weights whose duplicate-id gradient sums
         # were accumulated with fp32 atomics in a different order (last bits differ run to run)
         assert la == pytest.approx(lb, rel=1e-6 if i == 0 else 1e-4)
-    # the two runs continue together (duplicate ids are summed with fp32 atomics: the order, hence the last bits, may differ)
+    # The two runs continue together.  Duplicate ids are summed with fp32 atomics, so the last bits of an updated row depend on
+    # the arrival order; in bf16 a last-bit difference of a master weight occasionally flips the rounding of its bf16 shadow
+    # or of an activation (0.4 % of that element), which the next step's gradients carry on: 2 in 10 runs of this test
+    # exceeded rtol 1e-4 on some element.  The bound is therefore the one of the graph-vs-eager test.
     for va, vb in zip(a.trainable_variables, b_model.trainable_variables):
-        assert torch.allclose(va.value, vb.value, rtol=1e-4, atol=1e-6), va.name
+        assert torch.allclose(va.value, vb.value, rtol=2e-3, atol=2e-5), va.name
     other = _model(tt, mk())
     with pytest.raises(ValueError):
         other.user_model = tt.Sequential([tt.layers.Embedding(901, 128), tt.layers.Dense(256, "relu"), tt.layers.Dense(128)])

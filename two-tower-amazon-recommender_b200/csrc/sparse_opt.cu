@@ -21,6 +21,7 @@
 // order over duplicates is not fixed (same as TF's GPU unsorted_segment_sum).
 #include "common.cuh"
 #include <limits.h>
+#include <stdlib.h>
 #include <algorithm>
 
 namespace tt {
@@ -36,7 +37,6 @@ struct SparseWs {
   int* hpos;                 // [nnz]
   int* bag_of;               // [nnz]
   float* accum;              // [nnz, d]
-  int* sync;                 // [8]: 0 blocks of the dedup launch done, 1 dedup complete (flag), 2 blocks of the step launch done
   int64_t cap;
 };
 
@@ -51,7 +51,7 @@ static int64_t ws_layout(int64_t nnz, int64_t d, void* base, SparseWs* ws) {
   int64_t off = 0;
   auto take = [&](int64_t bytes) { int64_t o = off; off += round_up(bytes, 256); return o; };
   int64_t o_keys = take(cap * 8), o_first = take(cap * 4), o_cnt = take(cap * 4), o_done = take(cap * 4),
-          o_hpos = take(nnz * 4), o_bag = take(nnz * 4), o_acc = take(nnz * d * 4), o_sync = take(32);
+          o_hpos = take(nnz * 4), o_bag = take(nnz * 4), o_acc = take(nnz * d * 4);
   if (ws) {
     char* b = (char*)base;
     ws->keys = (unsigned long long*)(b + o_keys);
@@ -61,7 +61,6 @@ static int64_t ws_layout(int64_t nnz, int64_t d, void* base, SparseWs* ws) {
     ws->hpos = (int*)(b + o_hpos);
     ws->bag_of = (int*)(b + o_bag);
     ws->accum = (float*)(b + o_acc);
-    ws->sync = (int*)(b + o_sync);
     ws->cap = cap;
   }
   return off;
@@ -99,7 +98,6 @@ __global__ void sparse_ws_init_kernel(SparseWs ws, int64_t nnz, int64_t d) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t k = i; k < ws.cap; k += stride) { ws.keys[k] = kEmpty; ws.first[k] = INT_MAX; ws.cnt[k] = 0; ws.done[k] = 0; }
   for (int64_t k = i; k < nnz * d; k += stride) ws.accum[k] = 0.f;
-  if (i < 8) ws.sync[i] = 0;
 }
 
 __global__ void __launch_bounds__(256)
@@ -480,53 +478,34 @@ static int run_dense_multi(const char* name, bool adam, const tt_dense_var* vars
 //     occurrence with 128-bit reductions and take a ticket; the LAST arriver applies the update and
 //     cleans the slot ("last block done", per key).  Dense variables: 4 lanes share a float4 of weights
 //     and each folds a quarter of the split-K partials (fixed association: deterministic).
-// The dedup may run on a side stream next to the forward pass.  Instead of a stream join ahead of the optimizer launch
-// (a join turns that launch -- or whichever launch it precedes -- into a full dependency: 6 us of idle in the cfg2
-// step against ~1 us for a programmatic edge), the hand-off is a FLAG in the table's workspace: the last block of the
-// dedup launch sets sync[1], the table's blocks of optimizer_step_kernel poll it (it was set ~100 us earlier) and the
-// last of them clears it again.  The caller joins the side stream after the optimizer launch, off the critical path.
 __global__ void __launch_bounds__(256) sparse_prepare_kernel(const __grid_constant__ SparseMultiArgs a) {
   tl_mark(g_tl, 6, true);
   const SparseMultiVar& V = a.v[blockIdx.y];
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < V.nnz) {
-    int64_t id = V.values[j];
-    if (V.shard && id >= 0) {                     // global id of a row-sharded table: keep what this rank owns
-      const int64_t w = V.shard >> 16, me = V.shard & 0xffff;
-      id = (id % w == me) ? id / w : -1;
-    }
-    if (id < 0 || id >= V.vocab) {
-      V.ws.hpos[j] = -1;
-    } else {
-      const uint64_t mask = (uint64_t)V.ws.cap - 1;
-      uint64_t h = mix64((uint64_t)id) & mask;
-      while (true) {
-        unsigned long long prev = atomicCAS(&V.ws.keys[h], kEmpty, (unsigned long long)id);
-        if (prev == kEmpty || prev == (unsigned long long)id) break;
-        h = (h + 1) & mask;
-      }
-      V.ws.hpos[j] = (int)h;
-      atomicMin(&V.ws.first[h], (int)j);
-      atomicAdd(&V.ws.cnt[h], 1);
-      if (V.offsets) {
-        int64_t lo = 0, hi = V.num_rows;
-        while (hi - lo > 1) {
-          int64_t mid = (lo + hi) >> 1;
-          if (V.offsets[mid] <= j) lo = mid; else hi = mid;
-        }
-        V.ws.bag_of[j] = (int)lo;
-      }
-    }
+  if (j >= V.nnz) return;
+  int64_t id = V.values[j];
+  if (V.shard && id >= 0) {                     // global id of a row-sharded table: keep what this rank owns
+    const int64_t w = V.shard >> 16, me = V.shard & 0xffff;
+    id = (id % w == me) ? id / w : -1;
   }
-  if (V.nnz == 0) return;                         // table not part of this launch's work (uniform per blockIdx.y)
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    if (atomicAdd(&V.ws.sync[0], 1) == (int)gridDim.x - 1) {
-      V.ws.sync[0] = 0;
-      __threadfence();
-      atomicExch(&V.ws.sync[1], 1);
+  if (id < 0 || id >= V.vocab) { V.ws.hpos[j] = -1; return; }
+  const uint64_t mask = (uint64_t)V.ws.cap - 1;
+  uint64_t h = mix64((uint64_t)id) & mask;
+  while (true) {
+    unsigned long long prev = atomicCAS(&V.ws.keys[h], kEmpty, (unsigned long long)id);
+    if (prev == kEmpty || prev == (unsigned long long)id) break;
+    h = (h + 1) & mask;
+  }
+  V.ws.hpos[j] = (int)h;
+  atomicMin(&V.ws.first[h], (int)j);
+  atomicAdd(&V.ws.cnt[h], 1);
+  if (V.offsets) {
+    int64_t lo = 0, hi = V.num_rows;
+    while (hi - lo > 1) {
+      int64_t mid = (lo + hi) >> 1;
+      if (V.offsets[mid] <= j) lo = mid; else hi = mid;
     }
+    V.ws.bag_of[j] = (int)lo;
   }
 }
 
@@ -619,14 +598,6 @@ __device__ __forceinline__ void optimizer_step_body(const StepArgs& a, float lr_
   int vi = 0;
   while (vi + 1 < a.n_sparse && bid >= a.sparse_blocks[vi + 1]) ++vi;
   const SparseMultiVar& V = a.sparse.v[vi];
-  if (threadIdx.x == 0) {                         // the table's dedup (possibly on another stream) is complete
-    int spins = 0;
-    while (atomicAdd(&V.ws.sync[1], 0) == 0) {
-      if (++spins > (1 << 26)) { printf("libtwotower: optimizer step waits for a dedup that never ran (tt_optimizer_prepare_sparse)\n"); __trap(); }
-    }
-    __threadfence();
-  }
-  __syncthreads();
   const int64_t j = (int64_t)(bid - a.sparse_blocks[vi]) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (j >= V.nnz) return;
   const int h = V.ws.hpos[j];
@@ -673,8 +644,10 @@ __device__ __forceinline__ void optimizer_step_body(const StepArgs& a, float lr_
   if (lane == 0) { V.ws.keys[h] = kEmpty; V.ws.first[h] = INT_MAX; V.ws.cnt[h] = 0; V.ws.done[h] = 0; }
 }
 
-template <bool ADAM>
-__global__ void __launch_bounds__(256)
+// MINB resident blocks per SM: the kernel is a chain of dependent memory round trips per row, so it lives on occupancy
+// (a variant at 53 registers instead of 40 took 26 us instead of 17.6 in the cfg2 step)
+template <bool ADAM, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 optimizer_step_kernel(const __grid_constant__ StepArgs a, float lr_or_alpha, const float* __restrict__ alpha_dev,
                       float b1, float b2, float eps) {
   pdl_wait();                       // launched while the backward tower kernel drains
@@ -683,17 +656,6 @@ optimizer_step_kernel(const __grid_constant__ StepArgs a, float lr_or_alpha, con
   tl_mark(tl, 5, true);
   if (alpha_dev != nullptr) lr_or_alpha = __ldg(alpha_dev);      // Adam: bias-corrected step size of THIS iteration (graph-replayable)
   optimizer_step_body<ADAM>(a, lr_or_alpha, b1, b2, eps);
-  if ((int)blockIdx.x >= a.dense_blocks[a.n_dense]) {          // table blocks: the last one through re-arms the dedup flag
-    int vi = 0;
-    while (vi + 1 < a.n_sparse && (int)blockIdx.x >= a.sparse_blocks[vi + 1]) ++vi;
-    const SparseMultiVar& V = a.sparse.v[vi];
-    __syncthreads();
-    if (threadIdx.x == 0 && atomicAdd(&V.ws.sync[2], 1) == a.sparse_blocks[vi + 1] - a.sparse_blocks[vi] - 1) {
-      V.ws.sync[2] = 0;
-      __threadfence();
-      atomicExch(&V.ws.sync[1], 0);
-    }
-  }
   if (tl) {                         // timeline only: the span runs to the EXIT of the last block
     __syncthreads();
     tl_mark(tl, 5, false);
@@ -803,8 +765,11 @@ static int run_step(const char* name, bool adam, const tt_dense_var* dense, int 
   args.n_dense = nd; args.n_sparse = ns;
   if (blocks == 0) return TT_OK;
   TT_PROF("optimizer_step_kernel", stream);
-  if (adam) TT_CUDA_OK(launch_pdl(optimizer_step_kernel<true>, dim3(blocks), dim3(256), (size_t)0, stream, args, lr_or_alpha, alpha_dev, b1, b2, eps));
-  else TT_CUDA_OK(launch_pdl(optimizer_step_kernel<false>, dim3(blocks), dim3(256), (size_t)0, stream, args, lr_or_alpha, alpha_dev, b1, b2, eps));
+  static const int minb = [] { const char* e = getenv("TT_OPT_MINB"); return e ? atoi(e) : 6; }();     // A/B runs: 6 or 8
+  if (adam && minb == 8) TT_CUDA_OK(launch_pdl(optimizer_step_kernel<true, 8>, dim3(blocks), dim3(256), (size_t)0, stream, args, lr_or_alpha, alpha_dev, b1, b2, eps));
+  else if (adam) TT_CUDA_OK(launch_pdl(optimizer_step_kernel<true, 6>, dim3(blocks), dim3(256), (size_t)0, stream, args, lr_or_alpha, alpha_dev, b1, b2, eps));
+  else if (minb == 8) TT_CUDA_OK(launch_pdl(optimizer_step_kernel<false, 8>, dim3(blocks), dim3(256), (size_t)0, stream, args, lr_or_alpha, alpha_dev, b1, b2, eps));
+  else TT_CUDA_OK(launch_pdl(optimizer_step_kernel<false, 6>, dim3(blocks), dim3(256), (size_t)0, stream, args, lr_or_alpha, alpha_dev, b1, b2, eps));
   TT_LAUNCH_OK("optimizer_step_kernel");
   return TT_OK;
 }

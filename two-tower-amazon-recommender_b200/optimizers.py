@@ -14,7 +14,6 @@ from .core import DenseGrad, IndexedSlices, Variable
 
 
 _INLINE_PREPARE = os.environ.get("TT_PREPARE_INLINE", "0") == "1"      # measured slower (below): kept for A/B runs
-_JOIN_BEFORE_BACKWARD = os.environ.get("TT_JOIN_BEFORE_BACKWARD", "0") == "1"   # the round-1 placement of the join (A/B runs)
 
 
 class Optimizer:
@@ -89,10 +88,10 @@ class Optimizer:
         self._side_busy = True
 
     def join_prepare(self) -> None:
-        """Round-1 placement of the side-stream join (between forward and backward; TT_JOIN_BEFORE_BACKWARD=1).  By default
-        a no-op: the optimizer kernel waits for the dedup through a device flag and apply_gradients joins the side stream
-        after the optimizer launch."""
-        if self._side_busy and _JOIN_BEFORE_BACKWARD:
+        """Make the current stream wait for the side-stream id dedup now.  Model.train_step calls this between the
+        forward and the backward pass: the dedup has long finished there, and the optimizer launch then follows the
+        backward tower kernel directly (a programmatic dependent launch) instead of an event wait."""
+        if self._side_busy:
             torch.cuda.current_stream().wait_stream(self._side)
             self._side_busy = False
 
@@ -115,6 +114,9 @@ class Optimizer:
                 raise TypeError(f"unsupported gradient type {type(g)} for {v.name}")
         if sparse:
             self._check_sparse_supported()
+        if self._side_busy:
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._side_busy = False
         self._prepared.clear()
         self._prepared_vars = []
         if late:
@@ -127,11 +129,6 @@ class Optimizer:
                 ops.optimizer_step(self.kind, chunk_d, chunk_s[:8], hyper)
         for lo in range(8, len(sparse), 8):
             ops.optimizer_step(self.kind, [], sparse[lo:lo + 8], hyper)
-        # The step kernel waits for the side-stream id dedup through a device flag in each table's workspace
-        # (csrc/sparse_opt.cu); the stream join comes AFTER its launch, where it delays nothing.
-        if self._side_busy:
-            torch.cuda.current_stream().wait_stream(self._side)
-            self._side_busy = False
 
     @staticmethod
     def _sparse_ws(var: Variable, nnz: int) -> ops.SparseWorkspace:
