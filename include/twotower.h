@@ -271,6 +271,12 @@ typedef struct tt_tower_mlp2 {
   float* dw2_parts;
   float* db1_parts;
   float* db2_parts;
+  /* forward, optional: a tt_sparse_workspace_* buffer of the optimizer for this tower's table.  When non-NULL (the
+   * tower must then have exactly one unsharded ID feature) the forward kernel also performs the hash insert of
+   * tt_optimizer_prepare_sparse for the tower's ids -- hidden under its row gather -- so that the step needs neither
+   * that launch nor a side stream for it; tt_adagrad_step / tt_lazy_adam_step then run on the same workspace. */
+  void* prepare_workspace;
+  int64_t prepare_workspace_bytes;
 } tt_tower_mlp2;
 int32_t tt_tower_mlp2_supported(int32_t d_in, int32_t d_hid, int32_t d_out);
 int tt_tower_mlp2_fwd(const tt_tower_mlp2* host_towers, int32_t num_towers, int32_t* id_fault_flag,

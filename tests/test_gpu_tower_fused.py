@@ -346,6 +346,38 @@ class TestFusedTrainStep:
         before = tt.ops.LAUNCHES
         a.train_step(batch)
         assert tt.ops.LAUNCHES - before == 8
+        # with the id dedup done by the tower forward's dedup warp: one launch fewer
+        tt.layers.Sequential.fuse_prepare = True
+        try:
+            a.train_step(batch)
+            before = tt.ops.LAUNCHES
+            a.train_step(batch)
+            assert tt.ops.LAUNCHES - before == 7
+        finally:
+            tt.layers.Sequential.fuse_prepare = False
+
+    def test_id_dedup_inside_the_tower_forward_equals_the_separate_launch(self, tt, monkeypatch):
+        """The fused prepare stage (tt_tower_mlp2.prepare_workspace) and tt_optimizer_prepare_sparse on a side stream
+        lead to the same tables: identical row sets, values up to the atomics order of duplicate rows."""
+        vu, vi, d, mlp, B, T, lr = 3000, 2500, 128, (256, 128), 1000, 0.5, 0.05      # ragged last row block, many duplicates
+        tt.set_seed(6)
+        a = self._model(tt, vu, vi, d, mlp, T, lr, fuse=True)
+        b = self._model(tt, vu, vi, d, mlp, T, lr, fuse=True)
+        rng = synth.rng_for(43)
+        batches = [{"user_id_encoded": synth.draw_ids(rng, B, vu, 1.3), "item_id_encoded": synth.draw_ids(rng, B, vi, 1.3)}
+                   for _ in range(3)]
+        a.test_step(batches[0]); b.test_step(batches[0])
+        for la, lb in zip(a.user_model.layers + a.item_model.layers, b.user_model.layers + b.item_model.layers):
+            lb.set_weights(la.get_weights())
+        for bt in batches:
+            monkeypatch.setattr(tt.layers.Sequential, "fuse_prepare", True)
+            oa = a.train_step(bt)
+            monkeypatch.setattr(tt.layers.Sequential, "fuse_prepare", False)
+            ob = b.train_step(bt)
+            assert float(oa["loss"].item()) == pytest.approx(float(ob["loss"].item()), rel=1e-5)
+        for la, lb in zip(a.user_model.layers[:1] + a.item_model.layers[:1], b.user_model.layers[:1] + b.item_model.layers[:1]):
+            wa, wb = la.get_weights()[0], lb.get_weights()[0]
+            np.testing.assert_allclose(wa, wb, rtol=1e-4, atol=1e-6)
 
     def test_three_steps_track_the_oracle(self, tt):
         vu, vi, d, mlp, B, T, lr = 2000, 1500, 128, (256, 128), 512, 0.5, 0.05

@@ -30,6 +30,8 @@ buf = torch.zeros(2 * 16 * 256, dtype=torch.int64, device="cuda")
 
 
 def run():
+    for s in specs:                       # the forward's dedup warp fills a fresh sparse-optimizer workspace
+        s["prepare_ws"] = ops.SparseWorkspace(B, d_in, "cuda")
     outs = ops.tower_mlp2_fwd(specs)
     ops.tower_mlp2_bwd([dict(s, x=x, h=h, dy_parts=p, dy_splits=2) for s, (x, h, y), p in zip(specs, outs, parts)])
 
@@ -41,8 +43,8 @@ run()
 torch.cuda.synchronize()
 tt._lib.check(lib.tt_debug_tower_trace(None))
 tr = buf.cpu().numpy().reshape(2, 256, 16)
-labels = {0: ["entry", "setup", "gathered", "weights", "mma1", "h staged", "mma2", "y staged", "exit"],
-          1: ["entry", "setup", "dy tile", "loads", "mma a+b", "dh staged", "dW2 out", "mma c", "mma d", "dW1 out", "exit"]}
+labels = {0: ["entry", "setup", "gathered", "mma1 half0", "h half0", "h half1", "mma2", "y staged", "exit", "dedup: ids", "dedup: done"],
+          1: ["entry", "setup", "dy tile", "mma a", "dh staged", "dW2 out", "mma c", "dx out", "mma d", "dW1 out", "exit"]}
 for k, name in enumerate(["forward", "backward"]):
     rec = tr[k][tr[k][:, 0] > 0]
     t0 = rec[:, 0].min()

@@ -37,7 +37,8 @@ class tt_tower_mlp2(C.Structure):
                 ("x", C.c_void_p), ("h", C.c_void_p), ("y", C.c_void_p),
                 ("dy_parts", C.c_void_p), ("dy_splits", C.c_int32), ("reserved", C.c_int32),
                 ("dx", C.c_void_p), ("dw1_parts", C.c_void_p), ("dw2_parts", C.c_void_p),
-                ("db1_parts", C.c_void_p), ("db2_parts", C.c_void_p)]
+                ("db1_parts", C.c_void_p), ("db2_parts", C.c_void_p),
+                ("prepare_workspace", C.c_void_p), ("prepare_workspace_bytes", C.c_int64)]
 
 
 class tt_dense_var(C.Structure):

@@ -190,10 +190,13 @@ class GradientTape:
         return GradientTape._stack[-1] if GradientTape._stack else None
 
     @staticmethod
-    def note_sparse_lookup(lookups) -> None:
+    def note_sparse_lookup(lookups, fused: bool = False):
+        """fused: the caller's own kernel performs the id dedup (the fused tower forward); the callback then only
+        registers the lookups and returns one sparse-optimizer workspace per lookup (None without a listener)."""
         t = GradientTape.current()
         if t is not None and t.on_sparse_lookup is not None:
-            t.on_sparse_lookup(lookups)
+            return t.on_sparse_lookup(lookups, fused=True) if fused else t.on_sparse_lookup(lookups)
+        return None
 
     @staticmethod
     def record(fn: Callable[[], None]) -> None:

@@ -20,78 +20,14 @@
 // Duplicate rows are summed with atomics: the SET of updated rows is exact, the fp32 sum
 // order over duplicates is not fixed (same as TF's GPU unsorted_segment_sum).
 #include "common.cuh"
+#include "sparse_ws.cuh"
 #include <limits.h>
 #include <stdlib.h>
 #include <algorithm>
 
 namespace tt {
 
-static constexpr unsigned long long kEmpty = 0xFFFFFFFFFFFFFFFFull;
 TT_TL_DEFINE(set_timeline_opt)
-
-struct SparseWs {
-  unsigned long long* keys;  // [cap]
-  int* first;                // [cap]
-  int* cnt;                  // [cap] occurrences of the key in this batch (fused step)
-  int* done;                 // [cap] arrival tickets of the duplicates (fused step)
-  int* hpos;                 // [nnz]
-  int* bag_of;               // [nnz]
-  float* accum;              // [nnz, d]
-  int64_t cap;
-};
-
-static int64_t hash_capacity(int64_t nnz) {
-  int64_t cap = 1024;
-  while (cap < 2 * nnz) cap <<= 1;
-  return cap;
-}
-
-static int64_t ws_layout(int64_t nnz, int64_t d, void* base, SparseWs* ws) {
-  const int64_t cap = hash_capacity(nnz);
-  int64_t off = 0;
-  auto take = [&](int64_t bytes) { int64_t o = off; off += round_up(bytes, 256); return o; };
-  int64_t o_keys = take(cap * 8), o_first = take(cap * 4), o_cnt = take(cap * 4), o_done = take(cap * 4),
-          o_hpos = take(nnz * 4), o_bag = take(nnz * 4), o_acc = take(nnz * d * 4);
-  if (ws) {
-    char* b = (char*)base;
-    ws->keys = (unsigned long long*)(b + o_keys);
-    ws->first = (int*)(b + o_first);
-    ws->cnt = (int*)(b + o_cnt);
-    ws->done = (int*)(b + o_done);
-    ws->hpos = (int*)(b + o_hpos);
-    ws->bag_of = (int*)(b + o_bag);
-    ws->accum = (float*)(b + o_acc);
-    ws->cap = cap;
-  }
-  return off;
-}
-
-// The layout of a caller-owned workspace is a function of its SIZE, not of the batch at hand: a workspace made for
-// nnz entries is reused for every batch with at most that many (ragged bags change nnz from step to step), and every
-// array boundary -- in particular the accumulation rows, which must be zero between launches -- has to stay where
-// tt_sparse_workspace_init put it.  capacity = the largest entry count whose layout fits the buffer.
-static int64_t ws_capacity(int64_t workspace_bytes, int64_t d) {
-  if (ws_layout(0, d, nullptr, nullptr) > workspace_bytes) return -1;
-  int64_t lo = 0, hi = 1;
-  while (hi < ((int64_t)1 << 31) && ws_layout(hi, d, nullptr, nullptr) <= workspace_bytes) { lo = hi; hi <<= 1; }
-  while (hi - lo > 1) {
-    const int64_t mid = lo + (hi - lo) / 2;
-    if (ws_layout(mid, d, nullptr, nullptr) <= workspace_bytes) lo = mid; else hi = mid;
-  }
-  return lo;
-}
-// carve `workspace` for a batch of nnz entries; false if it is too small
-static bool ws_carve(int64_t nnz, int64_t d, void* workspace, int64_t workspace_bytes, SparseWs* ws) {
-  const int64_t cap = ws_capacity(workspace_bytes, d);
-  if (cap < nnz) return false;
-  ws_layout(cap, d, workspace, ws);
-  return true;
-}
-
-__device__ __forceinline__ uint64_t mix64(uint64_t x) {
-  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
-  return x;
-}
 
 __global__ void sparse_ws_init_kernel(SparseWs ws, int64_t nnz, int64_t d) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -489,16 +425,7 @@ __global__ void __launch_bounds__(256) sparse_prepare_kernel(const __grid_consta
     id = (id % w == me) ? id / w : -1;
   }
   if (id < 0 || id >= V.vocab) { V.ws.hpos[j] = -1; return; }
-  const uint64_t mask = (uint64_t)V.ws.cap - 1;
-  uint64_t h = mix64((uint64_t)id) & mask;
-  while (true) {
-    unsigned long long prev = atomicCAS(&V.ws.keys[h], kEmpty, (unsigned long long)id);
-    if (prev == kEmpty || prev == (unsigned long long)id) break;
-    h = (h + 1) & mask;
-  }
-  V.ws.hpos[j] = (int)h;
-  atomicMin(&V.ws.first[h], (int)j);
-  atomicAdd(&V.ws.cnt[h], 1);
+  sparse_prepare_entry(V.ws, j, id);
   if (V.offsets) {
     int64_t lo = 0, hi = V.num_rows;
     while (hi - lo > 1) {

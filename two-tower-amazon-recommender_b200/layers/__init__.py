@@ -5,6 +5,7 @@ tf.keras.layers surface a TFRS two-tower model is built from (siz
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Optional, Sequence
 
 import numpy as np
@@ -271,15 +272,26 @@ class PendingTowers:
             return
         lookups = [l._lookup_note(f) for _, emb_layers, feats, _, _, _ in items for l, f in zip(emb_layers, feats)]
         lookups = [n for n in lookups if n is not None]       # None: announced later (peer-memory exchange)
+        # ID-only local towers: the tower kernel's control warp dedups the ids itself (no launch, no stream join)
+        def id_only_local(emb_layers, feats, x_input):
+            return (x_input is None and len(feats) == 1 and len(emb_layers) == 1 and feats[0][2] is None
+                    and not isinstance(feats[0][0], ops.PeerTable) and emb_layers[0]._lookup_note(feats[0]) is not None)
+        fused_prepare = Sequential.fuse_prepare and bool(lookups) and all(id_only_local(e, f, xi) for _, e, f, _, _, xi in items)
+        prepare_ws = None
         if lookups:
-            GradientTape.note_sparse_lookup(lookups)
+            if fused_prepare:
+                prepare_ws = GradientTape.note_sparse_lookup(lookups, fused=True)
+            else:
+                GradientTape.note_sparse_lookup(lookups)
         specs = []
-        for seq, emb_layers, feats, batch, out, x_input in items:
+        for k, (seq, emb_layers, feats, batch, out, x_input) in enumerate(items):
             d1, d2 = seq.layers[1], seq.layers[2]
             spec = dict(features=feats, batch=batch, w1=d1.kernel.shadow, b1=d1.bias.value,
                         w2=d2.kernel.shadow, b2=d2.bias.value)
             if x_input is not None:
                 spec["x_input"] = x_input.bf16
+            if prepare_ws is not None:
+                spec["prepare_ws"] = prepare_ws[k]
             specs.append(spec)
         results = ops.tower_mlp2_fwd(specs)
         for (seq, emb_layers, feats, batch, out, x_input), spec, (x, h, y) in zip(items, specs, results):
@@ -325,6 +337,11 @@ class Sequential(Layer):
     tower kernels; anything else runs layer by layer."""
 
     fuse = True
+    # id dedup by a dedicated warp of the tower forward (ID-only towers) instead of tt_optimizer_prepare_sparse on a side
+    # stream.  OFF by default: under the memory load of the gather a dependent round trip costs 1.3-2 us, the insert
+    # needs >= 3 of them per id (id -> key line -> CAS), and the tower kernel waits for its slowest chain: measured at
+    # cfg2 the forward grows by 5.6 us while the removed stream join saves 2.9 us.
+    fuse_prepare = os.environ.get("TT_FUSED_PREPARE", "0") == "1"
 
     def __init__(self, layers: Sequence[Layer] = (), name: Optional[str] = None):
         self.layers = list(layers)

@@ -444,11 +444,15 @@ def _fill_tower(dst, t):
     dst.batch = t["batch"]
     dst.w1, dst.b1 = _ptr(t["w1"], torch.bfloat16), _ptr(t["b1"], torch.float32)
     dst.w2, dst.b2 = _ptr(t["w2"], torch.bfloat16), _ptr(t["b2"], torch.float32)
+    ws = t.get("prepare_ws")                    # SparseWorkspace: the forward kernel also dedups this tower's ids
+    dst.prepare_workspace = _ptr(ws.buf) if ws is not None else None
+    dst.prepare_workspace_bytes = ws.nbytes if ws is not None else 0
 
 
 def tower_mlp2_fwd(towers, fault_flag: Optional[torch.Tensor] = None):
-    """towers: [dict(features=[(table, values, offsets, mode)], batch, w1 bf16 [in,hid], b1, w2 bf16 [hid,out], b2)].
-    One launch for all towers.  Returns [(x bf16 [B,in], h bf16 [B,hid], y bf16 [B,out])]."""
+    """towers: [dict(features=[(table, values, offsets, mode)], batch, w1 bf16 [in,hid], b1, w2 bf16 [hid,out], b2
+    [, prepare_ws=SparseWorkspace])].  One launch for all towers.  With prepare_ws (ID-only towers) the kernel also
+    performs sparse_prepare for the tower's ids.  Returns [(x bf16 [B,in], h bf16 [B,hid], y bf16 [B,out])]."""
     lib = _lib.load()
     arr = (_lib.tt_tower_mlp2 * len(towers))()
     outs = []
@@ -476,7 +480,7 @@ def tower_mlp2_bwd(towers):
     arr = (_lib.tt_tower_mlp2 * len(towers))()
     outs = []
     for i, t in enumerate(towers):
-        _fill_tower(arr[i], dict(t, features=[]))
+        _fill_tower(arr[i], dict(t, features=[], prepare_ws=None))
         dev, B = t["w1"].device, t["batch"]
         d_in, d_hid, d_out = arr[i].d_in, arr[i].d_hid, arr[i].d_out
         P = (B + 127) // 128

@@ -56,10 +56,23 @@ class Optimizer:
             self._prepared.clear()
         self._prepared_vars = []
 
-    def prepare_sparse(self, lookups) -> None:
+    def prepare_sparse(self, lookups, fused: bool = False):
         """lookups: [(variable, values, offsets, mode)].  Enqueue the id dedup (hash insert) of these tables
-        on a side stream; apply_gradients joins it."""
+        on a side stream; apply_gradients joins it.  fused=True: nothing is launched -- the caller's kernel (the
+        fused tower forward) does the insert -- and the workspace of every lookup is returned."""
         self._check_sparse_supported()
+        if fused:
+            out = []
+            for look in lookups:
+                var, values, offsets, mode = look[:4]
+                if len(look) > 4 and look[4] is not None or offsets is not None or values.numel() == 0:
+                    raise ValueError("fused id dedup: unsharded ID lookups only")
+                if id(var) in self._prepared:
+                    raise NotImplementedError("an embedding table used twice in one step is not supported")
+                out.append(self._sparse_ws(var, values.numel()))
+                self._prepared[id(var)] = values
+                self._prepared_vars.append(var)
+            return out
         items = []
         for look in lookups:
             var, values, offsets, mode = look[:4]
