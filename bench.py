@@ -59,12 +59,13 @@ def workload_name(cfg, n_gpus):
     return s
 
 
-def config_dict(cfg, world, graph=True):
+def config_dict(cfg, world, graph=True, spe=1):
     """The `config` object of the JSON line: identical for both arms (the reference arm runs the same workload)."""
     return {"workload": workload_name(cfg, world), "global_batch": cfg.batch * world,
             "l2_policy": f"inputs larger than L2: {N_POOL} distinct batches of random ids over tables + Adagrad slots far larger "
                          "than the 126 MB L2; no flush",
-            "launch": "cuda graph replay" if graph else "eager",
+            "launch": ("cuda graph replay" + (f", {spe} train steps per graph launch (Keras steps_per_execution={spe})" if spe > 1 else ""))
+            if graph else "eager",
             "exchange": None if world == 1 else os.environ.get("TT_EXCHANGE", "peer") +
             " (peer: every exchange is a kernel on the symmetric NVLink workspace, no NCCL in the step)"}
 
@@ -217,7 +218,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "examples/s", "n_gpus": args.gpus,
         "steps": len(times), "warmup": min(args.warmup, 2), "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_dict(cfg, world),
+        "config": config_dict(cfg, world, True, steps_per_execution(args, world, args.steps)),
         "cpu_baseline": {"value": value, "unit": "examples/s", "cores": threads, "kind": "port",
                          "sample": sample + " of the numpy TFRS-equivalent restatement (oracle/; TensorFlow/TFRS are not "
                                             f"installable here), BLAS threads set explicitly: {blas}" + note},
@@ -292,12 +293,21 @@ def measure_training(args, tt, torch, dist, cfg, world, rank, local_rank, group,
 
     model.test_step(dev_pool[0])                      # builds the Dense layers
     warm = max(3, args.warmup)
-    step = model.make_graphed_train_step(dev_pool[0], warmup=warm) if use_graph else model.train_step
-    # device-resident batches in the packed layout of the graph's static inputs: one D2D copy per step, issued on the
-    # step's copy stream (it overlaps the previous replay)
-    run_pool = [step.pack(b) for b in dev_pool] if use_graph else dev_pool
+    # S train steps per graph launch (Keras steps_per_execution): inside one graph step i + 1 follows step i as a
+    # programmatic dependent launch instead of across a graph-launch boundary.  One GPU only; S must divide K.
+    S = steps_per_execution(args, world, steps) if use_graph else 1
+    gstep = model.make_graphed_train_step(dev_pool[0], warmup=warm, steps_per_execution=S) if use_graph else model.train_step
+    group_of = lambda pool, j: pool[j % n_pool] if S == 1 else tuple(pool[(S * j + k) % n_pool] for k in range(S))
+    # device-resident batches in the packed layout of the graph's static inputs: one D2D copy per execution, issued on
+    # the step's copy stream (it overlaps the previous replay)
+    n_groups = n_pool // S
+    packed_pool = [gstep.pack(group_of(dev_pool, j)) for j in range(n_groups)] if use_graph else dev_pool
+
+    def step(i):                                      # steps S*i .. S*i + S - 1 on device-resident batches
+        return gstep(packed_pool[i % n_groups])
+
     for i in range(warm):
-        step(run_pool[i % n_pool])
+        step(i)
     barrier()
 
     # ---- kernel-side timed region: inputs already in HBM, EXACTLY K steps, CUDA events, max over ranks
@@ -309,17 +319,17 @@ def measure_training(args, tt, torch, dist, cfg, world, rank, local_rank, group,
         t_pre = time.perf_counter()
         i = 0
         while time.perf_counter() - t_pre < 0.6 or i < args.warmup:
-            step(run_pool[i % n_pool])
+            step(i)
             i += 1
             if i % 64 == 0:
                 torch.cuda.synchronize()
     else:
         for i in range(args.warmup):
-            step(run_pool[i % n_pool])
+            step(i)
     barrier()
     e0.record()
-    for i in range(steps):
-        step(run_pool[i % n_pool])
+    for i in range(steps // S):
+        step(i)
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -330,7 +340,7 @@ def measure_training(args, tt, torch, dist, cfg, world, rank, local_rank, group,
         ms_total = float(t.item())
     ms_step = ms_total / steps
     rec = {"value": cfg.batch * world / (ms_step / 1e3), "ms_per_step": ms_step, "gpu_launches": gpu_launches, "steps": steps,
-           "global_batch": cfg.batch * world}
+           "global_batch": cfg.batch * world, "steps_per_execution": S}
 
     # ---- end to end through the public API: pinned host ids -> H2D -> step -> loss D2H, every step.  The loss of
     # every step is copied to its own slot of a pinned host array on the step's stream (a training loop that logs each
@@ -339,14 +349,15 @@ def measure_training(args, tt, torch, dist, cfg, world, rank, local_rank, group,
         loss_host_all = torch.empty(steps, dtype=torch.float32).pin_memory()
         barrier()
         t0 = time.perf_counter()
-        for i in range(steps):
-            hb = host_pool[i % n_pool]
+        for i in range(steps // S):
+            hb = group_of(host_pool, i)
             if use_graph:
-                res = step(hb)                        # copies into the graph's static inputs (H2D), replays
+                res = gstep(hb)                       # copies into the graph's static inputs (ONE H2D copy), replays
             else:
-                res = step({k: (tuple(a.to(dev, non_blocking=True) for a in v) if isinstance(v, tuple) else v.to(dev, non_blocking=True))
-                            for k, v in hb.items()})
-            loss_host_all[i:i + 1].copy_(res["loss"], non_blocking=True)      # D2H read of the step's result
+                res = gstep({k: (tuple(a.to(dev, non_blocking=True) for a in v) if isinstance(v, tuple) else v.to(dev, non_blocking=True))
+                             for k, v in hb.items()})
+            for k, r in enumerate([res] if S == 1 else res):                  # D2H read of every step's result
+                loss_host_all[S * i + k:S * i + k + 1].copy_(r["loss"], non_blocking=True)
         barrier()
         e2e_s = time.perf_counter() - t0
         assert bool(torch.isfinite(loss_host_all).all()), "a step produced a non-finite loss"
@@ -359,7 +370,18 @@ def measure_training(args, tt, torch, dist, cfg, world, rank, local_rank, group,
                       "readback": "each step's loss is copied D2H (async, stream-ordered) into its own pinned slot; all inside the timed region"}
     if clocks is not None:
         clocks.__exit__(None, None, None)
-    return rec, model, step, dev_pool
+    return rec, model, gstep, dev_pool
+
+
+def steps_per_execution(args, world, steps):
+    """Largest S <= TT_STEPS_PER_EXECUTION (default 10) that divides the K timed steps; 1 on several GPUs."""
+    want = int(os.environ.get("TT_STEPS_PER_EXECUTION", "10"))
+    if world > 1:
+        return 1
+    for s in range(min(want, N_POOL), 1, -1):
+        if steps % s == 0:
+            return s
+    return 1
 
 
 def run_ours(args):
@@ -407,6 +429,8 @@ def run_ours(args):
                  5: "optimizer_step_kernel", 15: "retrieval_dq_finalize_kernel(block entries)"}
         tl = torch.tensor([I64MAX, 0] * 16, dtype=torch.int64, device=dev)
         lib0 = tt._lib.load()
+        if rec.get("steps_per_execution", 1) > 1:      # spans of ONE step: a one-step graph of the same model
+            step = model.make_graphed_train_step(dev_pool[0], warmup=1)
         for i in range(3):
             if i == 2:
                 torch.cuda.synchronize()
@@ -524,7 +548,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "examples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "config": config_dict(cfg, world, use_graph),
+        "config": config_dict(cfg, world, use_graph, rec.get("steps_per_execution", 1)),
         "clocks": clocks.summary(),
         "e2e": rec["e2e"],
         "gpu_launches": rec["gpu_launches"],

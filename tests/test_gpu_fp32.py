@@ -426,6 +426,35 @@ class TestTrainStepFp32:
             lb = float(graphed(b)["loss"].item())
             assert lb == pytest.approx(la, rel=1e-5)
 
+    def test_three_steps_per_execution_equal_three_eager_steps(self, tt):
+        """make_graphed_train_step(steps_per_execution=3): one replay = three consecutive train steps on three batches
+        (host batches: one H2D copy for all of them); losses and the iteration count follow the eager model."""
+        model_a = self._build(tt, 500, 400, 30, 64, (64, 32), 0.5, lr=0.01)
+        model_b = self._build(tt, 500, 400, 30, 64, (64, 32), 0.5, lr=0.01)
+        rng = synth.rng_for(78)
+        mkb = lambda: {"user_id_encoded": torch.as_tensor(synth.draw_ids(rng, 128, 500)),
+                       "item_id_encoded": torch.as_tensor(synth.draw_ids(rng, 128, 400)),
+                       "category": tuple(torch.as_tensor(a) for a in synth.draw_bags(rng, 128, 30, 2, 2))}
+        cuda = lambda b: {k: (tuple(a.cuda() for a in v) if isinstance(v, tuple) else v.cuda()) for k, v in b.items()}
+        b0 = mkb()
+        model_a.test_step(cuda(b0)); model_b.test_step(cuda(b0))
+        for va, vb in zip(model_a.trainable_variables, model_b.trainable_variables):
+            vb.assign(va.numpy())
+        graphed = model_b.make_graphed_train_step(cuda(b0), warmup=1, steps_per_execution=3)
+        model_a.train_step(cuda(b0))        # mirror the warm-up step (capture itself executes nothing)
+        it0 = model_b.optimizer.iterations
+        for rnd in range(2):
+            group = [mkb() for _ in range(3)]
+            la = [float(model_a.train_step(cuda(b))["loss"].item()) for b in group]
+            outs = graphed(group if rnd == 0 else graphed.pack([cuda(b) for b in group]))   # host batches / packed device batches
+            assert len(outs) == 3
+            torch.cuda.synchronize()
+            for x, o in zip(la, outs):
+                assert float(o["loss"].item()) == pytest.approx(x, rel=1e-5)
+        assert model_b.optimizer.iterations == it0 + 6
+        with pytest.raises(ValueError):
+            graphed([mkb()])
+
 
 # ---------------------------------------------------------------- sharding helpers (8e)
 class TestShardingHelpers:
