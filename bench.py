@@ -356,8 +356,10 @@ def measure_training(args, tt, torch, dist, cfg, world, rank, local_rank, group,
             else:
                 res = gstep({k: (tuple(a.to(dev, non_blocking=True) for a in v) if isinstance(v, tuple) else v.to(dev, non_blocking=True))
                              for k, v in hb.items()})
-            for k, r in enumerate([res] if S == 1 else res):                  # D2H read of every step's result
-                loss_host_all[S * i + k:S * i + k + 1].copy_(r["loss"], non_blocking=True)
+            if use_graph:                             # D2H read of every step's result: the S losses of the execution
+                loss_host_all[S * i:S * i + S].copy_(gstep.losses, non_blocking=True)      # are one device tensor
+            else:
+                loss_host_all[i:i + 1].copy_(res["loss"], non_blocking=True)
         barrier()
         e2e_s = time.perf_counter() - t0
         assert bool(torch.isfinite(loss_host_all).all()), "a step produced a non-finite loss"
@@ -367,7 +369,8 @@ def measure_training(args, tt, torch, dist, cfg, world, rank, local_rank, group,
             e2e_s = float(t.item())
         rec["e2e"] = {"value": cfg.batch * world * steps / e2e_s, "unit": "examples/s", "h2d_bytes_per_step": h2d_bytes,
                       "d2h_bytes_per_step": 4, "last_loss": float(loss_host_all[-1]),
-                      "readback": "each step's loss is copied D2H (async, stream-ordered) into its own pinned slot; all inside the timed region"}
+                      "readback": "each step's loss is copied D2H (async, stream-ordered) into its own pinned slot -- the losses of the steps of "
+                                  "one graph launch in one copy; all inside the timed region"}
     if clocks is not None:
         clocks.__exit__(None, None, None)
     return rec, model, gstep, dev_pool

@@ -451,6 +451,8 @@ class TestTrainStepFp32:
             torch.cuda.synchronize()
             for x, o in zip(la, outs):
                 assert float(o["loss"].item()) == pytest.approx(x, rel=1e-5)
+            # the losses of one execution are also ONE contiguous device tensor (a single D2H copy reads them)
+            assert torch.equal(graphed.losses, torch.cat([o["loss"] for o in outs]))
         assert model_b.optimizer.iterations == it0 + 6
         with pytest.raises(ValueError):
             graphed([mkb()])

@@ -196,10 +196,22 @@ class GraphedStep:
             packed = first if b == 0 else _PackedInputs(example)
             graph = torch.cuda.CUDAGraph()
             before = ops.LAUNCHES
-            with torch.cuda.graph(graph):
-                outs = [model.train_step(v) for v in views(packed)]
+            # the S losses of an execution land in ONE tensor (the first retrieval loss of each step): `losses`
+            losses = torch.zeros(S, dtype=torch.float32, device=packed.flat_dev.device)
+            free = []
+            ops.loss_allocator = lambda: free.pop() if free else None
+            try:
+                with torch.cuda.graph(graph):
+                    outs = []
+                    for k, v in enumerate(views(packed)):
+                        free[:] = [losses[k:k + 1]]
+                        outs.append(model.train_step(v))
+            finally:
+                ops.loss_allocator = None
             self.launches_per_replay = ops.LAUNCHES - before
-            self._slots.append(_Slot(packed, graph, outs[0] if S == 1 else outs))
+            slot = _Slot(packed, graph, outs[0] if S == 1 else outs)
+            slot.losses = losses
+            self._slots.append(slot)
         model.optimizer.iterations = iterations       # the captures executed nothing: no step was taken
         self._copy_stream = torch.cuda.Stream()
         self._next = 0
@@ -238,6 +250,7 @@ class GraphedStep:
         slot.consumed.record(main)
         ops._count(self.launches_per_replay)
         self.model.optimizer.iterations += self.steps_per_execution   # host mirror of the step count (Adam's device counter advanced in-graph)
+        self.losses = slot.losses                     # device [S]: the retrieval losses of this execution's steps, contiguous
         return slot.out
 
 

@@ -542,7 +542,7 @@ def retrieval_loss_fwd(precision: str, q, c, inv_temperature: float, label_offse
     dev = q.device
     lse = torch.empty((nq,), dtype=torch.float32, device=dev)
     pos = torch.empty((nq,), dtype=torch.float32, device=dev)
-    loss = torch.empty((1,), dtype=torch.float32, device=dev)
+    loss = _new_loss(dev)
     nbytes = int(lib.tt_retrieval_workspace_bytes(pc, nq, nc, d))
     ws = _workspace(nbytes, dev, "retrieval")
     check(lib.tt_retrieval_loss_fwd(pc, _ptr(q, dt), _ptr(c, dt), nq, nc, d, inv_temperature, label_offset,
@@ -584,6 +584,19 @@ def retrieval_bwd_num_splits(nq: int, nc: int, d: int):
     return sq.value, sc.value
 
 
+# Where the scalar loss of a retrieval forward goes.  GraphedStep(steps_per_execution = S) sets this while it captures
+# so that the S losses of one execution are the S elements of ONE device tensor (one D2H copy reads them all).
+loss_allocator = None
+
+
+def _new_loss(dev) -> torch.Tensor:
+    if loss_allocator is not None:
+        t = loss_allocator()
+        if t is not None:
+            return t
+    return torch.empty((1,), dtype=torch.float32, device=dev)
+
+
 def retrieval_fwd_dq_supported(nq: int, nc: int, d: int) -> bool:
     return int(_lib.load().tt_retrieval_fwd_dq_workspace_bytes(nq, nc, d)) > 0
 
@@ -611,7 +624,7 @@ def retrieval_loss_fwd_dq(q, c, inv_temperature: float, label_offset: int = 0, s
     dev = q.device
     lse = torch.empty((nq,), dtype=torch.float32, device=dev)
     pos = torch.empty((nq,), dtype=torch.float32, device=dev)
-    loss = torch.empty((1,), dtype=torch.float32, device=dev)
+    loss = _new_loss(dev)
     dq = torch.empty((nq, d), dtype=torch.float32, device=dev)
     nbytes = int(lib.tt_retrieval_fwd_dq_workspace_bytes(nq, nc, d))
     if nbytes <= 0:
@@ -904,7 +917,7 @@ def hard_negative_loss_fwd(precision: str, q, c, selected, inv_temperature: floa
     lse = torch.empty((nq,), dtype=torch.float32, device=dev)
     pos = torch.empty((nq,), dtype=torch.float32, device=dev)
     row_loss = torch.empty((nq,), dtype=torch.float32, device=dev)
-    loss = torch.empty((1,), dtype=torch.float32, device=dev)
+    loss = _new_loss(dev)
     check(_lib.load().tt_hard_negative_loss_fwd(pc, _ptr(q, dt), _ptr(c, dt), _ptr(selected, torch.int64), nq, c.shape[0], K, d,
                                                 inv_temperature, _ptr(sample_weight, torch.float32), _ptr(scores), _ptr(lse),
                                                 _ptr(pos), _ptr(row_loss), _ptr(loss), _stream()))
