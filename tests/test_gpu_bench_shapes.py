@@ -178,6 +178,56 @@ class TestCfg3Step:
             assert lb == pytest.approx(la, rel=1e-4), s
 
 
+class TestReferenceTowerSpec:
+    """The reference's own `model:` block (/root/reference/configs/data_config.yaml:54-71): embedding_dim 128, three Dense
+    layers [512, 256, 128] per tower, batch_size 1024, temperature 0.1 (vocabularies reduced for the host oracle).  Three
+    layers / hidden 512 are outside the fused two-layer tower kernel: the towers run as the gather kernel + per-layer
+    tcgen05 GEMMs (tt_dense_fwd / tt_dense_bwd), and must match the oracle like the fused path does."""
+
+    CFG = synth.Config("reference-spec", 5471, 1024, 128, 20_000, 15_000, (512, 256, 128), 0.1)
+
+    def test_one_step_matches_the_oracle(self, tt):
+        cfg = self.CFG
+        tt.set_precision("bf16")
+        tt.set_seed(11)
+        tt.layers._layer_counter[0] = 0
+        model = recipes.build_two_tower(cfg, lr=0.05)
+        batch = synth.make_batch(cfg, 0)
+        model.test_step(batch)
+        assert not model.user_model._fusable()          # three Dense layers: the per-layer path is the one tested
+        qs, cs = _oracle_specs(cfg)
+        qp, cp = _oracle_params_from(model, cfg)
+        q_dev = model.user_model(batch[recipes.USER_KEY])
+        q_ref, _ = oracle.tower_forward(qs, qp, {recipes.USER_KEY: batch[recipes.USER_KEY]}, bf16=True)
+        e = norm_err(q_dev.numpy(), oracle.bf16_round(q_ref.astype(np.float32)))
+        print(f"reference spec, user tower output: norm err {e:.2e}")
+        assert e < BF16_RTOL
+        tab0 = qp["tables"][recipes.USER_KEY].copy()
+        k0 = [k.copy() for k in qp["kernels"]]
+        out = model.train_step(batch)
+        ref = oracle.two_tower_train_step(qs, cs, qp, cp, _slots_like(qp), _slots_like(cp),
+                                          {recipes.USER_KEY: batch[recipes.USER_KEY]}, {recipes.ITEM_KEY: batch[recipes.ITEM_KEY]},
+                                          temperature=cfg.temperature, lr=0.05, bf16=True)
+        got = float(out["loss"].item())
+        print(f"reference spec step: loss {got:.4f} oracle {ref['loss']:.4f}")
+        assert got == pytest.approx(ref["loss"], rel=BF16_RTOL)
+        tab = model.user_model.layers[0].get_weights()[0].astype(np.float64)
+        touched = np.unique(batch[recipes.USER_KEY])
+        rest = np.setdiff1d(np.arange(tab.shape[0]), touched)
+        assert np.array_equal(tab[rest], tab0[rest])
+        assert np.array_equal(np.sort(ref["unique"][f"q/{recipes.USER_KEY}"]), touched)
+        du, dr = (tab - tab0)[touched].ravel(), (qp["tables"][recipes.USER_KEY] - tab0)[touched].ravel()
+        cos = float(du @ dr / (np.linalg.norm(du) * np.linalg.norm(dr)))
+        print(f"reference spec, user table update: cosine {cos:.4f}, norm ratio {np.linalg.norm(du) / np.linalg.norm(dr):.4f}")
+        assert cos > 0.98 and np.linalg.norm(du) == pytest.approx(np.linalg.norm(dr), rel=5e-2)
+        for j, layer in enumerate(model.user_model.layers[1:]):
+            du = (layer.get_weights()[0].astype(np.float64) - k0[j]).ravel()
+            dr = (qp["kernels"][j] - k0[j]).ravel()
+            cos = float(du @ dr / (np.linalg.norm(du) * np.linalg.norm(dr)))
+            print(f"reference spec, user Dense {j} update: cosine {cos:.4f}")
+            assert cos > 0.97 and np.linalg.norm(du) == pytest.approx(np.linalg.norm(dr), rel=7e-2)
+
+
 class TestUpdatedTableTolerance:
     """north_star: embeddings within 1e-5 (fp32) / 2e-2 (bf16) relative.  The updated table is w - lr * g / sqrt(acc + g^2):
     with lr = 0.1 the UPDATE is as large as the table itself, so max|got - ref| / max|ref table| measures the error of the

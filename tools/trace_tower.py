@@ -1,5 +1,5 @@
 """Per-CTA phase timeline (globaltimer ns) of the fused tower kernels at cfg2 shape (2 towers x 8192 rows).
-   python tools/trace_tower.py"""
+   python tools/trace_tower.py [--dedup]"""
 import sys
 from pathlib import Path
 
@@ -30,8 +30,9 @@ buf = torch.zeros(2 * 16 * 256, dtype=torch.int64, device="cuda")
 
 
 def run():
-    for s in specs:                       # the forward's dedup warp fills a fresh sparse-optimizer workspace
-        s["prepare_ws"] = ops.SparseWorkspace(B, d_in, "cuda")
+    if "--dedup" in sys.argv:             # the forward's dedup warp fills a fresh sparse-optimizer workspace (off by default)
+        for s in specs:
+            s["prepare_ws"] = ops.SparseWorkspace(B, d_in, "cuda")
     outs = ops.tower_mlp2_fwd(specs)
     ops.tower_mlp2_bwd([dict(s, x=x, h=h, dy_parts=p, dy_splits=2) for s, (x, h, y), p in zip(specs, outs, parts)])
 
