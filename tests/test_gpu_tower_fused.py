@@ -358,26 +358,41 @@ class TestFusedTrainStep:
 
     def test_id_dedup_inside_the_tower_forward_equals_the_separate_launch(self, tt, monkeypatch):
         """The fused prepare stage (tt_tower_mlp2.prepare_workspace) and tt_optimizer_prepare_sparse on a side stream
-        lead to the same tables: identical row sets, values up to the atomics order of duplicate rows."""
+        lead to the same tables: identical row sets, values up to the atomics order of duplicate rows.
+
+        Both models start EVERY step from the same state (weights and Adagrad accumulators copied over).  The fp32 sum
+        of a duplicated id's gradient rows depends on the order the reductions arrive in (1e-7 relative); carried into
+        the next step, such a difference can flip the bf16 rounding of a gathered table row (2^-8 relative) and grow to
+        3e-4 in the tables -- measured between two IDENTICAL models on the side-stream path, for one initialisation in
+        six -- which says nothing about the equivalence this test is about."""
         vu, vi, d, mlp, B, T, lr = 3000, 2500, 128, (256, 128), 1000, 0.5, 0.05      # ragged last row block, many duplicates
         tt.set_seed(6)
+        tt.layers._layer_counter[0] = 0
         a = self._model(tt, vu, vi, d, mlp, T, lr, fuse=True)
         b = self._model(tt, vu, vi, d, mlp, T, lr, fuse=True)
         rng = synth.rng_for(43)
         batches = [{"user_id_encoded": synth.draw_ids(rng, B, vu, 1.3), "item_id_encoded": synth.draw_ids(rng, B, vi, 1.3)}
                    for _ in range(3)]
         a.test_step(batches[0]); b.test_step(batches[0])
-        for la, lb in zip(a.user_model.layers + a.item_model.layers, b.user_model.layers + b.item_model.layers):
-            lb.set_weights(la.get_weights())
-        for bt in batches:
+        for k, bt in enumerate(batches):
+            for va, vb in zip(a.trainable_variables, b.trainable_variables):
+                vb.assign(va.value.cpu().numpy())
+                for key, slot in va.slots.items():
+                    if isinstance(slot, torch.Tensor) and not key.startswith("_"):
+                        vb.assign_slot(key, slot)
+            before = [la.get_weights()[0].copy() for la in a.user_model.layers[:1] + a.item_model.layers[:1]]
             monkeypatch.setattr(tt.layers.Sequential, "fuse_prepare", True)
             oa = a.train_step(bt)
             monkeypatch.setattr(tt.layers.Sequential, "fuse_prepare", False)
             ob = b.train_step(bt)
-            assert float(oa["loss"].item()) == pytest.approx(float(ob["loss"].item()), rel=1e-5)
-        for la, lb in zip(a.user_model.layers[:1] + a.item_model.layers[:1], b.user_model.layers[:1] + b.item_model.layers[:1]):
-            wa, wb = la.get_weights()[0], lb.get_weights()[0]
-            np.testing.assert_allclose(wa, wb, rtol=1e-4, atol=1e-6)
+            assert float(oa["loss"].item()) == pytest.approx(float(ob["loss"].item()), rel=1e-6)
+            feats = [bt["user_id_encoded"], bt["item_id_encoded"]]
+            for la, lb, w0, ids in zip(a.user_model.layers[:1] + a.item_model.layers[:1], b.user_model.layers[:1] + b.item_model.layers[:1], before, feats):
+                wa, wb = la.get_weights()[0], lb.get_weights()[0]
+                np.testing.assert_allclose(wa, wb, rtol=1e-5, atol=1e-7)
+                moved = np.flatnonzero((wa != w0).any(axis=1))
+                looked_up = np.unique(ids)
+                assert np.isin(moved, looked_up).all() and len(moved) >= 0.99 * len(looked_up), f"step {k}: rows outside the id set moved"
 
     def test_three_steps_track_the_oracle(self, tt):
         vu, vi, d, mlp, B, T, lr = 2000, 1500, 128, (256, 128), 512, 0.5, 0.05

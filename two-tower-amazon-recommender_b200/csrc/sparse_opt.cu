@@ -86,34 +86,44 @@ sparse_accumulate_kernel(SparseWs ws, const int64_t* __restrict__ offsets, int m
   }
 }
 
+// fence.acq_rel at device scope: what the ticket protocol needs (__threadfence() is the sequentially consistent fence)
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
 struct AdagradRule {
   float* acc; float lr, eps;
-  __device__ __forceinline__ void apply(float* w_row, int64_t row_off, int c, float4 g) const {
-    float4* wp = reinterpret_cast<float4*>(w_row) + c;
-    float4* ap = reinterpret_cast<float4*>(acc + row_off) + c;
-    float4 w = *wp, a = *ap;
+  // the arithmetic alone, on a chunk already in registers (the fused step keeps the rows of several entries in flight)
+  __device__ __forceinline__ void update(float4& w, float4& a, const float4 g) const {
 #define TT_ADAGRAD_1(X)                                                        \
     a.X = __fadd_rn(a.X, __fmul_rn(g.X, g.X));                                 \
     w.X = __fsub_rn(w.X, __fdiv_rn(__fmul_rn(lr, g.X), __fsqrt_rn(__fadd_rn(a.X, eps))));
     TT_ADAGRAD_1(x) TT_ADAGRAD_1(y) TT_ADAGRAD_1(z) TT_ADAGRAD_1(w)
 #undef TT_ADAGRAD_1
+  }
+  __device__ __forceinline__ void apply(float* w_row, int64_t row_off, int c, float4 g) const {
+    float4* wp = reinterpret_cast<float4*>(w_row) + c;
+    float4* ap = reinterpret_cast<float4*>(acc + row_off) + c;
+    float4 w = *wp, a = *ap;
+    update(w, a, g);
     *wp = w; *ap = a;
   }
 };
 
 struct LazyAdamRule {
   float* m; float* v; float alpha, b1, b2, eps;
-  __device__ __forceinline__ void apply(float* w_row, int64_t row_off, int c, float4 g) const {
-    float4* wp = reinterpret_cast<float4*>(w_row) + c;
-    float4* mp = reinterpret_cast<float4*>(m + row_off) + c;
-    float4* vp = reinterpret_cast<float4*>(v + row_off) + c;
-    float4 w = *wp, mm = *mp, vv = *vp;
+  __device__ __forceinline__ void update(float4& w, float4& mm, float4& vv, const float4 g) const {
 #define TT_ADAM_1(X)                                                                         \
     mm.X = __fadd_rn(mm.X, __fmul_rn(__fsub_rn(g.X, mm.X), 1.f - b1));                       \
     vv.X = __fadd_rn(vv.X, __fmul_rn(__fsub_rn(__fmul_rn(g.X, g.X), vv.X), 1.f - b2));       \
     w.X = __fsub_rn(w.X, __fdiv_rn(__fmul_rn(mm.X, alpha), __fadd_rn(__fsqrt_rn(vv.X), eps)));
     TT_ADAM_1(x) TT_ADAM_1(y) TT_ADAM_1(z) TT_ADAM_1(w)
 #undef TT_ADAM_1
+  }
+  __device__ __forceinline__ void apply(float* w_row, int64_t row_off, int c, float4 g) const {
+    float4* wp = reinterpret_cast<float4*>(w_row) + c;
+    float4* mp = reinterpret_cast<float4*>(m + row_off) + c;
+    float4* vp = reinterpret_cast<float4*>(v + row_off) + c;
+    float4 w = *wp, mm = *mp, vv = *vp;
+    update(w, mm, vv, g);
     *wp = w; *mp = mm; *vp = vv;
   }
 };
@@ -439,10 +449,12 @@ __global__ void __launch_bounds__(256) sparse_prepare_kernel(const __grid_consta
 struct StepArgs {
   DenseMultiArgs dense;
   SparseMultiArgs sparse;
-  int dense_blocks[TT_MAX_DENSE_VARS + 1];    // prefix sums of the blocks of each dense variable
-  int sparse_blocks[TT_MAX_SPARSE_VARS + 1];  // prefix sums (after the dense blocks)
+  int sparse_blocks[TT_MAX_SPARSE_VARS + 1];  // prefix sums of the blocks of each table (the grid starts with them)
+  int dense_blocks[TT_MAX_DENSE_VARS + 1];    // prefix sums of the blocks of each dense variable (after the table blocks)
   int n_dense, n_sparse;
+  int entries_per_block;                      // table entries handled by one block (<= kStepMaxEntries)
 };
+static constexpr int kStepMaxEntries = 128;
 
 template <bool ADAM>
 __device__ __forceinline__ void apply_row(const SparseMultiVar& V, int64_t id, int c, float4 g, float lr_or_alpha,
@@ -460,8 +472,9 @@ template <bool ADAM>
 __device__ __forceinline__ void optimizer_step_body(const StepArgs& a, float lr_or_alpha, float b1, float b2, float eps) {
   const int lane = threadIdx.x & 31;
   const int bid = blockIdx.x;
-  if (bid < a.dense_blocks[a.n_dense]) {
-    // ---------------- dense variable: 4 lanes per float4 of weights, each folds partials q, q+4, ...
+  if (bid >= a.dense_blocks[0]) {
+    // ---------------- dense variable (behind the table blocks: short blocks on L2-resident partials make the shorter
+    // tail): 4 lanes per float4 of weights, each folds partials q, q+4, ...
     int vi = 0;
     while (bid >= a.dense_blocks[vi + 1]) ++vi;
     const DenseMultiVar& V = a.dense.v[vi];
@@ -521,58 +534,190 @@ __device__ __forceinline__ void optimizer_step_body(const StepArgs& a, float lr_
     if (V.shadow) V.shadow[i] = float_to_bf16_bits(wv);
     return;
   }
-  // ---------------- table entries: warp per entry
+  // ---------------- table entries: `entries_per_block` consecutive entries of one table per block, in phases.
+  // Phase 1, THREAD per entry: the chain of small dependent loads (slot position -> key, first occurrence, count; bag ->
+  //   bag length) runs once per entry with coalesced accesses; its results go to shared memory.
+  // Phase 2 (only if the block holds duplicates), WARP per duplicate entry: the gradient row is added into the first
+  //   occurrence's accumulation row (128-bit reductions), 4 rows of a warp in flight.
+  // Phase 3, THREAD per duplicate entry: release fence, arrival ticket, acquire fence -- once per BLOCK instead of once
+  //   per entry (a device-scope fence is a round trip that waits for every reduction the thread has in flight; one pair
+  //   per warp and entry was 30 % of the kernel's stall samples at the cfg3 shape).  The last arriver of an id applies it.
+  // Phase 4, WARP per applying entry (ids that occur once, last arrivers), U entries of a warp in flight together: with
+  //   everything the earlier phases found in shared memory, the 512-byte rows (gradient or accumulated sum, table,
+  //   slots) of U entries are requested back to back -- the kernel lives on the bytes it keeps in flight (a
+  //   warp-per-entry version that walked the whole chain alone ran at 2.1-2.4 TB/s at the cfg2 / cfg3 shapes).
   int vi = 0;
   while (vi + 1 < a.n_sparse && bid >= a.sparse_blocks[vi + 1]) ++vi;
   const SparseMultiVar& V = a.sparse.v[vi];
-  const int64_t j = (int64_t)(bid - a.sparse_blocks[vi]) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (j >= V.nnz) return;
-  const int h = V.ws.hpos[j];
-  if (h < 0) { if (V.first_flag && lane == 0) V.first_flag[j] = 0; return; }
-  const int leader = V.ws.first[h];
-  const int count = V.ws.cnt[h];
-  if (V.first_flag && lane == 0) V.first_flag[j] = leader == (int)j ? 1 : 0;
-  const int64_t id = (int64_t)V.ws.keys[h];
-  int64_t row = j;
-  float L = 1.f;
-  if (V.offsets) {
-    row = V.ws.bag_of[j];
-    if (V.mode == TT_POOL_MEAN) L = (float)(V.offsets[row + 1] - V.offsets[row]);
+  const int E = a.entries_per_block;
+  const int64_t j0 = (int64_t)(bid - a.sparse_blocks[vi]) * E;
+  __shared__ long long s_id[kStepMaxEntries];
+  __shared__ int s_row[kStepMaxEntries], s_h[kStepMaxEntries], s_leader[kStepMaxEntries], s_count[kStepMaxEntries];
+  __shared__ float s_L[kStepMaxEntries];
+  int has_dup = 0;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    const int64_t j = j0 + e;
+    int h = -1, leader = 0, count = 0, row = 0;
+    long long id = 0;
+    float L = 1.f;
+    if (j < V.nnz) {
+      h = V.ws.hpos[j];
+      if (h >= 0) {
+        leader = V.ws.first[h];
+        count = V.ws.cnt[h];
+        id = (long long)V.ws.keys[h];
+        row = (int)j;
+        if (V.offsets) {
+          row = V.ws.bag_of[j];
+          if (V.mode == TT_POOL_MEAN) L = (float)(V.offsets[row + 1] - V.offsets[row]);
+        }
+        has_dup |= count != 1;
+      }
+      if (V.first_flag) V.first_flag[j] = (h >= 0 && leader == (int)j) ? 1 : 0;
+    }
+    s_h[e] = h; s_leader[e] = leader; s_count[e] = count; s_row[e] = row; s_id[e] = id; s_L[e] = L;
   }
-  const float4* gp = reinterpret_cast<const float4*>(V.grad + row * V.d);
+  has_dup = __syncthreads_or(has_dup);
+  const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int nch = (int)(V.d >> 2);
-  if (count == 1) {
+  if (nch <= 32) {
+    // rows of up to 128 floats: one 16-byte chunk per lane
+    const bool mine = lane < nch;
+    float4* const T4 = reinterpret_cast<float4*>(V.table);
+    float4* const S4 = reinterpret_cast<float4*>(V.s0);
+    float4* const M4 = reinterpret_cast<float4*>(V.s1);
+    float4* const A4 = reinterpret_cast<float4*>(V.ws.accum);
+    const float4* const G4 = reinterpret_cast<const float4*>(V.grad);
+    if (has_dup) {
+      constexpr int UD = 4;
+      bool issued = false;
+      for (int e0 = warp; e0 < E; e0 += nw * UD) {
+        float4 g[UD];
+        bool on[UD];
+#pragma unroll
+        for (int u = 0; u < UD; ++u) {
+          const int e = e0 + u * nw;
+          on[u] = e < E && s_h[e] >= 0 && s_count[e] != 1 && mine;
+          if (on[u]) g[u] = __ldg(G4 + (int64_t)s_row[e] * nch + lane);
+        }
+#pragma unroll
+        for (int u = 0; u < UD; ++u) {
+          if (!on[u]) continue;
+          const int e = e0 + u * nw;
+          const float L = s_L[e];
+          if (L != 1.f) { g[u].x = __fdiv_rn(g[u].x, L); g[u].y = __fdiv_rn(g[u].y, L); g[u].z = __fdiv_rn(g[u].z, L); g[u].w = __fdiv_rn(g[u].w, L); }
+          atomicAdd(A4 + (int64_t)s_leader[e] * nch + lane, g[u]);
+          issued = true;
+        }
+      }
+      // every thread waits for ITS OWN reductions to be performed at device scope (one fence per warp and block, not
+      // per entry); the barrier then orders them before the tickets, which other threads take
+      if (issued) fence_acq_rel_gpu();
+      __syncthreads();
+      for (int e = threadIdx.x; e < E; e += blockDim.x) {
+        const int h = s_h[e];
+        if (h < 0 || s_count[e] == 1) continue;
+        fence_acq_rel_gpu();
+        const int ticket = atomicAdd(&V.ws.done[h], 1);
+        fence_acq_rel_gpu();
+        if (ticket != s_count[e] - 1) s_h[e] = -1;       // an earlier arriver: done
+      }
+      __syncthreads();
+    }
+    constexpr int U = 2;
+    for (int e0 = warp; e0 < E; e0 += nw * U) {
+      int h[U], count[U];
+      float4 g[U], w4[U], s4[U], t4[U];
+      int64_t ro[U], ao[U];            // float4 index of this lane's chunk in the table / slot rows and in the accumulation row
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int e = e0 + u * nw;
+        h[u] = e < E ? s_h[e] : -1;
+        count[u] = 0;
+        g[u] = w4[u] = s4[u] = t4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ro[u] = ao[u] = 0;
+        if (h[u] < 0) continue;
+        count[u] = s_count[e];
+        ro[u] = (int64_t)s_id[e] * nch + lane;
+        ao[u] = (int64_t)s_leader[e] * nch + lane;
+        if (mine) {
+          // L1-bypassing loads throughout: the rows have no reuse, and the accumulated sums live in L2
+          if (count[u] == 1) {
+            g[u] = __ldg(G4 + (int64_t)s_row[e] * nch + lane);
+            const float L = s_L[e];
+            if (L != 1.f) { g[u].x = __fdiv_rn(g[u].x, L); g[u].y = __fdiv_rn(g[u].y, L); g[u].z = __fdiv_rn(g[u].z, L); g[u].w = __fdiv_rn(g[u].w, L); }
+          } else {
+            g[u] = __ldcg(A4 + ao[u]);
+          }
+          w4[u] = __ldcg(T4 + ro[u]);
+          s4[u] = __ldcg(S4 + ro[u]);
+          if (ADAM) t4[u] = __ldcg(M4 + ro[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (h[u] < 0) continue;
+        if (mine) {
+          if (count[u] != 1) A4[ao[u]] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ADAM) {
+            LazyAdamRule rule{V.s0, V.s1, lr_or_alpha, b1, b2, eps};
+            rule.update(w4[u], s4[u], t4[u], g[u]);
+            T4[ro[u]] = w4[u]; S4[ro[u]] = s4[u]; M4[ro[u]] = t4[u];
+          } else {
+            AdagradRule rule{V.s0, lr_or_alpha, eps};
+            rule.update(w4[u], s4[u], g[u]);
+            T4[ro[u]] = w4[u]; S4[ro[u]] = s4[u];
+          }
+        }
+        if (lane == 0) {
+          V.ws.keys[h[u]] = kEmpty; V.ws.first[h[u]] = INT_MAX; V.ws.cnt[h[u]] = 0;
+          if (count[u] != 1) V.ws.done[h[u]] = 0;
+        }
+      }
+    }
+    return;
+  }
+  // wider rows: chunk loop, one entry at a time
+  for (int e = warp; e < E; e += nw) {
+    const int h = s_h[e];
+    if (h < 0) continue;
+    const int leader = s_leader[e], count = s_count[e];
+    const int64_t id = s_id[e];
+    const float L = s_L[e];
+    const float4* gp = reinterpret_cast<const float4*>(V.grad + (int64_t)s_row[e] * V.d);
+    if (count == 1) {
+      for (int c = lane; c < nch; c += 32) {
+        float4 g = __ldg(gp + c);
+        if (L != 1.f) { g.x = __fdiv_rn(g.x, L); g.y = __fdiv_rn(g.y, L); g.z = __fdiv_rn(g.z, L); g.w = __fdiv_rn(g.w, L); }
+        apply_row<ADAM>(V, id, c, g, lr_or_alpha, b1, b2, eps);
+      }
+      if (lane == 0) { V.ws.keys[h] = kEmpty; V.ws.first[h] = INT_MAX; V.ws.cnt[h] = 0; }
+      continue;
+    }
+    float4* acc = reinterpret_cast<float4*>(V.ws.accum + (int64_t)leader * V.d);
     for (int c = lane; c < nch; c += 32) {
       float4 g = __ldg(gp + c);
       if (L != 1.f) { g.x = __fdiv_rn(g.x, L); g.y = __fdiv_rn(g.y, L); g.z = __fdiv_rn(g.z, L); g.w = __fdiv_rn(g.w, L); }
+      atomicAdd(acc + c, g);
+    }
+    __threadfence();
+    __syncwarp();
+    int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(&V.ws.done[h], 1);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if (ticket != count - 1) continue;
+    __threadfence();
+    for (int c = lane; c < nch; c += 32) {
+      const float4 g = __ldcg(acc + c);
+      acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
       apply_row<ADAM>(V, id, c, g, lr_or_alpha, b1, b2, eps);
     }
-    if (lane == 0) { V.ws.keys[h] = kEmpty; V.ws.first[h] = INT_MAX; V.ws.cnt[h] = 0; }
-    return;
+    if (lane == 0) { V.ws.keys[h] = kEmpty; V.ws.first[h] = INT_MAX; V.ws.cnt[h] = 0; V.ws.done[h] = 0; }
   }
-  float4* acc = reinterpret_cast<float4*>(V.ws.accum + (int64_t)leader * V.d);
-  for (int c = lane; c < nch; c += 32) {
-    float4 g = __ldg(gp + c);
-    if (L != 1.f) { g.x = __fdiv_rn(g.x, L); g.y = __fdiv_rn(g.y, L); g.z = __fdiv_rn(g.z, L); g.w = __fdiv_rn(g.w, L); }
-    atomicAdd(acc + c, g);
-  }
-  __threadfence();
-  __syncwarp();
-  int ticket = 0;
-  if (lane == 0) ticket = atomicAdd(&V.ws.done[h], 1);
-  ticket = __shfl_sync(0xffffffffu, ticket, 0);
-  if (ticket != count - 1) return;
-  __threadfence();
-  for (int c = lane; c < nch; c += 32) {
-    const float4 g = __ldcg(acc + c);
-    acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    apply_row<ADAM>(V, id, c, g, lr_or_alpha, b1, b2, eps);
-  }
-  if (lane == 0) { V.ws.keys[h] = kEmpty; V.ws.first[h] = INT_MAX; V.ws.cnt[h] = 0; V.ws.done[h] = 0; }
 }
 
-// MINB resident blocks per SM: the kernel is a chain of dependent memory round trips per row, so it lives on occupancy
-// (a variant at 53 registers instead of 40 took 26 us instead of 17.6 in the cfg2 step)
+// MINB resident blocks per SM: phase 2 holds the rows of U entries in registers (U * 12 data registers and as many
+// addresses), so the register budget, not the occupancy, is what the launch bound protects
 template <bool ADAM, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 optimizer_step_kernel(const __grid_constant__ StepArgs a, float lr_or_alpha, const float* __restrict__ alpha_dev,
@@ -668,8 +813,25 @@ static int run_step(const char* name, bool adam, const tt_dense_var* dense, int 
   for (int i = 0; i < ns; ++i)
     TT_REQUIRE(sparse[i].slot0 && sparse[i].grad && aligned16(sparse[i].slot0) && aligned16(sparse[i].grad) && (!adam || sparse[i].slot1),
                "%s: table %d has a null or unaligned slot / gradient", name, i);
+  // entries per block: 32, or more when that would be over two waves of table blocks (short blocks keep the tail short;
+  // more entries per block amortise phase 1 and the block launch)
+  static const int env_epb = [] { const char* e = getenv("TT_OPT_ENTRIES"); return e ? atoi(e) : 0; }();
+  int epb = 32;
+  if (env_epb == 32 || env_epb == 64 || env_epb == 128) epb = env_epb;
+  else {
+    int64_t total = 0;
+    for (int i = 0; i < ns; ++i) total += sparse[i].nnz;
+    while (epb < kStepMaxEntries && ceil_div(total, (int64_t)epb) > 2 * 148 * 4) epb *= 2;
+  }
+  args.entries_per_block = epb;
   int blocks = 0;
-  args.dense_blocks[0] = 0;
+  args.sparse_blocks[0] = 0;
+  for (int i = 0; i < ns; ++i) {
+    blocks += (int)ceil_div(sparse[i].nnz, (int64_t)epb);
+    args.sparse_blocks[i + 1] = blocks;
+  }
+  for (int i = ns; i < TT_MAX_SPARSE_VARS; ++i) args.sparse_blocks[i + 1] = blocks;
+  args.dense_blocks[0] = blocks;
   for (int i = 0; i < nd; ++i) {
     const tt_dense_var& s = dense[i];
     TT_REQUIRE(s.w && s.slot0 && s.grad_parts && (!adam || s.slot1), "%s: dense variable %d has a null buffer", name, i);
@@ -683,20 +845,14 @@ static int run_step(const char* name, bool adam, const tt_dense_var* dense, int 
     args.dense_blocks[i + 1] = blocks;
   }
   for (int i = nd; i < TT_MAX_DENSE_VARS; ++i) args.dense_blocks[i + 1] = blocks;
-  args.sparse_blocks[0] = blocks;
-  for (int i = 0; i < ns; ++i) {
-    blocks += (int)ceil_div(sparse[i].nnz, 8);
-    args.sparse_blocks[i + 1] = blocks;
-  }
-  for (int i = ns; i < TT_MAX_SPARSE_VARS; ++i) args.sparse_blocks[i + 1] = blocks;
   args.n_dense = nd; args.n_sparse = ns;
   if (blocks == 0) return TT_OK;
   TT_PROF("optimizer_step_kernel", stream);
-  static const int minb = [] { const char* e = getenv("TT_OPT_MINB"); return e ? atoi(e) : 6; }();     // A/B runs: 6 or 8
-  if (adam && minb == 8) TT_CUDA_OK(launch_pdl(optimizer_step_kernel<true, 8>, dim3(blocks), dim3(256), (size_t)0, stream, args, lr_or_alpha, alpha_dev, b1, b2, eps));
-  else if (adam) TT_CUDA_OK(launch_pdl(optimizer_step_kernel<true, 6>, dim3(blocks), dim3(256), (size_t)0, stream, args, lr_or_alpha, alpha_dev, b1, b2, eps));
-  else if (minb == 8) TT_CUDA_OK(launch_pdl(optimizer_step_kernel<false, 8>, dim3(blocks), dim3(256), (size_t)0, stream, args, lr_or_alpha, alpha_dev, b1, b2, eps));
-  else TT_CUDA_OK(launch_pdl(optimizer_step_kernel<false, 6>, dim3(blocks), dim3(256), (size_t)0, stream, args, lr_or_alpha, alpha_dev, b1, b2, eps));
+  static const int minb = [] { const char* e = getenv("TT_OPT_MINB"); return e ? atoi(e) : 4; }();     // A/B runs: 2, 3 or 4
+#define TT_STEP_LAUNCH(A, M) TT_CUDA_OK(launch_pdl(optimizer_step_kernel<A, M>, dim3(blocks), dim3(256), (size_t)0, stream, args, lr_or_alpha, alpha_dev, b1, b2, eps))
+  if (adam) { if (minb == 2) TT_STEP_LAUNCH(true, 2); else if (minb == 4) TT_STEP_LAUNCH(true, 4); else TT_STEP_LAUNCH(true, 3); }
+  else { if (minb == 2) TT_STEP_LAUNCH(false, 2); else if (minb == 4) TT_STEP_LAUNCH(false, 4); else TT_STEP_LAUNCH(false, 3); }
+#undef TT_STEP_LAUNCH
   TT_LAUNCH_OK("optimizer_step_kernel");
   return TT_OK;
 }

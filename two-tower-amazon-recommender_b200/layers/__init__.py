@@ -290,6 +290,15 @@ class PendingTowers:
                         w2=d2.kernel.shadow, b2=d2.bias.value)
             if x_input is not None:
                 spec["x_input"] = x_input.bf16
+            elif Sequential.pregather_bags and (len(feats) > 1 or any(f[2] is not None for f in feats)) \
+                    and not any(isinstance(f[0], ops.PeerTable) for f in feats):
+                # Several rows per example (bags, several features): the stand-alone gather kernel -- a warp per output
+                # row, every SM full of them -- pools the tower input at 3 TB/s, where the 128 CTAs of the tower kernel
+                # keep 8 gathering warps each (cfg3 item tower, 7 rows per example: 21.6 us + a TMA-fed tower kernel
+                # against 86 us for the in-kernel gather).  One row per example stays in the tower kernel.
+                _, xb = ops.tower_input_fwd(feats, batch, d1.kernel.shape[0], want_f32=False, want_bf16=True)
+                spec["features"] = []
+                spec["x_input"] = xb
             if prepare_ws is not None:
                 spec["prepare_ws"] = prepare_ws[k]
             specs.append(spec)
@@ -342,6 +351,8 @@ class Sequential(Layer):
     # needs >= 3 of them per id (id -> key line -> CAS), and the tower kernel waits for its slowest chain: measured at
     # cfg2 the forward grows by 5.6 us while the removed stream join saves 2.9 us.
     fuse_prepare = os.environ.get("TT_FUSED_PREPARE", "0") == "1"
+    # towers with bags / several features: pool the tower input with the stand-alone gather kernel ahead of the fused MLP launch
+    pregather_bags = os.environ.get("TT_PREGATHER", "1") == "1"
 
     def __init__(self, layers: Sequence[Layer] = (), name: Optional[str] = None):
         self.layers = list(layers)
