@@ -303,6 +303,45 @@ class TestFusedOptimizerStep:
             ops.sparse_update_multi("adagrad", sparse_items, hyper)
 
 
+    @pytest.mark.parametrize("d,nnz,V", [(64, 3000, 500), (256, 3000, 500), (128, 40000, 2500), (128, 90000, 3000), (32, 90000, 100000)])
+    def test_row_widths_and_entries_per_block(self, ops, d, nnz, V):
+        """The step kernel's launch shapes: rows narrower than a warp's 128 floats (idle lanes), wider rows (chunk loop), and
+        id lists long enough for 64 and 128 entries per block -- duplicate-heavy (every block runs the reduce / ticket
+        phases) and duplicate-poor.  Dyadic gradients: the duplicate sums are order-independent, so the oracle is met to
+        rounding; the second launch on the same workspaces checks that every slot and accumulation row was left clean."""
+        rng = synth.rng_for(1000 + d + nnz)
+        table = rng.normal(size=(V, d)).astype(np.float32)
+        ids = synth.draw_ids(rng, nnz, V, 1.1 if V < 10000 else None)
+        ids[::97] = -1
+        B = nnz // 3
+        bag_table = rng.normal(size=(V, d)).astype(np.float32)
+        values, offsets = synth.draw_bags(rng, B, V, 0, 5)
+        grads = [synth.exact_matrix(rng, nnz, d, 4), synth.exact_matrix(rng, B, d, 4)]
+        cases = [(table, ids, None, "sum", grads[0]), (bag_table, values, offsets, "mean", grads[1])]
+        expand = TestFusedOptimizerStep._expand
+        items = []
+        for tab, v, off, mode, g in cases:
+            t = dev(tab)
+            items.append((t, dev(np.full(tab.shape, 0.1, np.float32)), None, dev(v), None if off is None else dev(off), mode, dev(g),
+                          ops.SparseWorkspace(len(v), d, t.device), torch.zeros(len(v), dtype=torch.uint8, device="cuda")))
+        refs = [(tab.astype(np.float64), np.full(tab.shape, 0.1)) for tab, *_ in cases]
+        for launch in range(2):
+            ops.sparse_prepare(items)
+            ops.optimizer_step("adagrad", [], items, (0.05, 1e-7))
+            for k, ((tab, v, off, mode, g), it) in enumerate(zip(cases, items)):
+                rows = expand(self, v, off, mode, g)
+                ok = v >= 0
+                w, acc, uniq = oracle.adagrad_sparse(refs[k][0], refs[k][1], v[ok], rows[ok], lr=0.05)
+                refs[k] = (w, acc)
+                got = it[0].cpu().numpy()
+                assert np.abs(got - w).max() <= 2e-5 * np.abs(w).max(), (launch, k)
+                assert np.abs(it[1].cpu().numpy() - acc).max() <= 2e-5 * np.abs(acc).max(), (launch, k)
+                untouched = np.setdiff1d(np.arange(tab.shape[0]), np.unique(v[ok]))
+                assert np.array_equal(got[untouched], tab[untouched])
+                first = np.zeros(len(v), bool); first[np.flatnonzero(ok)[np.unique(v[ok], return_index=True)[1]]] = True
+                assert np.array_equal(it[8].cpu().numpy().astype(bool), first)
+
+
 class TestFusedTrainStep:
     """Model-level: the TFRS-shaped surface picks the fused kernels for a 128-256-128 tower and the
     step still tracks the oracle."""
