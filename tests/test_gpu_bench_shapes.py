@@ -173,9 +173,17 @@ class TestCfg3Step:
         graphed = twin.make_graphed_train_step(to_dev(synth.make_batch(cfg, 1, pad_bags=True)), warmup=1)
         model.train_step(batch)                                      # mirror the warm-up step
         for s in range(2, 5):
+            # every compared step starts from the SAME state (copied in place: the captured graph sees it).  Most category
+            # ids are duplicated, their gradient sums depend on the order of the fp32 atomics, and over several steps a
+            # last-bit difference can flip a bf16 rounding and grow (tests/test_gpu_checkpoint.py)
+            for va, vb in zip(model.trainable_variables, twin.trainable_variables):
+                vb.assign(va.numpy())
+                for key, slot in va.slots.items():
+                    if isinstance(slot, torch.Tensor) and not key.startswith("_"):
+                        vb.assign_slot(key, slot)
             la = float(model.train_step(synth.make_batch(cfg, s))["loss"].item())
             lb = float(graphed(to_dev(synth.make_batch(cfg, s, pad_bags=True)))["loss"].item())
-            assert lb == pytest.approx(la, rel=1e-4), s
+            assert lb == pytest.approx(la, rel=1e-5), s
 
 
 class TestReferenceTowerSpec:

@@ -46,17 +46,21 @@ def test_restored_model_continues_identically(tt, tmp_path, opt_name):
         for k, s in va.slots.items():
             if isinstance(s, torch.Tensor) and not k.startswith("_"):
                 assert torch.equal(s, vb.slots[k]), (va.name, k)
+    # The two runs continue together, each step from the SAME state (the second one after another save / restore).
+    # Duplicate ids are summed with fp32 atomics, so the last bits of an updated row depend on the arrival order; carried
+    # into a further step, a last-bit difference of a master weight can flip the rounding of its bf16 shadow or of an
+    # activation (0.4 % of that element) and, with an Adagrad / Adam update as large as the weights themselves, grow to
+    # several per cent of a table row -- between two runs of the SAME model just as well.  One step from identical state
+    # is what "the restored model continues like the original" can be held to.
     for i, bt in enumerate(batches[2:]):
+        if i > 0:
+            a.save_weights(path)
+            b_model.load_weights(path)
         la, lb = float(a.train_step(bt)["loss"].item()), float(b_model.train_step(bt)["loss"].item())
-        # first step: bit-identical weights in, the same loss out.  Later steps see weights whose duplicate-id gradient sums
-        # were accumulated with fp32 atomics in a different order (last bits differ run to run)
-        assert la == pytest.approx(lb, rel=1e-6 if i == 0 else 1e-4)
-    # The two runs continue together.  Duplicate ids are summed with fp32 atomics, so the last bits of an updated row depend on
-    # the arrival order; in bf16 a last-bit difference of a master weight occasionally flips the rounding of its bf16 shadow
-    # or of an activation (0.4 % of that element), which the next step's gradients carry on: 2 in 10 runs of this test
-    # exceeded rtol 1e-4 on some element.  The bound is therefore the one of the graph-vs-eager test.
-    for va, vb in zip(a.trainable_variables, b_model.trainable_variables):
-        assert torch.allclose(va.value, vb.value, rtol=2e-3, atol=2e-5), va.name
+        assert la == pytest.approx(lb, rel=1e-6)       # bit-identical weights in, the same loss out
+        for va, vb in zip(a.trainable_variables, b_model.trainable_variables):
+            assert torch.allclose(va.value, vb.value, rtol=1e-5, atol=1e-7), (i, va.name)
+        assert b_model.optimizer.iterations == a.optimizer.iterations == 3 + i
     other = _model(tt, mk())
     with pytest.raises(ValueError):
         other.user_model = tt.Sequential([tt.layers.Embedding(901, 128), tt.layers.Dense(256, "relu"), tt.layers.Dense(128)])
@@ -83,7 +87,7 @@ def test_graphed_lazy_adam_matches_eager_and_counts_iterations(tt):
     for s in range(6):
         bt = mkb()
         la, lb = float(a.train_step(bt)["loss"].item()), float(graphed(bt)["loss"].item())
-        assert lb == pytest.approx(la, rel=2e-4), s
+        assert lb == pytest.approx(la, rel=2e-4 if s < 2 else 2e-3), s
     assert a.optimizer.iterations == b.optimizer.iterations == 8
     assert int(b.optimizer._dev_state[0].item()) == 8
     # alpha_8 on the device == the host formula at t = 8 (it would be alpha_3 if frozen at capture)
@@ -91,8 +95,11 @@ def test_graphed_lazy_adam_matches_eager_and_counts_iterations(tt):
     assert float(b.optimizer._dev_state[1].item()) == pytest.approx(b.optimizer._alpha(), rel=5e-5)
     frozen = tt.optimizers.LazyAdam(0.01); frozen.iterations = 3
     assert abs(float(b.optimizer._dev_state[1].item()) - frozen._alpha()) > 1e-4
+    # six steps of two runs: atomics-order noise amplified by bf16 rounding flips and Adam's normalised update (see
+    # above) can reach 1e-3 on single elements; a frozen alpha moves EVERY touched element by ~1e-2 over these steps
     for va, vb in zip(a.trainable_variables, b.trainable_variables):
-        assert torch.allclose(va.value, vb.value, rtol=2e-3, atol=2e-5), va.name
+        diff = (va.value - vb.value).abs()
+        assert float(diff.max()) < 5e-3 and float(diff.mean()) < 1e-4, (va.name, float(diff.max()), float(diff.mean()))
 
 
 def test_checkpoint_restore_is_seen_by_a_captured_graph(tt, tmp_path):
