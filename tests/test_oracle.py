@@ -169,6 +169,30 @@ class TestTowersAndOptimizers:
         np.testing.assert_allclose(t_k[[1, 4]], t_l[[1, 4]], rtol=1e-12)
 
 
+    def test_lazy_adam_matches_torch_sparse_adam_over_three_steps(self):
+        """torch.optim.SparseAdam is the same lazy rule written independently (moments of the rows present in the gradient
+        only, duplicates coalesced first, step size lr * sqrt(1 - b2^t) / (1 - b1^t), eps outside the square root).  The
+        oracle forms 1 - beta in fp32 as Keras does (0.00100005 for beta2): 5e-5 relative on v, hence the tolerance."""
+        rng = np.random.default_rng(21)
+        V, d = 12, 4
+        w = rng.normal(size=(V, d))
+        w0, seen = w.copy(), set()
+        tw = torch.nn.Parameter(torch.tensor(w.copy()))
+        opt = torch.optim.SparseAdam([tw], lr=0.01, betas=(0.9, 0.999), eps=1e-7)
+        m, v = np.zeros_like(w), np.zeros_like(w)
+        for step in range(1, 4):
+            ids = rng.integers(0, V, size=7)
+            seen.update(ids.tolist())
+            rows = rng.normal(size=(7, d))
+            tw.grad = torch.sparse_coo_tensor(torch.tensor(ids)[None, :], torch.tensor(rows), size=(V, d))
+            opt.step()
+            w, m, v, u = oracle.lazy_adam_sparse(w, m, v, ids, rows, step=step, lr=0.01)
+            assert u.tolist() == list(dict.fromkeys(ids.tolist()))                      # tf.unique order
+            np.testing.assert_allclose(w, tw.detach().numpy(), rtol=2e-4, atol=1e-7)
+        never = np.setdiff1d(np.arange(V), sorted(seen))
+        assert np.array_equal(w[never], w0[never]) and np.array_equal(m[never], np.zeros((len(never), d)))
+
+
 class TestTopK:
     def test_ties_resolve_to_lower_index(self):
         s = np.array([[1.0, 3.0, 3.0, 2.0, 3.0]])
@@ -230,6 +254,58 @@ class TestTrainStep:
         untouched = np.setdiff1d(np.arange(50), bq["user"])
         assert np.array_equal(qp["tables"]["user"][untouched], before[untouched])
         assert r["regularization_loss"] > 0
+
+    def test_full_train_step_matches_an_independent_torch_autograd_model(self):
+        """End to end against an INDEPENDENT statement of the same published semantics: torch modules (embedding lookups,
+        mean-pooled bag with duplicates and an empty bag, Dense(relu) -> Dense, logits / T, cross entropy with
+        reduction = sum against the diagonal, L2 kernel regulariser), autograd for every gradient, and Keras Adagrad written
+        out (acc += g^2; w -= lr * g / sqrt(acc + eps); on a table, g = 0 leaves a row and its accumulator alone).  Two
+        steps, so that the second one runs on updated accumulators."""
+        rng = synth.rng_for(8)
+        d, mlp, T, lr, l2, B = 8, (16, 8), 0.25, 0.1, 1e-3, 14
+        qs = oracle.TowerSpec([("user", "id", 30, None)], d, mlp)
+        cs = oracle.TowerSpec([("item", "id", 25, None), ("cat", "bag", 9, "mean")], d, mlp)
+        qp, cp = oracle.init_tower(qs, rng, np.float64), oracle.init_tower(cs, rng, np.float64)
+        mk = lambda p: {"tables": {k: np.full_like(v, 0.1) for k, v in p["tables"].items()},
+                        "kernels": [np.full_like(k, 0.1) for k in p["kernels"]],
+                        "biases": [np.full_like(b, 0.1) for b in p["biases"]]}
+        qsl, csl = mk(qp), mk(cp)
+        t = lambda a: torch.tensor(np.asarray(a, dtype=np.float64), requires_grad=True)
+        P = {"user": t(qp["tables"]["user"]), "item": t(cp["tables"]["item"]), "cat": t(cp["tables"]["cat"]),
+             "qk": [t(k) for k in qp["kernels"]], "qb": [t(b) for b in qp["biases"]],
+             "ck": [t(k) for k in cp["kernels"]], "cb": [t(b) for b in cp["biases"]]}
+        leaves = [P["user"], P["item"], P["cat"], *P["qk"], *P["qb"], *P["ck"], *P["cb"]]
+        acc = [torch.full_like(v, 0.1) for v in leaves]
+        for step in range(2):
+            users, items = synth.draw_ids(rng, B, 30, 1.2), synth.draw_ids(rng, B, 25, 1.2)
+            vals, offs = synth.draw_bags(rng, B, 9, 1, 3, empty_frac=0.25)
+            assert (np.diff(offs) == 0).any() and len(np.unique(vals)) < len(vals)      # empty bags and duplicates present
+            r = oracle.two_tower_train_step(qs, cs, qp, cp, qsl, csl, {"user": users}, {"item": items, "cat": (vals, offs)},
+                                            temperature=T, lr=lr, l2=l2)
+            lens = np.diff(offs)
+            bag_of = torch.tensor(np.repeat(np.arange(B), lens))
+            pooled = torch.zeros((B, d), dtype=torch.float64).index_add(0, bag_of, P["cat"][torch.tensor(vals)])
+            pooled = pooled / torch.tensor(np.maximum(lens, 1), dtype=torch.float64)[:, None]
+            mlp_t = lambda x, ks, bs: torch.relu(x @ ks[0] + bs[0]) @ ks[1] + bs[1]
+            q = mlp_t(P["user"][torch.tensor(users)], P["qk"], P["qb"])
+            c = mlp_t(P["item"][torch.tensor(items)] + pooled, P["ck"], P["cb"])
+            loss = torch.nn.functional.cross_entropy(q @ c.T / T, torch.arange(B), reduction="sum")
+            reg = l2 * sum((k * k).sum() for k in P["qk"] + P["ck"])
+            assert r["loss"] == pytest.approx(float(loss.detach()), rel=1e-12)
+            assert r["regularization_loss"] == pytest.approx(float(reg.detach()), rel=1e-12)
+            grads = torch.autograd.grad(loss + reg, leaves)
+            with torch.no_grad():
+                for v, a, g in zip(leaves, acc, grads):
+                    a += g * g
+                    v -= lr * g / torch.sqrt(a + 1e-7)
+            got = [qp["tables"]["user"], cp["tables"]["item"], cp["tables"]["cat"], *qp["kernels"], *qp["biases"],
+                   *cp["kernels"], *cp["biases"]]
+            slots = [qsl["tables"]["user"], csl["tables"]["item"], csl["tables"]["cat"], *qsl["kernels"], *qsl["biases"],
+                     *csl["kernels"], *csl["biases"]]
+            for v, a, w, sa in zip(leaves, acc, got, slots):
+                np.testing.assert_allclose(w, v.detach().numpy(), rtol=1e-10, atol=1e-13)
+                np.testing.assert_allclose(sa, a.numpy(), rtol=1e-10, atol=1e-13)
+            assert np.array_equal(np.sort(r["unique"]["c/cat"]), np.unique(vals))
 
     def test_bf16_round_is_rne(self):
         x = np.array([1.0, 1.00390625, 1.01171875, -2.5, 3.14159], dtype=np.float32)
