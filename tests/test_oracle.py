@@ -103,6 +103,50 @@ class TestRetrievalSemantics:
         with pytest.raises(ValueError):
             oracle.retrieval_scores(self.q, self.c, remove_accidental_hits=True)
 
+    def test_every_option_together_matches_torch_autograd(self):
+        """tfrs.tasks.Retrieval.call with temperature, sample weights, candidate_sampling_probability (clipped logQ) and
+        accidental-hit removal at once, restated in torch (fp64) with autograd for dq / dc; a rectangular score matrix
+        (more candidates than queries, as with global-batch negatives) and candidate ids with duplicates of positives."""
+        rng = np.random.default_rng(17)
+        nq, nc, d, T = 9, 14, 6, 0.2
+        q, c = rng.normal(size=(nq, d)), rng.normal(size=(nc, d))
+        ids = rng.integers(0, 6, size=nc)                       # many duplicates, also among the positives ids[:nq]
+        p = rng.uniform(1e-8, 0.4, size=nc); p[3] = 5e-7        # below the 1e-6 clip
+        w = rng.uniform(0.2, 2.0, size=nq)
+        r = oracle.retrieval_loss_and_grads(q, c, temperature=T, sample_weight=w, candidate_sampling_probability=p,
+                                            candidate_ids=ids, remove_accidental_hits=True)
+        tq, tc = torch.tensor(q, requires_grad=True), torch.tensor(c, requires_grad=True)
+        s = tq @ tc.T / T - torch.log(torch.clamp(torch.tensor(p), 1e-6, 1.0))[None, :]
+        labels = torch.eye(nq, nc, dtype=torch.float64)
+        dup = (torch.tensor(ids)[:nq, None] == torch.tensor(ids)[None, :]).double() - labels
+        s = s + dup * (float(np.finfo(np.float32).min) / 100.0)
+        per_row = -(labels * torch.log_softmax(s, dim=1)).sum(1)
+        loss = (torch.tensor(w) * per_row).sum()
+        loss.backward()
+        assert (dup.sum(1) > 0).any()                           # accidental hits are present
+        assert r["loss"] == pytest.approx(float(loss.detach()), rel=1e-12)
+        np.testing.assert_allclose(r["dq"], tq.grad.numpy(), rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(r["dc"], tc.grad.numpy(), rtol=1e-9, atol=1e-12)
+
+    def test_hard_negative_mining_matches_torch_autograd(self):
+        """tfrs.layers.loss.HardNegativeMining(n): per row the positive and the n highest-scoring negatives survive
+        (top_k of scores + labels * MAX_FLOAT, k = n + 1), the loss is the cross entropy over the gathered columns."""
+        rng = np.random.default_rng(23)
+        nq, nc, d, T, n = 8, 20, 5, 0.3, 4
+        q, c = rng.normal(size=(nq, d)), rng.normal(size=(nc, d))
+        r = oracle.retrieval_loss_and_grads(q, c, temperature=T, num_hard_negatives=n)
+        tq, tc = torch.tensor(q, requires_grad=True), torch.tensor(c, requires_grad=True)
+        s = tq @ tc.T / T
+        labels = torch.eye(nq, nc, dtype=torch.float64)
+        _, idx = torch.topk(s.detach() + labels * 1e30, n + 1, dim=1)
+        gs, gl = torch.gather(s, 1, idx), torch.gather(labels, 1, idx)
+        assert (gl.sum(1) == 1).all()                          # the positive is among the survivors of every row
+        loss = -(gl * torch.log_softmax(gs, dim=1)).sum()
+        loss.backward()
+        assert r["loss"] == pytest.approx(float(loss.detach()), rel=1e-12)
+        np.testing.assert_allclose(r["dq"], tq.grad.numpy(), rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(r["dc"], tc.grad.numpy(), rtol=1e-9, atol=1e-12)
+
     def test_hard_negatives_keep_positive_plus_n(self):
         r = oracle.retrieval_loss_and_grads(self.q, self.c, num_hard_negatives=3)
         assert ((r["dq"] != 0).any())
